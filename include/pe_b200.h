@@ -1,0 +1,178 @@
+/*
+ * pe_b200.h — C ABI of the B200-native volumetric renderer for PlayableEnvironments.
+ *
+ * The reference has no FFI of its own (it is pure Python/PyTorch); this
+ * header is the boundary its Python modules bind through ctypes.  Each
+ * entry point names the reference interface it replaces (paths relative to the upstream tree).
+ *
+ * Conventions
+ *  - plain-old-data structs, raw DEVICE pointers (tensor.data_ptr()), sizes in elements;
+ *  - no allocation and no ownership transfer: every buffer, including the workspace, belongs to
+ *    the caller; calls are asynchronous on the supplied CUDA stream, never synchronise the
+ *    device and never read device memory from the host;
+ *  - all floating point tensors are contiguous fp32 unless stated; leading dims (B,O,C) of the
+ *    reference are flattened into `images`;
+ *  - return value 0 = success, negative = error (pe_last_error() gives a thread-local message);
+ *  - re-entrant: no global mutable state, safe from several host threads on different streams
+ *    (nn.DataParallel replicas, train.py:61).
+ */
+#ifndef PE_B200_H
+#define PE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PE_ABI_VERSION 1
+#define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
+#define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
+#define PE_MAX_OCTAVES 16
+
+typedef void* pe_stream_t;    /* cudaStream_t */
+
+enum PeNerfKind   { PE_NERF_ADAIN = 0,      /* model/nerf_models/adain_style_nerf_model.py          */
+                    PE_NERF_SKYBOX_V3 = 1   /* model/nerf_models/skybox_adain_style_nerf_model_v3.py */ };
+enum PeBenderKind { PE_BENDER_ZEROED = 0,   /* model/nerf_models/zeroed_ray_bender_model.py          */
+                    PE_BENDER_POSITIONAL = 1/* model/nerf_models/positional_ray_bender_model.py      */ };
+enum PePrecision  { PE_PRECISION_FP32 = 0,  /* CUDA-core fp32 FMA path, any shape                    */
+                    PE_PRECISION_FP16 = 1,  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate     */
+                    PE_PRECISION_FP16X2 = 2 /* tcgen05, weights split hi+lo fp16 (2 MMA passes)      */ };
+enum PeError      { PE_OK = 0, PE_ERR_INVALID = -1, PE_ERR_UNSUPPORTED = -2, PE_ERR_CUDA = -3, PE_ERR_WORKSPACE = -4 };
+
+/* Architecture + geometry of one object model
+ * (model/nerf_models/ray_bending_style_nerf_model.py:17-50 and its two sub-model configs). */
+typedef struct PeObjectDesc {
+    int32_t nerf_kind, bender_kind;
+    int32_t width, layers, skip, octaves, features;      /* nerf_model: layers_width, backbone_layers_count, skip_layer_idx, octaves, output_features */
+    int32_t style_features, deformation_features;
+    int32_t b_width, b_layers, b_skip, b_octaves;        /* ray_bender_model (positional)         */
+    int32_t positions;                                   /* positions_count_coarse                */
+    int32_t is_static;                                   /* object_ids_helper.py:47-55            */
+    int32_t canonical_pose;                              /* zero the displacements (:108-110)     */
+    float bbox[6];                                       /* x_lo,x_hi,y_lo,y_hi,z_lo,z_hi          */
+    float z_near_min, z_far_max, empty_space_alpha;
+    float b_anneal[PE_MAX_OCTAVES];                      /* annealable_positional_encoder.py:54-58, evaluated on the host from current_step */
+    const void* packed;                                  /* blob written by pe_pack_object (device)*/
+} PeObjectDesc;
+
+/* fp32 parameter tensors of one object model, nn.Linear layout [out][in]
+ * (state_dict names in SURVEY.md section 3.3). NULL where the architecture has none. */
+typedef struct PeObjectParams {
+    const float* backbone_w[PE_MAX_LAYERS];  const float* backbone_b[PE_MAX_LAYERS];   /* nerf_model.backbone_layers.{i} */
+    const float* alpha_w;  const float* alpha_b;                                        /* nerf_model.alpha_head          */
+    const float* head0_w;                                                               /* features_head.0 (no bias)      */
+    const float* affine1_w; const float* affine1_b; const float* bn1_mean; const float* bn1_var;  /* features_head.1     */
+    const float* head3_w;                                                               /* features_head.3 (no bias)      */
+    const float* affine2_w; const float* affine2_b; const float* bn2_mean; const float* bn2_var;  /* features_head.4     */
+    const float* head6_w;  const float* head6_b;                                        /* features_head.6                */
+    const float* bender_w[PE_MAX_LAYERS];    const float* bender_b[PE_MAX_LAYERS];     /* ray_bender.backbone_layers.{i} */
+    const float* bender_out_w;                                                          /* ray_bender.output_head (no bias) */
+} PeObjectParams;
+
+/* One composer call: model/object_composer.py:786-812 (ObjectComposer.forward). */
+typedef struct PeScene {
+    int32_t images;            /* B*O*C                                                      */
+    int32_t rays;              /* samples_per_image                                          */
+    int32_t objects;           /* object instances (transformation_matrix_w2o.size(-1))      */
+    int32_t static_objects;    /* leading instances that are static (fix_object_overlaps)    */
+    int32_t perturb;           /* stratified jitter + raw-alpha noise                        */
+    int32_t training;          /* BatchNorm uses batch statistics (adain.py:47)              */
+    int32_t fix_object_overlaps; /* utils/configuration.py:191-192                           */
+    int32_t apply_activation;  /* sigmoid on features (object_composer.py:548-549)           */
+    int32_t precision;         /* PePrecision                                                */
+    int32_t explicit_positions;/* 0: sample along rays; 1: field evaluation on given points  */
+    PeObjectDesc object[PE_MAX_OBJECTS];
+} PeScene;
+
+typedef struct PeInputs {
+    const float* ray_origins;        /* [images][3]                world space               */
+    const float* ray_directions;     /* [images][rays][3]                                    */
+    const float* w2o;                /* [images][objects][3][4]    rows of the 4x4 (:828)     */
+    const float* style[PE_MAX_OBJECTS];        /* [images][style_features]                   */
+    const float* deformation[PE_MAX_OBJECTS];  /* [images][deformation_features]             */
+    const uint8_t* object_in_scene;  /* [images][objects]                                    */
+    const float* rand[PE_MAX_OBJECTS];         /* [images][rays][P_k] uniform, replaces torch.rand (ray_helper.py:1275); NULL unless perturb */
+    const float* noise[PE_MAX_OBJECTS];        /* [images][rays][P_k] normal, replaces torch.randn (object_composer.py:194) in the per-object integrate */
+    const float* noise_global;       /* [images][rays][sum P]     same, for the composed scene */
+    const float* positions;          /* explicit_positions: [images][rays][3] object space   */
+} PeInputs;
+
+/* Result of ObjectComposer.integrate (model/object_composer.py:724-784). Any pointer may be NULL. */
+typedef struct PeIntegrated {
+    float* integrated_features;      /* [images][rays][features]                             */
+    float* opacity;                  /* [images][rays]                                       */
+    float* weights;                  /* [images][rays][P]                                    */
+    float* depth;                    /* [images][rays]                                       */
+    float* disparity;                /* [images][rays]                                       */
+    float* integrated_displacements_magnitude;  /* [images][rays]                            */
+    float* integrated_divergence;    /* [images][rays]  (zeros: Hutchinson term, see DESIGN)  */
+} PeIntegrated;
+
+typedef struct PeOutputs {
+    PeIntegrated object[PE_MAX_OBJECTS];        /* results["coarse"]["object_k"]             */
+    PeIntegrated global;                        /* results["coarse"]["global"]               */
+    /* per-sample tensors (optional; [images][rays][P_k] (+[features]|[3])): the return value of
+     * RayBendingStyleNerfModel.forward (ray_bending_style_nerf_model.py:137-219)              */
+    float* raw_features[PE_MAX_OBJECTS];
+    float* raw_alphas[PE_MAX_OBJECTS];
+    float* displacements[PE_MAX_OBJECTS];
+    float* positions_t[PE_MAX_OBJECTS];
+    /* training: BatchNorm batch statistics [2][C] (mean, unbiased variance) per AdaIn layer; the
+     * caller applies the momentum update to its running buffers                                  */
+    float* bn1_running[PE_MAX_OBJECTS];
+    float* bn2_running[PE_MAX_OBJECTS];
+} PeOutputs;
+
+/* -- library ------------------------------------------------------------------------------- */
+int         pe_abi_version(void);
+const char* pe_last_error(void);
+/* number of kernels launched by this thread since the last call of this function */
+int64_t     pe_take_launch_count(void);
+
+/* -- parameters: replaces nn.Module parameter storage of model/nerf_models/*.py --------------- */
+size_t pe_packed_bytes(const PeObjectDesc* desc);
+int    pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* params, void* packed, pe_stream_t stream);
+
+/* -- the hot path: replaces ObjectComposer.forward (model/object_composer.py:786-892) and, through
+ *    it, forward_object :486-580, RayHelper.transform_rays / create_ray_positions
+ *    (utils/lib_3d/ray_helper.py:1203-1282), RayBendingStyleNerfModel.forward, compose :399-447 and
+ *    integrate :724-784.  TensorBatchifier chunking (utils/tensor_batchifier.py) is unnecessary:
+ *    the workspace is O(rays), so the whole frame is one call.                                  */
+size_t pe_workspace_bytes(const PeScene* scene);
+int    pe_render_forward(const PeScene* scene, const PeInputs* in, const PeOutputs* out,
+                         void* workspace, size_t workspace_bytes, pe_stream_t stream);
+
+/* -- stand-alone operators (module-level API of the reference) ---------------------------------- */
+/* PositionalEncoder.forward / AnnealablePositionalEncoder.forward
+ * (model/positional_encoder.py:41-65, model/annealable_positional_encoder.py:46-76).
+ * x [n][dims] -> out [n][dims*(append_original + 2*octaves)]; weights NULL or [octaves].        */
+int pe_positional_encoding(const float* x, int64_t n, int32_t dims, int32_t octaves, int32_t append_original,
+                           const float* weights, float* out, pe_stream_t stream);
+/* RayHelper.create_camera_rays + sample_all_rays_strided_grid + transform_rays(c2w)
+ * (utils/lib_3d/ray_helper.py:15-52, 433-482, 1203-1227): focal [images], c2w [images][3][4],
+ * strides[n_strides]; writes directions [images][R][3], origins [images][3], positions [images][R][2]
+ * with R = sum_s (H/s)*(W/s).                                                                   */
+int pe_generate_rays(const float* focal, const float* c2w, int32_t images, int32_t height, int32_t width,
+                     const int32_t* strides, int32_t n_strides, float* directions, float* origins,
+                     float* positions, pe_stream_t stream);
+/* fold_strided_tensors + run_decoder_on_results channel split
+ * (model/environment_model_backpropagated_autoencoder.py:129-168,
+ *  model/environment_model_multiresolution_backpropagated_autoencoder.py:59-99):
+ * features [images][R][F] -> per stride s a CHW grid [images][channels_s][H/s][W/s] taking the
+ * channel range starting at sum of previous channels.                                            */
+int pe_fold_feature_grids(const float* features, int32_t images, int32_t height, int32_t width, int32_t n_features,
+                          const int32_t* strides, const int32_t* channels, int32_t n_strides,
+                          float* const* grids, pe_stream_t stream);
+
+/* -- debug / validation ---------------------------------------------------------------------- */
+/* D[128][n] = A[128][k] * B[n][k]^T through the same tcgen05 building blocks as the fused kernel
+ * (fp16 operands, fp32 accumulate).  Used by tests to validate descriptors on the device.       */
+int pe_debug_umma_gemm(const float* a, const float* b, float* d, int32_t n, int32_t k, pe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PE_B200_H */

@@ -1,0 +1,237 @@
+// extern "C" entry points of libpe_b200.so (see include/pe_b200.h) and the host-side orchestration of one
+// ObjectComposer.forward call (model/object_composer.py:786-892).
+#include <stdarg.h>
+#include <string.h>
+
+#include "pe_kernels.cuh"
+
+static thread_local char g_error[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void pe_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void pe_count_launch(int n) { g_launches += n; }
+
+int pe_device_sm_count(int* out) {
+    int dev = 0;
+    PE_CUDA_CHECK(cudaGetDevice(&dev));
+    PE_CUDA_CHECK(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return PE_OK;
+}
+
+extern "C" int pe_abi_version(void) { return PE_ABI_VERSION; }
+extern "C" const char* pe_last_error(void) { return g_error; }
+extern "C" int64_t pe_take_launch_count(void) { const int64_t n = g_launches; g_launches = 0; return n; }
+
+static int validate_object(const PeObjectDesc& d) {
+    if (d.nerf_kind != PE_NERF_ADAIN && d.nerf_kind != PE_NERF_SKYBOX_V3) { pe_set_error("unknown nerf model kind %d", d.nerf_kind); return PE_ERR_INVALID; }
+    if (d.bender_kind != PE_BENDER_ZEROED && d.bender_kind != PE_BENDER_POSITIONAL) { pe_set_error("unknown ray bender kind %d", d.bender_kind); return PE_ERR_INVALID; }
+    if (d.layers < 1 || d.layers > PE_MAX_LAYERS || d.skip < 0) { pe_set_error("backbone_layers_count must be in [1,%d]", PE_MAX_LAYERS); return PE_ERR_INVALID; }
+    if (d.skip >= d.layers) { pe_set_error("Skip layer must refer to a valid backbone layer idx"); return PE_ERR_INVALID; }   // adain_style_nerf_model.py:32-33
+    if (d.octaves < 0 || d.octaves > PE_MAX_OCTAVES || d.b_octaves > PE_MAX_OCTAVES) { pe_set_error("at most %d octaves", PE_MAX_OCTAVES); return PE_ERR_INVALID; }
+    if (d.width < 8 || d.width % 8 || d.features < 1 || d.positions < 1 || d.positions > 0xffff) { pe_set_error("bad field shape"); return PE_ERR_INVALID; }
+    if (d.bender_kind == PE_BENDER_POSITIONAL && (d.b_layers < 1 || d.b_layers > PE_MAX_LAYERS || d.b_width < 8 || d.b_width % 8)) { pe_set_error("bad ray bender shape"); return PE_ERR_INVALID; }
+    return PE_OK;
+}
+
+extern "C" size_t pe_packed_bytes(const PeObjectDesc* desc) {
+    if (!desc || validate_object(*desc) != PE_OK) return 0;
+    return (size_t)pe_layout(*desc).total;
+}
+
+extern "C" int pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* params, void* packed, pe_stream_t stream) {
+    if (!desc || !params || !packed) { pe_set_error("null argument"); return PE_ERR_INVALID; }
+    int rc = validate_object(*desc);
+    if (rc != PE_OK) return rc;
+    return pe_launch_pack(*desc, pe_layout(*desc), *params, packed, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+struct ObjWorkspace {
+    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2;
+    uint8_t* inbox;
+    double* stats;
+};
+
+struct Workspace {
+    ObjWorkspace obj[PE_MAX_OBJECTS];
+    size_t bytes;
+};
+
+static bool object_uses_tc(const PeScene& s, int k) {
+    return s.precision != PE_PRECISION_FP32 && !s.training && !s.explicit_positions && pe_tc_shape_ok(s.object[k]);
+}
+
+// per-sample features are only materialised where something downstream reads them
+static bool needs_feature_buffer(const PeScene& s, int k) {
+    if (s.explicit_positions) return false;                 // caller supplies raw_features
+    if (!object_uses_tc(s, k)) return true;                 // the fp32 path integrates in the compositor
+    return s.objects > 1;                                   // tc path integrates its own object; the composition needs them
+}
+
+static Workspace carve(const PeScene& s, void* base) {
+    Workspace w = {};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off = (off + bytes + 255) / 256 * 256; return p; };
+    for (int k = 0; k < s.objects; ++k) {
+        const PeObjectDesc& d = s.object[k];
+        const size_t P = s.explicit_positions ? 1 : d.positions;
+        const size_t n = (size_t)s.images * s.rays * P;
+        ObjWorkspace& o = w.obj[k];
+        o.t = (float*)take(n * 4);
+        o.raw = (float*)take(n * 4);
+        o.dispmag = (float*)take(n * 4);
+        o.inbox = (uint8_t*)take(n);
+        o.feat = needs_feature_buffer(s, k) ? (float*)take(n * d.features * 4) : nullptr;
+        o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
+        o.aff2 = (float*)take((size_t)s.images * d.width * 4);
+        o.stats = (double*)take((size_t)(3 * d.width + 4) * 8);
+        o.run1 = (float*)take((size_t)2 * d.width * 4);
+        o.run2 = (float*)take((size_t)d.width * 4);
+    }
+    w.bytes = off;
+    return w;
+}
+
+static int validate_scene(const PeScene& s) {
+    if (s.objects < 1 || s.objects > PE_MAX_OBJECTS) { pe_set_error("objects must be in [1,%d]", PE_MAX_OBJECTS); return PE_ERR_INVALID; }
+    if (s.images < 0 || s.rays < 0) { pe_set_error("negative sizes"); return PE_ERR_INVALID; }
+    for (int k = 0; k < s.objects; ++k) {
+        int rc = validate_object(s.object[k]);
+        if (rc != PE_OK) return rc;
+        if (!s.object[k].packed) { pe_set_error("object %d has no packed parameters", k); return PE_ERR_INVALID; }
+        if (s.object[k].features != s.object[0].features) { pe_set_error("all objects must share output_features"); return PE_ERR_INVALID; }
+    }
+    return PE_OK;
+}
+
+extern "C" size_t pe_workspace_bytes(const PeScene* scene) {
+    if (!scene || validate_scene(*scene) != PE_OK) return 0;
+    return carve(*scene, nullptr).bytes + 256;
+}
+
+extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const PeOutputs* out, void* workspace,
+                                 size_t workspace_bytes, pe_stream_t stream_) {
+    if (!scene || !in || !out) { pe_set_error("null argument"); return PE_ERR_INVALID; }
+    const PeScene& s = *scene;
+    int rc = validate_scene(s);
+    if (rc != PE_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if ((size_t)workspace % 256) { pe_set_error("workspace must be 256-byte aligned"); return PE_ERR_WORKSPACE; }
+    const Workspace ws = carve(s, workspace);
+    if (ws.bytes > workspace_bytes) { pe_set_error("workspace too small: %zu < %zu", workspace_bytes, ws.bytes); return PE_ERR_WORKSPACE; }
+    if (s.perturb && !s.explicit_positions) {
+        for (int k = 0; k < s.objects; ++k)
+            if (!in->rand[k]) { pe_set_error("perturb needs rand[%d]", k); return PE_ERR_INVALID; }
+    }
+    if (s.images == 0 || s.rays == 0) return PE_OK;
+    int sm_count = 148;
+    rc = pe_device_sm_count(&sm_count);
+    if (rc != PE_OK) return rc;
+
+    for (int k = 0; k < s.objects; ++k) {
+        const PeObjectDesc& d = s.object[k];
+        const PeLayout L = pe_layout(d);
+        const ObjWorkspace& o = ws.obj[k];
+        const unsigned char* blob = (const unsigned char*)d.packed;
+        auto P32 = [&](int64_t off) { return (const float*)(blob + off); };
+        const bool tc = object_uses_tc(s, k);
+
+        PeFieldArgs fa = {};
+        fa.ob = d; fa.L = L;
+        fa.images = s.images; fa.rays = s.rays; fa.objects = s.objects; fa.k = k;
+        fa.perturb = s.perturb; fa.explicit_positions = s.explicit_positions; fa.training = s.training;
+        fa.apply_activation = s.apply_activation; fa.precision = s.precision;
+        fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
+        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.positions = in->positions; fa.ois = in->object_in_scene;
+        fa.aff1 = o.aff1; fa.aff2 = o.aff2;
+        fa.t_out = out->positions_t[k] ? out->positions_t[k] : o.t;
+        fa.raw_out = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
+        fa.feat_out = out->raw_features[k] ? out->raw_features[k] : o.feat;
+        fa.disp_out = out->displacements[k];
+        fa.dispmag_out = o.dispmag;
+        fa.inbox_out = o.inbox;
+        fa.stats = o.stats;
+        fa.integ = out->object[k];
+        fa.noise = s.perturb ? in->noise[k] : nullptr;
+        if (!tc && !fa.feat_out) { pe_set_error("internal: no feature buffer for object %d", k); return PE_ERR_INVALID; }
+        if (d.bender_kind == PE_BENDER_POSITIONAL && !fa.deformation) { pe_set_error("object %d needs a deformation code", k); return PE_ERR_INVALID; }
+        if (!in->style[k]) { pe_set_error("object %d needs a style code", k); return PE_ERR_INVALID; }
+
+        PeStyleArgs s1 = {};
+        s1.images = s.images; s1.style_features = d.style_features; s1.channels = d.width; s1.training = 0;
+        s1.style = in->style[k]; s1.aff_w = P32(L.aff1_w); s1.aff_b = P32(L.aff1_b);
+        s1.run_mean = P32(L.bn1_mean); s1.run_var = P32(L.bn1_var); s1.stats = o.stats; s1.out = o.aff1; s1.running_out = o.run1;
+        PeStyleArgs s2 = s1;
+        s2.channels = d.width / 2; s2.aff_w = P32(L.aff2_w); s2.aff_b = P32(L.aff2_b);
+        s2.run_mean = P32(L.bn2_mean); s2.run_var = P32(L.bn2_var); s2.stats = o.stats + 2 * d.width + 2; s2.out = o.aff2; s2.running_out = o.run2;
+
+        auto launch_field = [&](int phase) {
+            fa.phase = phase;
+            const PeIntegrated none = {};
+            return tc ? pe_launch_field_tc(fa, s.objects == 1 ? out->global : none, sm_count, stream) : pe_launch_field_fp32(fa, sm_count, stream);
+        };
+        if (s.training) {
+            // train-mode BatchNorm (adain.py:47): statistics over all in-box samples of this object in this call.
+            // Three passes, two global reductions.
+            PE_CUDA_CHECK(cudaMemsetAsync(o.stats, 0, (size_t)(3 * d.width + 4) * 8, stream));
+            rc = pe_launch_style(s1, stream); if (rc) return rc;      // any valid affine for the unused epilogue
+            rc = pe_launch_style(s2, stream); if (rc) return rc;
+            rc = launch_field(1); if (rc) return rc;
+            s1.training = 1;
+            rc = pe_launch_style(s1, stream); if (rc) return rc;
+            rc = launch_field(2); if (rc) return rc;
+            s2.training = 1;
+            rc = pe_launch_style(s2, stream); if (rc) return rc;
+            rc = launch_field(0); if (rc) return rc;
+            if (out->bn1_running[k]) PE_CUDA_CHECK(cudaMemcpyAsync(out->bn1_running[k], o.run1, (size_t)2 * d.width * 4, cudaMemcpyDeviceToDevice, stream));
+            if (out->bn2_running[k]) PE_CUDA_CHECK(cudaMemcpyAsync(out->bn2_running[k], o.run2, (size_t)d.width * 4, cudaMemcpyDeviceToDevice, stream));
+        } else {
+            rc = pe_launch_style(s1, stream); if (rc) return rc;
+            rc = pe_launch_style(s2, stream); if (rc) return rc;
+            rc = launch_field(0); if (rc) return rc;
+        }
+    }
+    if (s.explicit_positions) return PE_OK;
+
+    PeCompositeArgs ca = {};
+    ca.images = s.images; ca.rays = s.rays; ca.objects = s.objects; ca.static_objects = s.static_objects;
+    ca.features = s.object[0].features; ca.fix_overlaps = s.fix_object_overlaps; ca.perturb = s.perturb;
+    ca.dirs = in->ray_directions;
+    ca.noise_global = s.perturb ? in->noise_global : nullptr;
+    bool all_tc = true;
+    for (int k = 0; k < s.objects; ++k) {
+        const ObjWorkspace& o = ws.obj[k];
+        ca.positions[k] = s.object[k].positions;
+        ca.total_positions += s.object[k].positions;
+        ca.t[k] = out->positions_t[k] ? out->positions_t[k] : o.t;
+        ca.raw[k] = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
+        ca.feat[k] = out->raw_features[k] ? out->raw_features[k] : o.feat;
+        ca.dispmag[k] = o.dispmag;
+        ca.inbox[k] = o.inbox;
+        ca.noise[k] = s.perturb ? in->noise[k] : nullptr;
+        ca.object[k] = out->object[k];
+        all_tc = all_tc && object_uses_tc(s, k);
+    }
+    ca.global = out->global;
+    // objects evaluated by the tcgen05 kernel integrate themselves in its epilogue; a single such object IS the scene
+    ca.do_objects = all_tc ? 0 : 1;
+    ca.do_global = (all_tc && s.objects == 1) ? 0 : 1;
+    if (all_tc && s.objects > 1) ca.do_objects = 0;
+    if (!all_tc) {
+        // mixed scenes: the compositor integrates the fp32 objects; tc objects already wrote theirs
+        for (int k = 0; k < s.objects; ++k)
+            if (object_uses_tc(s, k)) memset(&ca.object[k], 0, sizeof(PeIntegrated));
+    }
+    if (ca.do_objects || ca.do_global) {
+        rc = pe_launch_composite(ca, stream);
+        if (rc) return rc;
+    }
+    return PE_OK;
+}

@@ -1,0 +1,55 @@
+"""Entry of the hot path as the scene model sees it (reference: EnvironmentModel.batchified_composer_call and
+merge_dictionaries, model/environment_model.py:474-545).
+
+``install(environment_model)`` swaps the composer of an already-built reference ``EnvironmentModel`` (any of its
+autoencoder-coupled subclasses) for the B200 one and rebinds ``batchified_composer_call`` — train.py, train_autoencoder.py and
+play.py then run unchanged.  See INTEGRATION.md."""
+import types
+from typing import Dict, List
+
+import torch
+
+from .object_composer import ObjectComposer
+
+
+def merge_dictionaries(dictionaries: List[Dict], dimension: int) -> Dict:
+    """Reference :523-545 (drops the ``pytorch_hook`` dummy)."""
+    merged = {}
+    for key in list(dictionaries[0].keys()):
+        if key == "pytorch_hook":
+            continue
+        if torch.is_tensor(dictionaries[0][key]):
+            merged[key] = torch.cat([d[key] for d in dictionaries], dim=dimension)
+        else:
+            merged[key] = merge_dictionaries([d[key] for d in dictionaries], dimension)
+    return merged
+
+
+def batchified_composer_call(object_composer: ObjectComposer, ray_origins, ray_directions, focal_normals, transformation_matrix_w2o,
+                             style, deformation, object_in_scene, perturb: bool, samples_per_image_batching: int = 0,
+                             video_indexes=None, canonical_pose: bool = False) -> Dict:
+    """Reference :474-521.  ``samples_per_image_batching`` exists there only to bound activation memory (12 sequential composer
+    calls per 288x512 frame); the fused path keeps O(1) state per ray, so the argument is accepted and the frame is ONE call."""
+    results = object_composer(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o, style, deformation,
+                              object_in_scene, perturb, video_indexes=video_indexes, canonical_pose=canonical_pose)
+    results.pop("pytorch_hook", None)
+    return results
+
+
+def install(environment_model, precision: str = "fp16"):
+    """Replaces ``environment_model.object_composer`` (a reference ObjectComposer) by the B200 composer carrying the same
+    parameters, and routes ``batchified_composer_call`` to the single-call version."""
+    reference = environment_model.object_composer
+    config = dict(environment_model.config)
+    composer = ObjectComposer(config)
+    composer.load_state_dict(reference.state_dict())
+    composer.precision = precision
+    composer.to(next(reference.parameters()).device)
+    composer.train(reference.training)
+    environment_model.object_composer = composer
+
+    def _call(self, *args, **kwargs):
+        return batchified_composer_call(self.object_composer, *args, **kwargs)
+
+    environment_model.batchified_composer_call = types.MethodType(_call, environment_model)
+    return environment_model

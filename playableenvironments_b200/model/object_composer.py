@@ -1,0 +1,111 @@
+"""ObjectComposer (reference: model/object_composer.py:18-892) on the B200 fused render path.
+
+Same constructor (``config``), sub-module names (``object_models_coarse.{m}....`` — checkpoints load unchanged),
+``forward`` / ``set_step`` signatures and result dictionary.  Where the reference runs ~10^2 ATen kernels per object and
+materialises (…, R, P, 192) tensors, ``forward`` is a handful of launches: per object a style prologue and one fused
+field kernel (sampling + encoding + MLP [+ integration]), then one compositing kernel."""
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from .. import _cabi, registry
+from .utils.object_ids_helper import ObjectIDsHelper
+from . import render
+
+
+class ObjectComposer(nn.Module):
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.object_models_coarse = nn.ModuleList(self.create_object_models(fine=False))
+        self.object_models_fine = nn.ModuleList(self.create_object_models(fine=True))
+        self.apply_activation = self.config["model"]["apply_activation"]
+        if self.object_models_coarse[0].model_config["nerf_model"]["output_features"] != 3 and self.apply_activation:
+            raise Exception("The application of activations to the nerf output is requested, but the model seem not to output colors directly. Please make sure this is the behavior you desire")
+        self.object_id_helper = ObjectIDsHelper(self.config)
+        # compute type of the tensor-core path: "fp16" (1 pass), "fp16x2" (weights split hi+lo), "fp32" (CUDA cores only)
+        self.precision = self.config["model"].get("b200_precision", "fp16")
+
+    def create_object_models(self, fine: bool) -> List[nn.Module]:
+        object_models = []
+        for current_object_config in self.config["model"]["object_models"]:
+            if fine and "use_fine" in current_object_config and current_object_config["use_fine"] == False:  # noqa: E712
+                current_model = None
+            elif fine:
+                raise NotImplementedError("hierarchical fine sampling (use_fine: True) is not on the B200 path yet; "
+                                          "every shipped config sets use_fine: False")
+            else:
+                current_model = registry.build(current_object_config["architecture"], self.config, current_object_config)
+            object_models.append(current_model)
+        return object_models
+
+    def set_step(self, current_step: int):
+        for current_object_model in self.object_models_coarse:
+            current_object_model.set_step(current_step)
+        for current_object_model in self.object_models_fine:
+            if current_object_model is not None:
+                current_object_model.set_step(current_step)
+
+    def _descs(self, canonical_pose: bool):
+        helper = self.object_id_helper
+        descs = []
+        for object_idx in range(helper.objects_count):
+            model_idx = helper.model_idx_by_object_idx(object_idx)
+            m = self.object_models_coarse[model_idx]
+            descs.append(m.object_desc(m.model_config["positions_count_coarse"], helper.is_static(model_idx), canonical_pose))
+        return descs
+
+    def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
+                transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
+                perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None) -> Dict:
+        """Same contract as the reference (:786-812).  ``rand`` / ``noise`` optionally supply the perturbation tensors
+        (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample."""
+        objects_count = self.object_id_helper.objects_count
+        if transformation_matrix_w2o.size(-1) != objects_count:
+            raise Exception(f"Transformation matrix must specifies transformations for"
+                            f"({transformation_matrix_w2o.size(-1)}) objects instead of ({objects_count})")
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters()) and self.training
+            or any(t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
+        if needs_grad and not getattr(self, "allow_forward_without_grad", False):
+            raise NotImplementedError("the backward kernels of the B200 render path are not implemented yet; run under "
+                                      "torch.no_grad() (set composer.allow_forward_without_grad = True to evaluate a "
+                                      "train-mode forward without building a graph)")
+        if self.precision not in _cabi.PRECISIONS:
+            raise Exception(f"unknown b200_precision '{self.precision}'")
+        bn_running: List = []
+        with torch.no_grad():
+            res = render.render_scene(self._descs(canonical_pose), self.object_id_helper.static_objects_count, ray_origins,
+                                      ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
+                                      self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
+                                      _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running)
+            if self.training:
+                self._update_running_statistics(bn_running)
+        results = {"coarse": {}}
+        for k in range(objects_count):
+            r = res[f"object_{k}"]
+            r["extra_outputs"] = {}
+            results["coarse"][f"object_{k}"] = r
+        results["coarse"]["global"] = res["global"]
+        # dummy tensor the reference adds for nn.DataParallel's hook handling (:889-890)
+        results["pytorch_hook"] = torch.zeros((1, 1, 1, 1, 1, 1, 1, 1, 1), device=ray_directions.device)
+        return results
+
+    def _update_running_statistics(self, bn_running):
+        """BatchNorm running-stat update of the two AdaIn layers, in object order like the reference's sequential
+        per-instance model calls (a model shared by two instances is updated twice)."""
+        helper = self.object_id_helper
+        for object_idx, (b1, b2) in enumerate(bn_running):
+            head = self.object_models_coarse[helper.model_idx_by_object_idx(object_idx)].nerf_model.features_head
+            for layer, b in ((head[1], b1), (head[4], b2)):
+                bn = layer.ada_in.normalization
+                momentum = bn.momentum if bn.momentum is not None else 0.1
+                bn.running_mean.mul_(1.0 - momentum).add_(b[0], alpha=momentum)
+                bn.running_var.mul_(1.0 - momentum).add_(b[1], alpha=momentum)
+                bn.num_batches_tracked += 1
+
+
+def model(config):
+    return ObjectComposer(config)
