@@ -1,0 +1,266 @@
+"""Benchmark of the per-frame NeRF render path (BASELINE.json metric: ray-samples/sec of the fused style-MLP ray-march
+at 256x256 rays x 128 samples/ray).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|fp16x2|fp32] [--impl b200|reference]
+
+A step = one pass of the hot path over one synthetic frame per GPU (BASELINE configs[1]: one static field, shipped
+8x256/192-feature architecture, camera inside the box so all 8 388 608 samples are in-box), followed for N > 1 by the
+single all-gather of the rendered feature grids (weak scaling: one frame per rank).  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's CPU implementation of the same path — the oracle port of oracle/render_oracle.py
+(the upstream code is Python/PyTorch and is not shipped to the GPU box; the port is pinned against it by
+tests/golden) — on the host cores, on a bounded ray subset of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")]
+
+FLOP_PER_SAMPLE = 2 * 614144          # matmul MACs of the shipped field x 2
+HEIGHT, WIDTH, POSITIONS = 256, 256, 128
+WORKLOAD = "cfg2: 1 static field (W=256,L=8,skip=4,10 oct,F=192), 256x256 rays x 128 samples/ray, 100% in-box, forward"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"burst": p["bf16_tflops"], "sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_scene():
+    import scenes
+    return scenes.scene_static(seed=12, height=HEIGHT, width=WIDTH, P=POSITIONS)
+
+
+def cpu_reference(sample_rays: int, reps: int, warmup: int):
+    """Times the CPU port of the reference path on `sample_rays` rays of the workload, all host threads."""
+    import scenes  # noqa: F401
+    from helpers import INPUT_KEYS
+    from oracle import render_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    config, state, inputs = build_scene()
+    inputs = dict(inputs)
+    inputs["ray_directions"] = inputs["ray_directions"][..., :sample_rays, :].contiguous()
+    args = [inputs[k] for k in INPUT_KEYS]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            # the reference bounds activation memory with samples_per_image_batching=1000 (environment_model.py:584)
+            O.batchified_composer_call(config, state, *args, perturb=False, samples_per_image_batching=1000)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    samples = sample_rays * POSITIONS
+    return samples, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_rays = 2048
+    samples, times = cpu_reference(sample_rays, max(args.steps, 1), min(args.warmup, 1))
+    mean = sum(times) / len(times)
+    value = samples / mean
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "ray-samples/sec (style-MLP ray-march, fwd)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample_rays} rays x {POSITIONS} samples of the frame per step"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_rays} of 65536 rays ({samples} samples) per step, chunks of 1000 rays like the reference"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+    from playableenvironments_b200.model import render
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    scene = build_scene()
+    config, state, inputs, comp, dev = build_composer(scene, args.precision, device=device)
+    call_args = [dev[k] for k in INPUT_KEYS]
+    rays = dev["ray_directions"].size(-2)
+    samples_per_rank = rays * POSITIONS
+    F = 192
+    gathered = torch.empty((world, rays, F), dtype=torch.float32, device=device) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
+
+    def step():
+        with torch.no_grad():
+            res = comp(*call_args, False)
+        feats = res["coarse"]["global"]["integrated_features"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, feats.reshape(rays, F))     # the single collective of the path
+        return feats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    render.take_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                       # L2 flush between timed iterations (outside the per-step events)
+            starts[i].record()
+            step()
+            ends[i].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+    launches = render.take_launch_count()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms.item()) / 1e3
+    value = world * samples_per_rank * args.steps / total_s
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    host_in = {k: v.contiguous().pin_memory() for k, v in inputs.items()}
+    host_out = torch.empty((rays, F), dtype=torch.float32).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h = host_out.numel() * 4
+
+    def e2e_step():
+        d = [host_in[k].to(device, non_blocking=True) for k in INPUT_KEYS]
+        with torch.no_grad():
+            res = comp(*d, False)
+        feats = res["coarse"]["global"]["integrated_features"].reshape(rays, F)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, feats)
+        host_out.copy_(feats, non_blocking=True)
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = args.steps
+    s_ev.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e_ev.record()
+    barrier()
+    e2e_ms = torch.tensor([s_ev.elapsed_time(e_ev)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * samples_per_rank * e2e_steps / (float(e2e_ms.item()) / 1e3)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ms_per_step = total_s * 1e3 / args.steps
+        # dominant kernel = the fused field kernel; the step is that kernel plus two tiny style prologues (share > 99.9 %, profiles/)
+        achieved_tflops = samples_per_rank * FLOP_PER_SAMPLE / (ms_per_step / 1e3) / 1e12
+        line = {
+            "metric": "ray-samples/sec (style-MLP ray-march, fwd)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp16": "f16 operands, f32 accumulate", "fp16x2": "f16 operands (weights hi+lo), f32 accumulate",
+                                           "fp32": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MB memset)",
+                       "frames_per_s": world * args.steps / total_s, "collective": "all_gather(feature grid)" if world > 1 else "none"},
+            "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
+                         "frac": achieved_tflops / peaks["burst"], "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
+                         "frac_of_sustained": achieved_tflops / peaks["sustained"],
+                         "tensor_passes": 2 if args.precision == "fp16x2" else (1 if args.precision == "fp16" else 0)},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "wall_s": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            samples, times = cpu_reference(1024, 2, 1)
+            mean = sum(times) / len(times)
+            line["cpu_baseline"] = {"value": samples / mean, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"1024 of 65536 rays ({samples} samples), 2 timed reps after 1 warm-up, chunks of 1000 rays"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "fp16"), choices=["fp16", "fp16x2", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

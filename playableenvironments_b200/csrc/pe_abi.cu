@@ -72,7 +72,9 @@ static bool object_uses_tc(const PeScene& s, int k) {
 static bool needs_feature_buffer(const PeScene& s, int k) {
     if (s.explicit_positions) return false;                 // caller supplies raw_features
     if (!object_uses_tc(s, k)) return true;                 // the fp32 path integrates in the compositor
-    return s.objects > 1;                                   // tc path integrates its own object; the composition needs them
+    // tc path integrates its own object; the composition needs the samples when there are several objects, or when
+    // perturb is on (the composed scene draws its own raw-alpha noise, object_composer.py:886 -> :194)
+    return s.objects > 1 || s.perturb;
 }
 
 static Workspace carve(const PeScene& s, void* base) {
@@ -175,7 +177,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         auto launch_field = [&](int phase) {
             fa.phase = phase;
             const PeIntegrated none = {};
-            return tc ? pe_launch_field_tc(fa, s.objects == 1 ? out->global : none, sm_count, stream) : pe_launch_field_fp32(fa, sm_count, stream);
+            return tc ? pe_launch_field_tc(fa, (s.objects == 1 && !s.perturb) ? out->global : none, sm_count, stream) : pe_launch_field_fp32(fa, sm_count, stream);
         };
         if (s.training) {
             // train-mode BatchNorm (adain.py:47): statistics over all in-box samples of this object in this call.
@@ -222,7 +224,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     ca.global = out->global;
     // objects evaluated by the tcgen05 kernel integrate themselves in its epilogue; a single such object IS the scene
     ca.do_objects = all_tc ? 0 : 1;
-    ca.do_global = (all_tc && s.objects == 1) ? 0 : 1;
+    ca.do_global = (all_tc && s.objects == 1 && !s.perturb) ? 0 : 1;
     if (all_tc && s.objects > 1) ca.do_objects = 0;
     if (!all_tc) {
         // mixed scenes: the compositor integrates the fp32 objects; tc objects already wrote theirs

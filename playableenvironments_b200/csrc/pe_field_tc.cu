@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         unsigned char* abuf = a_buf[g];
         const uint32_t taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + g * 256;
         const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
-        const bool single = A.objects == 1;
+        const bool single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         uint32_t acc_phase = 0;
         float* scr = reinterpret_cast<float*>(abuf);
         float* t_s = reinterpret_cast<float*>(abuf + SCR_T);

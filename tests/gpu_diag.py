@@ -18,10 +18,14 @@ from gpu_common import build_composer, run_composer  # noqa: E402
 from playableenvironments_b200 import _cabi  # noqa: E402
 
 report = {}
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]
+TAG = "_".join(ONLY) if ONLY else "all"
 
 
 def section(name):
     def deco(fn):
+        if ONLY and not any(name.startswith(o) for o in ONLY):
+            return fn
         t0 = time.time()
         try:
             torch.cuda.synchronize()
@@ -190,5 +194,5 @@ for k, v in report.items():
         w = r.get("worst") if isinstance(r, dict) and "worst" in r else r
         print(f"ok    {k}: {w}")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w") as fh:
+with open(os.path.join(ROOT, "gpurun_out", f"diag_{TAG}.json"), "w") as fh:
     json.dump(report, fh, indent=1, default=str)
