@@ -168,9 +168,10 @@ int pe_fold_feature_grids(const float* features, int32_t images, int32_t height,
                           float* const* grids, pe_stream_t stream);
 
 /* -- debug / validation ---------------------------------------------------------------------- */
-/* D[128][n] = A[128][k] * B[n][k]^T through the same tcgen05 building blocks as the fused kernel
- * (fp16 operands, fp32 accumulate).  Used by tests to validate descriptors on the device.       */
-int pe_debug_umma_gemm(const float* a, const float* b, float* d, int32_t n, int32_t k, pe_stream_t stream);
+/* D[128][n] = A[128][k] * B[n][k]^T (+ bias[n], NULL for none, added by the rank-1 "ones" MMA) through
+ * the same tcgen05 building blocks as the fused kernel (fp16 operands, fp32 accumulate).  Used by
+ * tests to validate descriptors on the device.                                                  */
+int pe_debug_umma_gemm(const float* a, const float* b, const float* bias, float* d, int32_t n, int32_t k, pe_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -131,7 +131,7 @@ def lib() -> C.CDLL:
     L.pe_fold_feature_grids.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
     L.pe_debug_umma_gemm.restype = C.c_int
-    L.pe_debug_umma_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.pe_debug_umma_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     if L.pe_abi_version() != PE_ABI_VERSION:
         raise PeError(f"libpe_b200.so ABI {L.pe_abi_version()} != binding {PE_ABI_VERSION}; rebuild")
     _lib = L

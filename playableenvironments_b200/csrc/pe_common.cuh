@@ -85,6 +85,7 @@ __host__ __device__ inline int64_t pe_tc_pass_bytes() {
     b += 8LL * 256 * 32 * 2;                  // H0
     b += 8LL * 128 * 32 * 2;                  // H3
     b += 4LL * 192 * 32 * 2;                  // H6
+    b += 8LL * 256 * 32 + 192 * 32;           // bias slabs (N x 16 fp16) of L0-L7 and H6
     return b;
 }
 

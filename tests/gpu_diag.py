@@ -64,11 +64,14 @@ def _():
         g = torch.Generator(device="cpu").manual_seed(n * 1000 + k)
         a = torch.randn(128, k, generator=g).cuda()
         b = torch.randn(n, k, generator=g).cuda()
-        d = torch.full((128, n), float("nan"), device="cuda")
-        _cabi.check(_cabi.lib().pe_debug_umma_gemm(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, torch.cuda.current_stream().cuda_stream))
-        torch.cuda.synchronize()
-        ref = a.half().float() @ b.half().float().t()
-        out[f"{n}x{k}"] = float("%.3g" % ((d - ref).abs().max() / ref.abs().max()).item())
+        bias = torch.randn(n, generator=g).cuda()
+        for with_bias in (False, True):
+            d = torch.full((128, n), float("nan"), device="cuda")
+            _cabi.check(_cabi.lib().pe_debug_umma_gemm(a.data_ptr(), b.data_ptr(), bias.data_ptr() if with_bias else None, d.data_ptr(), n, k,
+                                                       torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            ref = a.half().float() @ b.half().float().t() + (bias if with_bias else 0.0)
+            out[f"{n}x{k}" + ("+bias" if with_bias else "")] = float("%.3g" % ((d - ref).abs().max() / ref.abs().max()).item())
     return out
 
 
