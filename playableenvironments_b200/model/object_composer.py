@@ -27,6 +27,8 @@ class ObjectComposer(nn.Module):
         self.object_id_helper = ObjectIDsHelper(self.config)
         # compute type of the tensor-core path: "fp16" (1 pass), "fp16x2" (weights split hi+lo), "fp32" (CUDA cores only)
         self.precision = self.config["model"].get("b200_precision", "fp16")
+        # diagnostic switch: also return the per-sample raw alphas of every object under results["coarse"]["object_k"]["raw_alphas"]
+        self.return_raw_alphas = False
 
     def create_object_models(self, fine: bool) -> List[nn.Module]:
         object_models = []
@@ -80,7 +82,8 @@ class ObjectComposer(nn.Module):
             res = render.render_scene(self._descs(canonical_pose), self.object_id_helper.static_objects_count, ray_origins,
                                       ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
                                       self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
-                                      _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running)
+                                      _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running,
+                                      return_raw_alphas=self.return_raw_alphas)
             if self.training:
                 self._update_running_statistics(bn_running)
         results = {"coarse": {}}

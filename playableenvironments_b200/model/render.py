@@ -52,7 +52,7 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
                  perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
                  rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
-                 bn_running: Optional[List] = None) -> Dict:
+                 bn_running: Optional[List] = None, return_raw_alphas: bool = False) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}."""
     device = ray_directions.device
     if device.type != "cuda":
@@ -115,6 +115,9 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
         r = _alloc_integrated(lead, rays, d.positions, F, device)
         _fill(outs.object[k], r)
         results[f"object_{k}"] = r
+        if return_raw_alphas:          # diagnostic: per-sample raw alphas (first return value family of the object models)
+            r["raw_alphas"] = torch.empty(lead + [rays, d.positions], dtype=torch.float32, device=device)
+            outs.raw_alphas[k] = _cabi.ptr(r["raw_alphas"])
         if training and bn_running is not None:
             b1 = torch.empty((2, d.width), dtype=torch.float32, device=device)
             b2 = torch.empty((2, d.width // 2), dtype=torch.float32, device=device)

@@ -83,7 +83,7 @@ for scene_name in ["cfg1", "static_small", "tennis_small", "tennis_dense", "tenn
         return {"worst": worst(e), "all": e}
 
 for prec in ["fp16", "fp16x2"]:
-    for scene_name in ["static_small", "tennis_small", "minecraft_small"]:
+    for scene_name in ["static_small", "tennis_small", "minecraft_small", "minecraft_absent"]:
         @section(f"{prec}/{scene_name}")
         def _(scene_name=scene_name, prec=prec):
             _, _, _, comp, dev = build_composer(scene_name, prec)

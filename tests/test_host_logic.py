@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference interface: registry, state_dict names, helpers, ray sharding (CPU only)."""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import scenes
+from oracle import render_oracle as O
+from playableenvironments_b200 import registry, sharding
+from playableenvironments_b200.model.annealable_positional_encoder import annealing_weights
+from playableenvironments_b200.model.object_composer import ObjectComposer
+from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper
+from playableenvironments_b200.utils.tensor_batchifier import TensorBatchifier
+from playableenvironments_b200.utils.tensor_folder import TensorFolder
+
+
+def test_registry_resolves_reference_architecture_strings():
+    for name in ("model.nerf_models.ray_bending_style_nerf_model", "model.nerf_models.adain_style_nerf_model",
+                 "model.nerf_models.skybox_adain_style_nerf_model_v3", "model.nerf_models.zeroed_ray_bender_model",
+                 "model.nerf_models.positional_ray_bender_model"):
+        module = registry.resolve(name)
+        assert module.__name__ == "playableenvironments_b200." + name
+        assert callable(getattr(module, "model"))
+
+
+def test_state_dict_names_and_shapes_match_the_reference():
+    """Checkpoints of the reference must load unchanged: same keys, same shapes."""
+    for name in ("tennis_small", "minecraft_small", "cfg1"):
+        config, state, _ = scenes.SCENES[name]()
+        comp = ObjectComposer(copy.deepcopy(config))
+        own = comp.state_dict()
+        assert set(own.keys()) == set(state.keys())
+        for k, v in state.items():
+            assert tuple(own[k].shape) == tuple(v.shape), k
+    shipped = ObjectComposer(copy.deepcopy(scenes.SCENES["tennis_small"]()[0]))
+    assert sum(p.numel() for p in shipped.object_models_coarse[0].parameters()) == 666305     # SURVEY 8d cross-check
+    assert sum(p.numel() for p in shipped.object_models_coarse[1].ray_bender.parameters()) == 101248
+
+
+def test_composer_attributes_read_by_the_scene_model():
+    config, state, _ = scenes.SCENES["minecraft_small"]()
+    comp = ObjectComposer(copy.deepcopy(config))
+    m = comp.object_models_coarse[2]
+    assert m.model_config["positions_count_coarse"] == 32 and m.empty_space_alpha == -3.5
+    assert m.bounding_box.get_size().tolist() == pytest.approx([1.2, 2.1, 2.4])
+    h = comp.object_id_helper
+    assert (h.objects_count, h.static_objects_count, h.dynamic_objects_count) == (4, 2, 2)
+    assert [h.model_idx_by_object_idx(i) for i in range(4)] == [0, 1, 2, 2]
+    assert comp.object_models_fine[0] is None
+
+
+def test_wrong_object_count_raises_like_the_reference():
+    config, state, inputs = scenes.SCENES["cfg1"]()
+    comp = ObjectComposer(copy.deepcopy(config))
+    bad = torch.eye(4).reshape(1, 1, 1, 4, 4, 1).repeat(1, 1, 1, 1, 1, 2)
+    with pytest.raises(Exception, match="Transformation matrix must specifies"):
+        comp(inputs["ray_origins"], inputs["ray_directions"], inputs["focal_normals"], bad, inputs["style"], inputs["deformation"],
+             inputs["object_in_scene"], False)
+
+
+def test_set_step_drives_the_annealing_weights():
+    config, state, _ = scenes.SCENES["tennis_small"]()
+    comp = ObjectComposer(copy.deepcopy(config))
+    comp.load_state_dict(state)
+    enc = comp.object_models_coarse[1].ray_bender.positional_encoder
+    assert enc.host_step() == 60000
+    comp.set_step(21000)
+    assert enc.host_step() == 21000 and int(enc.current_step) == 21000
+    torch.testing.assert_close(annealing_weights(21000, 6, 60000), O.annealing_weights(21000, 6, 60000))
+
+
+def test_tensor_helpers():
+    x = torch.arange(2 * 3 * 7 * 5).reshape(2, 3, 7, 5)
+    chunks = TensorBatchifier.batchify(x, dim=-2, batch_size=3)
+    assert [c.size(-2) for c in chunks] == [3, 3, 1] and torch.equal(torch.cat(chunks, dim=-2), x)
+    flat, dims = TensorFolder.flatten(x, -1)
+    assert flat.shape == (42, 5) and dims == [2, 3, 7]
+    assert torch.equal(TensorFolder.fold(flat, dims), x)
+    with pytest.raises(Exception):
+        TensorFolder.fold(flat, [5])
+
+
+def test_ray_helper_shape_functions_match_the_oracle():
+    H, W = 16, 24
+    focal = torch.tensor([[30.0, 41.0]])
+    d, o, n = RayHelper.create_camera_rays([1, 2], H, W, focal)
+    rd, ro, rn = O.create_camera_rays([1, 2], H, W, focal)
+    assert torch.equal(d, rd) and torch.equal(o, ro) and torch.equal(n, rn)
+    obs = torch.rand(1, 2, 3, H, W)
+    sd, so, sp = RayHelper.sample_all_rays_strided_grid(d, obs, [4, 8])
+    od, op = O.sample_all_rays_strided_grid(rd, [4, 8])
+    assert torch.equal(sd, od) and torch.allclose(sp, op)
+    assert so.shape == (1, 2, sd.size(-2), 3)
+    folded = RayHelper.fold_strided_grid_samples(sd, [4, 8], (H, W), dim=-2)
+    assert [tuple(f.shape) for f in folded] == [(1, 2, 4, 6, 3), (1, 2, 2, 3, 3)]
+    with pytest.raises(Exception, match="not divisible"):
+        RayHelper.sample_strided_grid(d, 5)
+    c2w = torch.from_numpy(scenes.tennis_camera()).float().expand(1, 2, 4, 4)
+    to, td, tn = RayHelper.transform_rays(o, sd, n, c2w)
+    oo, od2, on = O.transform_rays(ro, od, rn, c2w)
+    torch.testing.assert_close(td, od2)
+    torch.testing.assert_close(to, oo)
+
+
+def test_ray_shards_partition_the_rays():
+    for rays, world, mult in [(65536, 8, 1), (11520, 8, 4), (10, 4, 1), (3, 8, 1), (1000, 3, 128)]:
+        spans = [sharding.ray_shard(rays, r, world, mult) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == rays
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert sum(sharding.shard_sizes(rays, world, mult)) == rays
+
+
+def _gather_worker(rank, world, port, rays, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(2 * rays * 5, dtype=torch.float32).reshape(2, rays, 5)
+    b, e = sharding.ray_shard(rays, rank, world)
+    out = sharding.all_gather_rays(full[:, b:e].contiguous(), rays, dim=-2)
+    ok = torch.equal(out, full)
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rays", [11, 64])
+def test_all_gather_of_ray_shards_world_size_2(tmp_path, rays):
+    """The single collective of the path (feature-grid all-gather) on the gloo backend, 2 ranks, uneven shards."""
+    port = 29500 + (os.getpid() + rays) % 2000
+    mp.spawn(_gather_worker, args=(2, port, rays, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
