@@ -3,7 +3,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "pe_kernels.cuh"
+
+#define PE_TC_DEFAULT_PAIR false
 
 static thread_local char g_error[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -177,7 +181,12 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         auto launch_field = [&](int phase) {
             fa.phase = phase;
             const PeIntegrated none = {};
-            return tc ? pe_launch_field_tc(fa, (s.objects == 1 && !s.perturb) ? out->global : none, sm_count, stream) : pe_launch_field_fp32(fa, sm_count, stream);
+            if (!tc) return pe_launch_field_fp32(fa, sm_count, stream);
+            const PeIntegrated& gout = (s.objects == 1 && !s.perturb) ? out->global : none;
+            // PE_TC_KERNEL=1 selects the single-CTA lockstep kernel, 2 (default) the CTA-pair ping-pong kernel
+            const char* which = getenv("PE_TC_KERNEL");
+            const bool pair = which ? atoi(which) == 2 : PE_TC_DEFAULT_PAIR;
+            return pair ? pe_launch_field_tc2(fa, gout, sm_count, stream) : pe_launch_field_tc(fa, gout, sm_count, stream);
         };
         if (s.training) {
             // train-mode BatchNorm (adain.py:47): statistics over all in-box samples of this object in this call.

@@ -60,6 +60,7 @@ struct PeLayout {
     // tcgen05 section
     int64_t tc_base;                // start of the fp16 slab stream (0 if the shape is unsupported)
     int64_t tc_bytes_per_pass;      // bytes of one weight pass (hi); lo pass follows at +tc_bytes_per_pass
+    int64_t tc2_base;               // same stream in the CTA-pair layout (pe_field_tc2.cu): [hi pass | lo pass]
     int32_t tc_supported;
     int64_t total;
 };
@@ -126,6 +127,8 @@ __host__ __device__ inline PeLayout pe_layout(const PeObjectDesc& d) {
     if (L.tc_supported) {
         L.tc_bytes_per_pass = pe_tc_pass_bytes();
         L.tc_base = off;
+        off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
+        L.tc2_base = off;
         off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
     }
     L.total = off;

@@ -64,6 +64,7 @@ struct PeStyleArgs {
 size_t pe_field_fp32_smem_bytes(const PeObjectDesc& ob, const PeLayout& L);
 int pe_launch_field_fp32(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
+int pe_launch_field_tc2(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream);
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream);
 int pe_launch_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);

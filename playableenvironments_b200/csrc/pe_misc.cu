@@ -149,6 +149,7 @@ static int copy_to(const float* src, void* blob, int64_t off, int64_t n, cudaStr
 }
 
 int pe_tc_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);
+int pe_tc2_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);
 
 int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
     int rc;
@@ -181,7 +182,10 @@ int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParam
         }
         PE_TRY(transpose_to(p.bender_out_w, packed, L.bd_out_w, 3, d.b_width, stream));
     }
-    if (L.tc_supported) PE_TRY(pe_tc_pack(d, L, p, packed, stream));
+    if (L.tc_supported) {
+        PE_TRY(pe_tc_pack(d, L, p, packed, stream));
+        PE_TRY(pe_tc2_pack(d, L, p, packed, stream));
+    }
 #undef PE_TRY
     return PE_OK;
 }

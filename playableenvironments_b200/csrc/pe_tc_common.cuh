@@ -1,0 +1,356 @@
+// Device code shared by the two tensor-core field kernels (pe_field_tc.cu: one CTA per SM, lockstep tile pair;
+// pe_field_tc2.cu: CTA pair with cta_group::2, epilogues overlapped with MMAs): operand layout, layer table, and the
+// complete per-tile work of an epilogue group (sampling, Fourier features, layer epilogues, volume rendering).
+#pragma once
+
+#include "pe_kernels.cuh"
+#include "pe_umma.cuh"
+
+namespace pe_tc {
+using namespace pe;
+
+constexpr int TILE_M = 128;
+constexpr int CHUNK_BYTES = 2048;                 // 8 K-columns of a 128-row operand: 16 row groups x 128 B
+constexpr int A_CHUNKS = 40;                      // K columns 0..255: activations, 256..319: positional encoding
+constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;   // 80 KB per tile
+constexpr int PE_CHUNK0 = 32;
+constexpr int NUM_LAYERS = 11;                    // L0..L7, H0, H3, H6
+constexpr int THREADS = 384;                      // producer, MMA, TMEM-alloc, spare + 2 x 4 epilogue warps
+constexpr int SCRATCH_STRIDE = 97;                // floats per row of the compositing scratch (bank-conflict free)
+constexpr int SCR_T = 50 * 1024, SCR_SH = SCR_T + 512, SCR_W = SCR_SH + 512;   // byte offsets inside the A buffer
+// per-tile constants staged in the (dead after L4) positional-encoding columns of the A buffer
+constexpr int CST_BASE = PE_CHUNK0 * CHUNK_BYTES; // byte offset inside the A buffer
+constexpr int CST_SC1 = 0, CST_SH1 = 256, CST_SC2 = 512, CST_SH2 = 640, CST_AW = 768;
+
+// layer l: N outputs, `slabs` K=32 weight slabs, first A chunk, bias added by the rank-1 MMA
+__host__ __device__ __forceinline__ void layer_spec(int l, int& n, int& slabs, int& chunk0, bool& has_bias) {
+    n = 256; slabs = 8; chunk0 = 0; has_bias = true;
+    if (l == 0) { slabs = 2; chunk0 = PE_CHUNK0; }
+    else if (l == 4) { slabs = 10; }
+    else if (l == 8) { has_bias = false; }
+    else if (l == 9) { n = 128; has_bias = false; }
+    else if (l == 10) { n = 192; slabs = 4; }
+}
+
+// relu + saturating conversion of two fp32 to packed fp16 (low half = a, high half = b)
+__device__ __forceinline__ uint32_t relu_pack_half2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// store 8 consecutive K values of row `m` into the K-major no-swizzle operand (chunk = K/8)
+__device__ __forceinline__ void store_a8(unsigned char* a_base, int chunk, int m, const float* v) {
+    uint4 q;
+    q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a_base + chunk * CHUNK_BYTES + m * 16) = q;
+}
+__device__ __forceinline__ void store_a8_relu(unsigned char* a_base, int chunk, int m, const float* v) {
+    uint4 q;
+    q.x = relu_pack_half2(v[0], v[1]); q.y = relu_pack_half2(v[2], v[3]); q.z = relu_pack_half2(v[4], v[5]); q.w = relu_pack_half2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a_base + chunk * CHUNK_BYTES + m * 16) = q;
+}
+
+// wait for outstanding tcgen05.ld; the registers are threaded through so no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// Epilogue of one hidden layer for row m: TMEM accumulators (bias already added by the rank-1 MMA) ->
+// [AdaIn affine] -> ReLU -> fp16 -> A operand of the next layer (in place).
+//   MODE 0: trunk layer            y = relu(acc)
+//   MODE 1: trunk output (L7)      y = relu(acc), also accumulates the alpha head dot product in fp32
+//   MODE 2: AdaIn layer            y = relu(acc * sc[c] + sh[c])   (BatchNorm folded into sc/sh, adain.py:58-59)
+template <int MODE, int N>
+__device__ __forceinline__ float hidden_epilogue(uint32_t taddr, unsigned char* abuf, int m, const float* __restrict__ c0s,
+                                                 const float* __restrict__ c1s, int dbg = 0) {
+    uint32_t v[2][32];
+    float alpha = 0.f;
+    if (dbg & 4) {       // timing experiment: no TMEM reads
+#pragma unroll
+        for (int q = 0; q < 32; ++q) { v[0][q] = 0x3f800000u; v[1][q] = 0x3f800000u; }
+    } else tmem_ld32(taddr, v[0]);
+#pragma unroll
+    for (int c = 0; c < N / 32; ++c) {
+        if (!(dbg & 4)) {
+            tmem_wait_ld_regs(v[c & 1]);
+            if (c + 1 < N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        }
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) y[q] = __uint_as_float(v[c & 1][q]);
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(c0s + c * 32 + 4 * q);      // smem broadcast
+                alpha = fmaf(fmaxf(y[4 * q + 0], 0.f), w4.x, alpha);
+                alpha = fmaf(fmaxf(y[4 * q + 1], 0.f), w4.y, alpha);
+                alpha = fmaf(fmaxf(y[4 * q + 2], 0.f), w4.z, alpha);
+                alpha = fmaf(fmaxf(y[4 * q + 3], 0.f), w4.w, alpha);
+            }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 s4 = *reinterpret_cast<const float4*>(c0s + c * 32 + 4 * q);
+                const float4 b4 = *reinterpret_cast<const float4*>(c1s + c * 32 + 4 * q);
+                y[4 * q + 0] = fmaf(y[4 * q + 0], s4.x, b4.x);
+                y[4 * q + 1] = fmaf(y[4 * q + 1], s4.y, b4.y);
+                y[4 * q + 2] = fmaf(y[4 * q + 2], s4.z, b4.z);
+                y[4 * q + 3] = fmaf(y[4 * q + 3], s4.w, b4.w);
+            }
+        }
+        if (!(dbg & 8)) {    // timing experiment: no shared-memory stores
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) store_a8_relu(abuf, c * 4 + cc, m, y + 8 * cc);
+        } else if (y[0] == 123.456f) store_a8_relu(abuf, c * 4, m, y);
+    }
+    return alpha;
+}
+
+// Everything an epilogue thread needs that does not change between tiles.
+struct TileCtx {
+    const PeFieldArgs* A;
+    const PeIntegrated* G2;      // outputs of the composed scene when this object IS the scene (else all NULL)
+    unsigned char* abuf;         // this group's A operand (shared memory)
+    uint32_t taddr;              // TMEM address of this thread's lane quadrant and this group's accumulator columns
+    uint32_t bar_id;             // named barrier of the group (128 threads)
+    int m, lane, wq;             // row of the tile (= TMEM lane), lane, warp within the group
+    int P, rpt, rows_used, tiles_per_image;
+    int64_t total_tiles;
+    float size[3];
+    float alpha_bias;
+    const float* alpha_w;
+    bool single;
+    int dbg;
+};
+
+// Per-tile work of one epilogue thread.  `Sync` provides wait_acc() (accumulators of the next layer are complete) and
+// arrive_ready() (this thread's part of the next A operand is written and its TMEM reads are done).
+template <class Sync>
+__device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync) {
+    const PeFieldArgs& A = *X.A;
+    const PeIntegrated& G2 = *X.G2;
+    const PeObjectDesc& ob = A.ob;
+    const int m = X.m, lane = X.lane, wq = X.wq, P = X.P, rpt = X.rpt;
+    unsigned char* abuf = X.abuf;
+    const uint32_t taddr = X.taddr, bar_id = X.bar_id;
+    float* scr = reinterpret_cast<float*>(abuf);
+    float* t_s = reinterpret_cast<float*>(abuf + SCR_T);
+    float* sh_s = reinterpret_cast<float*>(abuf + SCR_SH);
+    float* w_s = reinterpret_cast<float*>(abuf + SCR_W);
+    float* cst = reinterpret_cast<float*>(abuf + CST_BASE);
+
+    const bool tile_valid = tile < X.total_tiles;
+    const int img = tile_valid ? (int)(tile / X.tiles_per_image) : 0;
+    const int ray0 = tile_valid ? (int)(tile - (int64_t)img * X.tiles_per_image) * rpt : 0;
+
+    // ---- sampling (transform_rays, z bounds, create_ray_positions, in-box mask) ----
+    bool valid = false, inbox = false;
+    float t = 0.f, dnorm = 0.f, raw_alpha = ob.empty_space_alpha;
+    int64_t ray = -1;
+    int p = 0;
+    const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
+    float x[3] = {0.f, 0.f, 0.f};
+    if (tile_valid && m < X.rows_used) {
+        const int rl = m / P;
+        const int r = ray0 + rl;
+        if (r < A.rays) {
+            valid = true;
+            p = m - rl * P;
+            ray = (int64_t)img * A.rays + r;
+            const float* dw = A.dirs + ray * 3;
+            const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3, dw, in_scene);
+            const float u = A.perturb ? A.rand[ray * P + p] : 0.f;
+            t = pe_sample_t(pr, p, P, A.perturb != 0, u);
+            pe_position(pr, t, x);
+            inbox = pe_in_box(ob, x);
+            dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dw[0], dw[0]), __fmul_rn(dw[1], dw[1])), __fmul_rn(dw[2], dw[2])));
+        }
+    }
+    {
+        // Fourier features sin/cos(2^o * x): the argument is reduced EXACTLY (x/(2 pi) as a two-float value, scaled by the
+        // power of two, integer part dropped), then evaluated with the SFU on [-pi, pi] (abs error < 5e-7, far below the
+        // fp16 rounding of the operand).  Same values as positional_encoder.py:59-64 up to that error.
+        const float xn[3] = {__fdiv_rn(x[0], X.size[0]), __fdiv_rn(x[1], X.size[1]), __fdiv_rn(x[2], X.size[2])};
+        float enc[64];
+        enc[0] = xn[0]; enc[1] = xn[1]; enc[2] = xn[2];
+        float tp[3], tl[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float c_hi = 0.15915494f, c_lo = 6.4206382e-9f;      // 1/(2 pi) = c_hi + c_lo
+            tp[a] = xn[a] * c_hi;
+            tl[a] = fmaf(xn[a], c_lo, fmaf(xn[a], c_hi, -tp[a]));
+        }
+#pragma unroll
+        for (int o = 0; o < 10; ++o) {
+            const float f = (float)(1 << o);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float turns = tp[a] * f;                           // exact (power of two)
+                const float fr = (turns - rintf(turns)) + tl[a] * f;     // fractional turns in [-0.5, 0.5]
+                const float ang = fr * 6.2831855f;
+                enc[3 + 6 * o + a] = __sinf(ang);
+                enc[3 + 6 * o + 3 + a] = __cosf(ang);
+            }
+        }
+        enc[63] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
+    }
+    sync.arrive_ready();
+
+    // ---- the 10 hidden tensor-core layers ----
+    float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+    for (int l = 0; l < 10; ++l) {
+        sync.wait_acc();
+        if (l == 4) {
+            // the encoding columns are dead once L4 has run: reuse them for the constants of the later epilogues
+            // (AdaIn scale/shift of this image and the alpha-head weights); the loads overlap this layer's epilogue
+            const float* a1 = A.aff1 + (int64_t)img * 512;
+            const float* a2 = A.aff2 + (int64_t)img * 256;
+            const int i1 = 512 + m * 4;                                   // 1024 floats, 8 per thread
+            pre0 = __ldg(reinterpret_cast<const float4*>(a1 + m * 4));   // sc1|sh1
+            pre1 = i1 < 768 ? __ldg(reinterpret_cast<const float4*>(a2 + (i1 - 512))) : __ldg(reinterpret_cast<const float4*>(X.alpha_w + (i1 - 768)));
+        }
+        if (l == 7) named_bar_sync(bar_id, TILE_M);                        // constants written by the whole group at l == 4
+        if (l < 7) hidden_epilogue<0, 256>(taddr, abuf, m, nullptr, nullptr, X.dbg);
+        else if (l == 7) raw_alpha = hidden_epilogue<1, 256>(taddr, abuf, m, cst + CST_AW, nullptr, X.dbg) + X.alpha_bias;
+        else if (l == 8) hidden_epilogue<2, 256>(taddr, abuf, m, cst + CST_SC1, cst + CST_SH1, X.dbg);
+        else hidden_epilogue<2, 128>(taddr, abuf, m, cst + CST_SC2, cst + CST_SH2, X.dbg);
+        if (l == 4) {
+            *reinterpret_cast<float4*>(cst + m * 4) = pre0;
+            *reinterpret_cast<float4*>(cst + 512 + m * 4) = pre1;
+        }
+        sync.arrive_ready();
+    }
+
+    // ---- last layer: features in TMEM -> volume rendering of the tile's rays (ObjectComposer.integrate :724-784) ----
+    sync.wait_acc();
+    const int64_t gs = valid ? ray * P + p : 0;
+    float raw = (inbox && in_scene) ? raw_alpha : ob.empty_space_alpha;
+    if (valid) {
+        if (A.raw_out) A.raw_out[gs] = raw;
+        if (A.t_out) A.t_out[gs] = t;
+        if (A.inbox_out) A.inbox_out[gs] = inbox ? 1 : 0;
+        if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
+    }
+    t_s[m] = t;
+    named_bar_sync(bar_id, TILE_M);
+    float alpha = 0.f;
+    if (valid) {
+        const float delta = __fmul_rn(p == P - 1 ? 1e10f : __fsub_rn(t_s[m + 1], t), dnorm);     // :153-178
+        if (A.noise) raw = __fadd_rn(raw, A.noise[gs]);                                            // :193-195
+        alpha = __fsub_rn(1.f, expf(__fmul_rn(-fmaxf(raw, 0.f), delta)));                          // :197
+    }
+    // exclusive cumprod of (1 - alpha + 1e-10) along the samples of each ray (compute_weights :199-214):
+    // segmented warp scan + carry across the warps a ray spans
+    const float shifted = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+    const bool head = p == 0;
+    float incl = shifted;
+    bool closed = head;                              // a segment head lies in [first lane of the scan window, lane]
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, d);
+        const bool fu = __shfl_up_sync(0xffffffffu, closed ? 1 : 0, d) != 0;
+        if (lane >= d && !closed) { incl *= up; closed = fu; }
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0 || head) excl = 1.f;
+    if (lane == 31) { sh_s[wq] = incl; sh_s[4 + wq] = closed ? 1.f : 0.f; }
+    named_bar_sync(bar_id, TILE_M);
+    float T = excl;
+    if (!closed) {                                   // the ray started in an earlier warp of the tile
+        for (int v = wq - 1; v >= 0; --v) {
+            T *= sh_s[v];
+            if (sh_s[4 + v] != 0.f) break;
+        }
+    }
+    const float w = valid ? alpha * T : 0.f;
+    w_s[m] = w;
+    if (valid) {
+        if (A.integ.weights) A.integ.weights[gs] = w;
+        if (X.single && G2.weights) G2.weights[gs] = w;
+    }
+    const float wf = inbox ? w : 0.f;
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[2][32];
+        tmem_ld32(taddr + half * 96, v[0]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            tmem_wait_ld_regs(v[c & 1]);
+            if (c + 1 < 3) tmem_ld32(taddr + half * 96 + (c + 1) * 32, v[(c + 1) & 1]);
+            if (!A.apply_activation && !A.feat_out) {                  // common case: nothing per-sample leaves the SM
+#pragma unroll
+                for (int q = 0; q < 32; ++q) scr[m * SCRATCH_STRIDE + c * 32 + q] = wf * __uint_as_float(v[c & 1][q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    float f = __uint_as_float(v[c & 1][q]);            // head-6 bias already added by the rank-1 MMA
+                    if (A.apply_activation) f = 1.f / (1.f + expf(-f));
+                    if (A.feat_out && valid) A.feat_out[gs * 192 + half * 96 + c * 32 + q] = inbox ? f : 0.f;
+                    scr[m * SCRATCH_STRIDE + c * 32 + q] = wf * f;
+                }
+            }
+        }
+        named_bar_sync(bar_id, TILE_M);
+        for (int item = m; item < rpt * 96; item += TILE_M) {
+            const int rl = item / 96, c = item - rl * 96;
+            const int r = ray0 + rl;
+            if (tile_valid && r < A.rays) {
+                const float* col = scr + rl * P * SCRATCH_STRIDE + c;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int j = 0;
+                for (; j + 4 <= P; j += 4) {
+                    s0 += col[(j + 0) * SCRATCH_STRIDE]; s1 += col[(j + 1) * SCRATCH_STRIDE];
+                    s2 += col[(j + 2) * SCRATCH_STRIDE]; s3 += col[(j + 3) * SCRATCH_STRIDE];
+                }
+                for (; j < P; ++j) s0 += col[j * SCRATCH_STRIDE];
+                const float sum = (s0 + s1) + (s2 + s3);
+                const int64_t o = ((int64_t)img * A.rays + r) * 192 + half * 96 + c;
+                if (A.integ.integrated_features) A.integ.integrated_features[o] = sum;
+                if (X.single && G2.integrated_features) G2.integrated_features[o] = sum;
+            }
+        }
+        named_bar_sync(bar_id, TILE_M);
+    }
+    // per-ray scalars (:758-772): one warp per ray, lanes stride the samples
+    for (int rl = wq; rl < rpt; rl += 4) {
+        const int r = ray0 + rl;
+        if (!tile_valid || r >= A.rays) continue;
+        float opacity = 0.f, depth = 0.f;
+        for (int j = lane; j < P; j += 32) { const float wj = w_s[rl * P + j]; opacity += wj; depth += wj * t_s[rl * P + j]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            opacity += __shfl_xor_sync(0xffffffffu, opacity, o);
+            depth += __shfl_xor_sync(0xffffffffu, depth, o);
+        }
+        if (lane == 0) {
+            const int64_t gr = (int64_t)img * A.rays + r;
+            const float qd = depth / opacity;
+            const float disparity = 1.f / (qd != qd ? qd : fmaxf(qd, 1e-10f));
+            const PeIntegrated* outs[2] = {&A.integ, &G2};
+            for (int oi = 0; oi < (X.single ? 2 : 1); ++oi) {
+                const PeIntegrated& O = *outs[oi];
+                if (O.opacity) O.opacity[gr] = opacity;
+                if (O.depth) O.depth[gr] = depth;
+                if (O.disparity) O.disparity[gr] = disparity;
+                if (O.integrated_displacements_magnitude) O.integrated_displacements_magnitude[gr] = 0.f;
+                if (O.integrated_divergence) O.integrated_divergence[gr] = 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    named_bar_sync(bar_id, TILE_M);       // scratch is dead before the next tile's encoding overwrites it
+}
+
+}  // namespace pe_tc
