@@ -22,6 +22,8 @@ namespace {
 using namespace pe;
 using namespace pe_tc;
 
+constexpr int SPLIT = 1;                          // threads per tile row in the epilogue groups
+constexpr int THREADS = 128 + 2 * 128 * SPLIT;    // producer, MMA, TMEM-alloc, spare + 2 groups of 4*SPLIT epilogue warps
 constexpr int STAGE_BYTES = 16384;                // largest slab: 256 rows x 32 k x 2 B
 constexpr int NUM_STAGES = 4;
 constexpr int SMEM_BAR = 2 * A_BYTES + NUM_STAGES * STAGE_BYTES;
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, TILE_M); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, TILE_M * SPLIT); }
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -160,12 +162,15 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         }
     } else if (warp >= 4) {
         // ================================ epilogue groups ================================
-        const int g = (warp - 4) >> 2;                 // 0: tile X, 1: tile Y
+        const int g = (warp - 4) / (4 * SPLIT);        // 0: tile X, 1: tile Y
+        const int gw = (warp - 4) % (4 * SPLIT);       // warp inside the group
         TileCtx X;
         X.A = &A; X.G2 = &G2;
         X.abuf = smem + g * A_BYTES;                   // derived from the __shared__ base so accesses compile to LDS/STS
-        X.m = ((warp & 3) << 5) | lane; X.lane = lane; X.wq = warp & 3;
-        X.taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + g * 256;
+        X.wq = warp & 3;                               // TMEM lane quadrant this warp may access
+        X.m = (X.wq << 5) | lane; X.lane = lane; X.gw = gw;
+        X.half = gw >> 2;                              // the two warps of a quadrant split the columns of their 32 rows
+        X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16) + g * 256;
         X.bar_id = 1 + g;
         X.P = P; X.rpt = rpt; X.rows_used = rpt * P; X.tiles_per_image = tiles_per_image; X.total_tiles = total_tiles;
         X.size[0] = ob.bbox[1] - ob.bbox[0]; X.size[1] = ob.bbox[3] - ob.bbox[2]; X.size[2] = ob.bbox[5] - ob.bbox[4];
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.dbg = 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         Sync1 sync{acc_full + g, a_ready + g, 0u};
-        for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) epilogue_tile(X, pair * 2 + g, sync);
+        for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) epilogue_tile<SPLIT>(X, pair * 2 + g, sync);
     }
 
     tc_fence_before();

@@ -16,6 +16,7 @@ namespace {
 using namespace pe;
 using namespace pe_tc;
 
+constexpr int THREADS = 384;
 constexpr int NUM_STAGES2 = 8;
 constexpr int STAGE2_BYTES = 8192;                          // half slab: 128 rows x 32 k x 2 B
 constexpr int BIAS2_OFF = NUM_STAGES2 * STAGE2_BYTES;       // the bias chunk (<= 2 KB) sits behind the last stage
@@ -227,7 +228,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
         TileCtx X;
         X.A = &A; X.G2 = &G2;
         X.abuf = smem + g * A_BYTES;
-        X.m = ((warp & 3) << 5) | lane; X.lane = lane; X.wq = warp & 3;
+        X.m = ((warp & 3) << 5) | lane; X.lane = lane; X.wq = warp & 3; X.half = 0; X.gw = warp & 3;
         X.taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + g * 256;
         X.bar_id = 1 + g;
         X.P = P; X.rpt = rpt; X.rows_used = rpt * P; X.tiles_per_image = tiles_per_image; X.total_tiles = total_tiles;
@@ -244,7 +245,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
             sync.ts = rec ? reinterpret_cast<long long*>(A.stats) + 64 + 32 * g : nullptr;
             sync.n = 0;
             if (rec) sync.ts[30] = clock64();
-            epilogue_tile(X, it * 4 + 2 * g + rank, sync);
+            epilogue_tile<1>(X, it * 4 + 2 * g + rank, sync);
             if (rec) {
                 const long long* q = sync.ts;
                 printf("PE_TC2 epi g%d start=%lld |", g, q[30]);

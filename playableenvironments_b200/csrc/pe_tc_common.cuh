@@ -15,7 +15,6 @@ constexpr int A_CHUNKS = 40;                      // K columns 0..255: activatio
 constexpr int A_BYTES = A_CHUNKS * CHUNK_BYTES;   // 80 KB per tile
 constexpr int PE_CHUNK0 = 32;
 constexpr int NUM_LAYERS = 11;                    // L0..L7, H0, H3, H6
-constexpr int THREADS = 384;                      // producer, MMA, TMEM-alloc, spare + 2 x 4 epilogue warps
 constexpr int SCRATCH_STRIDE = 97;                // floats per row of the compositing scratch (bank-conflict free)
 constexpr int SCR_T = 50 * 1024, SCR_SH = SCR_T + 512, SCR_W = SCR_SH + 512;   // byte offsets inside the A buffer
 // per-tile constants staged in the (dead after L4) positional-encoding columns of the A buffer
@@ -71,20 +70,17 @@ __device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
 //   MODE 1: trunk output (L7)      y = relu(acc), also accumulates the alpha head dot product in fp32
 //   MODE 2: AdaIn layer            y = relu(acc * sc[c] + sh[c])   (BatchNorm folded into sc/sh, adain.py:58-59)
 template <int MODE, int N>
-__device__ __forceinline__ float hidden_epilogue(uint32_t taddr, unsigned char* abuf, int m, const float* __restrict__ c0s,
-                                                 const float* __restrict__ c1s, int dbg = 0) {
+__device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* abuf, int chunk0, int m, const float* __restrict__ c0s,
+                                                 const float* __restrict__ c1s) {
+    // tcol: TMEM address of the first of the N columns handled here; chunk0: A-operand chunk (= column / 8) they are stored to;
+    // c0s / c1s: per-column constants, already offset to the first column
     uint32_t v[2][32];
     float alpha = 0.f;
-    if (dbg & 4) {       // timing experiment: no TMEM reads
-#pragma unroll
-        for (int q = 0; q < 32; ++q) { v[0][q] = 0x3f800000u; v[1][q] = 0x3f800000u; }
-    } else tmem_ld32(taddr, v[0]);
+    tmem_ld32(tcol, v[0]);
 #pragma unroll
     for (int c = 0; c < N / 32; ++c) {
-        if (!(dbg & 4)) {
-            tmem_wait_ld_regs(v[c & 1]);
-            if (c + 1 < N / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-        }
+        tmem_wait_ld_regs(v[c & 1]);
+        if (c + 1 < N / 32) tmem_ld32(tcol + (c + 1) * 32, v[(c + 1) & 1]);
         float y[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) y[q] = __uint_as_float(v[c & 1][q]);
@@ -109,12 +105,27 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t taddr, unsigned char* 
                 y[4 * q + 3] = fmaf(y[4 * q + 3], s4.w, b4.w);
             }
         }
-        if (!(dbg & 8)) {    // timing experiment: no shared-memory stores
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) store_a8_relu(abuf, c * 4 + cc, m, y + 8 * cc);
-        } else if (y[0] == 123.456f) store_a8_relu(abuf, c * 4, m, y);
+        for (int cc = 0; cc < 4; ++cc) store_a8_relu(abuf, chunk0 + c * 4 + cc, m, y + 8 * cc);
     }
     return alpha;
+}
+
+// 16-column variants of the TMEM load / wait
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld_regs16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
 }
 
 // Everything an epilogue thread needs that does not change between tiles.
@@ -123,8 +134,10 @@ struct TileCtx {
     const PeIntegrated* G2;      // outputs of the composed scene when this object IS the scene (else all NULL)
     unsigned char* abuf;         // this group's A operand (shared memory)
     uint32_t taddr;              // TMEM address of this thread's lane quadrant and this group's accumulator columns
-    uint32_t bar_id;             // named barrier of the group (128 threads)
-    int m, lane, wq;             // row of the tile (= TMEM lane), lane, warp within the group
+    uint32_t bar_id;             // named barrier of the group
+    int m, lane, wq;             // row of the tile (= TMEM lane), lane, lane quadrant (warp % 4)
+    int half;                    // kSplit == 2: which half of the columns of row m this thread handles
+    int gw;                      // warp index inside the group (0 .. 4*kSplit-1)
     int P, rpt, rows_used, tiles_per_image;
     int64_t total_tiles;
     float size[3];
@@ -134,14 +147,39 @@ struct TileCtx {
     int dbg;
 };
 
+// 32 of the 64 positional-encoding columns of one sample (columns 32*H .. 32*H+31); layout of positional_encoder.py:59-64:
+// [x y z | sin(2^0 xyz) cos(2^0 xyz) | sin(2^1 xyz) ... ] (+ one zero pad column).  tp/tl: x/(2 pi) as a two-float value.
+template <int H>
+__device__ __forceinline__ void encode_half(const float (&xn)[3], const float (&tp)[3], const float (&tl)[3], float (&enc)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int idx = 32 * H + i;
+        float v;
+        if (idx < 3) v = xn[idx];
+        else if (idx == 63) v = 0.f;
+        else {
+            const int o = (idx - 3) / 6, r = (idx - 3) % 6, fn = r / 3, a = r % 3;
+            const float f = (float)(1 << o);
+            const float turns = tp[a] * f;                           // exact (power of two)
+            const float fr = (turns - rintf(turns)) + tl[a] * f;     // fractional turns in [-0.5, 0.5]
+            const float ang = fr * 6.2831855f;
+            v = fn ? __cosf(ang) : __sinf(ang);
+        }
+        enc[i] = v;
+    }
+}
+
 // Per-tile work of one epilogue thread.  `Sync` provides wait_acc() (accumulators of the next layer are complete) and
 // arrive_ready() (this thread's part of the next A operand is written and its TMEM reads are done).
-template <class Sync>
+// kSplit threads (in different warps of the same lane quadrant) share one row: each handles 1/kSplit of the columns.
+template <int kSplit, class Sync>
 __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync) {
+    constexpr int GROUP = TILE_M * kSplit;           // threads of the group
     const PeFieldArgs& A = *X.A;
     const PeIntegrated& G2 = *X.G2;
     const PeObjectDesc& ob = A.ob;
-    const int m = X.m, lane = X.lane, wq = X.wq, P = X.P, rpt = X.rpt;
+    const int m = X.m, lane = X.lane, wq = X.wq, P = X.P, rpt = X.rpt, hf = X.half;
+    const int tid = m + TILE_M * hf;
     unsigned char* abuf = X.abuf;
     const uint32_t taddr = X.taddr, bar_id = X.bar_id;
     float* scr = reinterpret_cast<float*>(abuf);
@@ -149,6 +187,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     float* sh_s = reinterpret_cast<float*>(abuf + SCR_SH);
     float* w_s = reinterpret_cast<float*>(abuf + SCR_W);
     float* cst = reinterpret_cast<float*>(abuf + CST_BASE);
+    float* alpha_part = cst + 1024;                  // [kSplit][128] partial alpha-head dot products
 
     const bool tile_valid = tile < X.total_tiles;
     const int img = tile_valid ? (int)(tile / X.tiles_per_image) : 0;
@@ -182,8 +221,6 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         // power of two, integer part dropped), then evaluated with the SFU on [-pi, pi] (abs error < 5e-7, far below the
         // fp16 rounding of the operand).  Same values as positional_encoder.py:59-64 up to that error.
         const float xn[3] = {__fdiv_rn(x[0], X.size[0]), __fdiv_rn(x[1], X.size[1]), __fdiv_rn(x[2], X.size[2])};
-        float enc[64];
-        enc[0] = xn[0]; enc[1] = xn[1]; enc[2] = xn[2];
         float tp[3], tl[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -191,26 +228,23 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             tp[a] = xn[a] * c_hi;
             tl[a] = fmaf(xn[a], c_lo, fmaf(xn[a], c_hi, -tp[a]));
         }
+        float enc[32];
+        if (kSplit == 1 || hf == 0) {
+            encode_half<0>(xn, tp, tl, enc);
 #pragma unroll
-        for (int o = 0; o < 10; ++o) {
-            const float f = (float)(1 << o);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float turns = tp[a] * f;                           // exact (power of two)
-                const float fr = (turns - rintf(turns)) + tl[a] * f;     // fractional turns in [-0.5, 0.5]
-                const float ang = fr * 6.2831855f;
-                enc[3 + 6 * o + a] = __sinf(ang);
-                enc[3 + 6 * o + 3 + a] = __cosf(ang);
-            }
+            for (int c = 0; c < 4; ++c) store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
         }
-        enc[63] = 0.f;
+        if (kSplit == 1 || hf == 1) {
+            encode_half<1>(xn, tp, tl, enc);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
+            for (int c = 0; c < 4; ++c) store_a8(abuf, PE_CHUNK0 + 4 + c, m, enc + 8 * c);
+        }
     }
     sync.arrive_ready();
 
     // ---- the 10 hidden tensor-core layers ----
-    float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+    float4 pre[2 / kSplit];
+    const uint32_t tcol = taddr + hf * (256 / kSplit);        // first accumulator column of this thread for 256-wide layers
     for (int l = 0; l < 10; ++l) {
         sync.wait_acc();
         if (l == 4) {
@@ -218,34 +252,42 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             // (AdaIn scale/shift of this image and the alpha-head weights); the loads overlap this layer's epilogue
             const float* a1 = A.aff1 + (int64_t)img * 512;
             const float* a2 = A.aff2 + (int64_t)img * 256;
-            const int i1 = 512 + m * 4;                                   // 1024 floats, 8 per thread
-            pre0 = __ldg(reinterpret_cast<const float4*>(a1 + m * 4));   // sc1|sh1
-            pre1 = i1 < 768 ? __ldg(reinterpret_cast<const float4*>(a2 + (i1 - 512))) : __ldg(reinterpret_cast<const float4*>(X.alpha_w + (i1 - 768)));
+#pragma unroll
+            for (int j = 0; j < 2 / kSplit; ++j) {
+                const int i0 = (j * GROUP + tid) * 4;                      // 1024 floats: sc1|sh1 (512), sc2|sh2 (256), alpha_w (256)
+                const float* src = i0 < 512 ? a1 + i0 : (i0 < 768 ? a2 + (i0 - 512) : X.alpha_w + (i0 - 768));
+                pre[j] = __ldg(reinterpret_cast<const float4*>(src));
+            }
         }
-        if (l == 7) named_bar_sync(bar_id, TILE_M);                        // constants written by the whole group at l == 4
-        if (l < 7) hidden_epilogue<0, 256>(taddr, abuf, m, nullptr, nullptr, X.dbg);
-        else if (l == 7) raw_alpha = hidden_epilogue<1, 256>(taddr, abuf, m, cst + CST_AW, nullptr, X.dbg) + X.alpha_bias;
-        else if (l == 8) hidden_epilogue<2, 256>(taddr, abuf, m, cst + CST_SC1, cst + CST_SH1, X.dbg);
-        else hidden_epilogue<2, 128>(taddr, abuf, m, cst + CST_SC2, cst + CST_SH2, X.dbg);
+        if (l == 7) named_bar_sync(bar_id, GROUP);                         // constants written by the whole group at l == 4
+        constexpr int W = 256 / kSplit, W2 = 128 / kSplit;
+        if (l < 7) hidden_epilogue<0, W>(tcol, abuf, hf * (W / 8), m, nullptr, nullptr);
+        else if (l == 7) raw_alpha = hidden_epilogue<1, W>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr);
+        else if (l == 8) hidden_epilogue<2, W>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W);
+        else hidden_epilogue<2, W2>(taddr + hf * W2, abuf, hf * (W2 / 8), m, cst + CST_SC2 + hf * W2, cst + CST_SH2 + hf * W2);
         if (l == 4) {
-            *reinterpret_cast<float4*>(cst + m * 4) = pre0;
-            *reinterpret_cast<float4*>(cst + 512 + m * 4) = pre1;
+#pragma unroll
+            for (int j = 0; j < 2 / kSplit; ++j) *reinterpret_cast<float4*>(cst + (j * GROUP + tid) * 4) = pre[j];
         }
+        if (l == 7 && kSplit == 2) alpha_part[hf * TILE_M + m] = raw_alpha;
         sync.arrive_ready();
     }
 
     // ---- last layer: features in TMEM -> volume rendering of the tile's rays (ObjectComposer.integrate :724-784) ----
+    // row scalars are computed redundantly by the kSplit threads of a row (identical values), stores by half 0 only
     sync.wait_acc();
     const int64_t gs = valid ? ray * P + p : 0;
+    t_s[m] = t;
+    named_bar_sync(bar_id, GROUP);
+    if (kSplit == 2) raw_alpha = alpha_part[m] + alpha_part[TILE_M + m];
+    raw_alpha += X.alpha_bias;
     float raw = (inbox && in_scene) ? raw_alpha : ob.empty_space_alpha;
-    if (valid) {
+    if (valid && hf == 0) {
         if (A.raw_out) A.raw_out[gs] = raw;
         if (A.t_out) A.t_out[gs] = t;
         if (A.inbox_out) A.inbox_out[gs] = inbox ? 1 : 0;
         if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
     }
-    t_s[m] = t;
-    named_bar_sync(bar_id, TILE_M);
     float alpha = 0.f;
     if (valid) {
         const float delta = __fmul_rn(p == P - 1 ? 1e10f : __fsub_rn(t_s[m + 1], t), dnorm);     // :153-178
@@ -266,8 +308,8 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     }
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0 || head) excl = 1.f;
-    if (lane == 31) { sh_s[wq] = incl; sh_s[4 + wq] = closed ? 1.f : 0.f; }
-    named_bar_sync(bar_id, TILE_M);
+    if (lane == 31 && hf == 0) { sh_s[wq] = incl; sh_s[4 + wq] = closed ? 1.f : 0.f; }
+    named_bar_sync(bar_id, GROUP);
     float T = excl;
     if (!closed) {                                   // the ray started in an earlier warp of the tile
         for (int v = wq - 1; v >= 0; --v) {
@@ -276,34 +318,37 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
     }
     const float w = valid ? alpha * T : 0.f;
-    w_s[m] = w;
-    if (valid) {
-        if (A.integ.weights) A.integ.weights[gs] = w;
-        if (X.single && G2.weights) G2.weights[gs] = w;
+    if (hf == 0) {
+        w_s[m] = w;
+        if (valid) {
+            if (A.integ.weights) A.integ.weights[gs] = w;
+            if (X.single && G2.weights) G2.weights[gs] = w;
+        }
     }
     const float wf = inbox ? w : 0.f;
-    for (int half = 0; half < 2; ++half) {
-        uint32_t v[2][32];
-        tmem_ld32(taddr + half * 96, v[0]);
+    constexpr int FC = 96 / kSplit;                  // feature columns per thread per pass (96 or 48)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int c_first = pass * 96 + hf * FC;     // first feature column of this thread in this pass
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            tmem_wait_ld_regs(v[c & 1]);
-            if (c + 1 < 3) tmem_ld32(taddr + half * 96 + (c + 1) * 32, v[(c + 1) & 1]);
+        for (int c = 0; c < FC / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c_first + c * 16, v);
+            tmem_wait_ld_regs16(v);
             if (!A.apply_activation && !A.feat_out) {                  // common case: nothing per-sample leaves the SM
 #pragma unroll
-                for (int q = 0; q < 32; ++q) scr[m * SCRATCH_STRIDE + c * 32 + q] = wf * __uint_as_float(v[c & 1][q]);
+                for (int q = 0; q < 16; ++q) scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = wf * __uint_as_float(v[q]);
             } else {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    float f = __uint_as_float(v[c & 1][q]);            // head-6 bias already added by the rank-1 MMA
+                for (int q = 0; q < 16; ++q) {
+                    float f = __uint_as_float(v[q]);                   // head-6 bias already added by the rank-1 MMA
                     if (A.apply_activation) f = 1.f / (1.f + expf(-f));
-                    if (A.feat_out && valid) A.feat_out[gs * 192 + half * 96 + c * 32 + q] = inbox ? f : 0.f;
-                    scr[m * SCRATCH_STRIDE + c * 32 + q] = wf * f;
+                    if (A.feat_out && valid) A.feat_out[gs * 192 + c_first + c * 16 + q] = inbox ? f : 0.f;
+                    scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = wf * f;
                 }
             }
         }
-        named_bar_sync(bar_id, TILE_M);
-        for (int item = m; item < rpt * 96; item += TILE_M) {
+        named_bar_sync(bar_id, GROUP);
+        for (int item = tid; item < rpt * 96; item += GROUP) {
             const int rl = item / 96, c = item - rl * 96;
             const int r = ray0 + rl;
             if (tile_valid && r < A.rays) {
@@ -316,15 +361,15 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
                 }
                 for (; j < P; ++j) s0 += col[j * SCRATCH_STRIDE];
                 const float sum = (s0 + s1) + (s2 + s3);
-                const int64_t o = ((int64_t)img * A.rays + r) * 192 + half * 96 + c;
+                const int64_t o = ((int64_t)img * A.rays + r) * 192 + pass * 96 + c;
                 if (A.integ.integrated_features) A.integ.integrated_features[o] = sum;
                 if (X.single && G2.integrated_features) G2.integrated_features[o] = sum;
             }
         }
-        named_bar_sync(bar_id, TILE_M);
+        named_bar_sync(bar_id, GROUP);
     }
     // per-ray scalars (:758-772): one warp per ray, lanes stride the samples
-    for (int rl = wq; rl < rpt; rl += 4) {
+    for (int rl = X.gw; rl < rpt; rl += 4 * kSplit) {
         const int r = ray0 + rl;
         if (!tile_valid || r >= A.rays) continue;
         float opacity = 0.f, depth = 0.f;
@@ -350,7 +395,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
     }
     tc_fence_before();
-    named_bar_sync(bar_id, TILE_M);       // scratch is dead before the next tile's encoding overwrites it
+    named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
 }
 
 }  // namespace pe_tc
