@@ -215,6 +215,35 @@ def run_b200(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * samples_per_rank * e2e_steps / (float(e2e_ms.item()) / 1e3)
 
+    # ---- the other tensor-core modes on the same frame + live parity of the timed mode against the fp32-class mode ----
+    modes, parity = {}, None
+    if rank == 0 and world == 1 and not args.quick:
+        feats_main = step().clone()
+        for other in ("fp16x2", "fp16x3"):
+            if other == args.precision:
+                continue
+            comp.precision = other
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_other = max(3, args.steps // 4)
+            s0.record()
+            for _ in range(n_other):
+                out_other = step()
+            e0.record()
+            torch.cuda.synchronize()
+            ms = s0.elapsed_time(e0) / n_other
+            modes[other] = {"ms_per_step": ms, "value": samples_per_rank / (ms / 1e3),
+                            "roofline_frac": samples_per_rank * FLOP_PER_SAMPLE / (ms / 1e3) / 1e12 / measured_peaks()["burst"]}
+            if other == "fp16x3":
+                ref = out_other.double()
+                diff = feats_main.double() - ref
+                parity = {"reference": "fp16x3 mode (fp32-class, itself within 1e-5 of the fp32 CUDA path) on the same frame",
+                          "rel_l2": float(diff.norm() / ref.norm()), "max_over_scale": float(diff.abs().max() / ref.abs().max()),
+                          "note": "max includes the ~1% of rays whose last-sample raw alpha sits on the opacity step (DESIGN.md section 5)"}
+        comp.precision = args.precision
+
     if rank == 0:
         peaks = measured_peaks()
         ms_per_step = total_s * 1e3 / args.steps
@@ -224,19 +253,23 @@ def run_b200(args):
             "metric": "ray-samples/sec (style-MLP ray-march, fwd)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp16": "f16 operands, f32 accumulate", "fp16x2": "f16 operands (weights hi+lo), f32 accumulate",
-                                           "fp32": "f32"}[args.precision],
+                                           "fp16x3": "f16 operands (weights and activations hi+lo), f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MB memset)",
                        "frames_per_s": world * args.steps / total_s, "collective": "all_gather(feature grid)" if world > 1 else "none"},
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / peaks["burst"], "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
                          "frac_of_sustained": achieved_tflops / peaks["sustained"],
-                         "tensor_passes": 2 if args.precision == "fp16x2" else (1 if args.precision == "fp16" else 0)},
+                         "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0}[args.precision]},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "wall_s": wall,
         }
+        if modes:
+            line["other_modes"] = modes
+        if parity:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             samples, times = cpu_reference(1024, 2, 1)
             mean = sum(times) / len(times)
@@ -253,8 +286,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "fp16"), choices=["fp16", "fp16x2", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "fp16"), choices=["fp16", "fp16x2", "fp16x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the other precision modes and the live parity check")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

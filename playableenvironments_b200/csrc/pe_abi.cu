@@ -159,10 +159,14 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;
         fa.t_out = out->positions_t[k] ? out->positions_t[k] : o.t;
         fa.raw_out = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
+        const bool self_contained = tc && s.objects == 1 && !s.perturb;     // the fused kernel integrates the whole scene itself
         fa.feat_out = out->raw_features[k] ? out->raw_features[k] : o.feat;
         fa.disp_out = out->displacements[k];
         fa.dispmag_out = o.dispmag;
         fa.inbox_out = o.inbox;
+        if (self_contained) {       // nothing downstream reads per-sample tensors: do not write them
+            fa.t_out = out->positions_t[k]; fa.raw_out = out->raw_alphas[k]; fa.dispmag_out = nullptr; fa.inbox_out = nullptr;
+        }
         fa.stats = o.stats;
         fa.integ = out->object[k];
         fa.noise = s.perturb ? in->noise[k] : nullptr;
@@ -185,7 +189,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
             const PeIntegrated& gout = (s.objects == 1 && !s.perturb) ? out->global : none;
             // PE_TC_KERNEL=1 selects the single-CTA lockstep kernel, 2 (default) the CTA-pair ping-pong kernel
             const char* which = getenv("PE_TC_KERNEL");
-            const bool pair = which ? atoi(which) == 2 : PE_TC_DEFAULT_PAIR;
+            const bool pair = (which ? atoi(which) == 2 : PE_TC_DEFAULT_PAIR) && s.precision != PE_PRECISION_FP16X3;
             return pair ? pe_launch_field_tc2(fa, gout, sm_count, stream) : pe_launch_field_tc(fa, gout, sm_count, stream);
         };
         if (s.training) {

@@ -38,7 +38,9 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
     __device__ __forceinline__ void arrive_ready() { fence_proxy_async(); tc_fence_before(); mbar_arrive(a_ready); }
 };
 
-__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes) {
+__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3) {
+    // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
+    // per k-step A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-class accuracy on the tensor cores); epilogue group Y idles
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -57,11 +59,11 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     const int rpt = TILE_M / P;                                   // rays per tile
     const int tiles_per_image = (A.rays + rpt - 1) / rpt;
     const int64_t total_tiles = (int64_t)tiles_per_image * A.images;
-    const int64_t total_pairs = (total_tiles + 1) / 2;
+    const int64_t total_pairs = x3 ? total_tiles : (total_tiles + 1) / 2;        // iterations of this kernel
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, TILE_M * SPLIT); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 2 * TILE_M : TILE_M * SPLIT); }
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     const uint32_t idesc = umma_idesc_f16(TILE_M, n);
                     const uint32_t lbo_b = (uint32_t)n * 16;          // bytes between K chunks of a slab: (n/8) core matrices
                     mbar_wait(a_ready + 0, ready_phase);
-                    mbar_wait(a_ready + 1, ready_phase);
+                    if (!x3) mbar_wait(a_ready + 1, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
                     for (int s = 0; s < slabs; ++s) {
@@ -130,6 +132,20 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                             tc_fence_after();
                             const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
                             const uint32_t b_addr = ring_addr + stage * STAGE_BYTES;
+                            if (x3) {
+                                // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
+                                    const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
+                                    umma_f16_ss(tmem_base, umma_smem_desc(a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128), db, idesc, (s | pass | j) != 0 ? 1u : 0u);
+                                    if (pass == 0) umma_f16_ss(tmem_base, umma_smem_desc(a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128), db, idesc, 1u);
+                                }
+                                if (last) umma_commit(acc_full + 0);
+                                umma_commit(empty_bar + stage);
+                                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
 #pragma unroll
                             for (int g = 0; g < 2; ++g) {
 #pragma unroll
@@ -151,6 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                         const uint64_t db = umma_smem_desc(ring_addr + stage * STAGE_BYTES, lbo_b, 128);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
+                            if (x3 && g == 1) break;
                             umma_f16_ss(tmem_base + g * 256, ones_desc, db, idesc, 1u);
                             umma_commit(acc_full + g);
                         }
@@ -167,6 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         TileCtx X;
         X.A = &A; X.G2 = &G2;
         X.abuf = smem + g * A_BYTES;                   // derived from the __shared__ base so accesses compile to LDS/STS
+        X.abuf_lo = smem + A_BYTES;
         X.wq = warp & 3;                               // TMEM lane quadrant this warp may access
         X.m = (X.wq << 5) | lane; X.lane = lane; X.gw = gw;
         X.half = gw >> 2;                              // the two warps of a quadrant split the columns of their 32 rows
@@ -179,7 +197,15 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.dbg = 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         Sync1 sync{acc_full + g, a_ready + g, 0u};
-        for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) epilogue_tile<SPLIT>(X, pair * 2 + g, sync);
+        if (x3) {
+            // one tile per iteration: the two epilogue groups become the two column halves of the same 128 rows
+            X.abuf = smem; X.half = g; X.gw = warp - 4; X.bar_id = 1;
+            X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
+            Sync1 sync3{acc_full, a_ready, 0u};
+            for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3);
+        } else {
+            for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) epilogue_tile<SPLIT, false>(X, pair * 2 + g, sync);
+        }
     }
 
     tc_fence_before();
@@ -343,14 +369,15 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
         pe_set_error("tensor-core field kernel: unsupported configuration");
         return PE_ERR_UNSUPPORTED;
     }
-    const int num_passes = args.precision == PE_PRECISION_FP16X2 ? 2 : 1;
+    const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
+    const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int rpt = TILE_M / args.ob.positions;
     const int64_t tiles = (int64_t)((args.rays + rpt - 1) / rpt) * args.images;
-    const int64_t pairs = (tiles + 1) / 2;
+    const int64_t pairs = x3 ? tiles : (tiles + 1) / 2;
     if (pairs == 0) return PE_OK;
     const int grid = (int)pe_min64(pairs, sm_count);
-    pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes);
+    pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
     return PE_OK;
 }

@@ -228,6 +228,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
         TileCtx X;
         X.A = &A; X.G2 = &G2;
         X.abuf = smem + g * A_BYTES;
+        X.abuf_lo = nullptr;
         X.m = ((warp & 3) << 5) | lane; X.lane = lane; X.wq = warp & 3; X.half = 0; X.gw = warp & 3;
         X.taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + g * 256;
         X.bar_id = 1 + g;
@@ -245,7 +246,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
             sync.ts = rec ? reinterpret_cast<long long*>(A.stats) + 64 + 32 * g : nullptr;
             sync.n = 0;
             if (rec) sync.ts[30] = clock64();
-            epilogue_tile<1>(X, it * 4 + 2 * g + rank, sync);
+            epilogue_tile<1, false>(X, it * 4 + 2 * g + rank, sync);
             if (rec) {
                 const long long* q = sync.ts;
                 printf("PE_TC2 epi g%d start=%lld |", g, q[30]);

@@ -53,6 +53,19 @@ __device__ __forceinline__ void store_a8_relu(unsigned char* a_base, int chunk, 
     *reinterpret_cast<uint4*>(a_base + chunk * CHUNK_BYTES + m * 16) = q;
 }
 
+// fp16x3 mode: activations are kept as hi + lo fp16 pairs (hi = fp16(max(v,0)), lo = fp16(max(v,0) - hi)) in two operand buffers
+__device__ __forceinline__ void store_a8_hilo(unsigned char* a_hi, unsigned char* a_lo, int chunk, int m, const float* v, bool relu) {
+    float h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float x = relu ? fminf(fmaxf(v[i], 0.f), 65504.f) : v[i];
+        h[i] = __half2float(__float2half_rn(x));
+        l[i] = x - h[i];
+    }
+    store_a8(a_hi, chunk, m, h);
+    store_a8(a_lo, chunk, m, l);
+}
+
 // wait for outstanding tcgen05.ld; the registers are threaded through so no use can be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -69,9 +82,9 @@ __device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
 //   MODE 0: trunk layer            y = relu(acc)
 //   MODE 1: trunk output (L7)      y = relu(acc), also accumulates the alpha head dot product in fp32
 //   MODE 2: AdaIn layer            y = relu(acc * sc[c] + sh[c])   (BatchNorm folded into sc/sh, adain.py:58-59)
-template <int MODE, int N>
+template <int MODE, int N, bool kHiLo = false>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* abuf, int chunk0, int m, const float* __restrict__ c0s,
-                                                 const float* __restrict__ c1s) {
+                                                 const float* __restrict__ c1s, unsigned char* abuf_lo = nullptr) {
     // tcol: TMEM address of the first of the N columns handled here; chunk0: A-operand chunk (= column / 8) they are stored to;
     // c0s / c1s: per-column constants, already offset to the first column
     uint32_t v[2][32];
@@ -106,7 +119,10 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* a
             }
         }
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) store_a8_relu(abuf, chunk0 + c * 4 + cc, m, y + 8 * cc);
+        for (int cc = 0; cc < 4; ++cc) {
+            if (kHiLo) store_a8_hilo(abuf, abuf_lo, chunk0 + c * 4 + cc, m, y + 8 * cc, true);
+            else store_a8_relu(abuf, chunk0 + c * 4 + cc, m, y + 8 * cc);
+        }
     }
     return alpha;
 }
@@ -133,6 +149,7 @@ struct TileCtx {
     const PeFieldArgs* A;
     const PeIntegrated* G2;      // outputs of the composed scene when this object IS the scene (else all NULL)
     unsigned char* abuf;         // this group's A operand (shared memory)
+    unsigned char* abuf_lo;      // fp16x3 mode: operand buffer of the low halves
     uint32_t taddr;              // TMEM address of this thread's lane quadrant and this group's accumulator columns
     uint32_t bar_id;             // named barrier of the group
     int m, lane, wq;             // row of the tile (= TMEM lane), lane, lane quadrant (warp % 4)
@@ -172,7 +189,7 @@ __device__ __forceinline__ void encode_half(const float (&xn)[3], const float (&
 // Per-tile work of one epilogue thread.  `Sync` provides wait_acc() (accumulators of the next layer are complete) and
 // arrive_ready() (this thread's part of the next A operand is written and its TMEM reads are done).
 // kSplit threads (in different warps of the same lane quadrant) share one row: each handles 1/kSplit of the columns.
-template <int kSplit, class Sync>
+template <int kSplit, bool kHiLo, class Sync>
 __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync) {
     constexpr int GROUP = TILE_M * kSplit;           // threads of the group
     const PeFieldArgs& A = *X.A;
@@ -232,12 +249,18 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         if (kSplit == 1 || hf == 0) {
             encode_half<0>(xn, tp, tl, enc);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
+            for (int c = 0; c < 4; ++c) {
+                if (kHiLo) store_a8_hilo(abuf, X.abuf_lo, PE_CHUNK0 + c, m, enc + 8 * c, false);
+                else store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
+            }
         }
         if (kSplit == 1 || hf == 1) {
             encode_half<1>(xn, tp, tl, enc);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) store_a8(abuf, PE_CHUNK0 + 4 + c, m, enc + 8 * c);
+            for (int c = 0; c < 4; ++c) {
+                if (kHiLo) store_a8_hilo(abuf, X.abuf_lo, PE_CHUNK0 + 4 + c, m, enc + 8 * c, false);
+                else store_a8(abuf, PE_CHUNK0 + 4 + c, m, enc + 8 * c);
+            }
         }
     }
     sync.arrive_ready();
@@ -261,10 +284,10 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
         if (l == 7) named_bar_sync(bar_id, GROUP);                         // constants written by the whole group at l == 4
         constexpr int W = 256 / kSplit, W2 = 128 / kSplit;
-        if (l < 7) hidden_epilogue<0, W>(tcol, abuf, hf * (W / 8), m, nullptr, nullptr);
-        else if (l == 7) raw_alpha = hidden_epilogue<1, W>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr);
-        else if (l == 8) hidden_epilogue<2, W>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W);
-        else hidden_epilogue<2, W2>(taddr + hf * W2, abuf, hf * (W2 / 8), m, cst + CST_SC2 + hf * W2, cst + CST_SH2 + hf * W2);
+        if (l < 7) hidden_epilogue<0, W, kHiLo>(tcol, abuf, hf * (W / 8), m, nullptr, nullptr, X.abuf_lo);
+        else if (l == 7) raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo);
+        else if (l == 8) hidden_epilogue<2, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W, X.abuf_lo);
+        else hidden_epilogue<2, W2, kHiLo>(taddr + hf * W2, abuf, hf * (W2 / 8), m, cst + CST_SC2 + hf * W2, cst + CST_SH2 + hf * W2, X.abuf_lo);
         if (l == 4) {
 #pragma unroll
             for (int j = 0; j < 2 / kSplit; ++j) *reinterpret_cast<float4*>(cst + (j * GROUP + tid) * 4) = pre[j];

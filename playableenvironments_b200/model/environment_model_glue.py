@@ -36,7 +36,7 @@ def batchified_composer_call(object_composer: ObjectComposer, ray_origins, ray_d
     return results
 
 
-def install(environment_model, precision: str = "fp16"):
+def install(environment_model, precision: str = "fp16x3"):
     """Replaces ``environment_model.object_composer`` (a reference ObjectComposer) by the B200 composer carrying the same
     parameters, and routes ``batchified_composer_call`` to the single-call version."""
     reference = environment_model.object_composer

@@ -25,8 +25,11 @@ class ObjectComposer(nn.Module):
         if self.object_models_coarse[0].model_config["nerf_model"]["output_features"] != 3 and self.apply_activation:
             raise Exception("The application of activations to the nerf output is requested, but the model seem not to output colors directly. Please make sure this is the behavior you desire")
         self.object_id_helper = ObjectIDsHelper(self.config)
-        # compute type of the tensor-core path: "fp16" (1 pass), "fp16x2" (weights split hi+lo), "fp32" (CUDA cores only)
-        self.precision = self.config["model"].get("b200_precision", "fp16")
+        # arithmetic of the shipped-shape fields (others always run the exact fp32 CUDA-core kernel):
+        #   "fp16x3" tensor cores, weights and activations split hi+lo — fp32-class parity (default)
+        #   "fp16x2" tensor cores, weights split hi+lo          "fp16" tensor cores, single pass (fastest)
+        #   "fp32"   CUDA cores only
+        self.precision = self.config["model"].get("b200_precision", "fp16x3")
         # diagnostic switch: also return the per-sample raw alphas of every object under results["coarse"]["object_k"]["raw_alphas"]
         self.return_raw_alphas = False
 

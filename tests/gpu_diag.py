@@ -82,7 +82,7 @@ for scene_name in ["cfg1", "static_small", "tennis_small", "tennis_dense", "tenn
         e = errs(run_composer(comp, dev), load_golden(scene_name))
         return {"worst": worst(e), "all": e}
 
-for prec in ["fp16", "fp16x2"]:
+for prec in ["fp16", "fp16x2", "fp16x3"]:
     for scene_name in ["static_small", "tennis_small", "minecraft_small", "minecraft_absent"]:
         @section(f"{prec}/{scene_name}")
         def _(scene_name=scene_name, prec=prec):

@@ -1,11 +1,13 @@
 """Parity of the CUDA render path (through the C ABI) against the upstream reference (golden fixtures) and the CPU oracle.
 
-Tolerances (relative to the tensor's scale: max|got - ref| / max|ref|):
+Tolerances (relative to the tensor's scale: max|got - ref| / max|ref|; BASELINE.json asks for 1e-3 relative):
   fp32   CUDA-core path (any architecture, any mode):                               2e-4  (measured <= 6e-5)
-  fp16x2 tcgen05 path, weights split hi+lo, on the headline 128-samples/ray shape:   1e-3  (measured 3-4e-4) — BASELINE tolerance
-  fp16   tcgen05 path, single pass, same shape:                                      1e-3 relative L2, 3e-3 scale-relative max
-  few-sample objects (P=4, P=16) amplify the fp16 activation rounding through exp(-relu(a) * delta) with delta ~ 20:
-  both tensor-core modes are held to 6e-3 / 2e-2 there and the fp32 path to 2e-4 (Numerics).
+  fp16x3 tcgen05 path, weights AND activations split hi+lo (fp32-class):             2e-4  on every golden scene (measured <= 9e-5)
+  fp16x2 tcgen05 path, weights split hi+lo, on the headline 128-samples/ray shape:   1e-3  (measured 3e-4 at 16x16 rays, 7e-4 at 256x256)
+  fp16   tcgen05 path, single pass, same shape:                                      1e-3 relative L2 (measured 5.4e-4) and
+                                                                                     2e-3 scale-relative max (measured 1.2e-3 at 256x256)
+  few-sample objects (P=4, P=16) amplify the fp16 activation rounding through exp(-relu(a) * delta) with delta ~ 20..85:
+  fp16/fp16x2 are held to 6e-3 / 8e-2 there; fp16x3 and fp32 stay at 2e-4 (Numerics).
 """
 import numpy as np
 import pytest
@@ -77,7 +79,15 @@ def test_train_mode_batchnorm_matches_reference(name):
             assert scale_rel_err(sd[k[6:]].cpu().numpy(), ref) < 1e-4, k
 
 
-@pytest.mark.parametrize("precision,tol", [("fp16x2", 1e-3), ("fp16", 3e-3)])
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_fp16x3_tensor_core_path_matches_reference(name):
+    """fp32-class tensor-core mode (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo) on every golden scene, ill-conditioned ones included."""
+    _, _, _, comp, dev = _build(name, "fp16x3")
+    bad = compare(flatten(_run(comp, dev)), load_golden(name), FP32_TOL)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16x3", 2e-4), ("fp16x2", 1e-3), ("fp16", 3e-3)])
 def test_tensor_core_path_on_the_headline_shape(precision, tol):
     """BASELINE configs[1] shape (static field, 128 samples/ray) at 16x16 rays against the reference golden."""
     _, _, _, comp, dev = _build("static_small", precision)
@@ -168,7 +178,7 @@ def test_object_model_forward_on_explicit_positions():
     assert scale_rel_err(d.cpu().numpy(), rd.numpy()) < FP32_TOL
 
 
-@pytest.mark.parametrize("precision", ["fp16", "fp16x2"])
+@pytest.mark.parametrize("precision", ["fp16", "fp16x2", "fp16x3"])
 def test_full_size_frame_properties(precision):
     """BASELINE configs[1] at full size (256x256 rays x 128 samples): size-independent properties of the render —
     rays are independent (any chunking gives bit-identical rays), the run is deterministic, opacity = sum of weights in [0,1],
@@ -199,11 +209,13 @@ def test_full_size_frame_properties(precision):
     raw_last = res["object_0"]["raw_alphas"][..., -1].reshape(-1)
     stable = (raw_last.abs() > 4e-3).cpu().numpy()
     assert stable.mean() > 0.97
-    tol = 1e-3 if precision == "fp16x2" else 3e-3
+    tol = {"fp16x3": 2e-4, "fp16x2": 1e-3, "fp16": 2e-3}[precision]
     for key in ("integrated_features", "opacity", "depth"):
         got = (full[key][..., ::13, :] if full[key].dim() == 5 else full[key][..., ::13]).cpu().numpy().reshape(stable.size, -1)[stable]
         want = ref[key].cpu().numpy().reshape(stable.size, -1)[stable]
         assert scale_rel_err(got, want) < tol, (key, scale_rel_err(got, want))
+        rel_l2 = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64)))
+        assert rel_l2 < 1e-3, (key, rel_l2)
 
 
 def test_launch_accounting_and_no_fallback():
