@@ -111,6 +111,9 @@ def run(name, variant="eval"):
         for k, v in comp.state_dict().items():
             if "running_" in k:
                 extra["state/" + k] = v.detach().numpy()
+    elif variant in ("grad", "grad_train"):
+        run_grad(name, variant, comp, args)
+        return
     else:
         raise ValueError(variant)
     flat = flatten(res)
@@ -124,6 +127,41 @@ def run(name, variant="eval"):
           f"size={os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def run_grad(name, variant, comp, args):
+    """Gradients of the seeded scalar ``scenes.grad_loss`` w.r.t. every parameter and every differentiable input, computed by
+    the upstream code's own autograd graph (eval-mode or train-mode BatchNorm)."""
+    comp.train(variant == "grad_train")
+    names = ("ray_origins", "ray_directions", "focal_normals", "transformation_matrix_w2o", "style", "deformation", "object_in_scene")
+    leaves = {}
+    for i, n in enumerate(names):
+        if n in scenes.GRAD_INPUT_KEYS:
+            args[i] = args[i].clone().requires_grad_(True)
+            leaves[n] = args[i]
+    res = comp(*args, False)["coarse"]
+    keys = []
+    for obj in res:
+        for out in scenes.GRAD_OUTPUT_KEYS:
+            v = res[obj][out]
+            if out == "disparity" and not (torch.isfinite(v).all() and res[obj]["opacity"].min() > 0.5):
+                continue            # 0/0 rays would poison every gradient with NaN
+            if not v.requires_grad:
+                continue
+            keys.append(f"{obj}/{out}")
+    loss = scenes.grad_loss(res, keys)
+    loss.backward()
+    flat = {"loss": np.array(loss.item(), dtype=np.float64), "loss_keys": np.array(keys)}
+    for n, t in leaves.items():
+        flat["input/" + n] = t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape), np.float32)
+    for n, p in comp.named_parameters():
+        g = p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+        flat["param/" + n] = scenes.grad_subsample(n, g)
+    path = os.path.join(HERE, f"{name}_{variant}.npz")
+    np.savez_compressed(path, **flat)
+    gn = {k: float(np.abs(v).max()) for k, v in flat.items() if k.startswith("input/")}
+    print(f"{name:18s} {variant:10s} -> {os.path.basename(path)} loss={loss.item():.4f} keys={len(keys)} "
+          f"size={os.path.getsize(path) / 1e3:.0f} kB  max|input grads|={gn}")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     for scene in scenes.SCENES:
@@ -134,3 +172,8 @@ if __name__ == "__main__":
     run("cfg1", "train")
     run("static_small", "train")
     run("tennis_dense", "train")
+    if "--no-grad" not in sys.argv:
+        for scene in ("cfg1", "static_small", "tennis_dense", "minecraft_small"):
+            run(scene, "grad")
+        for scene in ("cfg1", "tennis_dense"):
+            run(scene, "grad_train")

@@ -284,3 +284,43 @@ SCENES = {
     "minecraft_small": lambda: scene_minecraft(),
     "minecraft_absent": lambda: scene_minecraft(seed=17, absent=[(0, 0, 0, 3)]),
 }
+
+
+# ----------------------------------------------------------------------------
+# gradient pins: seeded cotangents and sub-sampling of large parameter gradients
+# ----------------------------------------------------------------------------
+
+GRAD_OUTPUT_KEYS = ("integrated_features", "opacity", "depth", "weights", "integrated_displacements_magnitude", "disparity")
+GRAD_INPUT_KEYS = ("ray_origins", "ray_directions", "transformation_matrix_w2o", "style", "deformation")
+GRAD_SAMPLE = 2048          # entries kept of parameter gradients larger than 2 * GRAD_SAMPLE
+
+
+def _key_seed(key: str) -> int:
+    import zlib
+    return zlib.crc32(key.encode())
+
+
+def cotangent(key: str, shape) -> torch.Tensor:
+    """Seeded upstream gradient of output ``key`` ("object_0/opacity", "global/integrated_features", ...)."""
+    rng = np.random.default_rng(_key_seed("cot:" + key))
+    return torch.from_numpy(rng.normal(0.0, 1.0, tuple(shape)).astype(np.float32))
+
+
+def grad_loss(coarse: dict, keys) -> torch.Tensor:
+    """Scalar whose gradient is pinned: sum over ``keys`` ("<object>/<output>") of <cotangent, output>."""
+    total = None
+    for key in keys:
+        obj, out = key.split("/")
+        v = coarse[obj][out]
+        term = (cotangent(key, v.shape).to(v.device) * v).sum()
+        total = term if total is None else total + term
+    return total
+
+
+def grad_subsample(name: str, g: np.ndarray) -> np.ndarray:
+    """Large gradients are stored as GRAD_SAMPLE seeded entries followed by [sum, L2 norm]."""
+    flat = np.asarray(g, dtype=np.float32).reshape(-1)
+    if flat.size <= 2 * GRAD_SAMPLE:
+        return flat
+    idx = np.random.default_rng(_key_seed("idx:" + name)).choice(flat.size, GRAD_SAMPLE, replace=False)
+    return np.concatenate([flat[idx], np.array([flat.astype(np.float64).sum(), np.sqrt((flat.astype(np.float64) ** 2).sum())], dtype=np.float32)])

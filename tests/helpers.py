@@ -50,3 +50,27 @@ def compare(flat_got, golden, tol, skip=(), only_prefix="coarse/"):
         if not (e <= tol):
             bad[k] = e
     return bad
+
+
+def compare_grads(got_inputs, got_params, golden, tol):
+    """got_inputs: {input name: array}, got_params: {state_dict name: array}; golden: a *_grad.npz dict
+    (parameter gradients sub-sampled by scenes.grad_subsample).  Returns {key: err} above tol, errors relative to the
+    golden tensor's max magnitude."""
+    import scenes
+    bad = {}
+    for k, ref in golden.items():
+        if k.startswith("input/"):
+            got = got_inputs[k[len("input/"):]]
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        elif k.startswith("param/"):
+            name = k[len("param/"):]
+            got = scenes.grad_subsample(name, got_params[name])
+        else:
+            continue
+        if not np.abs(ref).max() > 0:
+            e = float(np.abs(got).max())
+        else:
+            e = scale_rel_err(got, ref)
+        if not (e <= tol):
+            bad[k] = e
+    return bad

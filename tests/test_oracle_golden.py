@@ -70,3 +70,27 @@ def test_decoder_feature_grids_layout():
     assert g4.shape == (1, 1, 1, 64, 8, 16) and g8.shape == (1, 1, 1, 128, 4, 8)
     assert g4[0, 0, 0, 5, 1, 2] == feats[0, 0, 0, 1 * 16 + 2, 5]
     assert g8[0, 0, 0, 7, 3, 1] == feats[0, 0, 0, 8 * 16 + 3 * 8 + 1, 64 + 7]
+
+
+GRAD_CASES = [("cfg1", False), ("static_small", False), ("tennis_dense", False), ("minecraft_small", False),
+              ("cfg1", True), ("tennis_dense", True)]
+
+
+@pytest.mark.parametrize("name,training", GRAD_CASES)
+def test_gradients_match_reference_autograd(name, training):
+    """Autograd through the oracle against gradients recorded from the upstream code's own graph (make_golden.py run_grad):
+    every parameter and every differentiable input of ObjectComposer.forward."""
+    from helpers import compare_grads
+    golden = load_golden(f"{name}_grad_train" if training else f"{name}_grad")
+    config, state, inputs = scenes.SCENES[name]()
+    state = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in state.items()}
+    inputs = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in inputs.items()}
+    res = O.composer_forward(config, state, *[inputs[k] for k in INPUT_KEYS], perturb=False, training=training)["coarse"]
+    loss = scenes.grad_loss(res, [str(k) for k in golden["loss_keys"]])
+    assert abs(loss.item() - float(golden["loss"])) <= 2e-5 * max(1.0, abs(float(golden["loss"])))
+    loss.backward()
+    zeros = lambda t: np.zeros(tuple(t.shape), np.float32)
+    got_in = {k: (inputs[k].grad.numpy() if inputs[k].grad is not None else zeros(inputs[k])) for k in scenes.GRAD_INPUT_KEYS}
+    got_par = {k: (v.grad.numpy() if v.grad is not None else zeros(v)) for k, v in state.items() if v.is_floating_point() and "running_" not in k}
+    bad = compare_grads(got_in, got_par, golden, 2e-4)
+    assert not bad, bad
