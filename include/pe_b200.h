@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 1
+#define PE_ABI_VERSION 2
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -145,6 +145,53 @@ int    pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* params, vo
 size_t pe_workspace_bytes(const PeScene* scene);
 int    pe_render_forward(const PeScene* scene, const PeInputs* in, const PeOutputs* out,
                          void* workspace, size_t workspace_bytes, pe_stream_t stream);
+
+/* -- backward of the hot path: replaces the autograd graph the reference builds under ObjectComposer.forward
+ *    (loss.backward() in training/trainer.py:643 replays every op of model/object_composer.py:786-892).
+ *    The forward is recomputed from the inputs (nothing is saved between the two calls except what the caller
+ *    passes again), gradients are ACCUMULATED (+=) into caller-zeroed fp32 buffers; a NULL pointer skips that
+ *    gradient.  Instances that share one object model may point at the same parameter-gradient buffers.     */
+typedef struct PeIntegratedGrads {             /* dL/d(outputs of ObjectComposer.integrate); NULL = zero     */
+    const float* integrated_features;          /* [images][rays][features]                                   */
+    const float* opacity;                      /* [images][rays]                                             */
+    const float* weights;                      /* [images][rays][P]                                          */
+    const float* depth;                        /* [images][rays]                                             */
+    const float* disparity;                    /* [images][rays]                                             */
+    const float* integrated_displacements_magnitude;   /* [images][rays]                                     */
+} PeIntegratedGrads;
+
+typedef struct PeOutGrads {
+    PeIntegratedGrads object[PE_MAX_OBJECTS];
+    PeIntegratedGrads global;
+} PeOutGrads;
+
+typedef struct PeObjectParamGrads {            /* same tensors and layouts as PeObjectParams (nn.Linear [out][in]) */
+    float* backbone_w[PE_MAX_LAYERS];  float* backbone_b[PE_MAX_LAYERS];
+    float* alpha_w;  float* alpha_b;
+    float* head0_w;
+    float* affine1_w; float* affine1_b;
+    float* head3_w;
+    float* affine2_w; float* affine2_b;
+    float* head6_w;  float* head6_b;
+    float* bender_w[PE_MAX_LAYERS];    float* bender_b[PE_MAX_LAYERS];
+    float* bender_out_w;
+} PeObjectParamGrads;
+
+typedef struct PeInGrads {
+    float* ray_origins;                        /* [images][3]                                                */
+    float* ray_directions;                     /* [images][rays][3]                                          */
+    float* w2o;                                /* [images][objects][3][4]                                    */
+    float* style[PE_MAX_OBJECTS];              /* [images][style_features]                                   */
+    float* deformation[PE_MAX_OBJECTS];        /* [images][deformation_features]                             */
+    PeObjectParamGrads params[PE_MAX_OBJECTS]; /* per object instance                                        */
+} PeInGrads;
+
+size_t pe_backward_workspace_bytes(const PeScene* scene);
+/* `params[k]`: the fp32 parameter tensors of instance k (the transposed products W^T g read the nn.Linear layout
+ * directly).  `scene`/`in` must be the ones of the forward call (including rand/noise when perturb is set).  */
+int    pe_render_backward(const PeScene* scene, const PeInputs* in, const PeObjectParams* params,
+                          const PeOutGrads* grad_out, const PeInGrads* grad_in,
+                          void* workspace, size_t workspace_bytes, pe_stream_t stream);
 
 /* -- stand-alone operators (module-level API of the reference) ---------------------------------- */
 /* PositionalEncoder.forward / AnnealablePositionalEncoder.forward

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 1
+PE_ABI_VERSION = 2
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -88,9 +88,42 @@ class PeOutputs(C.Structure):
     ]
 
 
+class PeIntegratedGrads(C.Structure):
+    _fields_ = [
+        ("integrated_features", C.c_void_p), ("opacity", C.c_void_p), ("weights", C.c_void_p), ("depth", C.c_void_p),
+        ("disparity", C.c_void_p), ("integrated_displacements_magnitude", C.c_void_p),
+    ]
+
+
+class PeOutGrads(C.Structure):
+    _fields_ = [("object", PeIntegratedGrads * PE_MAX_OBJECTS), ("global_", PeIntegratedGrads)]
+
+
+class PeObjectParamGrads(C.Structure):
+    _fields_ = [
+        ("backbone_w", C.c_void_p * PE_MAX_LAYERS), ("backbone_b", C.c_void_p * PE_MAX_LAYERS),
+        ("alpha_w", C.c_void_p), ("alpha_b", C.c_void_p),
+        ("head0_w", C.c_void_p),
+        ("affine1_w", C.c_void_p), ("affine1_b", C.c_void_p),
+        ("head3_w", C.c_void_p),
+        ("affine2_w", C.c_void_p), ("affine2_b", C.c_void_p),
+        ("head6_w", C.c_void_p), ("head6_b", C.c_void_p),
+        ("bender_w", C.c_void_p * PE_MAX_LAYERS), ("bender_b", C.c_void_p * PE_MAX_LAYERS),
+        ("bender_out_w", C.c_void_p),
+    ]
+
+
+class PeInGrads(C.Structure):
+    _fields_ = [
+        ("ray_origins", C.c_void_p), ("ray_directions", C.c_void_p), ("w2o", C.c_void_p),
+        ("style", C.c_void_p * PE_MAX_OBJECTS), ("deformation", C.c_void_p * PE_MAX_OBJECTS),
+        ("params", PeObjectParamGrads * PE_MAX_OBJECTS),
+    ]
+
+
 EXPORTS = [
     "pe_abi_version", "pe_last_error", "pe_take_launch_count", "pe_packed_bytes", "pe_pack_object",
-    "pe_workspace_bytes", "pe_render_forward", "pe_positional_encoding", "pe_generate_rays",
+    "pe_workspace_bytes", "pe_render_forward", "pe_backward_workspace_bytes", "pe_render_backward", "pe_positional_encoding", "pe_generate_rays",
     "pe_fold_feature_grids", "pe_debug_umma_gemm",
 ]
 
@@ -122,6 +155,11 @@ def lib() -> C.CDLL:
     L.pe_workspace_bytes.argtypes = [C.POINTER(PeScene)]
     L.pe_render_forward.restype = C.c_int
     L.pe_render_forward.argtypes = [C.POINTER(PeScene), C.POINTER(PeInputs), C.POINTER(PeOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pe_backward_workspace_bytes.restype = C.c_size_t
+    L.pe_backward_workspace_bytes.argtypes = [C.POINTER(PeScene)]
+    L.pe_render_backward.restype = C.c_int
+    L.pe_render_backward.argtypes = [C.POINTER(PeScene), C.POINTER(PeInputs), C.POINTER(PeObjectParams), C.POINTER(PeOutGrads),
+                                     C.POINTER(PeInGrads), C.c_void_p, C.c_size_t, C.c_void_p]
     L.pe_positional_encoding.restype = C.c_int
     L.pe_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pe_generate_rays.restype = C.c_int

@@ -244,9 +244,196 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         for (int k = 0; k < s.objects; ++k)
             if (object_uses_tc(s, k)) memset(&ca.object[k], 0, sizeof(PeIntegrated));
     }
-    if (ca.do_objects || ca.do_global) {
+    auto wants = [](const PeIntegrated& o) {
+        return o.integrated_features || o.opacity || o.weights || o.depth || o.disparity || o.integrated_displacements_magnitude || o.integrated_divergence;
+    };
+    bool any_out = wants(ca.global);
+    for (int k = 0; k < s.objects; ++k) any_out = any_out || wants(ca.object[k]);
+    if ((ca.do_objects || ca.do_global) && any_out) {
         rc = pe_launch_composite(ca, stream);
         if (rc) return rc;
+    }
+    return PE_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct ObjBwdWorkspace {
+    float *cw_obj, *cw_glob, *g_raw, *g_t, *g_dm, *g_pos, *g_od, *adain_sums, *bn_fix;
+    double* bn_sums;
+};
+
+struct BwdWorkspace {
+    void* fwd;
+    size_t fwd_bytes;
+    ObjBwdWorkspace obj[PE_MAX_OBJECTS];
+    void* zero_begin;          // region cleared at the start of every call (sums)
+    size_t zero_bytes;
+    float* stash;
+    int64_t stash_floats;      // per block
+    size_t bytes;
+};
+
+static PeScene backward_scene(const PeScene& s) {
+    PeScene b = s;
+    b.precision = PE_PRECISION_FP32;       // the backward recomputes (and differentiates) the exact fp32 forward
+    return b;
+}
+
+static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
+    BwdWorkspace w = {};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off = (off + bytes + 255) / 256 * 256; return p; };
+    w.fwd_bytes = carve(s, nullptr).bytes;
+    w.fwd = take(w.fwd_bytes);
+    for (int k = 0; k < s.objects; ++k) {
+        const PeObjectDesc& d = s.object[k];
+        const size_t n = (size_t)s.images * s.rays * d.positions;
+        ObjBwdWorkspace& o = w.obj[k];
+        o.cw_obj = (float*)take(n * 4); o.cw_glob = (float*)take(n * 4);
+        o.g_raw = (float*)take(n * 4); o.g_t = (float*)take(n * 4); o.g_dm = (float*)take(n * 4);
+        o.g_pos = (float*)take(n * 12);
+        o.g_od = d.nerf_kind == PE_NERF_SKYBOX_V3 ? (float*)take(n * 24) : nullptr;
+    }
+    const size_t z0 = off;
+    w.zero_begin = base ? (char*)base + off : nullptr;
+    for (int k = 0; k < s.objects; ++k) {
+        const PeObjectDesc& d = s.object[k];
+        ObjBwdWorkspace& o = w.obj[k];
+        o.adain_sums = (float*)take((size_t)s.images * 3 * d.width * 4);
+        o.bn_sums = (double*)take((size_t)3 * d.width * 8);
+        o.bn_fix = (float*)take((size_t)3 * d.width * 4);
+    }
+    w.zero_bytes = off - z0;
+    int64_t stash = 0;
+    for (int k = 0; k < s.objects; ++k) {
+        const int64_t f = pe_field_bwd_stash_floats(s.object[k], pe_layout(s.object[k]));
+        stash = f > stash ? f : stash;
+    }
+    w.stash_floats = stash;
+    w.stash = (float*)take((size_t)stash * 4 * grid);
+    w.bytes = off;
+    return w;
+}
+
+static int backward_grid() {
+    int sm = 0;
+    if (pe_device_sm_count(&sm) != PE_OK || sm <= 0) sm = 160;     // sizing without a device: upper bound
+    return pe_field_bwd_grid(sm);
+}
+
+extern "C" size_t pe_backward_workspace_bytes(const PeScene* scene) {
+    if (!scene || validate_scene(*scene) != PE_OK) return 0;
+    if (scene->explicit_positions) { pe_set_error("backward on explicit positions is not supported"); return 0; }
+    return carve_backward(backward_scene(*scene), nullptr, backward_grid()).bytes + 256;
+}
+
+extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, const PeObjectParams* params, const PeOutGrads* grad_out,
+                                  const PeInGrads* grad_in, void* workspace, size_t workspace_bytes, pe_stream_t stream_) {
+    if (!scene || !in || !params || !grad_out || !grad_in) { pe_set_error("null argument"); return PE_ERR_INVALID; }
+    int rc = validate_scene(*scene);
+    if (rc != PE_OK) return rc;
+    if (scene->explicit_positions) { pe_set_error("backward on explicit positions is not supported"); return PE_ERR_UNSUPPORTED; }
+    const PeScene s = backward_scene(*scene);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if ((size_t)workspace % 256) { pe_set_error("workspace must be 256-byte aligned"); return PE_ERR_WORKSPACE; }
+    int sm_count = 148;
+    rc = pe_device_sm_count(&sm_count);
+    if (rc != PE_OK) return rc;
+    const int grid = pe_field_bwd_grid(sm_count);
+    const BwdWorkspace bw = carve_backward(s, workspace, grid);
+    if (bw.bytes > workspace_bytes) { pe_set_error("backward workspace too small: %zu < %zu", workspace_bytes, bw.bytes); return PE_ERR_WORKSPACE; }
+    if (s.images == 0 || s.rays == 0) return PE_OK;
+
+    // 1. recompute the forward: per-sample t / raw alpha / features / |displacement| / in-box flags, AdaIn scale-shift, BatchNorm sums
+    const PeOutputs none = {};
+    rc = pe_render_forward(&s, in, &none, bw.fwd, bw.fwd_bytes, stream_);
+    if (rc != PE_OK) return rc;
+    const Workspace ws = carve(s, bw.fwd);
+    PE_CUDA_CHECK(cudaMemsetAsync(bw.zero_begin, 0, bw.zero_bytes, stream));
+
+    // 2. compositing backward
+    PeCompositeBwdArgs cb = {};
+    PeCompositeArgs& ca = cb.f;
+    ca.images = s.images; ca.rays = s.rays; ca.objects = s.objects; ca.static_objects = s.static_objects;
+    ca.features = s.object[0].features; ca.fix_overlaps = s.fix_object_overlaps; ca.perturb = s.perturb;
+    ca.dirs = in->ray_directions;
+    ca.noise_global = s.perturb ? in->noise_global : nullptr;
+    for (int k = 0; k < s.objects; ++k) {
+        const ObjWorkspace& o = ws.obj[k];
+        ca.positions[k] = s.object[k].positions;
+        ca.total_positions += s.object[k].positions;
+        ca.t[k] = o.t; ca.raw[k] = o.raw; ca.feat[k] = o.feat; ca.dispmag[k] = o.dispmag; ca.inbox[k] = o.inbox;
+        ca.noise[k] = s.perturb ? in->noise[k] : nullptr;
+        cb.g_object[k] = grad_out->object[k];
+        cb.cw_obj[k] = bw.obj[k].cw_obj; cb.cw_glob[k] = bw.obj[k].cw_glob;
+        cb.g_raw[k] = bw.obj[k].g_raw; cb.g_t[k] = bw.obj[k].g_t; cb.g_dm[k] = bw.obj[k].g_dm;
+    }
+    cb.g_global = grad_out->global;
+    cb.g_dirs = grad_in->ray_directions;
+    rc = pe_launch_composite_bwd(cb, stream);
+    if (rc != PE_OK) return rc;
+
+    // 3. per object: field backward (three passes in train mode: the BatchNorm backward needs two global reductions), style, geometry
+    for (int k = 0; k < s.objects; ++k) {
+        const PeObjectDesc& d = s.object[k];
+        const PeLayout L = pe_layout(d);
+        const ObjWorkspace& o = ws.obj[k];
+        const ObjBwdWorkspace& b = bw.obj[k];
+        const int W = d.width;
+        PeFieldBwdArgs fb = {};
+        PeFieldArgs& fa = fb.f;
+        fa.ob = d; fa.L = L;
+        fa.images = s.images; fa.rays = s.rays; fa.objects = s.objects; fa.k = k;
+        fa.perturb = s.perturb; fa.training = s.training; fa.apply_activation = s.apply_activation; fa.precision = s.precision;
+        fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
+        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.ois = in->object_in_scene;
+        fa.aff1 = o.aff1; fa.aff2 = o.aff2;
+        fb.w = params[k];
+        fb.gw = grad_in->params[k];
+        fb.cw_obj = b.cw_obj; fb.cw_glob = b.cw_glob;
+        fb.g_feat_obj = grad_out->object[k].integrated_features;
+        fb.g_feat_glob = grad_out->global.integrated_features;
+        fb.g_raw = b.g_raw; fb.g_dm = b.g_dm;
+        fb.g_pos = b.g_pos; fb.g_od = b.g_od;
+        fb.adain_sums = b.adain_sums; fb.bn_sums = b.bn_sums; fb.bn_fix = b.bn_fix;
+        fb.g_deformation = grad_in->deformation[k];
+        fb.stash = bw.stash; fb.stash_floats = bw.stash_floats;
+        if (!fb.w.head0_w || !fb.w.head3_w || !fb.w.head6_w) { pe_set_error("backward needs the fp32 parameters of object %d", k); return PE_ERR_INVALID; }
+        if (s.training) {
+            fb.bwd_phase = 1;
+            rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
+            rc = pe_launch_bn_fix(o.stats + 2 * W + 2, b.bn_sums + 2 * W, W / 2, b.bn_fix + 2 * W, stream); if (rc) return rc;
+            fb.bwd_phase = 2;
+            rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
+            rc = pe_launch_bn_fix(o.stats, b.bn_sums, W, b.bn_fix, stream); if (rc) return rc;
+        }
+        fb.bwd_phase = 0;
+        rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
+
+        const unsigned char* blob = (const unsigned char*)d.packed;
+        auto P32 = [&](int64_t off) { return (const float*)(blob + off); };
+        PeStyleBwdArgs sb = {};
+        sb.images = s.images; sb.style_features = d.style_features; sb.channels = W; sb.training = s.training;
+        sb.style = in->style[k]; sb.aff_w = P32(L.aff1_w); sb.run_mean = P32(L.bn1_mean); sb.run_var = P32(L.bn1_var);
+        sb.stats = o.stats; sb.adain_sums = b.adain_sums; sb.adain_stride = 3 * W;
+        sb.g_aff_w = grad_in->params[k].affine1_w; sb.g_aff_b = grad_in->params[k].affine1_b; sb.g_style = grad_in->style[k];
+        rc = pe_launch_style_bwd(sb, stream); if (rc) return rc;
+        sb.channels = W / 2; sb.aff_w = P32(L.aff2_w); sb.run_mean = P32(L.bn2_mean); sb.run_var = P32(L.bn2_var);
+        sb.stats = o.stats + 2 * W + 2; sb.adain_sums = b.adain_sums + 2 * W;
+        sb.g_aff_w = grad_in->params[k].affine2_w; sb.g_aff_b = grad_in->params[k].affine2_b;
+        rc = pe_launch_style_bwd(sb, stream); if (rc) return rc;
+
+        if (grad_in->ray_origins || grad_in->ray_directions || grad_in->w2o) {
+            PeGeometryBwdArgs gb = {};
+            gb.ob = d; gb.images = s.images; gb.rays = s.rays; gb.objects = s.objects; gb.k = k; gb.perturb = s.perturb;
+            gb.origins = in->ray_origins; gb.dirs = in->ray_directions; gb.w2o = in->w2o; gb.ois = in->object_in_scene; gb.rand = in->rand[k];
+            gb.g_pos = b.g_pos; gb.g_t = b.g_t; gb.g_od = b.g_od;
+            gb.g_origins = grad_in->ray_origins; gb.g_dirs = grad_in->ray_directions; gb.g_w2o = grad_in->w2o;
+            rc = pe_launch_geometry_bwd(gb, stream); if (rc) return rc;
+        }
     }
     return PE_OK;
 }

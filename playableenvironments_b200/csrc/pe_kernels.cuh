@@ -61,6 +61,75 @@ struct PeStyleArgs {
     float* running_out;          // training: [2][C] batch mean / unbiased batch variance (host applies momentum 0.1)
 };
 
+// Arguments of the compositing backward (gradients of integrate / compose w.r.t. the per-sample tensors).
+struct PeCompositeBwdArgs {
+    PeCompositeArgs f;                            // forward view: per-sample t / raw / feat / dispmag / inbox of every object
+    PeIntegratedGrads g_object[PE_MAX_OBJECTS];   // upstream gradients
+    PeIntegratedGrads g_global;
+    float* cw_obj[PE_MAX_OBJECTS];                // out [images][rays][P]: d integrated_features(object) / d feature = cw_obj * I
+    float* cw_glob[PE_MAX_OBJECTS];               // out: same for the composed scene
+    float* g_raw[PE_MAX_OBJECTS];                 // out: dL/d raw alpha
+    float* g_t[PE_MAX_OBJECTS];                   // out: dL/d t
+    float* g_dm[PE_MAX_OBJECTS];                  // out: dL/d |displacement|
+    float* g_dirs;                                // accumulated [images][rays][3]: through |d| of compute_position_distances
+};
+
+// Arguments of the field backward kernel (pe_field_bwd.cu).
+struct PeFieldBwdArgs {
+    PeFieldArgs f;                 // the forward arguments (the tile is recomputed)
+    PeObjectParams w;              // fp32 parameters, nn.Linear layout [out][in]
+    PeObjectParamGrads gw;         // accumulated parameter gradients
+    int32_t bwd_phase;             // 0: full backward; 1 / 2: train-mode BatchNorm reductions of the second / first AdaIn layer
+    const float* cw_obj;           // [images][rays][P]
+    const float* cw_glob;
+    const float* g_feat_obj;       // [images][rays][F] dL/d integrated_features of this object (or NULL)
+    const float* g_feat_glob;      // [images][rays][F] dL/d integrated_features of the composed scene (or NULL)
+    const float* g_raw;            // [images][rays][P]
+    const float* g_dm;             // [images][rays][P]
+    float* g_pos;                  // out [images][rays][P][3]: dL/d sample position, object space
+    float* g_od;                   // out [images][rays][P][6] (skybox field): dL/d object-space origin and direction
+    float* adain_sums;             // accumulated [images][2W + W]: per image sum g (W), sum g*x (W) of AdaIn 1, then the same (W/2 each) of AdaIn 2
+    double* bn_sums;               // training, accumulated: [2W] of BatchNorm 1 (sum g*sc, sum g*sc*x), then [W] of BatchNorm 2
+    const float* bn_fix;           // [2W + W]: k1, k2 of BatchNorm 1 then 2 (g_x = g*sc - k1 - x*k2); zeros in eval mode
+    float* g_deformation;          // accumulated [images][D]
+    float* stash;                  // per-block activation stash
+    int64_t stash_floats;          // floats per block
+};
+
+// Style / BatchNorm backward (pe_backward.cu)
+struct PeStyleBwdArgs {
+    int32_t images, style_features, channels, training;
+    const float* style;            // [images][S]
+    const float* aff_w;            // [2C][S]
+    const float* run_mean; const float* run_var;
+    const double* stats;           // training: forward sums (sum x, sum x^2, count)
+    const float* adain_sums;       // + img * stride: A[C], B[C]
+    int64_t adain_stride;
+    float* g_aff_w; float* g_aff_b;   // accumulated
+    float* g_style;                // accumulated [images][S]
+};
+
+struct PeGeometryBwdArgs {
+    PeObjectDesc ob;
+    int32_t images, rays, objects, k, perturb;
+    const float* origins; const float* dirs; const float* w2o; const uint8_t* ois; const float* rand;
+    const float* g_pos;            // [images][rays][P][3]
+    const float* g_t;              // [images][rays][P]
+    const float* g_od;             // skybox: [images][rays][P][6] or NULL
+    float* g_origins;              // accumulated [images][3]
+    float* g_dirs;                 // accumulated [images][rays][3]
+    float* g_w2o;                  // accumulated [images][objects][12]
+};
+
+size_t pe_field_bwd_smem_bytes();
+int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);
+int pe_field_bwd_grid(int sm_count);
+int pe_launch_field_bwd(const PeFieldBwdArgs& args, int sm_count, cudaStream_t stream);
+int pe_launch_composite_bwd(const PeCompositeBwdArgs& args, cudaStream_t stream);
+int pe_launch_style_bwd(const PeStyleBwdArgs& args, cudaStream_t stream);
+int pe_launch_bn_fix(const double* fwd_stats, const double* bn_sums, int channels, float* bn_fix, cudaStream_t stream);
+int pe_launch_geometry_bwd(const PeGeometryBwdArgs& args, cudaStream_t stream);
+
 size_t pe_field_fp32_smem_bytes(const PeObjectDesc& ob, const PeLayout& L);
 int pe_launch_field_fp32(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);

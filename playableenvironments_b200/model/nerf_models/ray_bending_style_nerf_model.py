@@ -59,6 +59,30 @@ class RayBendingStyleNerfModel(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def parameter_struct(self):
+        """PeObjectParams of this model (device pointers of its fp32 tensors) + the list keeping them alive."""
+        return _param_struct(self.nerf_model, self.ray_bender)
+
+    def parameter_slots(self):
+        """[(PeObjectParamGrads field, index or None, parameter)] — every learnable tensor the backward produces a gradient for."""
+        nerf, bender = self.nerf_model, self.ray_bender
+        slots = []
+        for i, layer in enumerate(nerf.backbone_layers):
+            slots += [("backbone_w", i, layer.weight), ("backbone_b", i, layer.bias)]
+        if getattr(nerf, "HAS_ALPHA_HEAD", True):
+            slots += [("alpha_w", None, nerf.alpha_head.weight), ("alpha_b", None, nerf.alpha_head.bias)]
+        head = nerf.features_head
+        slots += [("head0_w", None, head[0].weight),
+                  ("affine1_w", None, head[1].affine_transform.weight), ("affine1_b", None, head[1].affine_transform.bias),
+                  ("head3_w", None, head[3].weight),
+                  ("affine2_w", None, head[4].affine_transform.weight), ("affine2_b", None, head[4].affine_transform.bias),
+                  ("head6_w", None, head[6].weight), ("head6_b", None, head[6].bias)]
+        if bender is not None and bender.KIND == _cabi.BENDER_POSITIONAL:
+            for i, layer in enumerate(bender.backbone_layers):
+                slots += [("bender_w", i, layer.weight), ("bender_b", i, layer.bias)]
+            slots.append(("bender_out_w", None, bender.output_head.weight))
+        return slots
+
     def forward(self, ray_positions: torch.Tensor, ray_origins: torch.Tensor, ray_directions: torch.Tensor, style: torch.Tensor,
                 deformation: torch.Tensor, video_indexes: torch.Tensor = None, canonical_pose: bool = False) -> Tuple[torch.Tensor]:
         """(..., P, 3) positions; (..., 3) origins/directions; (..., S) style; (..., D) deformation ->

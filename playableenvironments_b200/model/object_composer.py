@@ -71,23 +71,23 @@ class ObjectComposer(nn.Module):
         if transformation_matrix_w2o.size(-1) != objects_count:
             raise Exception(f"Transformation matrix must specifies transformations for"
                             f"({transformation_matrix_w2o.size(-1)}) objects instead of ({objects_count})")
-        needs_grad = torch.is_grad_enabled() and (
-            any(p.requires_grad for p in self.parameters()) and self.training
-            or any(t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
-        if needs_grad and not getattr(self, "allow_forward_without_grad", False):
-            raise NotImplementedError("the backward kernels of the B200 render path are not implemented yet; run under "
-                                      "torch.no_grad() (set composer.allow_forward_without_grad = True to evaluate a "
-                                      "train-mode forward without building a graph)")
         if self.precision not in _cabi.PRECISIONS:
             raise Exception(f"unknown b200_precision '{self.precision}'")
+        needs_grad = torch.is_grad_enabled() and (
+            any(p.requires_grad for p in self.parameters())
+            or any(torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
+        helper = self.object_id_helper
+        models = None
+        if needs_grad and not getattr(self, "allow_forward_without_grad", False):
+            models = [self.object_models_coarse[helper.model_idx_by_object_idx(k)] for k in range(objects_count)]
         bn_running: List = []
-        with torch.no_grad():
-            res = render.render_scene(self._descs(canonical_pose), self.object_id_helper.static_objects_count, ray_origins,
-                                      ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
-                                      self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
-                                      _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running,
-                                      return_raw_alphas=self.return_raw_alphas)
-            if self.training:
+        res = render.render_scene(self._descs(canonical_pose), helper.static_objects_count, ray_origins,
+                                  ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
+                                  self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
+                                  _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running,
+                                  return_raw_alphas=self.return_raw_alphas, models=models)
+        if self.training:
+            with torch.no_grad():
                 self._update_running_statistics(bn_running)
         results = {"coarse": {}}
         for k in range(objects_count):

@@ -48,85 +48,91 @@ def _fill(struct: _cabi.PeIntegrated, tensors: Dict[str, torch.Tensor]):
         setattr(struct, k, _cabi.ptr(tensors[k]))
 
 
-def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origins: torch.Tensor, ray_directions: torch.Tensor,
-                 w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
-                 perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
-                 rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
-                 bn_running: Optional[List] = None, return_raw_alphas: bool = False) -> Dict:
-    """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}."""
-    device = ray_directions.device
-    if device.type != "cuda":
-        raise _cabi.PeError("ObjectComposer.forward needs CUDA tensors: the B200 render path has no CPU implementation")
-    L = _cabi.lib()
+DIFF_KEYS = ("integrated_features", "opacity", "weights", "depth", "disparity", "integrated_displacements_magnitude")
+
+
+def _flatten_inputs(K: int, ray_origins, ray_directions, w2o, style, deformation, object_in_scene):
+    """(B, O, C) leading dims -> ``images``; plain torch ops, so autograd (when it is on) maps gradients back to the caller's tensors."""
     lead = list(ray_directions.shape[:-2])
     rays = ray_directions.size(-2)
     images = 1
     for v in lead:
         images *= v
-    K = len(descs)
-    if K > _cabi.PE_MAX_OBJECTS:
-        raise _cabi.PeError(f"at most {_cabi.PE_MAX_OBJECTS} object instances per composer call")
-    F = descs[0].features
+    f32 = lambda t: t.to(torch.float32)
+    origins = f32(ray_origins).expand(lead + [3]).reshape(images, 3).contiguous()
+    dirs = f32(ray_directions).reshape(images, rays, 3).contiguous()
+    # (..., 4, 4, objects) -> [images][objects][3][4]
+    m = f32(w2o).expand(lead + [4, 4, K]).reshape(images, 4, 4, K)[:, :3, :, :].permute(0, 3, 1, 2).contiguous()
+    S, D = style.size(-2), deformation.size(-2)
+    sty = f32(style).expand(lead + [S, style.size(-1)]).reshape(images, S, -1)
+    dfm = f32(deformation).expand(lead + [D, deformation.size(-1)]).reshape(images, D, -1)
+    styles = [sty[:, :, k].contiguous() for k in range(K)]
+    deforms = [dfm[:, :, k].contiguous() for k in range(K)]
+    ois = object_in_scene.expand(lead + [object_in_scene.size(-1)]).reshape(images, -1)[:, :K].to(torch.uint8).contiguous()
+    return lead, images, rays, origins, dirs, m, styles, deforms, ois
 
+
+def _scene_struct(meta, images: int, rays: int) -> _cabi.PeScene:
     scene = _cabi.PeScene()
-    scene.images, scene.rays, scene.objects, scene.static_objects = images, rays, K, static_objects
-    scene.perturb, scene.training = int(bool(perturb)), int(bool(training))
-    scene.fix_object_overlaps, scene.apply_activation = int(bool(fix_object_overlaps)), int(bool(apply_activation))
-    scene.precision, scene.explicit_positions = precision, 0
+    descs = meta["descs"]
+    scene.images, scene.rays, scene.objects, scene.static_objects = images, rays, len(descs), meta["static_objects"]
+    scene.perturb, scene.training = int(bool(meta["perturb"])), int(bool(meta["training"]))
+    scene.fix_object_overlaps, scene.apply_activation = int(bool(meta["fix_object_overlaps"])), int(bool(meta["apply_activation"]))
+    scene.precision, scene.explicit_positions = meta["precision"], 0
     for k, d in enumerate(descs):
         scene.object[k] = d
+    return scene
 
-    keep = []
 
-    def dev(t, shape):
-        c = _cabi.f32(t.expand(shape) if list(t.shape) != list(shape) else t).reshape(-1)
-        keep.append(c)
-        return c
-
+def _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep) -> _cabi.PeInputs:
+    descs = meta["descs"]
     ins = _cabi.PeInputs()
-    ins.ray_origins = _cabi.ptr(dev(ray_origins, lead + [3]))
-    ins.ray_directions = _cabi.ptr(dev(ray_directions, lead + [rays, 3]))
-    # (..., 4, 4, objects) -> [images][objects][3][4]
-    m = w2o.expand(lead + [4, 4, K]).reshape(images, 4, 4, K)[:, :3, :, :].permute(0, 3, 1, 2)
-    ins.w2o = _cabi.ptr(dev(m, [images, K, 3, 4]))
-    S, D = style.size(-2), deformation.size(-2)
-    sty = style.expand(lead + [S, style.size(-1)]).reshape(images, S, -1)
-    dfm = deformation.expand(lead + [D, deformation.size(-1)]).reshape(images, D, -1)
-    for k in range(K):
-        ins.style[k] = _cabi.ptr(dev(sty[:, :, k], [images, S]))
-        ins.deformation[k] = _cabi.ptr(dev(dfm[:, :, k], [images, D]))
-    ois = object_in_scene.expand(lead + [object_in_scene.size(-1)]).reshape(images, -1)[:, :K].to(torch.uint8).contiguous()
-    keep.append(ois)
-    ins.object_in_scene = _cabi.ptr(ois)
-    if perturb:
-        if rand is None or noise is None:
-            # torch's generator replaces the reference's torch.rand (ray_helper.py:1275) / torch.randn (object_composer.py:194)
-            rand = [torch.rand(lead + [rays, d.positions], device=device) for d in descs]
-            noise = {f"object_{k}": torch.randn(lead + [rays, d.positions], device=device) for k, d in enumerate(descs)}
-            noise["global"] = torch.randn(lead + [rays, sum(d.positions for d in descs)], device=device)
+    ins.ray_origins, ins.ray_directions, ins.w2o = _cabi.ptr(origins), _cabi.ptr(dirs), _cabi.ptr(w2o)
+    for k in range(len(descs)):
+        ins.style[k] = _cabi.ptr(styles[k])
+        ins.deformation[k] = _cabi.ptr(deforms[k])
+    ins.object_in_scene = _cabi.ptr(meta["ois"])
+    if meta["perturb"]:
+        rand, noise = meta["rand"], meta["noise"]
+
+        def dev(t, shape):
+            c = _cabi.f32(t.expand(shape) if list(t.shape) != list(shape) else t).reshape(-1)
+            keep.append(c)
+            return c
+
         for k, d in enumerate(descs):
             ins.rand[k] = _cabi.ptr(dev(rand[k], lead + [rays, d.positions]))
             ins.noise[k] = _cabi.ptr(dev(noise[f"object_{k}"], lead + [rays, d.positions]))
         ins.noise_global = _cabi.ptr(dev(noise["global"], lead + [rays, sum(d.positions for d in descs)]))
+    return ins
 
+
+def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms) -> Dict:
+    device = dirs.device
+    L = _cabi.lib()
+    descs = meta["descs"]
+    images, rays = dirs.size(0), dirs.size(1)
+    F = descs[0].features
+    scene = _scene_struct(meta, images, rays)
+    keep: List = []
+    ins = _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep)
     outs = _cabi.PeOutputs()
     results: Dict = {}
     for k, d in enumerate(descs):
         r = _alloc_integrated(lead, rays, d.positions, F, device)
         _fill(outs.object[k], r)
         results[f"object_{k}"] = r
-        if return_raw_alphas:          # diagnostic: per-sample raw alphas (first return value family of the object models)
+        if meta.get("return_raw_alphas"):   # diagnostic: per-sample raw alphas (first return value family of the object models)
             r["raw_alphas"] = torch.empty(lead + [rays, d.positions], dtype=torch.float32, device=device)
             outs.raw_alphas[k] = _cabi.ptr(r["raw_alphas"])
-        if training and bn_running is not None:
+        if meta["training"] and meta.get("bn_running") is not None:
             b1 = torch.empty((2, d.width), dtype=torch.float32, device=device)
             b2 = torch.empty((2, d.width // 2), dtype=torch.float32, device=device)
             outs.bn1_running[k], outs.bn2_running[k] = _cabi.ptr(b1), _cabi.ptr(b2)
-            bn_running.append((b1, b2))
+            meta["bn_running"].append((b1, b2))
     g = _alloc_integrated(lead, rays, sum(d.positions for d in descs), F, device)
     _fill(outs.global_, g)
     results["global"] = g
-
     with torch.cuda.device(device):
         nbytes = L.pe_workspace_bytes(C.byref(scene))
         if nbytes == 0:
@@ -136,6 +142,129 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                                         _cabi.current_stream(device)))
     del keep
     return results
+
+
+class RenderFunction(torch.autograd.Function):
+    """ObjectComposer.forward as ONE autograd node.  ``backward`` hands the upstream gradients of every integrated output to
+    ``pe_render_backward``, which recomputes the forward on the device and back-propagates through compositing, the style-modulated
+    MLPs, the ray bender, the positional encodings and the ray geometry (what the reference gets by replaying its ~10^3-op graph)."""
+
+    @staticmethod
+    def forward(ctx, meta, origins, dirs, w2o, *flat):
+        K = len(meta["descs"])
+        styles, deforms = list(flat[:K]), list(flat[K:2 * K])
+        res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms)
+        ctx.meta = meta
+        ctx.save_for_backward(origins, dirs, w2o, *styles, *deforms)
+        names = [f"object_{k}" for k in range(K)] + ["global"]
+        outs = [res[n][key] for n in names for key in DIFF_KEYS]
+        extra = [res[n]["integrated_divergence"] for n in names]
+        if meta.get("return_raw_alphas"):
+            extra += [res[f"object_{k}"]["raw_alphas"] for k in range(K)]
+        ctx.mark_non_differentiable(*extra)
+        return tuple(outs + extra)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        meta = ctx.meta
+        descs, models = meta["descs"], meta["models"]
+        K = len(descs)
+        saved = ctx.saved_tensors
+        origins, dirs, w2o = saved[0], saved[1], saved[2]
+        styles, deforms = list(saved[3:3 + K]), list(saved[3 + K:3 + 2 * K])
+        device = dirs.device
+        L = _cabi.lib()
+        images, rays = dirs.size(0), dirs.size(1)
+        scene = _scene_struct(meta, images, rays)
+        keep: List = []
+        ins = _inputs_struct(meta, meta["lead"], rays, origins, dirs, w2o, styles, deforms, keep)
+        gout = _cabi.PeOutGrads()
+        for i in range(K + 1):
+            target = gout.object[i] if i < K else gout.global_
+            for j, key in enumerate(DIFF_KEYS):
+                g = grads[i * len(DIFF_KEYS) + j]
+                if g is not None:
+                    g = g.to(torch.float32).contiguous()
+                    keep.append(g)
+                    setattr(target, key, _cabi.ptr(g))
+        need = ctx.needs_input_grad
+        gin = _cabi.PeInGrads()
+        zeros = lambda t: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format)
+        g_origins = zeros(origins) if need[1] else None
+        g_dirs = zeros(dirs) if need[2] else None
+        g_w2o = zeros(w2o) if need[3] else None
+        gin.ray_origins, gin.ray_directions, gin.w2o = _cabi.ptr(g_origins), _cabi.ptr(g_dirs), _cabi.ptr(g_w2o)
+        g_styles = [zeros(styles[k]) if need[4 + k] else None for k in range(K)]
+        g_deforms = [zeros(deforms[k]) if need[4 + K + k] else None for k in range(K)]
+        for k in range(K):
+            gin.style[k], gin.deformation[k] = _cabi.ptr(g_styles[k]), _cabi.ptr(g_deforms[k])
+        params = (_cabi.PeObjectParams * _cabi.PE_MAX_OBJECTS)()
+        g_params: List = []
+        idx = 4 + 2 * K
+        for k, m in enumerate(models):
+            ps, kp = m.parameter_struct()
+            keep.append(kp)
+            params[k] = ps
+            for field, i, tensor in m.parameter_slots():
+                g = zeros(tensor) if need[idx] else None
+                idx += 1
+                g_params.append(g)
+                if g is not None:
+                    if i is None:
+                        setattr(gin.params[k], field, _cabi.ptr(g))
+                    else:
+                        getattr(gin.params[k], field)[i] = _cabi.ptr(g)
+        with torch.cuda.device(device):
+            nbytes = L.pe_backward_workspace_bytes(C.byref(scene))
+            if nbytes == 0:
+                raise _cabi.PeError(f"pe_backward_workspace_bytes: {L.pe_last_error().decode()}")
+            ws = _Workspace.get(device, nbytes)
+            _cabi.check(L.pe_render_backward(C.byref(scene), C.byref(ins), params, C.byref(gout), C.byref(gin), _cabi.ptr(ws), ws.numel(),
+                                             _cabi.current_stream(device)))
+        del keep
+        return (None, g_origins, g_dirs, g_w2o, *g_styles, *g_deforms, *g_params)
+
+
+def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origins: torch.Tensor, ray_directions: torch.Tensor,
+                 w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
+                 perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
+                 rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
+                 bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None) -> Dict:
+    """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
+    With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node."""
+    device = ray_directions.device
+    if device.type != "cuda":
+        raise _cabi.PeError("ObjectComposer.forward needs CUDA tensors: the B200 render path has no CPU implementation")
+    K = len(descs)
+    if K > _cabi.PE_MAX_OBJECTS:
+        raise _cabi.PeError(f"at most {_cabi.PE_MAX_OBJECTS} object instances per composer call")
+    lead, images, rays, origins, dirs, m, styles, deforms, ois = _flatten_inputs(K, ray_origins, ray_directions, w2o, style, deformation,
+                                                                                 object_in_scene)
+    if perturb and (rand is None or noise is None):
+        # torch's generator replaces the reference's torch.rand (ray_helper.py:1275) / torch.randn (object_composer.py:194)
+        rand = [torch.rand(lead + [rays, d.positions], device=device) for d in descs]
+        noise = {f"object_{k}": torch.randn(lead + [rays, d.positions], device=device) for k, d in enumerate(descs)}
+        noise["global"] = torch.randn(lead + [rays, sum(d.positions for d in descs)], device=device)
+    meta = {"descs": descs, "static_objects": static_objects, "perturb": perturb, "training": training,
+            "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
+            "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
+            "return_raw_alphas": return_raw_alphas, "models": models}
+    if models is not None and torch.is_grad_enabled():
+        flat_params = [t for mdl in models for _, _, t in mdl.parameter_slots()]
+        flat = RenderFunction.apply(meta, origins, dirs, m, *styles, *deforms, *flat_params)
+        names = [f"object_{k}" for k in range(K)] + ["global"]
+        results: Dict = {}
+        it = iter(flat)
+        for n in names:
+            results[n] = {key: next(it) for key in DIFF_KEYS}
+        for n in names:
+            results[n]["integrated_divergence"] = next(it)
+        if return_raw_alphas:
+            for k in range(K):
+                results[f"object_{k}"]["raw_alphas"] = next(it)
+        return results
+    with torch.no_grad():
+        return _launch_forward(meta, lead, origins, dirs, m, styles, deforms)
 
 
 def field_on_positions(desc: _cabi.PeObjectDesc, images: int, n: int, positions, origins, directions, style, deformation,

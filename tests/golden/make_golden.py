@@ -173,7 +173,7 @@ if __name__ == "__main__":
     run("static_small", "train")
     run("tennis_dense", "train")
     if "--no-grad" not in sys.argv:
-        for scene in ("cfg1", "static_small", "tennis_dense", "minecraft_small"):
+        for scene in ("cfg1", "static_small", "tennis_dense", "minecraft_small", "toy_world"):
             run(scene, "grad")
-        for scene in ("cfg1", "tennis_dense"):
+        for scene in ("cfg1", "tennis_dense", "toy_world"):
             run(scene, "grad_train")

@@ -275,6 +275,28 @@ def scene_minecraft(seed=14, height=64, width=64, stride=4, lead=(1, 1, 1), abse
     return config, scene_state(seed, config), inputs
 
 
+def scene_toy_world(seed=18, height=64, width=64, stride=4, lead=(1, 2, 1)):
+    """Every component of the path with small, well-conditioned networks (4 octaves: the gradients are not dominated by fp32
+    cancellation, so the backward can be pinned tightly): ground (P=8) + skybox (P=1) static, one player model with a positional
+    ray bender shared by 2 instances (P=12), fix_object_overlaps on, two images with different codes."""
+    toy = lambda kind="adain_style_nerf_model": nerf_cfg(64, 4, 2, 4, 8, kind)
+    ground = object_cfg([[-10, 10], [-0.6, 2.0], [-10, 10]], 8, 0.05, 30.0, 16, 8, toy(), bender_cfg("zeroed"))
+    sky = object_cfg([[-200, 200], [-200, 200], [-200, 200]], 1, 90.0, 91.0, 16, 8, toy("skybox_adain_style_nerf_model_v3"), bender_cfg("zeroed"))
+    player = object_cfg([[-0.6, 0.6], [0.0, 2.1], [-1.2, 1.2]], 12, 0.05, 30.0, 16, 8, toy(),
+                        bender_cfg("positional", width=32, layers=3, skip=1, octaves=3))
+    config = scene_config([ground, sky, player], 2, [1, 1, 2], True)
+    c2w = homogeneous(rot_x(-0.25), [0.0, 1.6, 6.0])
+    orig, dirs, norm = camera_rays(lead, height, width, 0.8 * width, c2w, stride)
+    pa = np.linalg.inv(homogeneous(rot_z(0.1), [-0.8, 0.0, 1.0]))
+    pb = np.linalg.inv(homogeneous(np.eye(3), [1.0, 0.0, -0.5]))
+    inputs = build_inputs(seed, config, lead, orig, dirs, norm, [np.eye(4), np.eye(4), pa, pb])
+    state = scene_state(seed, config)
+    for k in list(state):                       # larger displacements: part of the samples hit the clamp at the box faces
+        if k.endswith("ray_bender.output_head.weight"):
+            state[k] = state[k] * 8.0
+    return config, state, inputs
+
+
 SCENES = {
     "cfg1": lambda: scene_cfg1(),
     "static_small": lambda: scene_static(),
@@ -283,6 +305,7 @@ SCENES = {
     "tennis_anneal": lambda: scene_tennis(seed=16, height=64, width=64, stride=4, lead=(1, 1, 1), step=21000, dense=True),
     "minecraft_small": lambda: scene_minecraft(),
     "minecraft_absent": lambda: scene_minecraft(seed=17, absent=[(0, 0, 0, 3)]),
+    "toy_world": lambda: scene_toy_world(),
 }
 
 

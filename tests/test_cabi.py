@@ -47,15 +47,17 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_sizes_match_the_c_definitions():
     from playableenvironments_b200 import _cabi
-    src = '#include <stdio.h>\n#include "pe_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(PeObjectDesc), sizeof(PeObjectParams), ' \
-          'sizeof(PeScene), sizeof(PeInputs), sizeof(PeIntegrated), sizeof(PeOutputs));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pe_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PeObjectDesc), sizeof(PeObjectParams), ' \
+          'sizeof(PeScene), sizeof(PeInputs), sizeof(PeIntegrated), sizeof(PeOutputs), sizeof(PeIntegratedGrads), sizeof(PeOutGrads), ' \
+          'sizeof(PeObjectParamGrads), sizeof(PeInGrads));return 0;}\n'
     with tempfile.TemporaryDirectory() as tmp:
         c = os.path.join(tmp, "sizes.c")
         open(c, "w").write(src)
         exe = os.path.join(tmp, "sizes")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()]
-    mine = [ctypes.sizeof(t) for t in (_cabi.PeObjectDesc, _cabi.PeObjectParams, _cabi.PeScene, _cabi.PeInputs, _cabi.PeIntegrated, _cabi.PeOutputs)]
+    mine = [ctypes.sizeof(t) for t in (_cabi.PeObjectDesc, _cabi.PeObjectParams, _cabi.PeScene, _cabi.PeInputs, _cabi.PeIntegrated, _cabi.PeOutputs,
+                                       _cabi.PeIntegratedGrads, _cabi.PeOutGrads, _cabi.PeObjectParamGrads, _cabi.PeInGrads)]
     assert mine == sizes
 
 

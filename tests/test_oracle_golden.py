@@ -72,8 +72,8 @@ def test_decoder_feature_grids_layout():
     assert g8[0, 0, 0, 7, 3, 1] == feats[0, 0, 0, 8 * 16 + 3 * 8 + 1, 64 + 7]
 
 
-GRAD_CASES = [("cfg1", False), ("static_small", False), ("tennis_dense", False), ("minecraft_small", False),
-              ("cfg1", True), ("tennis_dense", True)]
+GRAD_CASES = [("cfg1", False), ("static_small", False), ("tennis_dense", False), ("minecraft_small", False), ("toy_world", False),
+              ("cfg1", True), ("tennis_dense", True), ("toy_world", True)]
 
 
 @pytest.mark.parametrize("name,training", GRAD_CASES)
