@@ -125,6 +125,56 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_step_report(device, dense: bool):
+    """BASELINE configs[2]: Tennis scene (court + 2 players with positional ray benders, composed), 256x144 rays, forward and
+    forward+backward through ObjectComposer with every parameter and every differentiable input requiring a gradient.
+    Secondary figures (the headline stays configs[1]); the backward is the exact fp32 CUDA-core path."""
+    import scenes
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+    scene = scenes.scene_tennis(seed=13, height=144, width=256, stride=1, lead=(1, 1, 1), dense=dense)
+    config, state, inputs, comp, dev = build_composer(scene, "fp32", device=device, training=True)
+    comp.allow_forward_without_grad = False
+    dev = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in dev.items()}
+    call = [dev[k] for k in INPUT_KEYS]
+    rays = dev["ray_directions"].size(-2)
+    cot = torch.randn(rays, 192, device=device)
+
+    def fwd():
+        with torch.no_grad():
+            return comp(*call, False)
+
+    def fwd_bwd():
+        comp.zero_grad(set_to_none=True)
+        res = comp(*call, False)["coarse"]
+        loss = (res["global"]["integrated_features"].reshape(rays, 192) * cot).sum() + res["global"]["opacity"].sum()
+        loss.backward()
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            fn()
+        e0.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(e0) / reps
+
+    comp.return_raw_alphas = True
+    res = fwd()["coarse"]
+    comp.return_raw_alphas = False
+    slots, inbox = 0, 0
+    for k, m in enumerate(config["model"]["object_models"]):
+        ra = res[f"object_{k}"]["raw_alphas"]
+        slots += ra.numel()
+        inbox += int((ra != float(m["empty_space_alpha"])).sum().item())
+    ms_f, ms_fb = timed(fwd, 3), timed(fwd_bwd, 3)
+    return {"workload": f"cfg3 Tennis{' (dense: camera on a player)' if dense else ''}: court P=4 + 2 players P=32 with ray benders, 256x144 rays, train-mode BatchNorm",
+            "sample_slots": slots, "in_box_samples": inbox, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
+            "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3), "precision": "fp32 (CUDA cores)"}
+
+
 def run_b200(args):
     import torch.distributed as dist
     from helpers import INPUT_KEYS
@@ -273,6 +323,8 @@ def run_b200(args):
             "clocks": clocks.summary(),
             "wall_s": wall,
         }
+        if world == 1 and not args.quick:
+            line["train_step"] = [train_step_report(device, False), train_step_report(device, True)]
         if modes:
             line["other_modes"] = modes
         if parity:
