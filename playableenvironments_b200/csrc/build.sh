@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $PE_EXTRA_FLAGS"
 mkdir -p build
 pids=()
 for f in pe_abi pe_misc pe_composite pe_field_fp32 pe_field_tc pe_field_tc2 pe_field_bwd pe_backward; do

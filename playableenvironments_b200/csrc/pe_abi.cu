@@ -58,7 +58,7 @@ extern "C" int pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* pa
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct ObjWorkspace {
-    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2;
+    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s;
     uint8_t* inbox;
     double* stats;
 };
@@ -81,6 +81,14 @@ static bool needs_feature_buffer(const PeScene& s, int k) {
     return s.objects > 1 || s.perturb;
 }
 
+// Folded-head mode of the tcgen05 kernel (pe_tc_common.cuh): head layer 6 applied once per ray.  Possible when no
+// per-sample feature leaves the kernel and a warp's 32 rows belong to one ray.  PE_TC_FOLD=0 disables it.
+static bool object_folds_head(const PeScene& s, int k) {
+    const char* env = getenv("PE_TC_FOLD");
+    if (env && atoi(env) == 0) return false;
+    return object_uses_tc(s, k) && !needs_feature_buffer(s, k) && !s.apply_activation && s.object[k].positions % 32 == 0;
+}
+
 static Workspace carve(const PeScene& s, void* base) {
     Workspace w = {};
     size_t off = 0;
@@ -95,6 +103,9 @@ static Workspace carve(const PeScene& s, void* base) {
         o.dispmag = (float*)take(n * 4);
         o.inbox = (uint8_t*)take(n);
         o.feat = needs_feature_buffer(s, k) ? (float*)take(n * d.features * 4) : nullptr;
+        const bool fold = object_folds_head(s, k);
+        o.fold_v = fold ? (float*)take((size_t)s.images * s.rays * 128 * 4) : nullptr;
+        o.fold_s = fold ? (float*)take((size_t)s.images * s.rays * 4) : nullptr;
         o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
         o.aff2 = (float*)take((size_t)s.images * d.width * 4);
         o.stats = (double*)take((size_t)(3 * d.width + 4) * 8);
@@ -170,6 +181,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.stats = o.stats;
         fa.integ = out->object[k];
         fa.noise = s.perturb ? in->noise[k] : nullptr;
+        if (tc && !fa.feat_out && o.fold_v) { fa.fold_v = o.fold_v; fa.fold_s = o.fold_s; }
         if (!tc && !fa.feat_out) { pe_set_error("internal: no feature buffer for object %d", k); return PE_ERR_INVALID; }
         if (d.bender_kind == PE_BENDER_POSITIONAL && !fa.deformation) { pe_set_error("object %d needs a deformation code", k); return PE_ERR_INVALID; }
         if (!in->style[k]) { pe_set_error("object %d needs a style code", k); return PE_ERR_INVALID; }

@@ -34,11 +34,70 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
     uint64_t* acc_full;
     uint64_t* a_ready;
     uint32_t phase;
+    int lane;
     __device__ __forceinline__ void wait_acc() { mbar_wait(acc_full, phase); phase ^= 1; tc_fence_after(); }
-    __device__ __forceinline__ void arrive_ready() { fence_proxy_async(); tc_fence_before(); mbar_arrive(a_ready); }
+    // every thread publishes its operand writes to the async proxy and orders its TMEM reads; ONE arrival per warp
+    // (128 serialized arrivals on one mbarrier cost several hundred cycles per layer)
+    __device__ __forceinline__ void arrive_ready() {
+        fence_proxy_async(); tc_fence_before(); __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
 };
 
-__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3) {
+// State of the MMA-issuing thread that persists across layers: position in the weight ring, operand addresses.
+struct MmaRing {
+    uint64_t *full_bar, *empty_bar, *acc_full;
+    uint32_t a_addr[2], ring_addr, tmem_base;
+    int stage; uint32_t phase;
+    int num_passes, x3;
+};
+
+// Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
+// (D^T = W * A^T, folded-head mode, head layer 3) -- a separate instantiation so that the common loop stays branch-free.
+template <bool kSwap>
+__device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, int chunk0, bool has_bias, uint32_t idesc, uint32_t lbo_b) {
+    (void)l; (void)n;
+    const int num_passes = R.num_passes;
+    for (int s = 0; s < slabs; ++s) {
+        for (int pass = 0; pass < num_passes; ++pass) {
+            mbar_wait(R.full_bar + R.stage, R.phase);
+            tc_fence_after();
+            const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
+            const uint32_t b_addr = R.ring_addr + R.stage * STAGE_BYTES;
+            if (R.x3) {
+                // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
+                    const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
+                    const uint64_t da_hi = umma_smem_desc(R.a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+                    const uint64_t da_lo = umma_smem_desc(R.a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+                    const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
+                    umma_f16_ss(R.tmem_base, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
+                    if (pass == 0) umma_f16_ss(R.tmem_base, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+                }
+                if (last) umma_commit(R.acc_full + 0);
+            } else {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
+                        const uint64_t da = umma_smem_desc(R.a_addr[g] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+                        const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
+                        umma_f16_ss(R.tmem_base + g * 256, kSwap ? db : da, kSwap ? da : db, idesc, (s | pass | j) != 0 ? 1u : 0u);
+                    }
+                    if (last) umma_commit(R.acc_full + g);
+                }
+            }
+            umma_commit(R.empty_bar + R.stage);
+            if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3, const int fold, const int dbg) {
+    // fold: folded-head mode (pe_tc_common.cuh): head layer 6 is applied per ray by pe_head6_fold_kernel, 10 MMA layers per tile
     // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
     // per k-step A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-class accuracy on the tensor cores); epilogue group Y idles
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -60,10 +119,11 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     const int tiles_per_image = (A.rays + rpt - 1) / rpt;
     const int64_t total_tiles = (int64_t)tiles_per_image * A.images;
     const int64_t total_pairs = x3 ? total_tiles : (total_tiles + 1) / 2;        // iterations of this kernel
+    const int num_layers = fold ? NUM_LAYERS - 1 : NUM_LAYERS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 2 * TILE_M : TILE_M * SPLIT); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 8 : 4 * SPLIT); }
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -85,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
             int stage = 0; uint32_t phase = 0;
             for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
                 const unsigned char* src = blob + L.tc_base;
-                for (int l = 0; l < NUM_LAYERS; ++l) {
+                for (int l = 0; l < num_layers; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
@@ -112,12 +172,15 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
         if (elect_one()) {
-            int stage = 0; uint32_t phase = 0, ready_phase = 0;
-            const uint32_t a_addr[2] = {smem_u32(smem), smem_u32(smem + A_BYTES)};
-            const uint32_t ring_addr = smem_u32(ring);
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = x3;
             const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
             for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
-                for (int l = 0; l < NUM_LAYERS; ++l) {
+                for (int l = 0; l < num_layers; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t idesc = umma_idesc_f16(TILE_M, n);
@@ -126,53 +189,23 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     if (!x3) mbar_wait(a_ready + 1, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
-                    for (int s = 0; s < slabs; ++s) {
-                        for (int pass = 0; pass < num_passes; ++pass) {
-                            mbar_wait(full_bar + stage, phase);
-                            tc_fence_after();
-                            const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
-                            const uint32_t b_addr = ring_addr + stage * STAGE_BYTES;
-                            if (x3) {
-                                // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
-                                    const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
-                                    umma_f16_ss(tmem_base, umma_smem_desc(a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128), db, idesc, (s | pass | j) != 0 ? 1u : 0u);
-                                    if (pass == 0) umma_f16_ss(tmem_base, umma_smem_desc(a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128), db, idesc, 1u);
-                                }
-                                if (last) umma_commit(acc_full + 0);
-                                umma_commit(empty_bar + stage);
-                                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-                                continue;
-                            }
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
-                                    const uint64_t da = umma_smem_desc(a_addr[g] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
-                                    const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
-                                    umma_f16_ss(tmem_base + g * 256, da, db, idesc, (s | pass | j) != 0 ? 1u : 0u);
-                                }
-                                if (last) umma_commit(acc_full + g);
-                            }
-                            umma_commit(empty_bar + stage);
-                            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-                        }
-                    }
+                    // folded-head mode: head layer 3 is issued transposed (D^T = W3 * A^T: weights as the M operand, the tile's
+                    // samples as N) so that its epilogue can sum over a ray's samples inside one thread; both operands are
+                    // K-major in the same canonical layout, so the two descriptors simply swap roles
+                    if (fold && l == 9) mma_layer<true>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    else mma_layer<false>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {          // D += ones(128x16) * [bias_hi | bias_lo | 0..]^T : the bias, at fp32-class accuracy
-                        mbar_wait(full_bar + stage, phase);
+                        mbar_wait(full_bar + R.stage, R.phase);
                         tc_fence_after();
-                        const uint64_t db = umma_smem_desc(ring_addr + stage * STAGE_BYTES, lbo_b, 128);
+                        const uint64_t db = umma_smem_desc(R.ring_addr + R.stage * STAGE_BYTES, lbo_b, 128);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
                             if (x3 && g == 1) break;
                             umma_f16_ss(tmem_base + g * 256, ones_desc, db, idesc, 1u);
                             umma_commit(acc_full + g);
                         }
-                        umma_commit(empty_bar + stage);
-                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        umma_commit(empty_bar + R.stage);
+                        if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
                     }
                 }
             }
@@ -194,23 +227,72 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.size[0] = ob.bbox[1] - ob.bbox[0]; X.size[1] = ob.bbox[3] - ob.bbox[2]; X.size[2] = ob.bbox[5] - ob.bbox[4];
         X.alpha_bias = __ldg(reinterpret_cast<const float*>(blob + L.alpha_b));
         X.alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
-        X.dbg = 0;
+        X.dbg = dbg;
+        X.fold = fold != 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
-        Sync1 sync{acc_full + g, a_ready + g, 0u};
+        Sync1 sync{acc_full + g, a_ready + g, 0u, lane};
         if (x3) {
             // one tile per iteration: the two epilogue groups become the two column halves of the same 128 rows
             X.abuf = smem; X.half = g; X.gw = warp - 4; X.bar_id = 1;
             X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
-            Sync1 sync3{acc_full, a_ready, 0u};
-            for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3);
+            Sync1 sync3{acc_full, a_ready, 0u, lane};
+            TileAhead ahead;
+            for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3, ahead, tile + gridDim.x);
         } else {
-            for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) epilogue_tile<SPLIT, false>(X, pair * 2 + g, sync);
+            TileAhead ahead;
+            for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x)
+                epilogue_tile<SPLIT, false>(X, pair * 2 + g, sync, ahead, (pair + gridDim.x) * 2 + g);
         }
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// folded head layer 6: integrated_features[ray] = W6 * v[ray] + b6 * s[ray]   (exact fp32, once per RAY)
+//   v = sum_p w_p h_p over the in-box samples (128 wide), s = sum_p w_p; see epilogue_tile.  adain_style_nerf_model.py:88
+//   (the last nn.Linear of the head) commutes with the linear volume-rendering sum of object_composer.py:749.
+// ------------------------------------------------------------------------------------------------------
+constexpr int H6_RAYS = 32;        // rays per block
+constexpr int H6_THREADS = 192;    // one thread per output feature
+__global__ void __launch_bounds__(H6_THREADS) pe_head6_fold_kernel(const float* __restrict__ v, const float* __restrict__ s, const float* __restrict__ w6t,
+                                                                   const float* __restrict__ b6, float* __restrict__ out0, float* __restrict__ out1,
+                                                                   int64_t total_rays) {
+    __shared__ __align__(16) float vs[H6_RAYS][FOLD_K];
+    __shared__ float ss[H6_RAYS];
+    const int64_t ray0 = (int64_t)blockIdx.x * H6_RAYS;
+    const int n = (int)pe_min64(H6_RAYS, total_rays - ray0);
+    for (int i = threadIdx.x; i < H6_RAYS * FOLD_K / 4; i += H6_THREADS) {
+        const int r = i / (FOLD_K / 4);
+        const float4 q = r < n ? __ldg(reinterpret_cast<const float4*>(v + ray0 * FOLD_K) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(&vs[0][0])[i] = q;
+    }
+    if (threadIdx.x < H6_RAYS) ss[threadIdx.x] = threadIdx.x < n ? s[ray0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    const int c = threadIdx.x;
+    float acc[H6_RAYS];
+    const float bias = __ldg(b6 + c);
+#pragma unroll
+    for (int r = 0; r < H6_RAYS; ++r) acc[r] = bias * ss[r];
+    for (int k = 0; k < FOLD_K; k += 4) {
+        const float w0 = __ldg(w6t + (k + 0) * 192 + c), w1 = __ldg(w6t + (k + 1) * 192 + c);
+        const float w2 = __ldg(w6t + (k + 2) * 192 + c), w3 = __ldg(w6t + (k + 3) * 192 + c);
+#pragma unroll
+        for (int r = 0; r < H6_RAYS; ++r) {
+            const float4 q = *reinterpret_cast<const float4*>(&vs[r][k]);      // smem broadcast
+            acc[r] = fmaf(q.x, w0, fmaf(q.y, w1, fmaf(q.z, w2, fmaf(q.w, w3, acc[r]))));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < H6_RAYS; ++r) {
+        if (r < n) {
+            const int64_t o = (ray0 + r) * 192 + c;
+            if (out0) out0[o] = acc[r];
+            if (out1) out1[o] = acc[r];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -371,14 +453,27 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     }
     const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
     const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
+    const int fold = args.fold_v != nullptr ? 1 : 0;
+    if (fold && (!args.fold_s || args.feat_out || args.apply_activation || args.ob.positions % 32)) {
+        pe_set_error("tensor-core field kernel: folded head needs positions %% 32 == 0, no per-sample features, no output activation");
+        return PE_ERR_UNSUPPORTED;
+    }
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int rpt = TILE_M / args.ob.positions;
     const int64_t tiles = (int64_t)((args.rays + rpt - 1) / rpt) * args.images;
     const int64_t pairs = x3 ? tiles : (tiles + 1) / 2;
     if (pairs == 0) return PE_OK;
     const int grid = (int)pe_min64(pairs, sm_count);
-    pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3);
+    pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
+    if (fold && (args.integ.integrated_features || global_out.integrated_features)) {
+        const int64_t total_rays = (int64_t)args.images * args.rays;
+        const unsigned char* blob = reinterpret_cast<const unsigned char*>(args.ob.packed);
+        pe_head6_fold_kernel<<<(unsigned)((total_rays + H6_RAYS - 1) / H6_RAYS), H6_THREADS, 0, stream>>>(
+            args.fold_v, args.fold_s, reinterpret_cast<const float*>(blob + args.L.head6_w), reinterpret_cast<const float*>(blob + args.L.head6_b),
+            args.integ.integrated_features, global_out.integrated_features, total_rays);
+        PE_LAUNCH_CHECK("pe_head6_fold_kernel");
+    }
     return PE_OK;
 }
 

@@ -237,6 +237,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
         X.alpha_bias = __ldg(reinterpret_cast<const float*>(blob + L.alpha_b));
         X.alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
         X.dbg = dbg;
+        X.fold = false;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;
         Sync2 sync{acc_full + g, mapa_u32(smem_u32(a_ready + g), 0), 0u, 0LL, nullptr, 0};
         const long long t_begin = clock64();
@@ -246,7 +247,8 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
             sync.ts = rec ? reinterpret_cast<long long*>(A.stats) + 64 + 32 * g : nullptr;
             sync.n = 0;
             if (rec) sync.ts[30] = clock64();
-            epilogue_tile<1, false>(X, it * 4 + 2 * g + rank, sync);
+            TileAhead ahead;
+            epilogue_tile<1, false>(X, it * 4 + 2 * g + rank, sync, ahead, 0);
             if (rec) {
                 const long long* q = sync.ts;
                 printf("PE_TC2 epi g%d start=%lld |", g, q[30]);

@@ -28,6 +28,9 @@ struct PeFieldArgs {
     // fused per-object integration (tcgen05 path): outputs of ObjectComposer.integrate for this object
     PeIntegrated integ;
     const float* noise;          // [images][rays][P] raw-alpha noise or NULL
+    // folded-head mode of the tcgen05 kernel (both or neither): per-ray weighted sums of the last hidden layer
+    float* fold_v;               // [images][rays][128]
+    float* fold_s;               // [images][rays]
 };
 
 // Arguments of the compositing kernel (model/object_composer.py:399-447, 724-784).

@@ -20,6 +20,9 @@ constexpr int SCR_T = 50 * 1024, SCR_SH = SCR_T + 512, SCR_W = SCR_SH + 512;   /
 // per-tile constants staged in the (dead after L4) positional-encoding columns of the A buffer
 constexpr int CST_BASE = PE_CHUNK0 * CHUNK_BYTES; // byte offset inside the A buffer
 constexpr int CST_SC1 = 0, CST_SH1 = 256, CST_SC2 = 512, CST_SH2 = 640, CST_AW = 768;
+// folded-head mode (see epilogue_tile): scratch in the same dead columns, float offsets from CST_BASE
+constexpr int FOLD_T = 1280, FOLD_W = 1408, FOLD_WF = 1536, FOLD_SH = 1664, FOLD_PART = 1680, FOLD_PART_S = 2704;
+constexpr int FOLD_K = 128;                       // width of the last hidden layer (input of head layer 6)
 
 // layer l: N outputs, `slabs` K=32 weight slabs, first A chunk, bias added by the rank-1 MMA
 __host__ __device__ __forceinline__ void layer_spec(int l, int& n, int& slabs, int& chunk0, bool& has_bias) {
@@ -161,7 +164,8 @@ struct TileCtx {
     float alpha_bias;
     const float* alpha_w;
     bool single;
-    int dbg;
+    bool fold;                   // folded-head mode: composite the 128-wide input of head layer 6, skip that layer's MMAs
+    int dbg;                     // PE_TC_TIMELINE=1: thread 0 of epilogue group 0 of CTA 0 prints clock64 stamps of its third tile
 };
 
 // 32 of the 64 positional-encoding columns of one sample (columns 32*H .. 32*H+31); layout of positional_encoder.py:59-64:
@@ -186,11 +190,118 @@ __device__ __forceinline__ void encode_half(const float (&xn)[3], const float (&
     }
 }
 
+// Sampling state of one tile row (transform_rays, z bounds, create_ray_positions, in-box mask).
+struct RowSample {
+    bool tile_valid, valid, inbox, in_scene;
+    int img, ray0, p;
+    int64_t ray;
+    float t, dnorm;
+    float x[3];
+};
+
+__device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSample& s) {
+    const PeFieldArgs& A = *X.A;
+    const PeObjectDesc& ob = A.ob;
+    const int m = X.m, P = X.P, rpt = X.rpt;
+    s.tile_valid = tile < X.total_tiles;
+    s.img = s.tile_valid ? (int)(tile / X.tiles_per_image) : 0;
+    s.ray0 = s.tile_valid ? (int)(tile - (int64_t)s.img * X.tiles_per_image) * rpt : 0;
+    s.valid = false; s.inbox = false;
+    s.t = 0.f; s.dnorm = 0.f; s.ray = -1; s.p = 0;
+    s.in_scene = A.ois ? A.ois[(int64_t)s.img * A.objects + A.k] != 0 : true;
+    s.x[0] = s.x[1] = s.x[2] = 0.f;
+    if (s.tile_valid && m < X.rows_used) {
+        const int rl = m / P;
+        const int r = s.ray0 + rl;
+        if (r < A.rays) {
+            s.valid = true;
+            s.p = m - rl * P;
+            s.ray = (int64_t)s.img * A.rays + r;
+            const float* dw = A.dirs + s.ray * 3;
+            const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)s.img * A.objects + A.k) * 12, A.origins + (int64_t)s.img * 3, dw, s.in_scene);
+            const float u = A.perturb ? A.rand[s.ray * P + s.p] : 0.f;
+            s.t = pe_sample_t(pr, s.p, P, A.perturb != 0, u);
+            pe_position(pr, s.t, s.x);
+            s.inbox = pe_in_box(ob, s.x);
+            s.dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dw[0], dw[0]), __fmul_rn(dw[1], dw[1])), __fmul_rn(dw[2], dw[2])));
+        }
+    }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    uint4 q;
+    q.x = pack_half2(v[0], v[1]); q.y = pack_half2(v[2], v[3]); q.z = pack_half2(v[4], v[5]); q.w = pack_half2(v[6], v[7]);
+    return q;
+}
+
+// Fourier features sin/cos(2^o * x) of this thread's share of the 64 encoding columns, as packed fp16 operand chunks
+// (kHiLo: hi chunks then lo chunks).  The argument is reduced EXACTLY (x/(2 pi) as a two-float value, scaled by the power
+// of two, integer part dropped), then evaluated with the SFU on [-pi, pi] (abs error < 5e-7, far below the fp16 rounding of
+// the operand).  Same values as positional_encoder.py:59-64 up to that error.
+template <int kSplit, bool kHiLo>
+__device__ __forceinline__ void encode_row(const TileCtx& X, const float (&x)[3], uint4 (&q)[8]) {
+    const float xn[3] = {__fdiv_rn(x[0], X.size[0]), __fdiv_rn(x[1], X.size[1]), __fdiv_rn(x[2], X.size[2])};
+    float tp[3], tl[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float c_hi = 0.15915494f, c_lo = 6.4206382e-9f;      // 1/(2 pi) = c_hi + c_lo
+        tp[a] = xn[a] * c_hi;
+        tl[a] = fmaf(xn[a], c_lo, fmaf(xn[a], c_hi, -tp[a]));
+    }
+    float enc[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (kSplit == 2 && h != X.half) continue;
+        if (h == 0) encode_half<0>(xn, tp, tl, enc); else encode_half<1>(xn, tp, tl, enc);
+        const int base = kSplit == 2 ? 0 : 4 * h;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (kHiLo) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { hi[i] = __half2float(__float2half_rn(enc[8 * c + i])); lo[i] = enc[8 * c + i] - hi[i]; }
+                q[c] = pack8(hi);
+                q[4 + c] = pack8(lo);
+            } else {
+                q[base + c] = pack8(enc + 8 * c);
+            }
+        }
+    }
+}
+
+template <int kSplit, bool kHiLo>
+__device__ __forceinline__ void store_enc(const TileCtx& X, const uint4 (&q)[8]) {
+    const int m = X.m;
+    if (kHiLo) {
+        const int c0 = PE_CHUNK0 + (kSplit == 2 ? 4 * X.half : 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            *reinterpret_cast<uint4*>(X.abuf + (c0 + c) * CHUNK_BYTES + m * 16) = q[c];
+            *reinterpret_cast<uint4*>(X.abuf_lo + (c0 + c) * CHUNK_BYTES + m * 16) = q[4 + c];
+        }
+    } else if (kSplit == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(X.abuf + (PE_CHUNK0 + 4 * X.half + c) * CHUNK_BYTES + m * 16) = q[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(X.abuf + (PE_CHUNK0 + c) * CHUNK_BYTES + m * 16) = q[c];
+    }
+}
+
+// Look-ahead state carried from one tile to the next (folded-head mode): the next tile's rows are sampled and encoded
+// while the tensor core runs the last two layers of the current tile.
+struct TileAhead {
+    bool have = false;
+    RowSample rs;
+    uint4 enc[8];
+};
+
 // Per-tile work of one epilogue thread.  `Sync` provides wait_acc() (accumulators of the next layer are complete) and
 // arrive_ready() (this thread's part of the next A operand is written and its TMEM reads are done).
 // kSplit threads (in different warps of the same lane quadrant) share one row: each handles 1/kSplit of the columns.
 template <int kSplit, bool kHiLo, class Sync>
-__device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync) {
+__device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync, TileAhead& ahead, int64_t next_tile) {
+    static_assert(!(kHiLo && kSplit != 2) , "fp16x3 mode runs with two threads per row");
     constexpr int GROUP = TILE_M * kSplit;           // threads of the group
     const PeFieldArgs& A = *X.A;
     const PeIntegrated& G2 = *X.G2;
@@ -206,70 +317,140 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     float* cst = reinterpret_cast<float*>(abuf + CST_BASE);
     float* alpha_part = cst + 1024;                  // [kSplit][128] partial alpha-head dot products
 
-    const bool tile_valid = tile < X.total_tiles;
-    const int img = tile_valid ? (int)(tile / X.tiles_per_image) : 0;
-    const int ray0 = tile_valid ? (int)(tile - (int64_t)img * X.tiles_per_image) * rpt : 0;
-
-    // ---- sampling (transform_rays, z bounds, create_ray_positions, in-box mask) ----
-    bool valid = false, inbox = false;
-    float t = 0.f, dnorm = 0.f, raw_alpha = ob.empty_space_alpha;
-    int64_t ray = -1;
-    int p = 0;
-    const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
-    float x[3] = {0.f, 0.f, 0.f};
-    if (tile_valid && m < X.rows_used) {
-        const int rl = m / P;
-        const int r = ray0 + rl;
-        if (r < A.rays) {
-            valid = true;
-            p = m - rl * P;
-            ray = (int64_t)img * A.rays + r;
-            const float* dw = A.dirs + ray * 3;
-            const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3, dw, in_scene);
-            const float u = A.perturb ? A.rand[ray * P + p] : 0.f;
-            t = pe_sample_t(pr, p, P, A.perturb != 0, u);
-            pe_position(pr, t, x);
-            inbox = pe_in_box(ob, x);
-            dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dw[0], dw[0]), __fmul_rn(dw[1], dw[1])), __fmul_rn(dw[2], dw[2])));
-        }
+#ifdef PE_TC_TIMELINE      // diagnostic build (-DPE_TC_TIMELINE, run with PE_TC_TIMELINE=1): in-kernel timeline of one tile
+    long long ts[36];
+    const bool rec = X.dbg != 0 && blockIdx.x == 0 && m == 0 && hf == 0 && bar_id == 1 && tile / (2 * gridDim.x) == 2;
+#define PE_STAMP(i) do { if (rec) ts[i] = clock64(); } while (0)
+#else
+#define PE_STAMP(i) do { } while (0)
+#endif
+    PE_STAMP(0);
+    // ---- sampling + Fourier features (unless the previous tile's epilogue already did them) ----
+    if (!ahead.have) {
+        sample_row(X, tile, ahead.rs);
+        encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
     }
-    {
-        // Fourier features sin/cos(2^o * x): the argument is reduced EXACTLY (x/(2 pi) as a two-float value, scaled by the
-        // power of two, integer part dropped), then evaluated with the SFU on [-pi, pi] (abs error < 5e-7, far below the
-        // fp16 rounding of the operand).  Same values as positional_encoder.py:59-64 up to that error.
-        const float xn[3] = {__fdiv_rn(x[0], X.size[0]), __fdiv_rn(x[1], X.size[1]), __fdiv_rn(x[2], X.size[2])};
-        float tp[3], tl[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float c_hi = 0.15915494f, c_lo = 6.4206382e-9f;      // 1/(2 pi) = c_hi + c_lo
-            tp[a] = xn[a] * c_hi;
-            tl[a] = fmaf(xn[a], c_lo, fmaf(xn[a], c_hi, -tp[a]));
-        }
-        float enc[32];
-        if (kSplit == 1 || hf == 0) {
-            encode_half<0>(xn, tp, tl, enc);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (kHiLo) store_a8_hilo(abuf, X.abuf_lo, PE_CHUNK0 + c, m, enc + 8 * c, false);
-                else store_a8(abuf, PE_CHUNK0 + c, m, enc + 8 * c);
-            }
-        }
-        if (kSplit == 1 || hf == 1) {
-            encode_half<1>(xn, tp, tl, enc);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (kHiLo) store_a8_hilo(abuf, X.abuf_lo, PE_CHUNK0 + 4 + c, m, enc + 8 * c, false);
-                else store_a8(abuf, PE_CHUNK0 + 4 + c, m, enc + 8 * c);
-            }
-        }
-    }
+    store_enc<kSplit, kHiLo>(X, ahead.enc);
     sync.arrive_ready();
+    PE_STAMP(1);
+    ahead.have = false;
+    const bool tile_valid = ahead.rs.tile_valid, valid = ahead.rs.valid, inbox = ahead.rs.inbox, in_scene = ahead.rs.in_scene;
+    const int img = ahead.rs.img, ray0 = ahead.rs.ray0, p = ahead.rs.p;
+    const int64_t ray = ahead.rs.ray;
+    const float t = ahead.rs.t, dnorm = ahead.rs.dnorm;
+    float raw_alpha = ob.empty_space_alpha;
+
+    // ---- alpha compositing of the tile's rays (compute_position_distances / compute_alphas / compute_weights, :153-214) and
+    // the per-ray scalars of ObjectComposer.integrate (:758-772); scratch pointers differ between the two modes ----
+    const int64_t gs = valid ? ray * P + p : 0;
+    auto row_weight = [&](float* t_s, float* sh_s, float* w_s, float raw_alpha_v) -> float {
+        t_s[m] = t;
+        named_bar_sync(bar_id, GROUP);
+        if (kSplit == 2) raw_alpha_v = alpha_part[m] + alpha_part[TILE_M + m];
+        raw_alpha_v += X.alpha_bias;
+        float raw = (inbox && in_scene) ? raw_alpha_v : ob.empty_space_alpha;
+        if (valid && hf == 0) {
+            if (A.raw_out) A.raw_out[gs] = raw;
+            if (A.t_out) A.t_out[gs] = t;
+            if (A.inbox_out) A.inbox_out[gs] = inbox ? 1 : 0;
+            if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
+        }
+        float alpha = 0.f;
+        if (valid) {
+            const float delta = __fmul_rn(p == P - 1 ? 1e10f : __fsub_rn(t_s[m + 1], t), dnorm);     // :153-178
+            if (A.noise) raw = __fadd_rn(raw, A.noise[gs]);                                            // :193-195
+            alpha = __fsub_rn(1.f, expf(__fmul_rn(-fmaxf(raw, 0.f), delta)));                          // :197
+        }
+        // exclusive cumprod of (1 - alpha + 1e-10) along the samples of each ray (compute_weights :199-214):
+        // segmented warp scan + carry across the warps a ray spans
+        const float shifted = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+        const bool head = p == 0;
+        float incl = shifted;
+        bool closed = head;                              // a segment head lies in [first lane of the scan window, lane]
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, d);
+            const bool fu = __shfl_up_sync(0xffffffffu, closed ? 1 : 0, d) != 0;
+            if (lane >= d && !closed) { incl *= up; closed = fu; }
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0 || head) excl = 1.f;
+        if (lane == 31 && hf == 0) { sh_s[wq] = incl; sh_s[4 + wq] = closed ? 1.f : 0.f; }
+        named_bar_sync(bar_id, GROUP);
+        float T = excl;
+        if (!closed) {                                   // the ray started in an earlier warp of the tile
+            for (int v = wq - 1; v >= 0; --v) {
+                T *= sh_s[v];
+                if (sh_s[4 + v] != 0.f) break;
+            }
+        }
+        const float w = valid ? alpha * T : 0.f;
+        if (hf == 0) {
+            w_s[m] = w;
+            if (valid) {
+                if (A.integ.weights) A.integ.weights[gs] = w;
+                if (X.single && G2.weights) G2.weights[gs] = w;
+            }
+        }
+        return w;
+    };
+    // per-ray scalars (:758-772): one warp per ray, lanes stride the samples
+    auto ray_scalars = [&](const float* t_s, const float* w_s) {
+        for (int rl = X.gw; rl < rpt; rl += 4 * kSplit) {
+            const int r = ray0 + rl;
+            if (!tile_valid || r >= A.rays) continue;
+            float opacity = 0.f, depth = 0.f;
+            for (int j = lane; j < P; j += 32) { const float wj = w_s[rl * P + j]; opacity += wj; depth += wj * t_s[rl * P + j]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                opacity += __shfl_xor_sync(0xffffffffu, opacity, o);
+                depth += __shfl_xor_sync(0xffffffffu, depth, o);
+            }
+            if (lane == 0) {
+                const int64_t gr = (int64_t)img * A.rays + r;
+                const float qd = depth / opacity;
+                const float disparity = 1.f / (qd != qd ? qd : fmaxf(qd, 1e-10f));
+                const PeIntegrated* outs[2] = {&A.integ, &G2};
+                for (int oi = 0; oi < (X.single ? 2 : 1); ++oi) {
+                    const PeIntegrated& O = *outs[oi];
+                    if (O.opacity) O.opacity[gr] = opacity;
+                    if (O.depth) O.depth[gr] = depth;
+                    if (O.disparity) O.disparity[gr] = disparity;
+                    if (O.integrated_displacements_magnitude) O.integrated_displacements_magnitude[gr] = 0.f;
+                    if (O.integrated_divergence) O.integrated_divergence[gr] = 0.f;
+                }
+            }
+        }
+    };
 
     // ---- the 10 hidden tensor-core layers ----
+    const bool fold = X.fold;
     float4 pre[2 / kSplit];
     const uint32_t tcol = taddr + hf * (256 / kSplit);        // first accumulator column of this thread for 256-wide layers
     for (int l = 0; l < 10; ++l) {
+        if (fold && l == 8) {
+            // folded-head mode: the raw alphas are known after L7, so the compositing weights are computed here, while the
+            // tensor core runs head layer 0
+            const float w = row_weight(cst + FOLD_T, cst + FOLD_SH, cst + FOLD_W, raw_alpha);
+            const float wf = inbox ? w : 0.f;
+            float sw = wf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+            if (hf == 0) {
+                cst[FOLD_WF + m] = wf;
+                if (lane == 0) cst[FOLD_PART_S + wq] = sw;
+            }
+            named_bar_sync(bar_id, GROUP);
+            ray_scalars(cst + FOLD_T, cst + FOLD_W);
+            sample_row(X, next_tile, ahead.rs);              // look-ahead: the next tile's rows (hidden behind head layer 0)
+        }
+        if (fold && l == 9) {
+            encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);   // ... and their encoding (behind head layer 3)
+            ahead.have = true;
+        }
+        PE_STAMP(2 + 3 * l);
         sync.wait_acc();
+        PE_STAMP(3 + 3 * l);
         if (l == 4) {
             // the encoding columns are dead once L4 has run: reuse them for the constants of the later epilogues
             // (AdaIn scale/shift of this image and the alpha-head weights); the loads overlap this layer's epilogue
@@ -284,6 +465,75 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
         if (l == 7) named_bar_sync(bar_id, GROUP);                         // constants written by the whole group at l == 4
         constexpr int W = 256 / kSplit, W2 = 128 / kSplit;
+        if (fold && l == 9) {
+            // Folded head: integrated_features = sum_p w_p (W6 h_p + b6) = W6 (sum_p w_p h_p) + b6 sum_p w_p, so the
+            // volume-rendering sum (:749) is taken over the 128-wide h (fp32, straight from the accumulators) and head
+            // layer 6 runs once per ray afterwards (pe_head6_fold_kernel) instead of once per sample.
+            // Head layer 3 was issued TRANSPOSED for this (weights as the M operand, samples as N): TMEM lane = feature,
+            // column = sample, so the sum over a ray's samples is a plain in-thread loop.
+            const int c = m;                                // feature handled by this thread
+            const float sc = cst[CST_SC2 + c], sh = cst[CST_SH2 + c];
+            const float* wfs = cst + FOLD_WF;               // in-box compositing weight of each sample (row) of the tile
+            float* part = cst + FOLD_PART;                  // kSplit == 2: [half][ray][128] partial sums
+            constexpr int CW = 128 / kSplit;                // sample columns per thread
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < CW / 32; ++q) {
+                const int col0 = hf * CW + q * 32;
+                uint32_t v[32];
+                tmem_ld32(taddr + col0, v);
+                tmem_wait_ld_regs(v);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wfs + col0 + 4 * i);      // smem broadcast
+                    a0 = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * i + 0]), sc, sh), 0.f), w4.x, a0);
+                    a1 = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * i + 1]), sc, sh), 0.f), w4.y, a1);
+                    a0 = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * i + 2]), sc, sh), 0.f), w4.z, a0);
+                    a1 = fmaf(fmaxf(fmaf(__uint_as_float(v[4 * i + 3]), sc, sh), 0.f), w4.w, a1);
+                }
+                acc += a0 + a1;
+                if ((col0 + 32) % P == 0 || q == CW / 32 - 1) {          // last chunk of a ray (or of this thread's share of it)
+                    const int rl = col0 / P;
+                    const int r = ray0 + rl;
+                    if (kSplit == 1) {
+                        if (tile_valid && r < A.rays) A.fold_v[((int64_t)img * A.rays + r) * FOLD_K + c] = acc;
+                    } else {
+                        part[(hf * 4 + rl) * FOLD_K + c] = acc;
+                    }
+                    acc = 0.f;
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(bar_id, GROUP);
+            const int wpr = P >> 5;                          // warps (row quadrants) per ray
+            if (kSplit == 2 && hf == 0) {
+                for (int rl = 0; rl < rpt; ++rl) {
+                    const int r = ray0 + rl;
+                    if (!tile_valid || r >= A.rays) continue;
+                    // samples of ray rl: columns [rl*P, (rl+1)*P); half h owns columns [64h, 64h+64)
+                    float sum = 0.f;
+                    if (rl * P < 64) sum += part[(0 * 4 + rl) * FOLD_K + c];
+                    if ((rl + 1) * P > 64) sum += part[(1 * 4 + rl) * FOLD_K + c];
+                    A.fold_v[((int64_t)img * A.rays + r) * FOLD_K + c] = sum;
+                }
+            }
+            if (tid < rpt && tile_valid && ray0 + tid < A.rays) {
+                float sum = 0.f;
+                for (int j = 0; j < wpr; ++j) sum += cst[FOLD_PART_S + tid * wpr + j];
+                A.fold_s[(int64_t)img * A.rays + ray0 + tid] = sum;
+            }
+            named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
+            PE_STAMP(4 + 3 * l);
+#ifdef PE_TC_TIMELINE
+            if (rec) {
+                printf("PE_TC timeline (cycles since tile start; per layer: wait begin, acc ready, epilogue done): enc %lld |", ts[1] - ts[0]);
+                for (int q = 0; q < 10; ++q) printf(" L%d %lld %lld %lld |", q, ts[2 + 3 * q] - ts[0], ts[3 + 3 * q] - ts[0], ts[4 + 3 * q] - ts[0]);
+                printf("\n");
+            }
+#endif
+            return;
+        }
         if (l < 7) hidden_epilogue<0, W, kHiLo>(tcol, abuf, hf * (W / 8), m, nullptr, nullptr, X.abuf_lo);
         else if (l == 7) raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo);
         else if (l == 8) hidden_epilogue<2, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W, X.abuf_lo);
@@ -294,60 +544,13 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
         if (l == 7 && kSplit == 2) alpha_part[hf * TILE_M + m] = raw_alpha;
         sync.arrive_ready();
+        PE_STAMP(4 + 3 * l);
     }
 
     // ---- last layer: features in TMEM -> volume rendering of the tile's rays (ObjectComposer.integrate :724-784) ----
     // row scalars are computed redundantly by the kSplit threads of a row (identical values), stores by half 0 only
     sync.wait_acc();
-    const int64_t gs = valid ? ray * P + p : 0;
-    t_s[m] = t;
-    named_bar_sync(bar_id, GROUP);
-    if (kSplit == 2) raw_alpha = alpha_part[m] + alpha_part[TILE_M + m];
-    raw_alpha += X.alpha_bias;
-    float raw = (inbox && in_scene) ? raw_alpha : ob.empty_space_alpha;
-    if (valid && hf == 0) {
-        if (A.raw_out) A.raw_out[gs] = raw;
-        if (A.t_out) A.t_out[gs] = t;
-        if (A.inbox_out) A.inbox_out[gs] = inbox ? 1 : 0;
-        if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
-    }
-    float alpha = 0.f;
-    if (valid) {
-        const float delta = __fmul_rn(p == P - 1 ? 1e10f : __fsub_rn(t_s[m + 1], t), dnorm);     // :153-178
-        if (A.noise) raw = __fadd_rn(raw, A.noise[gs]);                                            // :193-195
-        alpha = __fsub_rn(1.f, expf(__fmul_rn(-fmaxf(raw, 0.f), delta)));                          // :197
-    }
-    // exclusive cumprod of (1 - alpha + 1e-10) along the samples of each ray (compute_weights :199-214):
-    // segmented warp scan + carry across the warps a ray spans
-    const float shifted = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-    const bool head = p == 0;
-    float incl = shifted;
-    bool closed = head;                              // a segment head lies in [first lane of the scan window, lane]
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float up = __shfl_up_sync(0xffffffffu, incl, d);
-        const bool fu = __shfl_up_sync(0xffffffffu, closed ? 1 : 0, d) != 0;
-        if (lane >= d && !closed) { incl *= up; closed = fu; }
-    }
-    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0 || head) excl = 1.f;
-    if (lane == 31 && hf == 0) { sh_s[wq] = incl; sh_s[4 + wq] = closed ? 1.f : 0.f; }
-    named_bar_sync(bar_id, GROUP);
-    float T = excl;
-    if (!closed) {                                   // the ray started in an earlier warp of the tile
-        for (int v = wq - 1; v >= 0; --v) {
-            T *= sh_s[v];
-            if (sh_s[4 + v] != 0.f) break;
-        }
-    }
-    const float w = valid ? alpha * T : 0.f;
-    if (hf == 0) {
-        w_s[m] = w;
-        if (valid) {
-            if (A.integ.weights) A.integ.weights[gs] = w;
-            if (X.single && G2.weights) G2.weights[gs] = w;
-        }
-    }
+    const float w = row_weight(t_s, sh_s, w_s, raw_alpha);
     const float wf = inbox ? w : 0.f;
     constexpr int FC = 96 / kSplit;                  // feature columns per thread per pass (96 or 48)
     for (int pass = 0; pass < 2; ++pass) {
@@ -391,32 +594,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
         named_bar_sync(bar_id, GROUP);
     }
-    // per-ray scalars (:758-772): one warp per ray, lanes stride the samples
-    for (int rl = X.gw; rl < rpt; rl += 4 * kSplit) {
-        const int r = ray0 + rl;
-        if (!tile_valid || r >= A.rays) continue;
-        float opacity = 0.f, depth = 0.f;
-        for (int j = lane; j < P; j += 32) { const float wj = w_s[rl * P + j]; opacity += wj; depth += wj * t_s[rl * P + j]; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            opacity += __shfl_xor_sync(0xffffffffu, opacity, o);
-            depth += __shfl_xor_sync(0xffffffffu, depth, o);
-        }
-        if (lane == 0) {
-            const int64_t gr = (int64_t)img * A.rays + r;
-            const float qd = depth / opacity;
-            const float disparity = 1.f / (qd != qd ? qd : fmaxf(qd, 1e-10f));
-            const PeIntegrated* outs[2] = {&A.integ, &G2};
-            for (int oi = 0; oi < (X.single ? 2 : 1); ++oi) {
-                const PeIntegrated& O = *outs[oi];
-                if (O.opacity) O.opacity[gr] = opacity;
-                if (O.depth) O.depth[gr] = depth;
-                if (O.disparity) O.disparity[gr] = disparity;
-                if (O.integrated_displacements_magnitude) O.integrated_displacements_magnitude[gr] = 0.f;
-                if (O.integrated_divergence) O.integrated_divergence[gr] = 0.f;
-            }
-        }
-    }
+    ray_scalars(t_s, w_s);
     tc_fence_before();
     named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
 }
