@@ -35,6 +35,7 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
     uint64_t* a_ready;
     uint32_t phase;
     int lane;
+    uint64_t* h6_full;
     __device__ __forceinline__ void wait_acc() { mbar_wait(acc_full, phase); phase ^= 1; tc_fence_after(); }
     // every thread publishes its operand writes to the async proxy and orders its TMEM reads; ONE arrival per warp
     // (128 serialized arrivals on one mbarrier cost several hundred cycles per layer)
@@ -42,6 +43,8 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
         fence_proxy_async(); tc_fence_before(); __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
     }
+    // folded-head mode: this warp's per-ray sums are in global memory (release: visible to the head-6 warp of the CTA)
+    __device__ __forceinline__ void arrive_fold() { __syncwarp(); if (lane == 0) mbar_arrive(h6_full); }
 };
 
 // State of the MMA-issuing thread that persists across layers: position in the weight ring, operand addresses.
@@ -106,7 +109,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     uint64_t* empty_bar = full_bar + NUM_STAGES;
     uint64_t* acc_full = empty_bar + NUM_STAGES;     // [2]
     uint64_t* a_ready = acc_full + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
+    uint64_t* h6_full = a_ready + 2;                 // [2] folded-head mode: per-ray sums of a tile are written
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h6_full + 2);
     unsigned char* ones = smem + SMEM_ONES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 8 : 4 * SPLIT); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 8 : 4 * SPLIT); mbar_init(h6_full + g, x3 ? 8 : 4 * SPLIT); }
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -210,6 +214,62 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                 }
             }
         }
+    } else if (fold && (warp == 2 || (warp == 3 && !x3))) {
+        // ================================ head layer 6, once per ray (folded-head mode) ================================
+        // integrated_features[ray] = W6 * v[ray] + b6 * s[ray] in exact fp32 (adain_style_nerf_model.py:88 commutes with the
+        // linear volume-rendering sum of object_composer.py:749); v, s were just written by this CTA's epilogue group
+        const int g = warp - 2;
+        const float* w6t = reinterpret_cast<const float*>(blob + L.head6_w);      // [128][192] (transposed nn.Linear weight)
+        const float* b6 = reinterpret_cast<const float*>(blob + L.head6_b);
+        float* out0 = A.integ.integrated_features;
+        float* out1 = G2.integrated_features;
+        uint32_t hphase = 0;
+        for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
+            const int64_t tile = x3 ? pair : pair * 2 + g;
+            mbar_wait(h6_full + g, hphase);
+            hphase ^= 1;
+            if (tile >= total_tiles) continue;
+            const int img = (int)(tile / tiles_per_image);
+            const int ray0 = (int)(tile - (int64_t)img * tiles_per_image) * rpt;
+            const int nr = min(rpt, A.rays - ray0);                                 // <= 4 (positions >= 32)
+            const int64_t gr0 = (int64_t)img * A.rays + ray0;
+            const float* v = A.fold_v + gr0 * FOLD_K;
+            float acc[4][6];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float sr = r < nr ? A.fold_s[gr0 + r] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[r][j] = __ldg(b6 + lane + 32 * j) * sr;
+            }
+#pragma unroll 2
+            for (int k = 0; k < FOLD_K; k += 4) {
+                float w[4][6];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) w[kk][j] = __ldg(w6t + (k + kk) * 192 + lane + 32 * j);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (r < nr) {
+                        const float4 q = *reinterpret_cast<const float4*>(v + r * FOLD_K + k);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            acc[r][j] = fmaf(q.x, w[0][j], fmaf(q.y, w[1][j], fmaf(q.z, w[2][j], fmaf(q.w, w[3][j], acc[r][j]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (r < nr) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int64_t o = (gr0 + r) * 192 + lane + 32 * j;
+                        if (out0) out0[o] = acc[r][j];
+                        if (out1) out1[o] = acc[r][j];
+                    }
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ================================ epilogue groups ================================
         const int g = (warp - 4) / (4 * SPLIT);        // 0: tile X, 1: tile Y
@@ -230,12 +290,12 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.dbg = dbg;
         X.fold = fold != 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
-        Sync1 sync{acc_full + g, a_ready + g, 0u, lane};
+        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g};
         if (x3) {
             // one tile per iteration: the two epilogue groups become the two column halves of the same 128 rows
             X.abuf = smem; X.half = g; X.gw = warp - 4; X.bar_id = 1;
             X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
-            Sync1 sync3{acc_full, a_ready, 0u, lane};
+            Sync1 sync3{acc_full, a_ready, 0u, lane, h6_full};
             TileAhead ahead;
             for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3, ahead, tile + gridDim.x);
         } else {
@@ -248,51 +308,6 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// folded head layer 6: integrated_features[ray] = W6 * v[ray] + b6 * s[ray]   (exact fp32, once per RAY)
-//   v = sum_p w_p h_p over the in-box samples (128 wide), s = sum_p w_p; see epilogue_tile.  adain_style_nerf_model.py:88
-//   (the last nn.Linear of the head) commutes with the linear volume-rendering sum of object_composer.py:749.
-// ------------------------------------------------------------------------------------------------------
-constexpr int H6_RAYS = 32;        // rays per block
-constexpr int H6_THREADS = 192;    // one thread per output feature
-__global__ void __launch_bounds__(H6_THREADS) pe_head6_fold_kernel(const float* __restrict__ v, const float* __restrict__ s, const float* __restrict__ w6t,
-                                                                   const float* __restrict__ b6, float* __restrict__ out0, float* __restrict__ out1,
-                                                                   int64_t total_rays) {
-    __shared__ __align__(16) float vs[H6_RAYS][FOLD_K];
-    __shared__ float ss[H6_RAYS];
-    const int64_t ray0 = (int64_t)blockIdx.x * H6_RAYS;
-    const int n = (int)pe_min64(H6_RAYS, total_rays - ray0);
-    for (int i = threadIdx.x; i < H6_RAYS * FOLD_K / 4; i += H6_THREADS) {
-        const int r = i / (FOLD_K / 4);
-        const float4 q = r < n ? __ldg(reinterpret_cast<const float4*>(v + ray0 * FOLD_K) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(&vs[0][0])[i] = q;
-    }
-    if (threadIdx.x < H6_RAYS) ss[threadIdx.x] = threadIdx.x < n ? s[ray0 + threadIdx.x] : 0.f;
-    __syncthreads();
-    const int c = threadIdx.x;
-    float acc[H6_RAYS];
-    const float bias = __ldg(b6 + c);
-#pragma unroll
-    for (int r = 0; r < H6_RAYS; ++r) acc[r] = bias * ss[r];
-    for (int k = 0; k < FOLD_K; k += 4) {
-        const float w0 = __ldg(w6t + (k + 0) * 192 + c), w1 = __ldg(w6t + (k + 1) * 192 + c);
-        const float w2 = __ldg(w6t + (k + 2) * 192 + c), w3 = __ldg(w6t + (k + 3) * 192 + c);
-#pragma unroll
-        for (int r = 0; r < H6_RAYS; ++r) {
-            const float4 q = *reinterpret_cast<const float4*>(&vs[r][k]);      // smem broadcast
-            acc[r] = fmaf(q.x, w0, fmaf(q.y, w1, fmaf(q.z, w2, fmaf(q.w, w3, acc[r]))));
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < H6_RAYS; ++r) {
-        if (r < n) {
-            const int64_t o = (ray0 + r) * 192 + c;
-            if (out0) out0[o] = acc[r];
-            if (out1) out1[o] = acc[r];
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -466,14 +481,6 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     const int grid = (int)pe_min64(pairs, sm_count);
     pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
-    if (fold && (args.integ.integrated_features || global_out.integrated_features)) {
-        const int64_t total_rays = (int64_t)args.images * args.rays;
-        const unsigned char* blob = reinterpret_cast<const unsigned char*>(args.ob.packed);
-        pe_head6_fold_kernel<<<(unsigned)((total_rays + H6_RAYS - 1) / H6_RAYS), H6_THREADS, 0, stream>>>(
-            args.fold_v, args.fold_s, reinterpret_cast<const float*>(blob + args.L.head6_w), reinterpret_cast<const float*>(blob + args.L.head6_b),
-            args.integ.integrated_features, global_out.integrated_features, total_rays);
-        PE_LAUNCH_CHECK("pe_head6_fold_kernel");
-    }
     return PE_OK;
 }
 

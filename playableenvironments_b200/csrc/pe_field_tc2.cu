@@ -38,6 +38,7 @@ struct Sync2 {        // epilogue <-> leader-CTA MMA handshakes across the pair
         if (ts) { ts[n++] = t0; ts[n++] = t1; }
     }
     __device__ __forceinline__ void arrive_ready() { fence_proxy_async(); tc_fence_before(); mbar_arrive_cluster(ready_addr); }
+    __device__ __forceinline__ void arrive_fold() {}      // folded-head mode is not used by this kernel
 };
 
 // one "sub-layer": up to 8 ring entries (slab x pass) consumed by tile X, then by tile Y

@@ -468,7 +468,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         if (fold && l == 9) {
             // Folded head: integrated_features = sum_p w_p (W6 h_p + b6) = W6 (sum_p w_p h_p) + b6 sum_p w_p, so the
             // volume-rendering sum (:749) is taken over the 128-wide h (fp32, straight from the accumulators) and head
-            // layer 6 runs once per ray afterwards (pe_head6_fold_kernel) instead of once per sample.
+            // layer 6 runs once per ray afterwards (by an otherwise idle warp of the CTA) instead of once per sample.
             // Head layer 3 was issued TRANSPOSED for this (weights as the M operand, samples as N): TMEM lane = feature,
             // column = sample, so the sum over a ray's samples is a plain in-thread loop.
             const int c = m;                                // feature handled by this thread
@@ -523,6 +523,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
                 for (int j = 0; j < wpr; ++j) sum += cst[FOLD_PART_S + tid * wpr + j];
                 A.fold_s[(int64_t)img * A.rays + ray0 + tid] = sum;
             }
+            sync.arrive_fold();                   // the head-6 warp of the CTA turns the sums into integrated_features
             named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
             PE_STAMP(4 + 3 * l);
 #ifdef PE_TC_TIMELINE

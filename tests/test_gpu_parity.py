@@ -224,4 +224,4 @@ def test_launch_accounting_and_no_fallback():
     _run(comp, dev)                                 # first call also packs the parameters
     render.take_launch_count()
     _run(comp, dev)
-    assert render.take_launch_count() == 4          # two style prologues + ONE fused field kernel + per-ray head layer 6
+    assert render.take_launch_count() == 3          # two style prologues + ONE fused field kernel
