@@ -27,7 +27,7 @@ constexpr int THREADS = 128 + 2 * 128 * SPLIT;    // producer, MMA, TMEM-alloc, 
 constexpr int STAGE_BYTES = 16384;                // largest slab: 256 rows x 32 k x 2 B
 constexpr int NUM_STAGES = 4;
 constexpr int SMEM_BAR = 2 * A_BYTES + NUM_STAGES * STAGE_BYTES;
-constexpr int SMEM_ONES = SMEM_BAR + 128;         // 256-byte "ones" operand of the rank-1 bias update
+constexpr int SMEM_ONES = SMEM_BAR + 256;         // 256-byte "ones" operand of the rank-1 bias update
 constexpr int SMEM_TOTAL = SMEM_ONES + 256;
 
 struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
@@ -36,6 +36,8 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
     uint32_t phase;
     int lane;
     uint64_t* h6_full;
+    uint64_t* h6_done;
+    uint32_t h6_phase;
     __device__ __forceinline__ void wait_acc() { mbar_wait(acc_full, phase); phase ^= 1; tc_fence_after(); }
     // every thread publishes its operand writes to the async proxy and orders its TMEM reads; ONE arrival per warp
     // (128 serialized arrivals on one mbarrier cost several hundred cycles per layer)
@@ -44,7 +46,12 @@ struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
         if (lane == 0) mbar_arrive(a_ready);
     }
     // folded-head mode: this warp's per-ray sums are in global memory (release: visible to the head-6 warp of the CTA)
-    __device__ __forceinline__ void arrive_fold() { __syncwarp(); if (lane == 0) mbar_arrive(h6_full); }
+    // (two-way handshake: the head-6 warp must have consumed the previous tile's phase before it can complete again)
+    __device__ __forceinline__ void arrive_fold() {
+        __syncwarp();
+        if (lane == 0) { mbar_wait(h6_done, h6_phase ^ 1); mbar_arrive(h6_full); }
+        h6_phase ^= 1;
+    }
 };
 
 // State of the MMA-issuing thread that persists across layers: position in the weight ring, operand addresses.
@@ -110,7 +117,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     uint64_t* acc_full = empty_bar + NUM_STAGES;     // [2]
     uint64_t* a_ready = acc_full + 2;                // [2]
     uint64_t* h6_full = a_ready + 2;                 // [2] folded-head mode: per-ray sums of a tile are written
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h6_full + 2);
+    uint64_t* h6_done = h6_full + 2;                 // [2] ... and consumed by the head-6 warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h6_done + 2);
     unsigned char* ones = smem + SMEM_ONES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 8 : 4 * SPLIT); mbar_init(h6_full + g, x3 ? 8 : 4 * SPLIT); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, x3 ? 8 : 4 * SPLIT); mbar_init(h6_full + g, x3 ? 8 : 4 * SPLIT); mbar_init(h6_done + g, 1); }
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -226,9 +234,10 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         uint32_t hphase = 0;
         for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
             const int64_t tile = x3 ? pair : pair * 2 + g;
-            mbar_wait(h6_full + g, hphase);
+            if (lane == 0) mbar_wait(h6_full + g, hphase);
+            __syncwarp();
             hphase ^= 1;
-            if (tile >= total_tiles) continue;
+            if (tile >= total_tiles) { if (lane == 0) mbar_arrive(h6_done + g); continue; }
             const int img = (int)(tile / tiles_per_image);
             const int ray0 = (int)(tile - (int64_t)img * tiles_per_image) * rpt;
             const int nr = min(rpt, A.rays - ray0);                                 // <= 4 (positions >= 32)
@@ -269,6 +278,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h6_done + g);
         }
     } else if (warp >= 4) {
         // ================================ epilogue groups ================================
@@ -290,12 +301,12 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.dbg = dbg;
         X.fold = fold != 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
-        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g};
+        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g, h6_done + g, 0u};
         if (x3) {
             // one tile per iteration: the two epilogue groups become the two column halves of the same 128 rows
             X.abuf = smem; X.half = g; X.gw = warp - 4; X.bar_id = 1;
             X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
-            Sync1 sync3{acc_full, a_ready, 0u, lane, h6_full};
+            Sync1 sync3{acc_full, a_ready, 0u, lane, h6_full, h6_done, 0u};
             TileAhead ahead;
             for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3, ahead, tile + gridDim.x);
         } else {
