@@ -36,9 +36,32 @@ def batchified_composer_call(object_composer: ObjectComposer, ray_origins, ray_d
     return results
 
 
-def install(environment_model, precision: str = "fp16x3"):
+RAY_SELECTION_FUNCTIONS = ("sample_rays", "sample_rays_weighted", "sample_rays_patched", "sample_rays_strided_patch",
+                           "sample_all_rays_strided_grid", "permutation_indices_to_positions")
+
+
+def install_ray_selection(reference_ray_helper=None):
+    """Rebinds the reference's ``RayHelper.sample_rays*`` (utils/lib_3d/ray_helper.py:55-183, 236-482, 611-795; called from
+    EnvironmentModel at model/environment_model.py:951-958, 1109-1116) to the tensorised versions of this package: same
+    results for the same torch RNG state, but no ``.item()`` device->host sync per image and object."""
+    import sys
+    from ..utils.lib_3d.ray_helper import RayHelper as Ours
+    if reference_ray_helper is None:
+        module = sys.modules.get("utils.lib_3d.ray_helper")
+        if module is None:
+            raise Exception("the reference's utils.lib_3d.ray_helper is not imported: pass its RayHelper class explicitly")
+        reference_ray_helper = module.RayHelper
+    for name in RAY_SELECTION_FUNCTIONS:
+        setattr(reference_ray_helper, name, staticmethod(getattr(Ours, name)))
+    return reference_ray_helper
+
+
+def install(environment_model, precision: str = "fp16x3", ray_selection: bool = False):
     """Replaces ``environment_model.object_composer`` (a reference ObjectComposer) by the B200 composer carrying the same
-    parameters, and routes ``batchified_composer_call`` to the single-call version."""
+    parameters, and routes ``batchified_composer_call`` to the single-call version.  ``ray_selection=True`` also rebinds
+    the reference's ray-selection helpers (``install_ray_selection``)."""
+    if ray_selection:
+        install_ray_selection()
     reference = environment_model.object_composer
     config = dict(environment_model.config)
     composer = ObjectComposer(config)

@@ -90,6 +90,191 @@ class RayHelper:
             all_o.append(o.reshape(list(o.shape[:-3]) + [-1, o.size(-1)]))
         return torch.cat(all_d, dim=-2), torch.cat(all_o, dim=-2), torch.cat(all_i, dim=-2)
 
+    # ------------------------------------------------------------------------------------------------------------------
+    # ray selection (reference :55-183, 236-431, 583-795).  Same results as the reference for the same torch RNG state --
+    # the random draws are made per image in the reference's order -- but tensorised over images and objects: no
+    # ``.item()`` device->host sync and no Python loop over pixels, so a training step can stay asynchronous.
+    # ------------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def coordinate_from_flat_index(index, image_width: int):
+        """Reference :583-596."""
+        return index // image_width, index % image_width
+
+    @staticmethod
+    def flat_index_from_coordinate(coordinate, image_width: int):
+        """Reference :598-610."""
+        row, column = coordinate
+        return (row * image_width) + column
+
+    @staticmethod
+    def permutation_indices_to_positions(permutation_indices: torch.Tensor, height: int, width: int) -> torch.Tensor:
+        """Reference :1157-1178: flat pixel indices -> (row / height, column / width)."""
+        rows = permutation_indices // width
+        cols = permutation_indices % width
+        return torch.stack([rows / height, cols / width], dim=-1)
+
+    @staticmethod
+    def _hwc(observations: torch.Tensor) -> torch.Tensor:
+        return observations.movedim(-3, -1)
+
+    @staticmethod
+    def _slice_bound(idx: torch.Tensor, size: int) -> torch.Tensor:
+        """Python slice semantics of ``tensor[a:b]`` for an integer bound (negative values count from the end)."""
+        return torch.where(idx < 0, (idx + size).clamp(min=0), idx.clamp(max=size))
+
+    @staticmethod
+    def bounding_box_weight_masks(bounding_boxes: torch.Tensor, weights: Sequence[float], height: int, width: int) -> torch.Tensor:
+        """Spatial sampling weights of reference :97-123 / :313-338 / :647-674: every object adds
+        ``weights[o] / area(o)`` inside its pixel-aligned (floor/ceil) box.  bounding_boxes (S, 4, objects) normalised
+        (left, top, right, bottom) -> (S, height, width).  Boxes of zero area add nothing (the reference does the same in
+        ``sample_rays_weighted`` and divides by zero in the patch samplers)."""
+        device = bounding_boxes.device
+        left = torch.floor(bounding_boxes[:, 0, :] * width).long()
+        right = torch.ceil(bounding_boxes[:, 2, :] * width).long()
+        top = torch.floor(bounding_boxes[:, 1, :] * height).long()
+        bottom = torch.ceil(bounding_boxes[:, 3, :] * height).long()
+        area = (right - left) * (bottom - top)
+        ys = torch.arange(height, device=device).view(1, height, 1)
+        xs = torch.arange(width, device=device).view(1, 1, width)
+        masks = torch.zeros((bounding_boxes.size(0), height, width), dtype=torch.float32, device=device)
+        for o in range(bounding_boxes.size(-1)):                     # objects in order: same float summation as the reference
+            t0 = RayHelper._slice_bound(top[:, o], height).view(-1, 1, 1)
+            b0 = RayHelper._slice_bound(bottom[:, o], height).view(-1, 1, 1)
+            l0 = RayHelper._slice_bound(left[:, o], width).view(-1, 1, 1)
+            r0 = RayHelper._slice_bound(right[:, o], width).view(-1, 1, 1)
+            inside = (ys >= t0) & (ys < b0) & (xs >= l0) & (xs < r0)
+            a = area[:, o].view(-1, 1, 1)
+            # python float division, rounded to fp32 when added to the mask -- like the reference's ``+=`` of a python scalar
+            value = (float(weights[o]) / a.double().clamp(min=1)).float()
+            masks = masks + torch.where(inside & (a != 0), value, torch.zeros_like(value))
+        return masks
+
+    @staticmethod
+    def _weighted_pixel_samples(masks: torch.Tensor, count: int, cdf_samples: torch.Tensor = None) -> torch.Tensor:
+        """``count`` pixel indices per image drawn from the (S, H, W) weight masks by inverse-CDF sampling (reference
+        :139-148).  The uniform numbers are drawn per image, in order, like the reference's ``torch.rand`` calls."""
+        flat = masks.reshape(masks.size(0), -1)
+        cdf = torch.cumsum(flat / flat.sum(dim=1, keepdim=True), dim=1)
+        if cdf_samples is None:
+            cdf_samples = torch.stack([torch.rand((count,), device=masks.device) for _ in range(masks.size(0))], dim=0)
+        idx = torch.searchsorted(cdf, cdf_samples.contiguous())
+        return torch.clamp(idx, max=cdf.size(1) - 1)
+
+    @staticmethod
+    def _gather_pixels(flat: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """flat (S, H*W, C), idx (S, n) (negative indices count from the end, like python indexing) -> (S, n, C)."""
+        n_pix = flat.size(1)
+        idx = torch.where(idx < 0, idx + n_pix, idx).long()
+        return torch.gather(flat, 1, idx.unsqueeze(-1).expand(-1, -1, flat.size(-1)))
+
+    @staticmethod
+    def sample_rays(ray_directions: torch.Tensor, observations: torch.Tensor, samples_per_image: int):
+        """Reference :730-795: ``samples_per_image`` uniformly chosen rays per image (0 = all rays, natural order)."""
+        lead = list(ray_directions.shape[:-3])
+        height, width = ray_directions.size(-3), ray_directions.size(-2)
+        flat_d = ray_directions.reshape(-1, height * width, 3)
+        flat_o = RayHelper._hwc(observations).reshape(-1, height * width, observations.size(-3))
+        if samples_per_image > 0:
+            perm = torch.stack([torch.randperm(height * width, device=ray_directions.device)[:samples_per_image]
+                                for _ in range(flat_d.size(0))], dim=0)
+            d, o = RayHelper._gather_pixels(flat_d, perm), RayHelper._gather_pixels(flat_o, perm)
+        else:
+            perm = torch.arange(height * width, dtype=ray_directions.dtype, device=ray_directions.device).repeat(flat_d.size(0), 1)
+            d, o = flat_d, flat_o
+        pos = RayHelper.permutation_indices_to_positions(perm, height, width)
+        return TensorFolder.fold(d, lead), TensorFolder.fold(o, lead), TensorFolder.fold(pos, lead)
+
+    @staticmethod
+    def sample_rays_weighted(ray_directions: torch.Tensor, observations: torch.Tensor, samples_per_image: int,
+                             bounding_boxes: torch.Tensor, weights: Sequence[float], cdf_samples: torch.Tensor = None):
+        """Reference :611-728: rays drawn in proportion to the per-object bounding-box weights."""
+        if samples_per_image <= 0:
+            return RayHelper.sample_rays(ray_directions, observations, 0)
+        lead = list(ray_directions.shape[:-3])
+        height, width = ray_directions.size(-3), ray_directions.size(-2)
+        flat_d = ray_directions.reshape(-1, height * width, 3)
+        flat_o = RayHelper._hwc(observations).reshape(-1, height * width, observations.size(-3))
+        boxes = bounding_boxes.reshape(-1, bounding_boxes.size(-2), bounding_boxes.size(-1))
+        masks = RayHelper.bounding_box_weight_masks(boxes, weights, height, width)
+        idx = RayHelper._weighted_pixel_samples(masks, samples_per_image, cdf_samples)
+        pos = RayHelper.permutation_indices_to_positions(idx, height, width)
+        return (TensorFolder.fold(RayHelper._gather_pixels(flat_d, idx), lead), TensorFolder.fold(RayHelper._gather_pixels(flat_o, idx), lead),
+                TensorFolder.fold(pos, lead))
+
+    @staticmethod
+    def sample_rays_patched(ray_directions: torch.Tensor, observations: torch.Tensor, patch_size: int, patch_count: int,
+                            bounding_boxes: torch.Tensor, weights: Sequence[float], cdf_samples: torch.Tensor = None):
+        """Reference :55-183: ``patch_count`` dense patch_size x patch_size patches per image around weighted centres."""
+        if patch_size % 2 != 0:
+            raise Exception("Patch size must be a multiple of 2")
+        lead = list(ray_directions.shape[:-3])
+        height, width = ray_directions.size(-3), ray_directions.size(-2)
+        flat_d = ray_directions.reshape(-1, height * width, 3)
+        flat_o = RayHelper._hwc(observations).reshape(-1, height * width, observations.size(-3))
+        boxes = bounding_boxes.reshape(-1, bounding_boxes.size(-2), bounding_boxes.size(-1))
+        masks = RayHelper.bounding_box_weight_masks(boxes, weights, height, width)
+        centre = RayHelper._weighted_pixel_samples(masks, patch_count, cdf_samples)              # (S, patches)
+        half = patch_size // 2
+        row = (centre // width).clamp(min=half).clamp(max=height - half) - half
+        col = (centre % width).clamp(min=half).clamp(max=width - half) - half
+        off = torch.arange(patch_size, device=centre.device)
+        rows = row.unsqueeze(-1) + off                                                                # (S, patches, ps)
+        cols = col.unsqueeze(-1) + off
+        idx = (rows.unsqueeze(-1) * width + cols.unsqueeze(-2)).reshape(centre.size(0), -1)
+        return TensorFolder.fold(RayHelper._gather_pixels(flat_d, idx), lead), TensorFolder.fold(RayHelper._gather_pixels(flat_o, idx), lead)
+
+    @staticmethod
+    def sample_rays_strided_patch(ray_directions: torch.Tensor, observations: torch.Tensor, patch_size: int, strides,
+                                  bounding_boxes: torch.Tensor, weights: Sequence[float], align_grid=False,
+                                  cdf_samples: torch.Tensor = None):
+        """Reference :236-431: one multi-stride patch per image.  The patch centre is drawn from the bounding-box weights,
+        moved inside the image and snapped so that every sampled ray is the centre pixel of a (stride x stride) cell; the
+        samples of each stride (smallest first, ``patch_size * strides[0] / stride`` per side) are concatenated."""
+        if not align_grid:
+            raise Exception("Align grid is required for patched ray sampling.")
+        if patch_size % 2 != 0:
+            raise Exception("Patch size must be a multiple of 2")
+        if not isinstance(strides, (list, tuple)):
+            strides = [strides]
+        smallest, biggest = strides[0], strides[-1]
+        if (patch_size * smallest) % (2 * biggest) != 0:
+            raise Exception("Patch size is not compatible with the chosen strides. Make patch size divisible by a higher power of 2")
+        patch_sizes = [(patch_size * smallest) // s for s in strides]
+        half = patch_sizes[-1] // 2                                   # half patch size at the biggest stride
+
+        lead = list(ray_directions.shape[:-3])
+        height, width = ray_directions.size(-3), ray_directions.size(-2)
+        device = ray_directions.device
+        flat_d = ray_directions.reshape(-1, height * width, 3)
+        flat_o = RayHelper._hwc(observations).reshape(-1, height * width, observations.size(-3))
+        boxes = bounding_boxes.reshape(-1, bounding_boxes.size(-2), bounding_boxes.size(-1))
+        masks = RayHelper.bounding_box_weight_masks(boxes, weights, height, width)
+        centre = RayHelper._weighted_pixel_samples(masks, 1, cdf_samples)[:, 0]                     # (S,)
+
+        backward_map = torch.tensor(list(range(biggest // 2, biggest)) + list(range(0, biggest // 2)), device=device)
+        forward_map = torch.tensor(list(range(biggest // 2 + biggest, biggest, -1)) + [0] + list(range(biggest - 1, biggest // 2, -1)),
+                                   device=device)
+
+        def start_of(c: torch.Tensor, size: int) -> torch.Tensor:
+            c = c.clamp(min=half * biggest).clamp(max=size - biggest * (half - 1) - 1)            # keep the patch inside the image
+            start = c - half * biggest
+            diff = start % biggest                                                                 # snap to the cell centres
+            moved = torch.where(start >= biggest // 2, start - backward_map[diff], start + forward_map[diff])
+            return torch.where(diff != biggest // 2, moved, start)
+
+        start_row, start_col = start_of(centre // width, height), start_of(centre % width, width)
+        all_idx = []
+        for s, ps in zip(strides, patch_sizes):
+            offset = biggest // 2 - s // 2
+            steps = torch.arange(ps, device=device) * s
+            rows = (start_row - offset).unsqueeze(-1) + steps                                      # (S, ps)
+            cols = (start_col - offset).unsqueeze(-1) + steps
+            all_idx.append((rows.unsqueeze(-1) * width + cols.unsqueeze(-2)).reshape(centre.size(0), -1))
+        idx = torch.cat(all_idx, dim=1)
+        pos = RayHelper.permutation_indices_to_positions(idx.int(), height, width)
+        return (TensorFolder.fold(RayHelper._gather_pixels(flat_d, idx), lead), TensorFolder.fold(RayHelper._gather_pixels(flat_o, idx), lead),
+                TensorFolder.fold(pos, lead))
+
     @staticmethod
     def fold_strided_grid_samples(samples: torch.Tensor, strides, original_size: Tuple[int], dim: int) -> List[torch.Tensor]:
         """Reference :484-531 (views only)."""

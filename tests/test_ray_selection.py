@@ -1,0 +1,70 @@
+"""Ray selection: the tensorised, sync-free mirror of the reference's RayHelper.sample_rays* against golden outputs
+of the upstream functions (tests/golden/make_golden_rays.py) for the same torch RNG seed.  Index work: bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.dirname(HERE), os.path.join(HERE, "golden")]
+from make_golden_rays import ray_cases  # noqa: E402
+from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper  # noqa: E402
+
+GOLDEN = np.load(os.path.join(HERE, "golden", "ray_selection.npz"))
+CASES = ray_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_the_reference_bit_exactly(name):
+    fn, seed, kwargs = CASES[name]
+    torch.manual_seed(seed)
+    res = getattr(RayHelper, fn)(**kwargs)
+    for i, t in enumerate(res):
+        want = GOLDEN[f"{name}/{i}"]
+        assert tuple(t.shape) == want.shape, (name, i, t.shape, want.shape)
+        np.testing.assert_array_equal(t.numpy(), want, err_msg=f"{name} output {i}")
+
+
+def test_strided_patch_rays_are_cell_centres_inside_the_image():
+    fn, seed, kwargs = CASES["strided_patch_tennis_like"]
+    torch.manual_seed(99)
+    _, _, pos = RayHelper.sample_rays_strided_patch(**kwargs)
+    h, w = kwargs["ray_directions"].shape[-3:-1]
+    splits = RayHelper.split_strided_patch_ray_samples(pos, kwargs["patch_size"], kwargs["strides"])
+    for stride, p in zip(kwargs["strides"], splits):
+        rows = (p[..., 0] * h).round().long()
+        cols = (p[..., 1] * w).round().long()
+        assert ((rows % stride) == stride // 2).all() and ((cols % stride) == stride // 2).all()
+        assert (rows >= 0).all() and (rows < h).all() and (cols >= 0).all() and (cols < w).all()
+
+
+def test_explicit_uniform_numbers_replace_the_generator():
+    fn, seed, kwargs = CASES["weighted"]
+    u = torch.rand((4, 200), generator=torch.Generator().manual_seed(5))
+    a = RayHelper.sample_rays_weighted(**kwargs, cdf_samples=u)
+    b = RayHelper.sample_rays_weighted(**kwargs, cdf_samples=u)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_argument_errors_match_the_reference():
+    fn, seed, kwargs = CASES["strided_patch_2strides"]
+    with pytest.raises(Exception, match="Align grid"):
+        RayHelper.sample_rays_strided_patch(**{**kwargs, "align_grid": False})
+    with pytest.raises(Exception, match="multiple of 2"):
+        RayHelper.sample_rays_strided_patch(**{**kwargs, "patch_size": 7})
+    with pytest.raises(Exception, match="not compatible"):
+        RayHelper.sample_rays_strided_patch(**{**kwargs, "patch_size": 2})
+
+
+def test_install_ray_selection_rebinds_a_reference_style_class():
+    from playableenvironments_b200.model.environment_model_glue import install_ray_selection, RAY_SELECTION_FUNCTIONS
+
+    class FakeReferenceRayHelper:          # stands in for the upstream class (not importable on the GPU box)
+        pass
+
+    install_ray_selection(FakeReferenceRayHelper)
+    for name in RAY_SELECTION_FUNCTIONS:
+        assert getattr(FakeReferenceRayHelper, name) is getattr(RayHelper, name)
