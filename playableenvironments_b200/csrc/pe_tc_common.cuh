@@ -494,11 +494,11 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
                 }
                 acc += a0 + a1;
                 if ((col0 + 32) % P == 0 || q == CW / 32 - 1) {          // last chunk of a ray (or of this thread's share of it)
-                    const int rl = col0 / P;
+                    const int rl = col0 / P;                // rl == rpt: the unused tail rows of the tile (128 % P != 0)
                     const int r = ray0 + rl;
                     if (kSplit == 1) {
-                        if (tile_valid && r < A.rays) A.fold_v[((int64_t)img * A.rays + r) * FOLD_K + c] = acc;
-                    } else {
+                        if (tile_valid && rl < rpt && r < A.rays) A.fold_v[((int64_t)img * A.rays + r) * FOLD_K + c] = acc;
+                    } else if (rl < rpt) {
                         part[(hf * 4 + rl) * FOLD_K + c] = acc;
                     }
                     acc = 0.f;
