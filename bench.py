@@ -175,6 +175,40 @@ def train_step_report(device, dense: bool):
             "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3), "precision": "fp32 (CUDA cores)"}
 
 
+def eval_frame_report(device, dense: bool):
+    """BASELINE configs[2] scene in EVAL mode (what play.py renders): court + 2 players with ray benders, forward only.
+    Players: exact fp32 sampling + ray-bender pre-pass, field on the tensor cores over the non-empty tiles; beside it the same
+    frame with the players' field on the fp32 CUDA-core kernel (PE_TC_PREPASS=0)."""
+    import scenes
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+    scene = scenes.scene_tennis(seed=13, height=144, width=256, stride=1, lead=(1, 1, 1), dense=dense)
+
+    def timed(precision, reps=5):
+        _, _, _, comp, dev = build_composer(scene, precision, device=device)
+        call = [dev[k] for k in INPUT_KEYS]
+        with torch.no_grad():
+            comp(*call, False)
+            torch.cuda.synchronize()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(reps):
+                comp(*call, False)
+            e0.record()
+            torch.cuda.synchronize()
+        return s0.elapsed_time(e0) / reps
+
+    out = {"workload": f"cfg3 Tennis{' (dense)' if dense else ''}, eval forward, 256x144 rays, court P=4 + 2 players P=32 with ray benders"}
+    for precision in ("fp16x3", "fp16"):
+        out[f"{precision}_ms"] = timed(precision)
+    os.environ["PE_TC_PREPASS"] = "0"
+    try:
+        out["players_on_fp32_field_ms"] = timed("fp16x3")
+    finally:
+        del os.environ["PE_TC_PREPASS"]
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from helpers import INPUT_KEYS
@@ -328,6 +362,7 @@ def run_b200(args):
         }
         if world == 1 and not args.quick:
             line["train_step"] = [train_step_report(device, False), train_step_report(device, True)]
+            line["eval_frame"] = [eval_frame_report(device, False), eval_frame_report(device, True)]
         if modes:
             line["other_modes"] = modes
         if parity:

@@ -58,7 +58,9 @@ extern "C" int pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* pa
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct ObjWorkspace {
-    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s;
+    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s, *bent;
+    uint8_t* flags;
+    int32_t *tile_list, *tile_count;
     uint8_t* inbox;
     double* stats;
 };
@@ -70,6 +72,14 @@ struct Workspace {
 
 static bool object_uses_tc(const PeScene& s, int k) {
     return s.precision != PE_PRECISION_FP32 && !s.training && !s.explicit_positions && pe_tc_shape_ok(s.object[k]);
+}
+
+// Objects with a positional ray bender: sampling + bender run as an exact fp32 pre-pass, the field runs on the tensor cores over
+// the non-empty tiles only, the compositor integrates the object.  PE_TC_PREPASS=0 sends them to the fp32 field kernel instead.
+static bool object_uses_prepass(const PeScene& s, int k) {
+    const char* env = getenv("PE_TC_PREPASS");
+    if (env && atoi(env) == 0) return false;
+    return s.precision != PE_PRECISION_FP32 && !s.training && !s.explicit_positions && pe_tc_prepass_ok(s.object[k]);
 }
 
 // per-sample features are only materialised where something downstream reads them
@@ -106,6 +116,12 @@ static Workspace carve(const PeScene& s, void* base) {
         const bool fold = object_folds_head(s, k);
         o.fold_v = fold ? (float*)take((size_t)s.images * s.rays * 128 * 4) : nullptr;
         o.fold_s = fold ? (float*)take((size_t)s.images * s.rays * 4) : nullptr;
+        const bool prepass = object_uses_prepass(s, k);
+        const size_t rpt = 128 / P, tiles = ((size_t)s.rays + rpt - 1) / rpt * (size_t)s.images;
+        o.bent = prepass ? (float*)take(n * 12) : nullptr;
+        o.flags = prepass ? (uint8_t*)take(n) : nullptr;
+        o.tile_list = prepass ? (int32_t*)take(tiles * 4) : nullptr;
+        o.tile_count = prepass ? (int32_t*)take(4) : nullptr;
         o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
         o.aff2 = (float*)take((size_t)s.images * d.width * 4);
         o.stats = (double*)take((size_t)(3 * d.width + 4) * 8);
@@ -194,9 +210,22 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         s2.channels = d.width / 2; s2.aff_w = P32(L.aff2_w); s2.aff_b = P32(L.aff2_b);
         s2.run_mean = P32(L.bn2_mean); s2.run_var = P32(L.bn2_var); s2.stats = o.stats + 2 * d.width + 2; s2.out = o.aff2; s2.running_out = o.run2;
 
+        const bool prepass = object_uses_prepass(s, k);
         auto launch_field = [&](int phase) {
             fa.phase = phase;
             const PeIntegrated none = {};
+            if (prepass) {
+                // 1. exact fp32 sampling + ray bender: t, bent positions, masks, displacements; empty-space values everywhere
+                PeFieldArgs pre = fa;
+                pre.phase = PE_PHASE_PREPASS; pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
+                int rc2 = pe_launch_field_fp32(pre, sm_count, stream); if (rc2) return rc2;
+                // 2. which tiles hold a sample to evaluate
+                rc2 = pe_launch_tile_list(pre, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
+                // 3. the field on the tensor cores over those tiles (the compositor integrates the object)
+                PeFieldArgs tcargs = pre;
+                tcargs.phase = 0; tcargs.tile_list = o.tile_list; tcargs.tile_count = o.tile_count;
+                return pe_launch_field_tc(tcargs, none, sm_count, stream);
+            }
             if (!tc) return pe_launch_field_fp32(fa, sm_count, stream);
             const PeIntegrated& gout = (s.objects == 1 && !s.perturb) ? out->global : none;
             // PE_TC_KERNEL=1 selects the single-CTA lockstep kernel, 2 (default) the CTA-pair ping-pong kernel

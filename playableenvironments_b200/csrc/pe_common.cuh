@@ -68,12 +68,17 @@ struct PeLayout {
 __host__ __device__ inline int64_t pe_min64(int64_t a, int64_t b) { return a < b ? a : b; }
 __host__ __device__ inline int64_t pe_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-// Shapes handled by the tcgen05 fused kernel (pe_field_tc.cu): the shipped field
+// Field shapes handled by the tcgen05 kernel (pe_field_tc.cu): the shipped field
 // (configs/tennis/193_*.yaml:141-163, configs/minecraft/013_*.yaml:138-160).
-__host__ __device__ inline bool pe_tc_shape_ok(const PeObjectDesc& d) {
-    return d.nerf_kind == PE_NERF_ADAIN && d.bender_kind == PE_BENDER_ZEROED && d.width == 256 && d.layers == 8 &&
-           d.skip == 4 && d.octaves == 10 && d.features == 192 && d.positions >= 1 && d.positions <= 128;
+__host__ __device__ inline bool pe_tc_field_ok(const PeObjectDesc& d) {
+    return d.nerf_kind == PE_NERF_ADAIN && d.width == 256 && d.layers == 8 && d.skip == 4 && d.octaves == 10 && d.features == 192 &&
+           d.positions >= 1 && d.positions <= 128;
 }
+// ... fully fused (sampling inside the kernel): objects without a ray bender
+__host__ __device__ inline bool pe_tc_shape_ok(const PeObjectDesc& d) { return pe_tc_field_ok(d) && d.bender_kind == PE_BENDER_ZEROED; }
+// ... behind the sampling / ray-bender pre-pass (pe_field_fp32.cu, phase PE_PHASE_PREPASS): objects with a positional ray bender
+__host__ __device__ inline bool pe_tc_prepass_ok(const PeObjectDesc& d) { return pe_tc_field_ok(d) && d.bender_kind == PE_BENDER_POSITIONAL; }
+#define PE_PHASE_PREPASS 3                    // fp32 field kernel: sampling + ray bender only (bent positions, flags, displacements)
 
 #define PE_TC_SLAB_K 32                       // K elements per streamed weight slab
 // number of K=32 slabs of one weight pass of the shipped field:
@@ -123,7 +128,7 @@ __host__ __device__ inline PeLayout pe_layout(const PeObjectDesc& d) {
         }
         L.bd_out_w = take((int64_t)d.b_width * 3);
     }
-    L.tc_supported = pe_tc_shape_ok(d) ? 1 : 0;
+    L.tc_supported = pe_tc_field_ok(d) ? 1 : 0;
     if (L.tc_supported) {
         L.tc_bytes_per_pass = pe_tc_pass_bytes();
         L.tc_base = off;

@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(NT, 1) pe_field_fp32_kernel(const PeFieldArgs 
         }
         const int any_inbox = __syncthreads_or(tid < TM ? (S.flags[tid] & 1) : 0);
         if (!any_inbox) {   // whole tile is empty space: features 0 (never read), alpha = empty_space_alpha
-            if (tid < TM && (S.flags[tid] & 4) && A.phase == 0) {
+            if (tid < TM && (S.flags[tid] & 4) && (A.phase == 0 || A.phase == PE_PHASE_PREPASS)) {
                 const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
                 A.raw_out[gs] = ob.empty_space_alpha;
                 A.inbox_out[gs] = 0;
+                if (A.phase == PE_PHASE_PREPASS) A.flags[gs] = 0;
                 if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
                 if (A.disp_out) { A.disp_out[gs * 3] = 0.f; A.disp_out[gs * 3 + 1] = 0.f; A.disp_out[gs * 3 + 2] = 0.f; }
             }
@@ -257,6 +258,26 @@ __global__ void __launch_bounds__(NT, 1) pe_field_fp32_kernel(const PeFieldArgs 
             S.flags[tid] = f;
         }
         __syncthreads();
+        if (A.phase == PE_PHASE_PREPASS) {
+            // sampling + ray bender only: the field itself runs on the tensor cores (pe_field_tc.cu) over the tiles that hold
+            // at least one sample whose bent position is in the box; everything else keeps the empty-space values set here
+            if (tid < TM && (S.flags[tid] & 4)) {
+                const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
+                const int f = S.flags[tid];
+                A.raw_out[gs] = ob.empty_space_alpha;
+                A.inbox_out[gs] = 0;
+                A.flags[gs] = (uint8_t)(f & 3);
+                float d2 = 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    const float dsp = (f & 1) ? S.aux[(6 + c) * TM + tid] : 0.f;
+                    if (A.disp_out) A.disp_out[gs * 3 + c] = dsp;
+                    d2 += dsp * dsp;
+                    A.bent[gs * 3 + c] = S.bent[c * TM + tid];
+                }
+                if (A.dispmag_out) A.dispmag_out[gs] = sqrtf(d2);
+            }
+            continue;
+        }
 
         // ---- 3. positional encoding (positional_encoder.py:41-65) ------------------------------
         for (int idx = tid; idx < L.enc * TM; idx += NT) {

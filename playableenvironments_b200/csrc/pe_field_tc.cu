@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     const int P = ob.positions;
     const int rpt = TILE_M / P;                                   // rays per tile
     const int tiles_per_image = (A.rays + rpt - 1) / rpt;
-    const int64_t total_tiles = (int64_t)tiles_per_image * A.images;
+    // pre-pass mode: the kernel walks the list of non-empty tiles built on the device
+    const int64_t total_tiles = A.tile_count ? (int64_t)__ldg(A.tile_count) : (int64_t)tiles_per_image * A.images;
     const int64_t total_pairs = x3 ? total_tiles : (total_tiles + 1) / 2;        // iterations of this kernel
     const int num_layers = fold ? NUM_LAYERS - 1 : NUM_LAYERS;
 
@@ -322,6 +323,29 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
 }
 
 // ------------------------------------------------------------------------------------------------------
+// pre-pass mode: list of the tiles (floor(128/P) rays each) that hold at least one sample to evaluate
+// ------------------------------------------------------------------------------------------------------
+__global__ void pe_tile_list_kernel(const uint8_t* __restrict__ flags, int rays, int P, int rpt, int tiles_per_image, int64_t total_tiles,
+                                    int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool any = false;
+    if (tile < total_tiles) {
+        const int img = (int)(tile / tiles_per_image);
+        const int ray0 = (int)(tile - (int64_t)img * tiles_per_image) * rpt;
+        const int n = min(rpt, rays - ray0) * P;
+        const uint8_t* f = flags + ((int64_t)img * rays + ray0) * P;
+        for (int i = 0; i < n && !any; ++i) any = (f[i] & 2) != 0;
+    }
+    // one atomic per warp; the order of the list does not matter (tiles are independent)
+    const unsigned mask = __ballot_sync(0xffffffffu, any);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && mask) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (any) list[base + __popc(mask & ((1u << lane) - 1))] = (int32_t)tile;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // weight packing into the slab stream
 // ------------------------------------------------------------------------------------------------------
 // slab element (n, kk) lives at (kk/8)*(N*16) + (n/8)*128 + (n%8)*16 + (kk%8)*2  (K-major, no swizzle)
@@ -473,9 +497,14 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
 }
 
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream) {
-    if (!pe_tc_shape_ok(args.ob) || args.training || args.explicit_positions || args.phase != 0) {
+    const bool prepass = args.bent != nullptr;
+    if (!(prepass ? pe_tc_prepass_ok(args.ob) : pe_tc_shape_ok(args.ob)) || args.training || args.explicit_positions || args.phase != 0) {
         pe_set_error("tensor-core field kernel: unsupported configuration");
         return PE_ERR_UNSUPPORTED;
+    }
+    if (prepass && (!args.flags || !args.tile_list || !args.tile_count || !args.t_out || !args.feat_out || !args.raw_out || args.fold_v)) {
+        pe_set_error("tensor-core field kernel: incomplete pre-pass hand-off");
+        return PE_ERR_INVALID;
     }
     const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
     const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
@@ -492,6 +521,18 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     const int grid = (int)pe_min64(pairs, sm_count);
     pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
+    return PE_OK;
+}
+
+int pe_launch_tile_list(const PeFieldArgs& args, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream) {
+    const int rpt = TILE_M / args.ob.positions;
+    const int tiles_per_image = (args.rays + rpt - 1) / rpt;
+    const int64_t tiles = (int64_t)tiles_per_image * args.images;
+    PE_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, sizeof(int32_t), stream));
+    if (tiles == 0) return PE_OK;
+    pe_tile_list_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, stream>>>(args.flags, args.rays, args.ob.positions, rpt, tiles_per_image, tiles,
+                                                                             tile_list, tile_count);
+    PE_LAUNCH_CHECK("pe_tile_list_kernel");
     return PE_OK;
 }
 

@@ -31,6 +31,12 @@ struct PeFieldArgs {
     // folded-head mode of the tcgen05 kernel (both or neither): per-ray weighted sums of the last hidden layer
     float* fold_v;               // [images][rays][128]
     float* fold_s;               // [images][rays]
+    // pre-pass hand-off (objects with a ray bender on the tcgen05 path): written by the fp32 kernel in phase PE_PHASE_PREPASS,
+    // read by the tcgen05 kernel, which then evaluates only the listed (non-empty) tiles
+    float* bent;                 // [images][rays][P][3] bent sample positions (object space)
+    uint8_t* flags;              // [images][rays][P]    bit 0: in the box, bit 1: bent position in the box (field evaluated)
+    const int32_t* tile_list;    // [*tile_count] tiles (of floor(128/P) rays) that hold at least one sample with bit 1
+    const int32_t* tile_count;
 };
 
 // Arguments of the compositing kernel (model/object_composer.py:399-447, 724-784).
@@ -136,6 +142,7 @@ int pe_launch_geometry_bwd(const PeGeometryBwdArgs& args, cudaStream_t stream);
 size_t pe_field_fp32_smem_bytes(const PeObjectDesc& ob, const PeLayout& L);
 int pe_launch_field_fp32(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
+int pe_launch_tile_list(const PeFieldArgs& args, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream);
 int pe_launch_field_tc2(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream);
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream);

@@ -204,6 +204,7 @@ __device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSa
     const PeObjectDesc& ob = A.ob;
     const int m = X.m, P = X.P, rpt = X.rpt;
     s.tile_valid = tile < X.total_tiles;
+    if (s.tile_valid && A.tile_list) tile = A.tile_list[tile];            // pre-pass mode: only the non-empty tiles are listed
     s.img = s.tile_valid ? (int)(tile / X.tiles_per_image) : 0;
     s.ray0 = s.tile_valid ? (int)(tile - (int64_t)s.img * X.tiles_per_image) * rpt : 0;
     s.valid = false; s.inbox = false;
@@ -218,11 +219,19 @@ __device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSa
             s.p = m - rl * P;
             s.ray = (int64_t)s.img * A.rays + r;
             const float* dw = A.dirs + s.ray * 3;
-            const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)s.img * A.objects + A.k) * 12, A.origins + (int64_t)s.img * 3, dw, s.in_scene);
-            const float u = A.perturb ? A.rand[s.ray * P + s.p] : 0.f;
-            s.t = pe_sample_t(pr, s.p, P, A.perturb != 0, u);
-            pe_position(pr, s.t, s.x);
-            s.inbox = pe_in_box(ob, s.x);
+            if (A.bent) {
+                // sampled (and bent) by the pre-pass: position, parameter t and masks come from memory
+                const int64_t gs = s.ray * P + s.p;
+                s.inbox = (A.flags[gs] & 2) != 0;
+                s.t = A.t_out[gs];
+                if (s.inbox) { s.x[0] = A.bent[gs * 3]; s.x[1] = A.bent[gs * 3 + 1]; s.x[2] = A.bent[gs * 3 + 2]; }
+            } else {
+                const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)s.img * A.objects + A.k) * 12, A.origins + (int64_t)s.img * 3, dw, s.in_scene);
+                const float u = A.perturb ? A.rand[s.ray * P + s.p] : 0.f;
+                s.t = pe_sample_t(pr, s.p, P, A.perturb != 0, u);
+                pe_position(pr, s.t, s.x);
+                s.inbox = pe_in_box(ob, s.x);
+            }
             s.dnorm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dw[0], dw[0]), __fmul_rn(dw[1], dw[1])), __fmul_rn(dw[2], dw[2])));
         }
     }
@@ -351,9 +360,9 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         float raw = (inbox && in_scene) ? raw_alpha_v : ob.empty_space_alpha;
         if (valid && hf == 0) {
             if (A.raw_out) A.raw_out[gs] = raw;
-            if (A.t_out) A.t_out[gs] = t;
+            if (A.t_out && !A.bent) A.t_out[gs] = t;
             if (A.inbox_out) A.inbox_out[gs] = inbox ? 1 : 0;
-            if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
+            if (A.dispmag_out && !A.bent) A.dispmag_out[gs] = 0.f;
         }
         float alpha = 0.f;
         if (valid) {

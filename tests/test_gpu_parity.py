@@ -142,6 +142,32 @@ def test_folded_head_equals_per_sample_head(monkeypatch):
             assert scale_rel_err(a[k], b[k]) < 1e-4, (k, scale_rel_err(a[k], b[k]))
 
 
+@pytest.mark.parametrize("name", ["tennis_small", "tennis_dense", "tennis_anneal", "minecraft_small"])
+def test_ray_bender_prepass_path_equals_fp32_field(name, monkeypatch):
+    """Objects with a positional ray bender: exact fp32 sampling + bender pre-pass, field on the tensor cores over the non-empty
+    tiles (fp16x3: fp32-class) -- against the same scene with those objects on the fp32 field kernel (PE_TC_PREPASS=0)."""
+    _, _, _, comp, dev = _build(name, "fp16x3")
+    a = flatten(_run(comp, dev))
+    monkeypatch.setenv("PE_TC_PREPASS", "0")
+    _, _, _, comp2, dev2 = _build(name, "fp16x3")
+    b = flatten(_run(comp2, dev2))
+    assert set(a) == set(b)
+    for k in b:
+        if k.startswith("coarse/") and "disparity" not in k:
+            assert scale_rel_err(a[k], b[k]) < 2e-4, (k, scale_rel_err(a[k], b[k]))
+
+
+def test_ray_bender_prepass_launches(monkeypatch):
+    """Tennis frame: court = 2 style prologues + fused kernel; each player = pre-pass + tile list + 2 style prologues + tensor-core
+    field; one compositor launch."""
+    from playableenvironments_b200.model import render
+    _, _, _, comp, dev = _build("tennis_small", "fp16x3")
+    _run(comp, dev)
+    render.take_launch_count()
+    _run(comp, dev)
+    assert render.take_launch_count() == 3 + 2 * 5 + 1
+
+
 def test_tensor_core_path_with_perturbation():
     from gpu_common import build_composer
     scene = scenes.scene_static(seed=21, height=8, width=8, P=128)
