@@ -215,15 +215,33 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
             fa.phase = phase;
             const PeIntegrated none = {};
             if (prepass) {
-                // 1. exact fp32 sampling + ray bender: t, bent positions, masks, displacements; empty-space values everywhere
                 PeFieldArgs pre = fa;
-                pre.phase = PE_PHASE_PREPASS; pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
-                int rc2 = pe_launch_field_fp32(pre, sm_count, stream); if (rc2) return rc2;
+                pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
+                pre.tile_list = o.tile_list; pre.tile_count = o.tile_count;
+                int rc2;
+                // The bender's output feeds 2^9-octave Fourier features (x2pi/size: an absolute error e of the normalised
+                // displacement becomes a phase error of 3217 e), so the tensor-core bender (hi/lo split, all four partial products,
+                // but the tensor core's own fp32 accumulation) lands at ~3e-4 of the reference on the rendered outputs: used in the
+                // performance modes (fp16, fp16x2); the parity-first mode (fp16x3) keeps the exact fp32 bender.  PE_TC_BENDER=0/1 forces.
+                const char* benv = getenv("PE_TC_BENDER");
+                const bool tc_bender = benv ? atoi(benv) != 0 : s.precision != PE_PRECISION_FP16X3;
+                if (pe_tc_bender_ok(d) && tc_bender) {
+                    // 1a. exact fp32 sampling: t, positions, outer mask; empty-space values everywhere
+                    pre.phase = PE_PHASE_SAMPLE;
+                    rc2 = pe_launch_field_fp32(pre, sm_count, stream); if (rc2) return rc2;
+                    // 1b. the ray bender on the tensor cores (fp16x3: fp32-class) over the tiles with samples inside the box
+                    rc2 = pe_launch_tile_list(pre, 1, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
+                    rc2 = pe_launch_bender_tc(pre, sm_count, stream); if (rc2) return rc2;
+                } else {
+                    // 1. exact fp32 sampling + ray bender: t, bent positions, masks, displacements; empty-space values everywhere
+                    pre.phase = PE_PHASE_PREPASS;
+                    rc2 = pe_launch_field_fp32(pre, sm_count, stream); if (rc2) return rc2;
+                }
                 // 2. which tiles hold a sample to evaluate
-                rc2 = pe_launch_tile_list(pre, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
+                rc2 = pe_launch_tile_list(pre, 2, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
                 // 3. the field on the tensor cores over those tiles (the compositor integrates the object)
                 PeFieldArgs tcargs = pre;
-                tcargs.phase = 0; tcargs.tile_list = o.tile_list; tcargs.tile_count = o.tile_count;
+                tcargs.phase = 0;
                 return pe_launch_field_tc(tcargs, none, sm_count, stream);
             }
             if (!tc) return pe_launch_field_fp32(fa, sm_count, stream);

@@ -61,6 +61,8 @@ struct PeLayout {
     int64_t tc_base;                // start of the fp16 slab stream (0 if the shape is unsupported)
     int64_t tc_bytes_per_pass;      // bytes of one weight pass (hi); lo pass follows at +tc_bytes_per_pass
     int64_t tc2_base;               // same stream in the CTA-pair layout (pe_field_tc2.cu): [hi pass | lo pass]
+    int64_t tcb_base;               // ray-bender slab stream [hi pass | lo pass] (0 if the bender shape is unsupported)
+    int64_t tcb_bytes_per_pass;
     int32_t tc_supported;
     int64_t total;
 };
@@ -79,6 +81,15 @@ __host__ __device__ inline bool pe_tc_shape_ok(const PeObjectDesc& d) { return p
 // ... behind the sampling / ray-bender pre-pass (pe_field_fp32.cu, phase PE_PHASE_PREPASS): objects with a positional ray bender
 __host__ __device__ inline bool pe_tc_prepass_ok(const PeObjectDesc& d) { return pe_tc_field_ok(d) && d.bender_kind == PE_BENDER_POSITIONAL; }
 #define PE_PHASE_PREPASS 3                    // fp32 field kernel: sampling + ray bender only (bent positions, flags, displacements)
+#define PE_PHASE_SAMPLE 4                     // fp32 field kernel: sampling only (positions, outer mask); the bender runs on tcgen05
+// Ray-bender shape handled by the tcgen05 bender kernel: the shipped one (configs/tennis/193_*.yaml:165-178: 6 x 128, skip at 3,
+// 6 octaves, 32 deformation features)
+__host__ __device__ inline bool pe_tc_bender_ok(const PeObjectDesc& d) {
+    return d.bender_kind == PE_BENDER_POSITIONAL && d.b_width == 128 && d.b_layers == 6 && d.b_skip == 3 && d.b_octaves == 6 &&
+           d.deformation_features == 32;
+}
+// bytes of one weight pass of the bender stream: L0 (K=96): 3 slabs; L1,2,4,5: 4; L3 (K=224): 7; out (N=16): 4; 6 bias slabs
+__host__ __device__ inline int64_t pe_tcb_pass_bytes() { return (3LL + 16 + 7) * 128 * 32 * 2 + 4LL * 16 * 32 * 2 + 6LL * 128 * 32; }
 
 #define PE_TC_SLAB_K 32                       // K elements per streamed weight slab
 // number of K=32 slabs of one weight pass of the shipped field:
@@ -135,6 +146,11 @@ __host__ __device__ inline PeLayout pe_layout(const PeObjectDesc& d) {
         off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
         L.tc2_base = off;
         off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
+    }
+    if (L.tc_supported && pe_tc_bender_ok(d)) {
+        L.tcb_bytes_per_pass = pe_tcb_pass_bytes();
+        L.tcb_base = off;
+        off = pe_align_up(off + 2 * L.tcb_bytes_per_pass, 256);
     }
     L.total = off;
     return L;
@@ -200,6 +216,22 @@ __device__ __forceinline__ float pe_sample_t(const PeRay& ray, int p, int P, boo
 __device__ __forceinline__ void pe_position(const PeRay& ray, float t, float x[3]) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(ray.o[a], __fmul_rn(ray.d[a], t));
+}
+
+__device__ __forceinline__ float pe_sincos_feature(float x, int fn) { return fn ? cosf(x) : sinf(x); }
+
+// Fourier features, layout of model/positional_encoder.py:41-65: [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...],
+// each block `dims` wide; optional per-octave weight (annealable_positional_encoder.py:54-76).
+__device__ __forceinline__ float pe_encoding_value(const float* x, int dims, int e, const float* anneal) {
+    if (e < dims) return x[e];
+    const int q = e - dims;
+    const int oct = q / (2 * dims);
+    const int rem = q - oct * 2 * dims;
+    const int fn = rem / dims;
+    const int dim = rem - fn * dims;
+    float v = pe_sincos_feature(__fmul_rn(exp2f((float)oct), x[dim]), fn);
+    if (anneal) v = __fmul_rn(v, anneal[oct]);
+    return v;
 }
 
 // compute_bounding_box_filtering_mask (ray_bending_style_nerf_model.py:62-85): inclusive bounds.

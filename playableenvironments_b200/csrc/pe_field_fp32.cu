@@ -22,22 +22,6 @@ struct Smem {
     int* flags;    // [TM] bit0: in-box (outer mask), bit1: inner mask, bit2: slot valid
 };
 
-__device__ __forceinline__ float pe_sincos_feature(float x, int fn) { return fn ? cosf(x) : sinf(x); }
-
-// Fourier features, layout of model/positional_encoder.py:41-65: [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...],
-// each block `dims` wide; optional per-octave weight (annealable_positional_encoder.py:54-76).
-__device__ __forceinline__ float pe_encoding_value(const float* x, int dims, int e, const float* anneal) {
-    if (e < dims) return x[e];
-    const int q = e - dims;
-    const int oct = q / (2 * dims);
-    const int rem = q - oct * 2 * dims;
-    const int fn = rem / dims;
-    const int dim = rem - fn * dims;
-    float v = pe_sincos_feature(__fmul_rn(exp2f((float)oct), x[dim]), fn);
-    if (anneal) v = __fmul_rn(v, anneal[oct]);
-    return v;
-}
-
 // out[n][m] = act( sum_k in[k][m] * WT[k][n] + bias[n] ), in = seg0 (K0 rows) followed by seg1 (K1 rows).
 // mode 0: linear, 1: ReLU, 2: ReLU(x*sc[n]+sh[n]) (AdaIn with folded BatchNorm)
 __device__ void dense_layer(const float* __restrict__ seg0, int K0, const float* __restrict__ seg1, int K1,
@@ -199,17 +183,33 @@ __global__ void __launch_bounds__(NT, 1) pe_field_fp32_kernel(const PeFieldArgs 
         }
         const int any_inbox = __syncthreads_or(tid < TM ? (S.flags[tid] & 1) : 0);
         if (!any_inbox) {   // whole tile is empty space: features 0 (never read), alpha = empty_space_alpha
-            if (tid < TM && (S.flags[tid] & 4) && (A.phase == 0 || A.phase == PE_PHASE_PREPASS)) {
+            if (tid < TM && (S.flags[tid] & 4) && (A.phase == 0 || A.phase == PE_PHASE_PREPASS || A.phase == PE_PHASE_SAMPLE)) {
                 const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
                 A.raw_out[gs] = ob.empty_space_alpha;
                 A.inbox_out[gs] = 0;
-                if (A.phase == PE_PHASE_PREPASS) A.flags[gs] = 0;
+                if (A.phase == PE_PHASE_PREPASS || A.phase == PE_PHASE_SAMPLE) A.flags[gs] = 0;
                 if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
                 if (A.disp_out) { A.disp_out[gs * 3] = 0.f; A.disp_out[gs * 3 + 1] = 0.f; A.disp_out[gs * 3 + 2] = 0.f; }
             }
             continue;
         }
 
+        if (A.phase == PE_PHASE_SAMPLE) {
+            // sampling only: the ray bender (pe_bender_tc_kernel) and the field (pe_field_tc_kernel) run on the tensor cores over
+            // the tiles that hold samples inside the box; everything else keeps the empty-space values set here
+            if (tid < TM && (S.flags[tid] & 4)) {
+                const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
+                A.raw_out[gs] = ob.empty_space_alpha;
+                A.inbox_out[gs] = 0;
+                A.flags[gs] = (uint8_t)(S.flags[tid] & 1);
+                for (int c = 0; c < 3; ++c) {
+                    A.bent[gs * 3 + c] = S.pos[c * TM + tid];
+                    if (A.disp_out) A.disp_out[gs * 3 + c] = 0.f;
+                }
+                if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
+            }
+            continue;
+        }
         // ---- 2. ray bender (positional_ray_bender_model.py:81-163) ------------------------------
         if (ob.bender_kind == PE_BENDER_POSITIONAL) {
             const int Eb = 3 * (1 + 2 * ob.b_octaves);

@@ -84,7 +84,8 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
                     const uint64_t da_lo = umma_smem_desc(R.a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
                     const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
                     umma_f16_ss(R.tmem_base, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
-                    if (pass == 0) umma_f16_ss(R.tmem_base, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+                    // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
+                    if (pass == 0 || R.x3 == 2) umma_f16_ss(R.tmem_base, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
                 }
                 if (last) umma_commit(R.acc_full + 0);
             } else {
@@ -323,10 +324,203 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Ray bender (model/nerf_models/positional_ray_bender_model.py:81-163) on the tensor cores, shipped shape:
+//   [PE(x/size, 6 octaves, annealed) | deformation(32)] (71 -> K 96) -> 6 x [Linear 128 + ReLU], [h | input] before layer 3
+//   -> Linear(128 -> 3, no bias) * size -> clamp into the box -> bent position, second in-box mask.
+// Same building blocks as pe_field_tc_kernel in its fp16x3 form (activations and weights as hi + lo fp16 pairs, three MMAs
+// per k-step: fp32-class results -- the displacement feeds ten octaves of Fourier features downstream), one 128-row tile per
+// iteration over the device-built list of tiles with samples inside the box.  Reads the positions written by the fp32 sampling
+// pass (PE_PHASE_SAMPLE) and overwrites them with the bent ones.
+// ------------------------------------------------------------------------------------------------------
+constexpr int B_LAYERS = 7;                       // 6 hidden + output
+constexpr int B_ENC_CHUNK0 = 16;                  // A operand: K columns 0..127 activations, 128..223 the bender's input (71, padded to 96)
+constexpr int B_A_CHUNKS = 28;
+constexpr int B_A_BYTES = B_A_CHUNKS * CHUNK_BYTES;
+constexpr int B_THREADS = 256;
+constexpr int B_SMEM_BAR = 2 * B_A_BYTES + NUM_STAGES * STAGE_BYTES;
+constexpr int B_SMEM_ONES = B_SMEM_BAR + 128;
+constexpr int B_SMEM_TOTAL = B_SMEM_ONES + 256;
+
+__host__ __device__ __forceinline__ void bender_layer_spec(int l, int& n, int& slabs, int& chunk0, bool& has_bias) {
+    n = 128; slabs = 4; chunk0 = 0; has_bias = true;
+    if (l == 0) { slabs = 3; chunk0 = B_ENC_CHUNK0; }
+    else if (l == 3) { slabs = 7; }                // [h | input]: chunks 0..27 are contiguous
+    else if (l == 6) { n = 16; has_bias = false; } // 3 outputs, padded to the smallest MMA N
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFieldArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = smem + B_A_BYTES;
+    unsigned char* ring = smem + 2 * B_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + B_SMEM_BAR);
+    uint64_t* empty_bar = full_bar + NUM_STAGES;
+    uint64_t* acc_full = empty_bar + NUM_STAGES;     // [1]
+    uint64_t* a_ready = acc_full + 1;                // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+    unsigned char* ones = smem + B_SMEM_ONES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PeObjectDesc& ob = A.ob;
+    const PeLayout& L = A.L;
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
+    const int P = ob.positions;
+    const int rpt = TILE_M / P;
+    const int tiles_per_image = (A.rays + rpt - 1) / rpt;
+    const int64_t total_tiles = (int64_t)__ldg(A.tile_count);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 128) {
+        const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+        reinterpret_cast<__half*>(ones)[threadIdx.x] = __float2half_rn((r < 8 && c < 2) ? 1.f : 0.f);
+    }
+    fence_proxy_async();
+    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {                            // weight producer: [hi | lo] passes of every slab, then the bias slab
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const unsigned char* src = blob + L.tcb_base;
+                for (int l = 0; l < B_LAYERS; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    bender_layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
+                    for (int s = 0; s < slabs; ++s) {
+                        for (int pass = 0; pass < 2; ++pass) {
+                            mbar_wait(empty_bar + stage, phase ^ 1);
+                            mbar_arrive_expect_tx(full_bar + stage, bytes);
+                            bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcb_bytes_per_pass, bytes, full_bar + stage);
+                            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        src += bytes;
+                    }
+                    if (has_bias) {
+                        const uint32_t bbytes = (uint32_t)n * 32;
+                        mbar_wait(empty_bar + stage, phase ^ 1);
+                        mbar_arrive_expect_tx(full_bar + stage, bbytes);
+                        bulk_copy_g2s(ring + stage * STAGE_BYTES, src, bbytes, full_bar + stage);
+                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        src += bbytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {                            // MMA issuer
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(a_hi); R.a_addr[1] = smem_u32(a_lo);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 2;
+            const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
+            for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                for (int l = 0; l < B_LAYERS; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    bender_layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, n);
+                    const uint32_t lbo_b = (uint32_t)n * 16;
+                    mbar_wait(a_ready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    mma_layer<false>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    if (has_bias) {
+                        mbar_wait(full_bar + R.stage, R.phase);
+                        tc_fence_after();
+                        const uint64_t db = umma_smem_desc(R.ring_addr + R.stage * STAGE_BYTES, lbo_b, 128);
+                        umma_f16_ss(tmem_base, ones_desc, db, idesc, 1u);
+                        umma_commit(acc_full);
+                        umma_commit(empty_bar + R.stage);
+                        if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // epilogue warps: thread = row of the tile = TMEM lane
+        const int wq = warp & 3;
+        const int m = (wq << 5) | lane;
+        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16);
+        Sync1 sync{acc_full, a_ready, 0u, lane, nullptr, nullptr, 0u};
+        const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
+        const int rows_used = rpt * P;
+        for (int64_t it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+            const int64_t tile = A.tile_list[it];
+            const int img = (int)(tile / tiles_per_image);
+            const int ray0 = (int)(tile - (int64_t)img * tiles_per_image) * rpt;
+            const int rl = m / P;
+            const int r = ray0 + rl;
+            const bool valid = m < rows_used && r < A.rays;
+            const int64_t gs = valid ? ((int64_t)img * A.rays + r) * P + (m - rl * P) : 0;
+            const int flag0 = valid ? (A.flags[gs] & 1) : 0;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (flag0) { x[0] = A.bent[gs * 3]; x[1] = A.bent[gs * 3 + 1]; x[2] = A.bent[gs * 3 + 2]; }
+            // input of the bender: annealed Fourier features of x / size (positional_ray_bender_model.py:96-100) | deformation code
+            {
+                const float xn[3] = {__fdiv_rn(x[0], size[0]), __fdiv_rn(x[1], size[1]), __fdiv_rn(x[2], size[2])};
+                const float* dfm = A.deformation + (int64_t)img * 32;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int e = 8 * c + i;
+                        v[i] = e < 39 ? pe_encoding_value(xn, 3, e, ob.b_anneal) : (e < 71 ? __ldg(dfm + (e - 39)) : 0.f);
+                    }
+                    store_a8_hilo(a_hi, a_lo, B_ENC_CHUNK0 + c, m, v, false);
+                }
+            }
+            sync.arrive_ready();
+            for (int l = 0; l < 6; ++l) {
+                sync.wait_acc();
+                hidden_epilogue<0, 128, true>(taddr, a_hi, 0, m, nullptr, nullptr, a_lo);
+                sync.arrive_ready();
+            }
+            sync.wait_acc();
+            uint32_t v[16];
+            tmem_ld16(taddr, v);
+            tmem_wait_ld_regs16(v);
+            tc_fence_before();
+            if (valid) {
+                float bent[3], d2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    float dsp = __fmul_rn(__uint_as_float(v[a]), size[a]);
+                    dsp = fmaxf(dsp, __fsub_rn(ob.bbox[2 * a], x[a]));           // clamp_output :116-140
+                    dsp = fminf(dsp, __fsub_rn(ob.bbox[2 * a + 1], x[a]));
+                    if (ob.canonical_pose) dsp = __fmul_rn(dsp, 0.f);
+                    if (!flag0) dsp = 0.f;
+                    bent[a] = __fadd_rn(x[a], dsp);
+                    d2 += dsp * dsp;
+                    if (A.disp_out) A.disp_out[gs * 3 + a] = dsp;
+                }
+                if (flag0) {
+                    A.bent[gs * 3] = bent[0]; A.bent[gs * 3 + 1] = bent[1]; A.bent[gs * 3 + 2] = bent[2];
+                    A.flags[gs] = (uint8_t)(1 | (pe_in_box(ob, bent) ? 2 : 0));  // inner mask of the field, adain_style_nerf_model.py:171-184
+                }
+                if (A.dispmag_out) A.dispmag_out[gs] = sqrtf(d2);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // pre-pass mode: list of the tiles (floor(128/P) rays each) that hold at least one sample to evaluate
 // ------------------------------------------------------------------------------------------------------
-__global__ void pe_tile_list_kernel(const uint8_t* __restrict__ flags, int rays, int P, int rpt, int tiles_per_image, int64_t total_tiles,
-                                    int32_t* __restrict__ list, int32_t* __restrict__ count) {
+__global__ void pe_tile_list_kernel(const uint8_t* __restrict__ flags, int flag_mask, int rays, int P, int rpt, int tiles_per_image,
+                                    int64_t total_tiles, int32_t* __restrict__ list, int32_t* __restrict__ count) {
     const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool any = false;
     if (tile < total_tiles) {
@@ -334,7 +528,7 @@ __global__ void pe_tile_list_kernel(const uint8_t* __restrict__ flags, int rays,
         const int ray0 = (int)(tile - (int64_t)img * tiles_per_image) * rpt;
         const int n = min(rpt, rays - ray0) * P;
         const uint8_t* f = flags + ((int64_t)img * rays + ray0) * P;
-        for (int i = 0; i < n && !any; ++i) any = (f[i] & 2) != 0;
+        for (int i = 0; i < n && !any; ++i) any = (f[i] & flag_mask) != 0;
     }
     // one atomic per warp; the order of the list does not matter (tiles are independent)
     const unsigned mask = __ballot_sync(0xffffffffu, any);
@@ -359,12 +553,13 @@ __host__ __device__ __forceinline__ int64_t slab_offset(int N, int n, int k) {
 // have a large common positive mean, so the systematic part sum_k dW[n][k] * mean(a) of the single-pass error cancels
 // (measured: -10..-30 % error on the rendered frame); lo = fp16(w - hi) is the second pass of the fp16x2 mode.
 __global__ void pe_tc_pack_layer_kernel(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
-                                        unsigned char* __restrict__ lo) {
+                                        unsigned char* __restrict__ lo, int N_real) {
+    // N: rows of the slab layout; rows >= N_real (padding up to the smallest MMA N) are zero
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float run = 0.f;
     for (int k = 0; k < K_pad; ++k) {
-        const float v = k < K_src ? w[(int64_t)n * K_src + k] : 0.f;
+        const float v = (k < K_src && n < N_real) ? w[(int64_t)n * K_src + k] : 0.f;
         const __half near = __float2half_rn(v);
         const float fn = __half2float(near);
         __half other = near;
@@ -483,7 +678,7 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
         const Item& it = items[l];
         if (!it.w || (l != 8 && l != 9 && !it.b)) { pe_set_error("missing parameter tensor for tensor-core layer %d", l); return PE_ERR_INVALID; }
         const int64_t total = (int64_t)it.N * it.K_pad;
-        pe_tc_pack_layer_kernel<<<(it.N + 63) / 64, 64, 0, stream>>>(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off);
+        pe_tc_pack_layer_kernel<<<(it.N + 63) / 64, 64, 0, stream>>>(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off, it.N);
         PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
         off += total * 2;
         if (it.b) {
@@ -493,6 +688,27 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
         }
     }
     if (off != L.tc_bytes_per_pass) { pe_set_error("internal: tensor-core weight stream size mismatch"); return PE_ERR_INVALID; }
+    if (L.tcb_base) {
+        // ray-bender stream: the 6 hidden layers (K padded 71 -> 96, 199 -> 224) with their bias slabs, then the 3-row output layer
+        unsigned char* bhi = (unsigned char*)packed + L.tcb_base;
+        unsigned char* blo = bhi + L.tcb_bytes_per_pass;
+        int64_t boff = 0;
+        for (int l = 0; l < 6; ++l) {
+            if (!p.bender_w[l] || !p.bender_b[l]) { pe_set_error("missing ray-bender parameter tensor of layer %d", l); return PE_ERR_INVALID; }
+            const int K_src = l == 0 ? 71 : (l == 3 ? 199 : 128), K_pad = l == 0 ? 96 : (l == 3 ? 224 : 128);
+            pe_tc_pack_layer_kernel<<<2, 64, 0, stream>>>(p.bender_w[l], 128, K_src, K_pad, bhi + boff, blo + boff, 128);
+            PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
+            boff += (int64_t)128 * K_pad * 2;
+            pe_tc_pack_bias_kernel<<<(128 * 16 + 255) / 256, 256, 0, stream>>>(p.bender_b[l], 128, bhi + boff);
+            PE_LAUNCH_CHECK("pe_tc_pack_bias_kernel");
+            boff += 128 * 32;
+        }
+        if (!p.bender_out_w) { pe_set_error("missing ray-bender output layer"); return PE_ERR_INVALID; }
+        pe_tc_pack_layer_kernel<<<1, 64, 0, stream>>>(p.bender_out_w, 16, 128, 128, bhi + boff, blo + boff, 3);
+        PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
+        boff += (int64_t)16 * 128 * 2;
+        if (boff != L.tcb_bytes_per_pass) { pe_set_error("internal: ray-bender weight stream size mismatch"); return PE_ERR_INVALID; }
+    }
     return PE_OK;
 }
 
@@ -524,15 +740,30 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     return PE_OK;
 }
 
-int pe_launch_tile_list(const PeFieldArgs& args, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream) {
+int pe_launch_tile_list(const PeFieldArgs& args, int flag_mask, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream) {
     const int rpt = TILE_M / args.ob.positions;
     const int tiles_per_image = (args.rays + rpt - 1) / rpt;
     const int64_t tiles = (int64_t)tiles_per_image * args.images;
     PE_CUDA_CHECK(cudaMemsetAsync(tile_count, 0, sizeof(int32_t), stream));
     if (tiles == 0) return PE_OK;
-    pe_tile_list_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, stream>>>(args.flags, args.rays, args.ob.positions, rpt, tiles_per_image, tiles,
-                                                                             tile_list, tile_count);
+    pe_tile_list_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, stream>>>(args.flags, flag_mask, args.rays, args.ob.positions, rpt, tiles_per_image,
+                                                                             tiles, tile_list, tile_count);
     PE_LAUNCH_CHECK("pe_tile_list_kernel");
+    return PE_OK;
+}
+
+int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stream) {
+    if (!pe_tc_prepass_ok(args.ob) || !pe_tc_bender_ok(args.ob) || !args.L.tcb_base || !args.bent || !args.flags || !args.tile_list ||
+        !args.tile_count || !args.deformation) {
+        pe_set_error("tensor-core ray bender: unsupported configuration");
+        return PE_ERR_UNSUPPORTED;
+    }
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bender_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_TOTAL));
+    const int rpt = TILE_M / args.ob.positions;
+    const int64_t tiles = (int64_t)((args.rays + rpt - 1) / rpt) * args.images;
+    if (tiles == 0) return PE_OK;
+    pe_bender_tc_kernel<<<(int)pe_min64(tiles, sm_count), B_THREADS, B_SMEM_TOTAL, stream>>>(args);
+    PE_LAUNCH_CHECK("pe_bender_tc_kernel");
     return PE_OK;
 }
 

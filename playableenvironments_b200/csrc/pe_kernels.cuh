@@ -142,7 +142,8 @@ int pe_launch_geometry_bwd(const PeGeometryBwdArgs& args, cudaStream_t stream);
 size_t pe_field_fp32_smem_bytes(const PeObjectDesc& ob, const PeLayout& L);
 int pe_launch_field_fp32(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
-int pe_launch_tile_list(const PeFieldArgs& args, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream);
+int pe_launch_tile_list(const PeFieldArgs& args, int flag_mask, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream);
+int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc2(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream);
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream);

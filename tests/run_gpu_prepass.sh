@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/prepass_pytest.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/prepass_pytest.log
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/prepass_pytest.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/prepass_pytest.log
 timeout 300 python - <<'PY'
 import sys, torch
 sys.path[:0]=['.','tests','tests/golden']
