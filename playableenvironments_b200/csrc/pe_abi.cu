@@ -227,8 +227,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 const bool tc_bender = benv ? atoi(benv) != 0 : s.precision != PE_PRECISION_FP16X3;
                 if (pe_tc_bender_ok(d) && tc_bender) {
                     // 1a. exact fp32 sampling: t, positions, outer mask; empty-space values everywhere
-                    pre.phase = PE_PHASE_SAMPLE;
-                    rc2 = pe_launch_field_fp32(pre, sm_count, stream); if (rc2) return rc2;
+                    rc2 = pe_launch_sample(pre, sm_count, stream); if (rc2) return rc2;
                     // 1b. the ray bender on the tensor cores (fp16x3: fp32-class) over the tiles with samples inside the box
                     rc2 = pe_launch_tile_list(pre, 1, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
                     rc2 = pe_launch_bender_tc(pre, sm_count, stream); if (rc2) return rc2;

@@ -81,7 +81,6 @@ __host__ __device__ inline bool pe_tc_shape_ok(const PeObjectDesc& d) { return p
 // ... behind the sampling / ray-bender pre-pass (pe_field_fp32.cu, phase PE_PHASE_PREPASS): objects with a positional ray bender
 __host__ __device__ inline bool pe_tc_prepass_ok(const PeObjectDesc& d) { return pe_tc_field_ok(d) && d.bender_kind == PE_BENDER_POSITIONAL; }
 #define PE_PHASE_PREPASS 3                    // fp32 field kernel: sampling + ray bender only (bent positions, flags, displacements)
-#define PE_PHASE_SAMPLE 4                     // fp32 field kernel: sampling only (positions, outer mask); the bender runs on tcgen05
 // Ray-bender shape handled by the tcgen05 bender kernel: the shipped one (configs/tennis/193_*.yaml:165-178: 6 x 128, skip at 3,
 // 6 octaves, 32 deformation features)
 __host__ __device__ inline bool pe_tc_bender_ok(const PeObjectDesc& d) {

@@ -183,33 +183,17 @@ __global__ void __launch_bounds__(NT, 1) pe_field_fp32_kernel(const PeFieldArgs 
         }
         const int any_inbox = __syncthreads_or(tid < TM ? (S.flags[tid] & 1) : 0);
         if (!any_inbox) {   // whole tile is empty space: features 0 (never read), alpha = empty_space_alpha
-            if (tid < TM && (S.flags[tid] & 4) && (A.phase == 0 || A.phase == PE_PHASE_PREPASS || A.phase == PE_PHASE_SAMPLE)) {
+            if (tid < TM && (S.flags[tid] & 4) && (A.phase == 0 || A.phase == PE_PHASE_PREPASS)) {
                 const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
                 A.raw_out[gs] = ob.empty_space_alpha;
                 A.inbox_out[gs] = 0;
-                if (A.phase == PE_PHASE_PREPASS || A.phase == PE_PHASE_SAMPLE) A.flags[gs] = 0;
+                if (A.phase == PE_PHASE_PREPASS) A.flags[gs] = 0;
                 if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
                 if (A.disp_out) { A.disp_out[gs * 3] = 0.f; A.disp_out[gs * 3 + 1] = 0.f; A.disp_out[gs * 3 + 2] = 0.f; }
             }
             continue;
         }
 
-        if (A.phase == PE_PHASE_SAMPLE) {
-            // sampling only: the ray bender (pe_bender_tc_kernel) and the field (pe_field_tc_kernel) run on the tensor cores over
-            // the tiles that hold samples inside the box; everything else keeps the empty-space values set here
-            if (tid < TM && (S.flags[tid] & 4)) {
-                const int64_t gs = (int64_t)img * slots_per_image + slot0 + tid;
-                A.raw_out[gs] = ob.empty_space_alpha;
-                A.inbox_out[gs] = 0;
-                A.flags[gs] = (uint8_t)(S.flags[tid] & 1);
-                for (int c = 0; c < 3; ++c) {
-                    A.bent[gs * 3 + c] = S.pos[c * TM + tid];
-                    if (A.disp_out) A.disp_out[gs * 3 + c] = 0.f;
-                }
-                if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
-            }
-            continue;
-        }
         // ---- 2. ray bender (positional_ray_bender_model.py:81-163) ------------------------------
         if (ob.bender_kind == PE_BENDER_POSITIONAL) {
             const int Eb = 3 * (1 + 2 * ob.b_octaves);

@@ -517,6 +517,37 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Sampling pass of the tensor-core ray-bender path, one thread per sample slot: transform_rays, z bounds, create_ray_positions,
+// outer in-box mask (the same device functions as the field kernels, so the values are identical), and the empty-space values
+// of every per-sample output; the bender and field kernels then only touch the tiles that hold samples inside the box.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pe_sample_kernel(const PeFieldArgs A) {
+    const PeObjectDesc& ob = A.ob;
+    const int P = ob.positions;
+    const int64_t per_image = (int64_t)A.rays * P;
+    const int64_t total = per_image * A.images;
+    for (int64_t gs = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gs < total; gs += (int64_t)gridDim.x * blockDim.x) {
+        const int img = (int)(gs / per_image);
+        const int64_t rem = gs - (int64_t)img * per_image;
+        const int r = (int)(rem / P), p = (int)(rem - (int64_t)r * P);
+        const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
+        const PeRay ray = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3,
+                                      A.dirs + ((int64_t)img * A.rays + r) * 3, in_scene);
+        const float u = A.perturb ? A.rand[gs] : 0.f;
+        const float t = pe_sample_t(ray, p, P, A.perturb != 0, u);
+        float x[3];
+        pe_position(ray, t, x);
+        A.t_out[gs] = t;
+        A.raw_out[gs] = ob.empty_space_alpha;
+        A.inbox_out[gs] = 0;
+        A.flags[gs] = pe_in_box(ob, x) ? 1 : 0;
+        A.bent[gs * 3] = x[0]; A.bent[gs * 3 + 1] = x[1]; A.bent[gs * 3 + 2] = x[2];
+        if (A.disp_out) { A.disp_out[gs * 3] = 0.f; A.disp_out[gs * 3 + 1] = 0.f; A.disp_out[gs * 3 + 2] = 0.f; }
+        if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // pre-pass mode: list of the tiles (floor(128/P) rays each) that hold at least one sample to evaluate
 // ------------------------------------------------------------------------------------------------------
 __global__ void pe_tile_list_kernel(const uint8_t* __restrict__ flags, int flag_mask, int rays, int P, int rpt, int tiles_per_image,
@@ -749,6 +780,18 @@ int pe_launch_tile_list(const PeFieldArgs& args, int flag_mask, int32_t* tile_li
     pe_tile_list_kernel<<<(unsigned)((tiles + 127) / 128), 128, 0, stream>>>(args.flags, flag_mask, args.rays, args.ob.positions, rpt, tiles_per_image,
                                                                              tiles, tile_list, tile_count);
     PE_LAUNCH_CHECK("pe_tile_list_kernel");
+    return PE_OK;
+}
+
+int pe_launch_sample(const PeFieldArgs& args, int sm_count, cudaStream_t stream) {
+    if (!args.t_out || !args.raw_out || !args.inbox_out || !args.flags || !args.bent || args.explicit_positions) {
+        pe_set_error("sampling pass: incomplete arguments");
+        return PE_ERR_INVALID;
+    }
+    const int64_t total = (int64_t)args.images * args.rays * args.ob.positions;
+    if (total == 0) return PE_OK;
+    pe_sample_kernel<<<(int)pe_min64((total + 255) / 256, (int64_t)sm_count * 8), 256, 0, stream>>>(args);
+    PE_LAUNCH_CHECK("pe_sample_kernel");
     return PE_OK;
 }
 

@@ -144,6 +144,7 @@ int pe_launch_field_fp32(const PeFieldArgs& args, int sm_count, cudaStream_t str
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_tile_list(const PeFieldArgs& args, int flag_mask, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream);
 int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
+int pe_launch_sample(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_field_tc2(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream);
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream);

@@ -570,36 +570,57 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             uint32_t v[16];
             tmem_ld16(taddr + c_first + c * 16, v);
             tmem_wait_ld_regs16(v);
-            if (!A.apply_activation && !A.feat_out) {                  // common case: nothing per-sample leaves the SM
+            if (!A.apply_activation && !A.feat_out) {                  // nothing per-sample leaves the SM
 #pragma unroll
                 for (int q = 0; q < 16; ++q) scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = wf * __uint_as_float(v[q]);
             } else {
+                // per-sample features are an output (multi-object scenes: input of the compositor): the scratch holds the
+                // masked, UNWEIGHTED feature so that it can be written out coalesced; the reduction below applies the weights
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                     float f = __uint_as_float(v[q]);                   // head-6 bias already added by the rank-1 MMA
                     if (A.apply_activation) f = 1.f / (1.f + expf(-f));
-                    if (A.feat_out && valid) A.feat_out[gs * 192 + c_first + c * 16 + q] = inbox ? f : 0.f;
-                    scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = wf * f;
+                    scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = A.feat_out ? (inbox ? f : 0.f) : wf * f;
                 }
             }
         }
         named_bar_sync(bar_id, GROUP);
-        for (int item = tid; item < rpt * 96; item += GROUP) {
-            const int rl = item / 96, c = item - rl * 96;
-            const int r = ray0 + rl;
-            if (tile_valid && r < A.rays) {
-                const float* col = scr + rl * P * SCRATCH_STRIDE + c;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                int j = 0;
-                for (; j + 4 <= P; j += 4) {
-                    s0 += col[(j + 0) * SCRATCH_STRIDE]; s1 += col[(j + 1) * SCRATCH_STRIDE];
-                    s2 += col[(j + 2) * SCRATCH_STRIDE]; s3 += col[(j + 3) * SCRATCH_STRIDE];
+        if (A.feat_out && tile_valid) {
+            // the tile's rows are consecutive sample slots: 96 consecutive floats per row, consecutive threads -> consecutive addresses
+            const int rows_valid = min(rpt, A.rays - ray0) * P;
+            float* dst = A.feat_out + ((int64_t)img * A.rays + ray0) * P * 192 + pass * 96;
+            for (int idx = tid; idx < rows_valid * 96; idx += GROUP) {
+                const int row = idx / 96, c = idx - row * 96;
+                dst[(int64_t)row * 192 + c] = scr[row * SCRATCH_STRIDE + c];
+            }
+        }
+        if (A.integ.integrated_features || (X.single && G2.integrated_features)) {
+            for (int item = tid; item < rpt * 96; item += GROUP) {
+                const int rl = item / 96, c = item - rl * 96;
+                const int r = ray0 + rl;
+                if (tile_valid && r < A.rays) {
+                    const float* col = scr + rl * P * SCRATCH_STRIDE + c;
+                    const float* wr = w_s + rl * P;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    int j = 0;
+                    if (A.feat_out) {
+                        for (; j + 4 <= P; j += 4) {
+                            s0 = fmaf(wr[j + 0], col[(j + 0) * SCRATCH_STRIDE], s0); s1 = fmaf(wr[j + 1], col[(j + 1) * SCRATCH_STRIDE], s1);
+                            s2 = fmaf(wr[j + 2], col[(j + 2) * SCRATCH_STRIDE], s2); s3 = fmaf(wr[j + 3], col[(j + 3) * SCRATCH_STRIDE], s3);
+                        }
+                        for (; j < P; ++j) s0 = fmaf(wr[j], col[j * SCRATCH_STRIDE], s0);
+                    } else {
+                        for (; j + 4 <= P; j += 4) {
+                            s0 += col[(j + 0) * SCRATCH_STRIDE]; s1 += col[(j + 1) * SCRATCH_STRIDE];
+                            s2 += col[(j + 2) * SCRATCH_STRIDE]; s3 += col[(j + 3) * SCRATCH_STRIDE];
+                        }
+                        for (; j < P; ++j) s0 += col[j * SCRATCH_STRIDE];
+                    }
+                    const float sum = (s0 + s1) + (s2 + s3);
+                    const int64_t o = ((int64_t)img * A.rays + r) * 192 + pass * 96 + c;
+                    if (A.integ.integrated_features) A.integ.integrated_features[o] = sum;
+                    if (X.single && G2.integrated_features) G2.integrated_features[o] = sum;
                 }
-                for (; j < P; ++j) s0 += col[j * SCRATCH_STRIDE];
-                const float sum = (s0 + s1) + (s2 + s3);
-                const int64_t o = ((int64_t)img * A.rays + r) * 192 + pass * 96 + c;
-                if (A.integ.integrated_features) A.integ.integrated_features[o] = sum;
-                if (X.single && G2.integrated_features) G2.integrated_features[o] = sum;
             }
         }
         named_bar_sync(bar_id, GROUP);
