@@ -220,6 +220,11 @@ int pe_fold_feature_grids(const float* features, int32_t images, int32_t height,
  * the same tcgen05 building blocks as the fused kernel (fp16 operands, fp32 accumulate).  Used by
  * tests to validate descriptors on the device.                                                  */
 int pe_debug_umma_gemm(const float* a, const float* b, const float* bias, float* d, int32_t n, int32_t k, pe_stream_t stream);
+/* Validation of two operand forms on one CTA.  mode 1: both operands MN-major, read from the activation layout of the field kernel with
+ * K = its 128 rows: d[m][n] = sum_r a[r][m] * b[r][n] (a: [k][128], b: [k][n], rows >= k zero; lbo / sbo = descriptor byte strides).
+ * mode 2: A operand from TMEM (TS form, written with tcgen05.st): d[m][n] = sum_k a[m][k] * b[n][k] (a: [128][k], b: [n][k]).     */
+int pe_debug_umma_gemm2(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t lbo, int32_t sbo,
+                        pe_stream_t stream);
 
 #ifdef __cplusplus
 }

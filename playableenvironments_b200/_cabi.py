@@ -124,7 +124,7 @@ class PeInGrads(C.Structure):
 EXPORTS = [
     "pe_abi_version", "pe_last_error", "pe_take_launch_count", "pe_packed_bytes", "pe_pack_object",
     "pe_workspace_bytes", "pe_render_forward", "pe_backward_workspace_bytes", "pe_render_backward", "pe_positional_encoding", "pe_generate_rays",
-    "pe_fold_feature_grids", "pe_debug_umma_gemm",
+    "pe_fold_feature_grids", "pe_debug_umma_gemm", "pe_debug_umma_gemm2",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpe_b200.so")
@@ -170,6 +170,8 @@ def lib() -> C.CDLL:
                                         C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
     L.pe_debug_umma_gemm.restype = C.c_int
     L.pe_debug_umma_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.pe_debug_umma_gemm2.restype = C.c_int
+    L.pe_debug_umma_gemm2.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     if L.pe_abi_version() != PE_ABI_VERSION:
         raise PeError(f"libpe_b200.so ABI {L.pe_abi_version()} != binding {PE_ABI_VERSION}; rebuild")
     _lib = L

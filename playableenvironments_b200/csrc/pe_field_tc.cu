@@ -691,6 +691,88 @@ __global__ void __launch_bounds__(128, 1) pe_debug_umma_kernel(const float* __re
     (void)lane;
 }
 
+// Validation of two operand forms the next kernels build on (tests/test_gpu_parity.py::test_umma_operand_forms):
+//   mode 1: both operands MN-major, read from the SAME shared-memory layout the field kernel uses for activations
+//           (element (row r, column c) at (c/8)*2048 + r*16 + (c%8)*2): with K = the 128 rows, D[m][n] = sum_r X[r][m] * Y[r][n]
+//           (the dW = G^T * A product of the backward); lbo / sbo: byte strides passed by the caller
+//   mode 2: A operand from TMEM (TS form), written by tcgen05.st: D[m][n] = sum_k A[m][k] * B[n][k]
+__global__ void __launch_bounds__(128, 1) pe_debug_umma2_kernel(int mode, const float* __restrict__ a, const float* __restrict__ b,
+                                                                 float* __restrict__ d, int n, int k, int lbo, int sbo) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sa = smem;                         // 128 rows x 256 columns, activation layout (64 KB)
+    unsigned char* sb = smem + 65536;                 // same
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 131072);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int warp = threadIdx.x >> 5;
+    const int r = threadIdx.x;                        // row of the stored matrices / TMEM lane
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (mode == 1) {
+        // X = a: [128 rows (K)][128 columns (M)], Y = b: [128 rows (K)][n columns (N)], rows >= k are zero
+        for (int c = 0; c < 128 / 8; ++c) {
+            float v[8];
+            for (int q = 0; q < 8; ++q) v[q] = r < k ? a[(int64_t)r * 128 + c * 8 + q] : 0.f;
+            store_a8(sa, c, r, v);
+        }
+        for (int c = 0; c < n / 8; ++c) {
+            float v[8];
+            for (int q = 0; q < 8; ++q) v[q] = r < k ? b[(int64_t)r * n + c * 8 + q] : 0.f;
+            store_a8(sb, c, r, v);
+        }
+    } else {
+        // B = b: [n][k] K-major slab layout; A = a: [128][k] -> TMEM columns 256 .. 256 + k/2
+        for (int64_t i = threadIdx.x; i < (int64_t)n * k; i += blockDim.x) {
+            const int row = (int)(i / k), kk = (int)(i - (int64_t)row * k);
+            const int64_t off = (int64_t)(kk >> 3) * (n * 16) + (row >> 3) * 128 + (row & 7) * 16 + (kk & 7) * 2;
+            *reinterpret_cast<__half*>(sb + off) = __float2half_rn(b[i]);
+        }
+        for (int j = 0; j < k / 16; ++j) {
+            uint32_t v[8];
+            for (int q = 0; q < 8; ++q) v[q] = pack_half2(a[(int64_t)r * k + j * 16 + 2 * q], a[(int64_t)r * k + j * 16 + 2 * q + 1]);
+            tmem_st8(tmem_base + (((uint32_t)warp * 32u) << 16) + 256 + j * 8, v);
+        }
+        tmem_wait_st();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1 && elect_one()) {
+        if (mode == 1) {
+            const uint32_t idesc = umma_idesc_f16_major(128, n, 1, 1);
+            for (int j = 0; j < 128 / 16; ++j) {      // K = the 128 stored rows: 16 rows (2 groups of 8, 128 B each) per MMA
+                const uint64_t da = umma_smem_desc(smem_u32(sa) + j * 256, (uint32_t)lbo, (uint32_t)sbo);
+                const uint64_t db = umma_smem_desc(smem_u32(sb) + j * 256, (uint32_t)lbo, (uint32_t)sbo);
+                umma_f16_ss(tmem_base, da, db, idesc, j != 0 ? 1u : 0u);
+            }
+        } else {
+            const uint32_t idesc = umma_idesc_f16(128, n);
+            const uint32_t lbo_b = (uint32_t)n * 16;
+            for (int j = 0; j < k / 16; ++j) {
+                const uint64_t db = umma_smem_desc(smem_u32(sb) + 2 * j * lbo_b, lbo_b, 128);
+                umma_f16_ts(tmem_base, tmem_base + 256 + j * 8, db, idesc, j != 0 ? 1u : 0u);
+            }
+        }
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (((uint32_t)warp * 32u) << 16) + c0, v);
+        tmem_wait_ld();
+        for (int q = 0; q < 32; ++q)
+            if (c0 + q < n) d[(int64_t)r * n + c0 + q] = __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
@@ -807,6 +889,19 @@ int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stre
     if (tiles == 0) return PE_OK;
     pe_bender_tc_kernel<<<(int)pe_min64(tiles, sm_count), B_THREADS, B_SMEM_TOTAL, stream>>>(args);
     PE_LAUNCH_CHECK("pe_bender_tc_kernel");
+    return PE_OK;
+}
+
+extern "C" int pe_debug_umma_gemm2(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t lbo, int32_t sbo,
+                                   pe_stream_t stream) {
+    if ((mode != 1 && mode != 2) || n < 32 || n > 256 || n % 32 || k < 16 || k > 128 || k % 16) {
+        pe_set_error("debug gemm2: mode 1|2, n multiple of 32 up to 256, k multiple of 16 up to 128");
+        return PE_ERR_INVALID;
+    }
+    const int smem = 131072 + 64;
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_debug_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pe_debug_umma2_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, a, b, d, n, k, lbo, sbo);
+    PE_LAUNCH_CHECK("pe_debug_umma2_kernel");
     return PE_OK;
 }
 

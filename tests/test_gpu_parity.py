@@ -50,6 +50,29 @@ def test_umma_descriptors_and_rank1_bias_update():
             assert float((d - ref).abs().max() / ref.abs().max()) < 5e-6
 
 
+def test_umma_operand_forms():
+    """Two tcgen05 operand forms pinned for the next kernels: (1) both operands MN-major, read from the very
+    activation layout of the field kernel with K = its 128 rows (descriptor: LBO = 128 B between the 8-row K groups, SBO = 2048 B
+    between the 8-column MN groups) -- the dW = G^T A product of a tensor-core backward; (2) the TS form, A operand in TMEM written by
+    tcgen05.st (lane = row, two consecutive K elements per 32-bit column)."""
+    from playableenvironments_b200 import _cabi
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(5)
+    for n, k in [(128, 128), (256, 64), (64, 16), (192 + 64, 96)]:
+        a, b = torch.randn(k, 128, generator=g).cuda(), torch.randn(k, n, generator=g).cuda()
+        d = torch.full((128, n), float("nan"), device="cuda")
+        _cabi.check(_cabi.lib().pe_debug_umma_gemm2(1, a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, 128, 2048, stream))
+        torch.cuda.synchronize()
+        ref = a.half().float().t() @ b.half().float()
+        assert float((d - ref).abs().max() / ref.abs().max()) < 5e-6
+        a, b = torch.randn(128, k, generator=g).cuda(), torch.randn(n, k, generator=g).cuda()
+        d = torch.full((128, n), float("nan"), device="cuda")
+        _cabi.check(_cabi.lib().pe_debug_umma_gemm2(2, a.data_ptr(), b.data_ptr(), d.data_ptr(), n, k, 0, 0, stream))
+        torch.cuda.synchronize()
+        ref = a.half().float() @ b.half().float().t()
+        assert float((d - ref).abs().max() / ref.abs().max()) < 5e-6
+
+
 @pytest.mark.parametrize("name", ALL_SCENES)
 def test_fp32_path_matches_reference(name):
     _, _, _, comp, dev = _build(name, "fp32")
