@@ -125,15 +125,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def train_step_report(device, dense: bool):
+def train_step_report(device, dense: bool, precision: str = "fp16x3"):
     """BASELINE configs[2]: Tennis scene (court + 2 players with positional ray benders, composed), 256x144 rays, forward and
     forward+backward through ObjectComposer with every parameter and every differentiable input requiring a gradient.
-    Secondary figures (the headline stays configs[1]); the backward is the exact fp32 CUDA-core path."""
+    Secondary figures (the headline stays configs[1]).  precision fp16x3 (the composer's default): train-mode forward and the
+    backward's forward recompute on the tensor cores (fp32-class mode), field backward on the exact fp32 CUDA-core kernel;
+    precision fp32: everything on the CUDA cores."""
     import scenes
     from helpers import INPUT_KEYS
     from gpu_common import build_composer
     scene = scenes.scene_tennis(seed=13, height=144, width=256, stride=1, lead=(1, 1, 1), dense=dense)
-    config, state, inputs, comp, dev = build_composer(scene, "fp32", device=device, training=True)
+    if precision == "fp32":
+        os.environ["PE_TC_BACKWARD_RECOMPUTE"] = "0"
+    config, state, inputs, comp, dev = build_composer(scene, precision, device=device, training=True)
     comp.allow_forward_without_grad = False
     dev = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in dev.items()}
     call = [dev[k] for k in INPUT_KEYS]
@@ -170,9 +174,11 @@ def train_step_report(device, dense: bool):
         slots += ra.numel()
         inbox += int((ra != float(m["empty_space_alpha"])).sum().item())
     ms_f, ms_fb = timed(fwd, 3), timed(fwd_bwd, 3)
+    os.environ.pop("PE_TC_BACKWARD_RECOMPUTE", None)
     return {"workload": f"cfg3 Tennis{' (dense: camera on a player)' if dense else ''}: court P=4 + 2 players P=32 with ray benders, 256x144 rays, train-mode BatchNorm",
             "sample_slots": slots, "in_box_samples": inbox, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
-            "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3), "precision": "fp32 (CUDA cores)"}
+            "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3),
+            "precision": "fp32 (CUDA cores only)" if precision == "fp32" else f"{precision} forward + recompute on tensor cores, fp32 field backward"}
 
 
 def eval_frame_report(device, dense: bool):
@@ -361,7 +367,8 @@ def run_b200(args):
             "wall_s": wall,
         }
         if world == 1 and not args.quick:
-            line["train_step"] = [train_step_report(device, False), train_step_report(device, True)]
+            line["train_step"] = [train_step_report(device, False), train_step_report(device, True),
+                                  train_step_report(device, False, "fp32"), train_step_report(device, True, "fp32")]
             line["eval_frame"] = [eval_frame_report(device, False), eval_frame_report(device, True)]
         if modes:
             line["other_modes"] = modes

@@ -70,21 +70,33 @@ struct Workspace {
     size_t bytes;
 };
 
-static bool object_uses_tc(const PeScene& s, int k) {
-    return s.precision != PE_PRECISION_FP32 && !s.training && !s.explicit_positions && pe_tc_shape_ok(s.object[k]);
+// Train mode (batch-statistics BatchNorm: three launches with the statistics phases of the tcgen05 kernel) runs on the tensor cores
+// too; PE_TC_TRAIN=0 keeps it on the fp32 field kernel.
+static bool tc_allowed(const PeScene& s) {
+    if (s.precision == PE_PRECISION_FP32 || s.explicit_positions) return false;
+    if (s.training) { const char* env = getenv("PE_TC_TRAIN"); if (env && atoi(env) == 0) return false; }
+    return true;
 }
+
+// Set while pe_render_backward recomputes the forward: every per-sample tensor must land in the workspace (the compositing backward
+// reads t / raw alpha / features / masks), so the self-contained and folded-head shortcuts are off.
+static thread_local bool g_keep_samples = false;
+struct KeepSamples { bool prev; KeepSamples() : prev(g_keep_samples) { g_keep_samples = true; } ~KeepSamples() { g_keep_samples = prev; } };
+
+static bool object_uses_tc(const PeScene& s, int k) { return tc_allowed(s) && pe_tc_shape_ok(s.object[k]); }
 
 // Objects with a positional ray bender: sampling + bender run as an exact fp32 pre-pass, the field runs on the tensor cores over
 // the non-empty tiles only, the compositor integrates the object.  PE_TC_PREPASS=0 sends them to the fp32 field kernel instead.
 static bool object_uses_prepass(const PeScene& s, int k) {
     const char* env = getenv("PE_TC_PREPASS");
     if (env && atoi(env) == 0) return false;
-    return s.precision != PE_PRECISION_FP32 && !s.training && !s.explicit_positions && pe_tc_prepass_ok(s.object[k]);
+    return tc_allowed(s) && pe_tc_prepass_ok(s.object[k]);
 }
 
 // per-sample features are only materialised where something downstream reads them
 static bool needs_feature_buffer(const PeScene& s, int k) {
     if (s.explicit_positions) return false;                 // caller supplies raw_features
+    if (g_keep_samples) return true;                        // forward recomputed for the backward
     if (!object_uses_tc(s, k)) return true;                 // the fp32 path integrates in the compositor
     // tc path integrates its own object; the composition needs the samples when there are several objects, or when
     // perturb is on (the composed scene draws its own raw-alpha noise, object_composer.py:886 -> :194)
@@ -186,7 +198,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;
         fa.t_out = out->positions_t[k] ? out->positions_t[k] : o.t;
         fa.raw_out = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
-        const bool self_contained = tc && s.objects == 1 && !s.perturb;     // the fused kernel integrates the whole scene itself
+        const bool self_contained = tc && s.objects == 1 && !s.perturb && !g_keep_samples;     // the fused kernel integrates the whole scene itself
         fa.feat_out = out->raw_features[k] ? out->raw_features[k] : o.feat;
         fa.disp_out = out->displacements[k];
         fa.dispmag_out = o.dispmag;
@@ -240,7 +252,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 rc2 = pe_launch_tile_list(pre, 2, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
                 // 3. the field on the tensor cores over those tiles (the compositor integrates the object)
                 PeFieldArgs tcargs = pre;
-                tcargs.phase = 0;
+                tcargs.phase = phase;
                 return pe_launch_field_tc(tcargs, none, sm_count, stream);
             }
             if (!tc) return pe_launch_field_fp32(fa, sm_count, stream);
@@ -336,7 +348,11 @@ struct BwdWorkspace {
 
 static PeScene backward_scene(const PeScene& s) {
     PeScene b = s;
-    b.precision = PE_PRECISION_FP32;       // the backward recomputes (and differentiates) the exact fp32 forward
+    // The backward needs the forward's per-sample tensors, AdaIn constants and BatchNorm sums again: recomputed in the fp32-class
+    // tensor-core mode where the shapes allow (exact fp32 kernels otherwise, or with PE_TC_BACKWARD_RECOMPUTE=0); the field backward
+    // itself (pe_field_bwd_kernel) recomputes and differentiates each tile in exact fp32.
+    const char* env = getenv("PE_TC_BACKWARD_RECOMPUTE");
+    b.precision = (env && atoi(env) == 0) ? PE_PRECISION_FP32 : PE_PRECISION_FP16X3;
     return b;
 }
 
@@ -344,6 +360,7 @@ static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
     BwdWorkspace w = {};
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off = (off + bytes + 255) / 256 * 256; return p; };
+    KeepSamples keep;
     w.fwd_bytes = carve(s, nullptr).bytes;
     w.fwd = take(w.fwd_bytes);
     for (int k = 0; k < s.objects; ++k) {
@@ -407,6 +424,7 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
 
     // 1. recompute the forward: per-sample t / raw alpha / features / |displacement| / in-box flags, AdaIn scale-shift, BatchNorm sums
     const PeOutputs none = {};
+    KeepSamples keep;
     rc = pe_render_forward(&s, in, &none, bw.fwd, bw.fwd_bytes, stream_);
     if (rc != PE_OK) return rc;
     const Workspace ws = carve(s, bw.fwd);

@@ -64,9 +64,12 @@ struct MmaRing {
 
 // Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
 // (D^T = W * A^T, folded-head mode, head layer 3) -- a separate instantiation so that the common loop stays branch-free.
-template <bool kSwap>
+template <bool kSwap, int kMBlocks = 1>
 __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, int chunk0, bool has_bias, uint32_t idesc, uint32_t lbo_b) {
     (void)l; (void)n;
+    // kSwap: D^T = W * A^T -- the weight slab is the M operand (blocks of 128 of its n rows: block b starts 2048 B into every K chunk and
+    // lands in accumulator columns 128 b ..), the tile's 128 samples are N; idesc must describe M = 128, N = 128
+    constexpr int mblocks = kMBlocks;                // 2: the 256-row slab of head layer 0 in the statistics phase
     const int num_passes = R.num_passes;
     for (int s = 0; s < slabs; ++s) {
         for (int pass = 0; pass < num_passes; ++pass) {
@@ -79,13 +82,17 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
-                    const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
                     const uint64_t da_hi = umma_smem_desc(R.a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
                     const uint64_t da_lo = umma_smem_desc(R.a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
                     const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
-                    umma_f16_ss(R.tmem_base, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
-                    // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
-                    if (pass == 0 || R.x3 == 2) umma_f16_ss(R.tmem_base, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+#pragma unroll
+                    for (int b = 0; b < mblocks; ++b) {
+                        const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
+                        const uint32_t td = R.tmem_base + b * 128;
+                        umma_f16_ss(td, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
+                        // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
+                        if (pass == 0 || R.x3 == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+                    }
                 }
                 if (last) umma_commit(R.acc_full + 0);
             } else {
@@ -95,8 +102,11 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
                         const uint64_t da = umma_smem_desc(R.a_addr[g] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
-                        const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b, lbo_b, 128);
-                        umma_f16_ss(R.tmem_base + g * 256, kSwap ? db : da, kSwap ? da : db, idesc, (s | pass | j) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int b = 0; b < mblocks; ++b) {
+                            const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
+                            umma_f16_ss(R.tmem_base + g * 256 + b * 128, kSwap ? db : da, kSwap ? da : db, idesc, (s | pass | j) != 0 ? 1u : 0u);
+                        }
                     }
                     if (last) umma_commit(R.acc_full + g);
                 }
@@ -107,6 +117,9 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
     }
 }
 
+// kStats: the train-mode instantiation (statistics phases of BatchNorm); the eval instantiation carries none of that code
+// kFoldOnly: the headline instantiation (folded head, sampling inside the kernel, eval)
+template <bool kStats, bool kFoldOnly>
 __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3, const int fold, const int dbg) {
     // fold: folded-head mode (pe_tc_common.cuh): head layer 6 is applied per ray by pe_head6_fold_kernel, 10 MMA layers per tile
     // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
@@ -133,7 +146,10 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     // pre-pass mode: the kernel walks the list of non-empty tiles built on the device
     const int64_t total_tiles = A.tile_count ? (int64_t)__ldg(A.tile_count) : (int64_t)tiles_per_image * A.images;
     const int64_t total_pairs = x3 ? total_tiles : (total_tiles + 1) / 2;        // iterations of this kernel
-    const int num_layers = fold ? NUM_LAYERS - 1 : NUM_LAYERS;
+    // train-mode BatchNorm (adain.py:47) needs the batch statistics of the two AdaIn inputs before it can go on: phase 1 stops after
+    // head layer 0 and accumulates its column sums, phase 2 after head layer 3 (three launches, two global reductions)
+    const int stat_phase = (kStats && A.training) ? A.phase : 0;
+    const int num_layers = stat_phase == 1 ? 9 : (stat_phase == 2 ? 10 : (fold ? NUM_LAYERS - 1 : NUM_LAYERS));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
@@ -197,7 +213,9 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                 for (int l = 0; l < num_layers; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
-                    const uint32_t idesc = umma_idesc_f16(TILE_M, n);
+                    // transposed layers (folded head: head layer 3; statistics phases: the layer whose column sums are wanted)
+                    const bool swap = (fold && l == 9) || (stat_phase != 0 && l == num_layers - 1);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, swap ? TILE_M : n);
                     const uint32_t lbo_b = (uint32_t)n * 16;          // bytes between K chunks of a slab: (n/8) core matrices
                     mbar_wait(a_ready + 0, ready_phase);
                     if (!x3) mbar_wait(a_ready + 1, ready_phase);
@@ -206,7 +224,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     // folded-head mode: head layer 3 is issued transposed (D^T = W3 * A^T: weights as the M operand, the tile's
                     // samples as N) so that its epilogue can sum over a ray's samples inside one thread; both operands are
                     // K-major in the same canonical layout, so the two descriptors simply swap roles
-                    if (fold && l == 9) mma_layer<true>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    if (kStats && swap && n == 256) mma_layer<true, 2>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    else if (swap) mma_layer<true>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     else mma_layer<false>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {          // D += ones(128x16) * [bias_hi | bias_lo | 0..]^T : the bias, at fp32-class accuracy
                         mbar_wait(full_bar + R.stage, R.phase);
@@ -302,6 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
         X.dbg = dbg;
         X.fold = fold != 0;
+        X.stat_phase = stat_phase;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g, h6_done + g, 0u};
         if (x3) {
@@ -310,11 +330,11 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
             X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
             Sync1 sync3{acc_full, a_ready, 0u, lane, h6_full, h6_done, 0u};
             TileAhead ahead;
-            for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true>(X, tile, sync3, ahead, tile + gridDim.x);
+            for (int64_t tile = blockIdx.x; tile < total_pairs; tile += gridDim.x) epilogue_tile<2, true, kStats, kFoldOnly>(X, tile, sync3, ahead, tile + gridDim.x);
         } else {
             TileAhead ahead;
             for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x)
-                epilogue_tile<SPLIT, false>(X, pair * 2 + g, sync, ahead, (pair + gridDim.x) * 2 + g);
+                epilogue_tile<SPLIT, false, kStats, kFoldOnly>(X, pair * 2 + g, sync, ahead, (pair + gridDim.x) * 2 + g);
         }
     }
 
@@ -827,7 +847,8 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
 
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream) {
     const bool prepass = args.bent != nullptr;
-    if (!(prepass ? pe_tc_prepass_ok(args.ob) : pe_tc_shape_ok(args.ob)) || args.training || args.explicit_positions || args.phase != 0) {
+    if (!(prepass ? pe_tc_prepass_ok(args.ob) : pe_tc_shape_ok(args.ob)) || args.explicit_positions || args.phase < 0 || args.phase > 2 ||
+        (args.phase != 0 && (!args.training || !args.stats))) {
         pe_set_error("tensor-core field kernel: unsupported configuration");
         return PE_ERR_UNSUPPORTED;
     }
@@ -837,18 +858,23 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     }
     const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
     const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
-    const int fold = args.fold_v != nullptr ? 1 : 0;
+    const int fold = (args.fold_v != nullptr && args.phase == 0) ? 1 : 0;
     if (fold && (!args.fold_s || args.feat_out || args.apply_activation || args.ob.positions % 32)) {
         pe_set_error("tensor-core field kernel: folded head needs positions %% 32 == 0, no per-sample features, no output activation");
         return PE_ERR_UNSUPPORTED;
     }
-    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int rpt = TILE_M / args.ob.positions;
     const int64_t tiles = (int64_t)((args.rays + rpt - 1) / rpt) * args.images;
     const int64_t pairs = x3 ? tiles : (tiles + 1) / 2;
     if (pairs == 0) return PE_OK;
     const int grid = (int)pe_min64(pairs, sm_count);
-    pe_field_tc_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0);
+    const int dbg = getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0;
+    if (args.training) pe_field_tc_kernel<true, false><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
+    else if (fold && !prepass) pe_field_tc_kernel<false, true><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
+    else pe_field_tc_kernel<false, false><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
     return PE_OK;
 }

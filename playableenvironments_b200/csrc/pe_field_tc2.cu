@@ -239,6 +239,7 @@ pe_field_tc2_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_pa
         X.alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
         X.dbg = dbg;
         X.fold = false;
+        X.stat_phase = 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;
         Sync2 sync{acc_full + g, mapa_u32(smem_u32(a_ready + g), 0), 0u, 0LL, nullptr, 0};
         const long long t_begin = clock64();

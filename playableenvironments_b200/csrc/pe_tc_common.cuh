@@ -164,6 +164,7 @@ struct TileCtx {
     float alpha_bias;
     const float* alpha_w;
     bool single;
+    int stat_phase;              // train-mode BatchNorm: 1 / 2 = this launch accumulates the statistics of head layer 0 / 3 and stops there
     bool fold;                   // folded-head mode: composite the 128-wide input of head layer 6, skip that layer's MMAs
     int dbg;                     // PE_TC_TIMELINE=1: thread 0 of epilogue group 0 of CTA 0 prints clock64 stamps of its third tile
 };
@@ -199,12 +200,31 @@ struct RowSample {
     float x[3];
 };
 
-__device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSample& s) {
+// world-space direction (and stratified-sampling number) of a tile row, loaded ahead of use
+struct RayPrefetch { float d[3]; float u; };
+
+template <bool kNoPrepass = false>
+__device__ __forceinline__ void prefetch_row(const TileCtx& X, int64_t tile, RayPrefetch& pf) {
+    const PeFieldArgs& A = *X.A;
+    pf.d[0] = pf.d[1] = pf.d[2] = 0.f; pf.u = 0.f;
+    if (tile >= X.total_tiles || X.m >= X.rows_used) return;
+    if (!kNoPrepass && A.tile_list) tile = A.tile_list[tile];
+    const int img = (int)(tile / X.tiles_per_image);
+    const int r = (int)(tile - (int64_t)img * X.tiles_per_image) * X.rpt + X.m / X.P;
+    if (r >= A.rays) return;
+    const int64_t ray = (int64_t)img * A.rays + r;
+    const float* dw = A.dirs + ray * 3;
+    pf.d[0] = dw[0]; pf.d[1] = dw[1]; pf.d[2] = dw[2];
+    if (A.perturb) pf.u = A.rand[ray * X.P + (X.m % X.P)];
+}
+
+template <bool kNoPrepass = false>
+__device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSample& s, const RayPrefetch* pf = nullptr) {
     const PeFieldArgs& A = *X.A;
     const PeObjectDesc& ob = A.ob;
     const int m = X.m, P = X.P, rpt = X.rpt;
     s.tile_valid = tile < X.total_tiles;
-    if (s.tile_valid && A.tile_list) tile = A.tile_list[tile];            // pre-pass mode: only the non-empty tiles are listed
+    if (!kNoPrepass && s.tile_valid && A.tile_list) tile = A.tile_list[tile];            // pre-pass mode: only the non-empty tiles are listed
     s.img = s.tile_valid ? (int)(tile / X.tiles_per_image) : 0;
     s.ray0 = s.tile_valid ? (int)(tile - (int64_t)s.img * X.tiles_per_image) * rpt : 0;
     s.valid = false; s.inbox = false;
@@ -218,8 +238,10 @@ __device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSa
             s.valid = true;
             s.p = m - rl * P;
             s.ray = (int64_t)s.img * A.rays + r;
-            const float* dw = A.dirs + s.ray * 3;
-            if (A.bent) {
+            float dw[3];
+            if (pf) { dw[0] = pf->d[0]; dw[1] = pf->d[1]; dw[2] = pf->d[2]; }
+            else { const float* dg = A.dirs + s.ray * 3; dw[0] = dg[0]; dw[1] = dg[1]; dw[2] = dg[2]; }
+            if (!kNoPrepass && A.bent) {
                 // sampled (and bent) by the pre-pass: position, parameter t and masks come from memory
                 const int64_t gs = s.ray * P + s.p;
                 s.inbox = (A.flags[gs] & 2) != 0;
@@ -227,7 +249,7 @@ __device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSa
                 if (s.inbox) { s.x[0] = A.bent[gs * 3]; s.x[1] = A.bent[gs * 3 + 1]; s.x[2] = A.bent[gs * 3 + 2]; }
             } else {
                 const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)s.img * A.objects + A.k) * 12, A.origins + (int64_t)s.img * 3, dw, s.in_scene);
-                const float u = A.perturb ? A.rand[s.ray * P + s.p] : 0.f;
+                const float u = A.perturb ? (pf ? pf->u : A.rand[s.ray * P + s.p]) : 0.f;
                 s.t = pe_sample_t(pr, s.p, P, A.perturb != 0, u);
                 pe_position(pr, s.t, s.x);
                 s.inbox = pe_in_box(ob, s.x);
@@ -301,6 +323,7 @@ __device__ __forceinline__ void store_enc(const TileCtx& X, const uint4 (&q)[8])
 // while the tensor core runs the last two layers of the current tile.
 struct TileAhead {
     bool have = false;
+    RayPrefetch pf;
     RowSample rs;
     uint4 enc[8];
 };
@@ -308,7 +331,8 @@ struct TileAhead {
 // Per-tile work of one epilogue thread.  `Sync` provides wait_acc() (accumulators of the next layer are complete) and
 // arrive_ready() (this thread's part of the next A operand is written and its TMEM reads are done).
 // kSplit threads (in different warps of the same lane quadrant) share one row: each handles 1/kSplit of the columns.
-template <int kSplit, bool kHiLo, class Sync>
+// kFoldOnly: instantiation for the folded-head mode without pre-pass (the headline path): everything else compiles away
+template <int kSplit, bool kHiLo, bool kStats = false, bool kFoldOnly = false, class Sync>
 __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sync& sync, TileAhead& ahead, int64_t next_tile) {
     static_assert(!(kHiLo && kSplit != 2) , "fp16x3 mode runs with two threads per row");
     constexpr int GROUP = TILE_M * kSplit;           // threads of the group
@@ -336,7 +360,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     PE_STAMP(0);
     // ---- sampling + Fourier features (unless the previous tile's epilogue already did them) ----
     if (!ahead.have) {
-        sample_row(X, tile, ahead.rs);
+        sample_row<kFoldOnly>(X, tile, ahead.rs);
         encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
     }
     store_enc<kSplit, kHiLo>(X, ahead.enc);
@@ -433,7 +457,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     };
 
     // ---- the 10 hidden tensor-core layers ----
-    const bool fold = X.fold;
+    const bool fold = kFoldOnly ? true : X.fold;
     float4 pre[2 / kSplit];
     const uint32_t tcol = taddr + hf * (256 / kSplit);        // first accumulator column of this thread for 256-wide layers
     for (int l = 0; l < 10; ++l) {
@@ -451,10 +475,11 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             }
             named_bar_sync(bar_id, GROUP);
             ray_scalars(cst + FOLD_T, cst + FOLD_W);
-            sample_row(X, next_tile, ahead.rs);              // look-ahead: the next tile's rows (hidden behind head layer 0)
+            prefetch_row<kFoldOnly>(X, next_tile, ahead.pf);   // look-ahead: the next tile's ray data (latency hidden behind head layer 0)
         }
         if (fold && l == 9) {
-            encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);   // ... and their encoding (behind head layer 3)
+            sample_row<kFoldOnly>(X, next_tile, ahead.rs, &ahead.pf);   // ... its rows and their encoding (behind head layer 3)
+            encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
             ahead.have = true;
         }
         PE_STAMP(2 + 3 * l);
@@ -474,6 +499,44 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         }
         if (l == 7) named_bar_sync(bar_id, GROUP);                         // constants written by the whole group at l == 4
         constexpr int W = 256 / kSplit, W2 = 128 / kSplit;
+        if (kStats && X.stat_phase != 0 && l == 7 + X.stat_phase) {
+            // Statistics phase of train-mode BatchNorm (adain.py:47; BatchNorm1d over all evaluated samples of this object): this layer was
+            // issued transposed (TMEM lane = feature, column = sample; 256-wide head layer 0 as two blocks of 128 columns), so each thread
+            // sums its feature over the tile's evaluated samples; double-precision atomics like the fp32 kernel (accumulate_stats)
+            float* rowmask = cst + FOLD_WF;
+            if (hf == 0) rowmask[m] = (valid && inbox) ? 1.f : 0.f;
+            named_bar_sync(bar_id, GROUP);
+            const int C = X.stat_phase == 1 ? 256 : 128;
+            double* stats = A.stats + (X.stat_phase == 1 ? 0 : 2 * 256 + 2);
+            constexpr int CW = 128 / kSplit;                // sample columns per thread
+            for (int blk = 0; blk < C / 128; ++blk) {
+                float sum = 0.f, sq = 0.f;
+#pragma unroll
+                for (int q = 0; q < CW / 32; ++q) {
+                    const int col0 = hf * CW + q * 32;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + blk * 128 + col0, v);
+                    tmem_wait_ld_regs(v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float y = __uint_as_float(v[i]) * rowmask[col0 + i];
+                        sum += y;
+                        sq = fmaf(y, y, sq);
+                    }
+                }
+                atomicAdd(stats + blk * 128 + m, (double)sum);
+                atomicAdd(stats + C + blk * 128 + m, (double)sq);
+            }
+            if (tid < 32) {                                  // number of samples the statistics run over (stats[2C])
+                float cnt = rowmask[tid] + rowmask[tid + 32] + rowmask[tid + 64] + rowmask[tid + 96];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (tid == 0 && cnt != 0.f) atomicAdd(stats + 2 * C, (double)cnt);
+            }
+            tc_fence_before();
+            named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
+            return;
+        }
         if (fold && l == 9) {
             // Folded head: integrated_features = sum_p w_p (W6 h_p + b6) = W6 (sum_p w_p h_p) + b6 sum_p w_p, so the
             // volume-rendering sum (:749) is taken over the 128-wide h (fp32, straight from the accumulators) and head

@@ -102,6 +102,36 @@ def test_train_mode_batchnorm_matches_reference(name):
             assert scale_rel_err(sd[k[6:]].cpu().numpy(), ref) < 1e-4, k
 
 
+@pytest.mark.parametrize("name", ["static_small", "tennis_dense"])
+def test_train_mode_on_the_tensor_cores_matches_reference(name):
+    """Train mode (batch-statistics BatchNorm + running-stat update) in the fp32-class tensor-core mode: three launches per object,
+    the two statistics phases accumulate the column sums of the transposed head layers 0 / 3 (TMEM lane = feature)."""
+    _, _, _, comp, dev = _build(name, "fp16x3", training=True)
+    golden = load_golden(name + "_train")
+    bad = compare(flatten(_run(comp, dev)), golden, 3e-4, skip=("integrated_divergence",))
+    assert not bad, bad
+    sd = comp.state_dict()
+    for k, ref in golden.items():
+        if k.startswith("state/"):
+            assert scale_rel_err(sd[k[6:]].cpu().numpy(), ref) < 1e-4, k
+
+
+def test_train_mode_tensor_core_path_is_used(monkeypatch):
+    from playableenvironments_b200.model import render
+    _, _, _, comp, dev = _build("static_small", "fp16x3", training=True)
+    _run(comp, dev)
+    render.take_launch_count()
+    _run(comp, dev)
+    n_tc = render.take_launch_count()
+    monkeypatch.setenv("PE_TC_TRAIN", "0")
+    _, _, _, comp2, dev2 = _build("static_small", "fp16x3", training=True)
+    a, b = flatten(_run(comp, dev)), flatten(_run(comp2, dev2))
+    for k in b:
+        if k.startswith("coarse/") and "disparity" not in k:
+            assert scale_rel_err(a[k], b[k]) < 2e-4, (k, scale_rel_err(a[k], b[k]))
+    assert n_tc >= 7          # 4 style launches + 3 field launches (+ compositor)
+
+
 @pytest.mark.parametrize("name", ALL_SCENES)
 def test_fp16x3_tensor_core_path_matches_reference(name):
     """fp32-class tensor-core mode (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo) on every golden scene, ill-conditioned ones included."""
