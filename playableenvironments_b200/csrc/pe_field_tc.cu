@@ -64,7 +64,8 @@ struct MmaRing {
 
 // Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
 // (D^T = W * A^T, folded-head mode, head layer 3) -- a separate instantiation so that the common loop stays branch-free.
-template <bool kSwap, int kMBlocks = 1>
+// kX3Mode: 0 = one A buffer per tile (fp16 / fp16x2), 1 = fp16x3 (hi and lo A buffers of one tile), 2 = all four partial products
+template <bool kSwap, int kMBlocks, int kX3Mode>
 __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, int chunk0, bool has_bias, uint32_t idesc, uint32_t lbo_b) {
     (void)l; (void)n;
     // kSwap: D^T = W * A^T -- the weight slab is the M operand (blocks of 128 of its n rows: block b starts 2048 B into every K chunk and
@@ -77,7 +78,7 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
             tc_fence_after();
             const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
             const uint32_t b_addr = R.ring_addr + R.stage * STAGE_BYTES;
-            if (R.x3) {
+            if (kX3Mode != 0) {
                 // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -91,7 +92,7 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
                         const uint32_t td = R.tmem_base + b * 128;
                         umma_f16_ss(td, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
                         // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
-                        if (pass == 0 || R.x3 == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+                        if (pass == 0 || kX3Mode == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
                     }
                 }
                 if (last) umma_commit(R.acc_full + 0);
@@ -119,8 +120,11 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
 
 // kStats: the train-mode instantiation (statistics phases of BatchNorm); the eval instantiation carries none of that code
 // kFoldOnly: the headline instantiation (folded head, sampling inside the kernel, eval)
-template <bool kStats, bool kFoldOnly>
-__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3, const int fold, const int dbg) {
+// kX3: the fp16x3 instantiation (one tile per iteration, both epilogue groups on its rows); the other modes do not carry its code
+template <bool kStats, bool kFoldOnly, bool kX3>
+__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3_arg, const int fold, const int dbg) {
+    constexpr int x3 = kX3 ? 1 : 0;
+    (void)x3_arg;
     // fold: folded-head mode (pe_tc_common.cuh): head layer 6 is applied per ray by pe_head6_fold_kernel, 10 MMA layers per tile
     // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
     // per k-step A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (fp32-class accuracy on the tensor cores); epilogue group Y idles
@@ -224,9 +228,9 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     // folded-head mode: head layer 3 is issued transposed (D^T = W3 * A^T: weights as the M operand, the tile's
                     // samples as N) so that its epilogue can sum over a ray's samples inside one thread; both operands are
                     // K-major in the same canonical layout, so the two descriptors simply swap roles
-                    if (kStats && swap && n == 256) mma_layer<true, 2>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
-                    else if (swap) mma_layer<true>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
-                    else mma_layer<false>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    if (kStats && swap && n == 256) mma_layer<true, 2, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    else if (swap) mma_layer<true, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    else mma_layer<false, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {          // D += ones(128x16) * [bias_hi | bias_lo | 0..]^T : the bias, at fp32-class accuracy
                         mbar_wait(full_bar + R.stage, R.phase);
                         tc_fence_after();
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.stat_phase = stat_phase;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g, h6_done + g, 0u};
-        if (x3) {
+        if constexpr (kX3) {
             // one tile per iteration: the two epilogue groups become the two column halves of the same 128 rows
             X.abuf = smem; X.half = g; X.gw = warp - 4; X.bar_id = 1;
             X.taddr = tmem_base + (((uint32_t)X.wq * 32u) << 16);
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
                     mbar_wait(a_ready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
-                    mma_layer<false>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    mma_layer<false, 1, 2>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {
                         mbar_wait(full_bar + R.stage, R.phase);
                         tc_fence_after();
@@ -863,18 +867,20 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
         pe_set_error("tensor-core field kernel: folded head needs positions %% 32 == 0, no per-sample features, no output activation");
         return PE_ERR_UNSUPPORTED;
     }
-    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_field_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    const int dbg = getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0;
     const int rpt = TILE_M / args.ob.positions;
     const int64_t tiles = (int64_t)((args.rays + rpt - 1) / rpt) * args.images;
     const int64_t pairs = x3 ? tiles : (tiles + 1) / 2;
     if (pairs == 0) return PE_OK;
     const int grid = (int)pe_min64(pairs, sm_count);
-    const int dbg = getenv("PE_TC_TIMELINE") ? atoi(getenv("PE_TC_TIMELINE")) : 0;
-    if (args.training) pe_field_tc_kernel<true, false><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
-    else if (fold && !prepass) pe_field_tc_kernel<false, true><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
-    else pe_field_tc_kernel<false, false><<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
+    // one instantiation per (train-mode statistics, headline specialisation, fp16x3) combination that occurs
+    using Kernel = void (*)(const PeFieldArgs, const PeIntegrated, const int, const int, const int, const int);
+    Kernel kernel;
+    if (args.training) kernel = x3 ? pe_field_tc_kernel<true, false, true> : pe_field_tc_kernel<true, false, false>;
+    else if (fold && !prepass) kernel = x3 ? pe_field_tc_kernel<false, true, true> : pe_field_tc_kernel<false, true, false>;
+    else kernel = x3 ? pe_field_tc_kernel<false, false, true> : pe_field_tc_kernel<false, false, false>;
+    PE_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
     return PE_OK;
 }

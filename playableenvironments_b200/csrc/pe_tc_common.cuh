@@ -460,6 +460,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     const bool fold = kFoldOnly ? true : X.fold;
     float4 pre[2 / kSplit];
     const uint32_t tcol = taddr + hf * (256 / kSplit);        // first accumulator column of this thread for 256-wide layers
+#pragma unroll 1
     for (int l = 0; l < 10; ++l) {
         if (fold && l == 8) {
             // folded-head mode: the raw alphas are known after L7, so the compositing weights are computed here, while the
@@ -475,10 +476,16 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             }
             named_bar_sync(bar_id, GROUP);
             ray_scalars(cst + FOLD_T, cst + FOLD_W);
+#ifdef PE_TC_SAMPLE_AT_L8
+            sample_row<kFoldOnly>(X, next_tile, ahead.rs);
+#else
             prefetch_row<kFoldOnly>(X, next_tile, ahead.pf);   // look-ahead: the next tile's ray data (latency hidden behind head layer 0)
+#endif
         }
         if (fold && l == 9) {
+#ifndef PE_TC_SAMPLE_AT_L8
             sample_row<kFoldOnly>(X, next_tile, ahead.rs, &ahead.pf);   // ... its rows and their encoding (behind head layer 3)
+#endif
             encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
             ahead.have = true;
         }
@@ -620,6 +627,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         PE_STAMP(4 + 3 * l);
     }
 
+    if (kFoldOnly) return;       // (unreachable: the folded-head path returned inside the loop; drops the code below from that instantiation)
     // ---- last layer: features in TMEM -> volume rendering of the tile's rays (ObjectComposer.integrate :724-784) ----
     // row scalars are computed redundantly by the kSplit threads of a row (identical values), stores by half 0 only
     sync.wait_acc();
