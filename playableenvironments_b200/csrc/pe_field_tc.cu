@@ -96,6 +96,23 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
                     }
                 }
                 if (last) umma_commit(R.acc_full + 0);
+            } else if (kMBlocks == 1) {
+                // the common case, kept minimal (the issue loop shares its scheduler with two epilogue warps): descriptor words
+                // advanced by 32-bit adds
+                constexpr uint32_t hi = umma_desc_hi(128);
+                const uint32_t b_lo = umma_desc_lo(b_addr, lbo_b);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a_lo = umma_desc_lo(R.a_addr[g] + (chunk0 + 4 * s) * CHUNK_BYTES, CHUNK_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t al = a_lo + j * (2 * CHUNK_BYTES >> 4), bl = b_lo + j * (2 * lbo_b >> 4);
+                        const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
+                        if (kSwap) umma_f16_ss_words(R.tmem_base + g * 256, bl, hi, al, hi, idesc, accum);
+                        else umma_f16_ss_words(R.tmem_base + g * 256, al, hi, bl, hi, idesc, accum);
+                    }
+                    if (last) umma_commit(R.acc_full + g);
+                }
             } else {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
@@ -121,9 +138,11 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
 // kStats: the train-mode instantiation (statistics phases of BatchNorm); the eval instantiation carries none of that code
 // kFoldOnly: the headline instantiation (folded head, sampling inside the kernel, eval)
 // kX3: the fp16x3 instantiation (one tile per iteration, both epilogue groups on its rows); the other modes do not carry its code
-template <bool kStats, bool kFoldOnly, bool kX3>
-__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes, const int x3_arg, const int fold, const int dbg) {
+// kPasses: weight passes per k-step known at compile time (1: fp16, 2: fp16x2 / fp16x3), 0: taken from the argument
+template <bool kStats, bool kFoldOnly, bool kX3, int kPasses>
+__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes_arg, const int x3_arg, const int fold, const int dbg) {
     constexpr int x3 = kX3 ? 1 : 0;
+    const int num_passes = kPasses ? kPasses : num_passes_arg;
     (void)x3_arg;
     // fold: folded-head mode (pe_tc_common.cuh): head layer 6 is applied per ray by pe_head6_fold_kernel, 10 MMA layers per tile
     // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
@@ -876,9 +895,9 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     // one instantiation per (train-mode statistics, headline specialisation, fp16x3) combination that occurs
     using Kernel = void (*)(const PeFieldArgs, const PeIntegrated, const int, const int, const int, const int);
     Kernel kernel;
-    if (args.training) kernel = x3 ? pe_field_tc_kernel<true, false, true> : pe_field_tc_kernel<true, false, false>;
-    else if (fold && !prepass) kernel = x3 ? pe_field_tc_kernel<false, true, true> : pe_field_tc_kernel<false, true, false>;
-    else kernel = x3 ? pe_field_tc_kernel<false, false, true> : pe_field_tc_kernel<false, false, false>;
+    if (args.training) kernel = x3 ? pe_field_tc_kernel<true, false, true, 2> : pe_field_tc_kernel<true, false, false, 0>;
+    else if (fold && !prepass) kernel = x3 ? pe_field_tc_kernel<false, true, true, 2> : (num_passes == 1 ? pe_field_tc_kernel<false, true, false, 1> : pe_field_tc_kernel<false, true, false, 2>);
+    else kernel = x3 ? pe_field_tc_kernel<false, false, true, 2> : pe_field_tc_kernel<false, false, false, 0>;
     PE_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");

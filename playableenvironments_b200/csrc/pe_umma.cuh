@@ -102,6 +102,22 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
         : "memory");
 }
 
+// The same descriptor as two 32-bit words: lo = start address | LBO (changes with the operand position: plain 32-bit adds of
+// (byte offset >> 4) move it), hi = SBO | version (constant per operand)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ void umma_f16_ss_words(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Instruction descriptor with selectable operand major-ness (0: K-major, 1: MN-major), see umma_idesc_f16
 __host__ __device__ constexpr uint32_t umma_idesc_f16_major(int M, int N, int a_mn_major, int b_mn_major) {
     return umma_idesc_f16(M, N) | ((uint32_t)(a_mn_major & 1) << 15) | ((uint32_t)(b_mn_major & 1) << 16);
