@@ -357,8 +357,8 @@ def run_b200(args):
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / peaks["burst"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one pe_field_tc_kernel launch on this workload
-                         # (profiles/r1b_tc_fold_summary.md; fp16: 3.3 MB + 147.9 MB, fp16x2: 4.4 MB + 147.1 MB)
-                         "traffic": {"fp16": 151281664, "fp16x2": 151431168}.get(args.precision), "peak_source": peaks["source"] + " bf16 burst",
+                         # (profiles/r1c_final_summary.md; fp16: 3.4 MB + 146.8 MB, fp16x2: 4.1 MB + 147.7 MB)
+                         "traffic": {"fp16": 150208768, "fp16x2": 151788032}.get(args.precision), "peak_source": peaks["source"] + " bf16 burst",
                          "frac_of_sustained": achieved_tflops / peaks["sustained"],
                          "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0}[args.precision]},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
