@@ -99,6 +99,39 @@ class ObjectComposer(nn.Module):
         results["pytorch_hook"] = torch.zeros((1, 1, 1, 1, 1, 1, 1, 1, 1), device=ray_directions.device)
         return results
 
+    @staticmethod
+    def compute_expected_positions(ray_positions: torch.Tensor, ray_displacements: torch.Tensor, weights: torch.Tensor, eps=1e-8):
+        """Reference :603-622: weighted average of the bent sample positions along each ray (weights detached)."""
+        weights = weights.detach().unsqueeze(-1)
+        return ((ray_positions + ray_displacements) * weights).sum(dim=-2) / (weights.sum(dim=-2) + eps)
+
+    def forward_expected_positions(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
+                                   transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor,
+                                   object_in_scene: torch.Tensor, object_id: int, perturb: bool, video_indexes: torch.Tensor = None,
+                                   canonical_pose: bool = False, rand=None, noise=None) -> Dict:
+        """Reference :624-722 for ONE object instance: inputs are that object's (..., 4, 4) pose, (..., S) style, (..., D) deformation
+        and (...) presence flag.  Returns {"coarse": (expected_positions (..., R, 3) in object space, opacity (..., R))}.
+
+        The samples (ray parameter t, displacement, compositing weights) come from the same kernels as ``forward`` in a single-object
+        scene; the weighted average itself is three small tensor ops.  Forward only: the pose-consistency / keypoint losses that
+        differentiate through it have weight 0 in every shipped config, so a call that would need a graph raises."""
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(
+                torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation))):
+            raise Exception("forward_expected_positions is forward-only in the B200 render path: call it under torch.no_grad()")
+        from ..utils.lib_3d.ray_helper import RayHelper
+        helper = self.object_id_helper
+        model_idx = helper.model_idx_by_object_idx(object_id)
+        m = self.object_models_coarse[model_idx]
+        desc = m.object_desc(m.model_config["positions_count_coarse"], helper.is_static(model_idx), canonical_pose)
+        res = render.render_scene([desc], 1 if helper.is_static(model_idx) else 0, ray_origins, ray_directions,
+                                  transformation_matrix_w2o.unsqueeze(-1), style.unsqueeze(-1), deformation.unsqueeze(-1),
+                                  object_in_scene.unsqueeze(-1), perturb, self.training, False, self.apply_activation,
+                                  _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, return_samples=True)["object_0"]
+        origins_o, directions_o, _ = RayHelper.transform_rays(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o)
+        positions = origins_o.unsqueeze(-2).unsqueeze(-2) + directions_o.unsqueeze(-2) * res["positions_t"].unsqueeze(-1)
+        expected = self.compute_expected_positions(positions, res["displacements"], res["weights"])
+        return {"coarse": (expected, res["opacity"])}
+
     def _update_running_statistics(self, bn_running):
         """BatchNorm running-stat update of the two AdaIn layers, in object order like the reference's sequential
         per-instance model calls (a model shared by two instances is updated twice)."""

@@ -125,6 +125,11 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms) -> Dict:
         if meta.get("return_raw_alphas"):   # diagnostic: per-sample raw alphas (first return value family of the object models)
             r["raw_alphas"] = torch.empty(lead + [rays, d.positions], dtype=torch.float32, device=device)
             outs.raw_alphas[k] = _cabi.ptr(r["raw_alphas"])
+        if meta.get("return_samples"):      # per-sample ray parameter t and displacement (forward_expected_positions)
+            r["positions_t"] = torch.empty(lead + [rays, d.positions], dtype=torch.float32, device=device)
+            r["displacements"] = torch.zeros(lead + [rays, d.positions, 3], dtype=torch.float32, device=device)
+            outs.positions_t[k] = _cabi.ptr(r["positions_t"])
+            outs.displacements[k] = _cabi.ptr(r["displacements"])
         if meta["training"] and meta.get("bn_running") is not None:
             b1 = torch.empty((2, d.width), dtype=torch.float32, device=device)
             b2 = torch.empty((2, d.width // 2), dtype=torch.float32, device=device)
@@ -229,7 +234,8 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
                  perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
                  rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
-                 bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None) -> Dict:
+                 bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
+                 return_samples: bool = False) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
     With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node."""
     device = ray_directions.device
@@ -248,7 +254,7 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
     meta = {"descs": descs, "static_objects": static_objects, "perturb": perturb, "training": training,
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
-            "return_raw_alphas": return_raw_alphas, "models": models}
+            "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples}
     if models is not None and torch.is_grad_enabled():
         flat_params = [t for mdl in models for _, _, t in mdl.parameter_slots()]
         flat = RenderFunction.apply(meta, origins, dirs, m, *styles, *deforms, *flat_params)

@@ -9,6 +9,8 @@ Tolerances (relative to the tensor's scale: max|got - ref| / max|ref|; BASELINE.
   few-sample objects (P=4, P=16) amplify the fp16 activation rounding through exp(-relu(a) * delta) with delta ~ 20..85:
   fp16/fp16x2 are held to 6e-3 / 8e-2 there; fp16x3 and fp32 stay at 2e-4 (Numerics).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -330,6 +332,25 @@ def test_full_size_frame_properties(precision):
         assert scale_rel_err(got, want) < tol, (key, scale_rel_err(got, want))
         rel_l2 = float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want.astype(np.float64)))
         assert rel_l2 < 1e-3, (key, rel_l2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("fp16x3", 3e-4)])
+def test_forward_expected_positions_matches_reference(precision, tol):
+    """ObjectComposer.forward_expected_positions (reference :624-722) for single object instances of the golden scenes, against
+    outputs of the upstream method (tests/golden/make_golden_expected.py)."""
+    from make_golden_expected import EXPECTED_CASES, object_inputs
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "expected_positions.npz"))
+    for name, k in EXPECTED_CASES:
+        _, _, inputs, comp, _ = _build(name, precision)
+        args = [t.cuda() for t in object_inputs(inputs, k)]
+        with torch.no_grad():
+            exp, opacity = comp.forward_expected_positions(*args, k, False)["coarse"]
+        torch.cuda.synchronize()
+        assert scale_rel_err(exp.cpu().numpy(), golden[f"{name}/{k}/expected_positions"]) < tol, (name, k)
+        assert scale_rel_err(opacity.cpu().numpy(), golden[f"{name}/{k}/opacity"]) < tol, (name, k)
+    comp.allow_forward_without_grad = False
+    with pytest.raises(Exception, match="forward-only"):
+        comp.forward_expected_positions(*args, k, False)
 
 
 def test_launch_accounting_and_no_fallback():
