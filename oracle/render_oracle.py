@@ -478,6 +478,34 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
     return results
 
 
+def forward_expected_positions(config: dict, state: Dict[str, Tensor], ray_origins: Tensor, ray_directions: Tensor, focal_normals: Tensor,
+                               transformation_matrix_w2o: Tensor, style: Tensor, deformation: Tensor, object_in_scene: Tensor,
+                               object_id: int, perturb: bool, canonical_pose: bool = False, training: bool = False,
+                               rand: Optional[Tensor] = None, noise: Optional[Tensor] = None) -> Dict:
+    """model/object_composer.py:624-722 (coarse pass) + compute_expected_positions :603-622, for ONE object instance:
+    ``transformation_matrix_w2o`` (..., 4, 4), ``style`` (..., S), ``deformation`` (..., D), ``object_in_scene`` (...).
+    Returns {"coarse": (expected_positions (..., R, 3) in object space, opacity (..., R))}."""
+    model_of, _ = object_ids(config)
+    mi = model_of[object_id]
+    cfg = config["model"]["object_models"][mi]
+    prefix = f"object_models_coarse.{mi}."
+    sd = {key[len(prefix):]: val for key, val in state.items() if key.startswith(prefix)}
+    bbox = torch.as_tensor(cfg["bounding_box"], dtype=torch.float32)
+    o, d, _ = transform_rays(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o)
+    zn, zf = raywise_object_z_bounds(o, d, bbox, object_in_scene)
+    zn = torch.clamp(zn, min=cfg["z_near_min"], max=cfg["z_far_max"])
+    zf = torch.clamp(zf, min=cfg["z_near_min"], max=cfg["z_far_max"])
+    pos, t = create_ray_positions(o, d, zn, zf, cfg["positions_count_coarse"], perturb, rand)
+    o_exp = o.unsqueeze(-2).expand(list(d.shape))
+    _, a, disp = ray_bending_style_nerf(sd, cfg, pos, o_exp, d, style.unsqueeze(-2), deformation.unsqueeze(-2), canonical_pose, training)
+    absent = torch.logical_not(object_in_scene)
+    a = torch.where(absent.reshape(list(absent.shape) + [1] * (a.dim() - absent.dim())), torch.full_like(a, cfg["empty_space_alpha"]), a)
+    weights = compute_weights(compute_alphas(a, position_distances(t, ray_directions), noise if perturb else None))
+    w = weights.detach().unsqueeze(-1)
+    expected = ((pos + disp) * w).sum(dim=-2) / (w.sum(dim=-2) + 1e-8)          # :603-622
+    return {"coarse": (expected, weights.sum(dim=-1))}
+
+
 class _Prefixed(dict):
     """dict view that writes ``prefix + key`` into a parent dict."""
 

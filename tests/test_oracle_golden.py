@@ -94,3 +94,19 @@ def test_gradients_match_reference_autograd(name, training):
     got_par = {k: (v.grad.numpy() if v.grad is not None else zeros(v)) for k, v in state.items() if v.is_floating_point() and "running_" not in k}
     bad = compare_grads(got_in, got_par, golden, 2e-4)
     assert not bad, bad
+
+
+def test_oracle_expected_positions_match_the_reference():
+    """forward_expected_positions (model/object_composer.py:624-722) of the oracle against outputs of the upstream method."""
+    import os
+    import numpy as np
+    import torch
+    from make_golden_expected import EXPECTED_CASES, object_inputs
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "expected_positions.npz"))
+    for name, k in EXPECTED_CASES:
+        config, state, inputs = scenes.SCENES[name]()
+        with torch.no_grad():
+            exp, opacity = O.forward_expected_positions(config, state, *object_inputs(inputs, k), k, False)["coarse"]
+        for got, key in ((exp, "expected_positions"), (opacity, "opacity")):
+            ref = golden[f"{name}/{k}/{key}"]
+            assert float(np.abs(got.numpy() - ref).max()) <= 2e-5 * max(float(np.abs(ref).max()), 1e-6), (name, k, key)
