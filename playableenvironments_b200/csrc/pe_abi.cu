@@ -58,7 +58,7 @@ extern "C" int pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* pa
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct ObjWorkspace {
-    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s, *bent;
+    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s, *bent, *h7;
     uint8_t* flags;
     int32_t *tile_list, *tile_count;
     uint8_t* inbox;
@@ -134,6 +134,11 @@ static Workspace carve(const PeScene& s, void* base) {
         o.flags = prepass ? (uint8_t*)take(n) : nullptr;
         o.tile_list = prepass ? (int32_t*)take(tiles * 4) : nullptr;
         o.tile_count = prepass ? (int32_t*)take(4) : nullptr;
+        // train-mode recompute for the backward on the tensor cores: the trunk output of every evaluated sample, so that the two
+        // BatchNorm-reduction passes of the field backward start from it (PE_BWD_TRUNK_CACHE=0 disables)
+        const char* cenv = getenv("PE_BWD_TRUNK_CACHE");
+        const bool cache = g_keep_samples && s.training && (object_uses_tc(s, k) || prepass) && !(cenv && atoi(cenv) == 0);
+        o.h7 = cache ? (float*)take(n * d.width * 4) : nullptr;
         o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
         o.aff2 = (float*)take((size_t)s.images * d.width * 4);
         o.stats = (double*)take((size_t)(3 * d.width + 4) * 8);
@@ -210,6 +215,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.integ = out->object[k];
         fa.noise = s.perturb ? in->noise[k] : nullptr;
         if (tc && !fa.feat_out && o.fold_v) { fa.fold_v = o.fold_v; fa.fold_s = o.fold_s; }
+        fa.h7_out = o.h7;
         if (!tc && !fa.feat_out) { pe_set_error("internal: no feature buffer for object %d", k); return PE_ERR_INVALID; }
         if (d.bender_kind == PE_BENDER_POSITIONAL && !fa.deformation) { pe_set_error("object %d needs a deformation code", k); return PE_ERR_INVALID; }
         if (!in->style[k]) { pe_set_error("object %d needs a style code", k); return PE_ERR_INVALID; }
@@ -477,6 +483,7 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
         fb.adain_sums = b.adain_sums; fb.bn_sums = b.bn_sums; fb.bn_fix = b.bn_fix;
         fb.g_deformation = grad_in->deformation[k];
         fb.stash = bw.stash; fb.stash_floats = bw.stash_floats;
+        fb.h7_cache = o.h7; fb.inbox_in = o.h7 ? o.inbox : nullptr;
         if (!fb.w.head0_w || !fb.w.head3_w || !fb.w.head6_w) { pe_set_error("backward needs the fp32 parameters of object %d", k); return PE_ERR_INVALID; }
         if (s.training) {
             fb.bwd_phase = 1;

@@ -259,6 +259,27 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         const int64_t gs0 = (int64_t)img * slots_per_image + slot0;
         const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
         __syncthreads();
+        float* bufs[2] = {S.bufA, S.bufB};
+        const float* cur = nullptr;
+        int curK = 0, which = 0;
+        // BatchNorm-reduction passes with the trunk output of the forward recompute at hand: only the head is evaluated
+        const bool from_cache = !full && B.h7_cache != nullptr && B.inbox_in != nullptr;
+        if (from_cache) {
+            if (tid < TB) {
+                const int64_t s = slot0 + tid;
+                int flag = 0;
+                if (s < slots_per_image) flag = 4 | (B.inbox_in[gs0 + tid] ? 3 : 0);
+                S.flags[tid] = flag;
+            }
+            const int any = __syncthreads_or(tid < TB ? (S.flags[tid] & 2) : 0);
+            if (!any) continue;
+            for (int idx = tid; idx < W * TB; idx += NT) {
+                const int m = idx / W, n = idx - m * W;                 // consecutive threads: consecutive features of one sample
+                bufs[0][n * TS + m] = (S.flags[m] & 2) ? B.h7_cache[(gs0 + m) * W + n] : 0.f;
+            }
+            cur = bufs[0]; curK = W; which = 1;
+            __syncthreads();
+        } else {
         // ================================ forward recompute ================================
         if (tid < TB) {
             const int64_t s = slot0 + tid;
@@ -294,7 +315,6 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             }
             continue;
         }
-        float* bufs[2] = {S.bufA, S.bufB};
         // ---- ray bender forward (positional_ray_bender_model.py:81-163) ----
         if (positional) {
             const int Eb = 3 * (1 + 2 * ob.b_octaves);
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             }
             __syncthreads();
             const float* cur = S.enc;
-            int curK = L.b_enc, which = 0;
+            int curK = L.b_enc, which = 0;          // (the bender's own chain; shadows the field's)
             for (int l = 0; l < ob.b_layers; ++l) {
                 float* nxt = bufs[which];
                 float* sto = st(ST.bh[l]);
@@ -377,8 +397,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         }
         __syncthreads();
         // ---- backbone ----
-        const float* cur = S.enc;
-        int curK = L.enc, which = 0;
+        cur = S.enc; curK = L.enc; which = 0;
         for (int l = 0; l < ob.layers; ++l) {
             float* nxt = bufs[which];
             float* sto = st(ST.h[l]);
@@ -391,6 +410,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             });
             cur = nxt; curK = W; which ^= 1;
         }
+        }   // !from_cache
         // ---- feature head with AdaIn ----
         const float* sc1 = A.aff1 + (int64_t)img * 2 * W;
         const float* sh1 = sc1 + W;

@@ -37,6 +37,7 @@ struct PeFieldArgs {
     uint8_t* flags;              // [images][rays][P]    bit 0: in the box, bit 1: bent position in the box (field evaluated)
     const int32_t* tile_list;    // [*tile_count] tiles (of floor(128/P) rays) that hold at least one sample with bit 1
     const int32_t* tile_count;
+    float* h7_out;               // [images][rays][P][W] trunk output of the evaluated samples (train-mode recompute for the backward) or NULL
 };
 
 // Arguments of the compositing kernel (model/object_composer.py:399-447, 724-784).
@@ -103,6 +104,8 @@ struct PeFieldBwdArgs {
     float* g_deformation;          // accumulated [images][D]
     float* stash;                  // per-block activation stash
     int64_t stash_floats;          // floats per block
+    const float* h7_cache;         // [images][rays][P][W] trunk output written by the forward recompute (tensor-core path) or NULL:
+    const uint8_t* inbox_in;       // ... with its evaluated-sample mask; the BatchNorm-reduction passes (bwd_phase 1, 2) start from them
 };
 
 // Style / BatchNorm backward (pe_backward.cu)

@@ -87,7 +87,8 @@ __device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&v)[32]) {
 //   MODE 2: AdaIn layer            y = relu(acc * sc[c] + sh[c])   (BatchNorm folded into sc/sh, adain.py:58-59)
 template <int MODE, int N, bool kHiLo = false>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* abuf, int chunk0, int m, const float* __restrict__ c0s,
-                                                 const float* __restrict__ c1s, unsigned char* abuf_lo = nullptr) {
+                                                 const float* __restrict__ c1s, unsigned char* abuf_lo = nullptr, float* h_out = nullptr) {
+    // h_out (MODE 1, train-mode recompute for the backward): this row's post-ReLU trunk output in fp32, first of its N columns
     // tcol: TMEM address of the first of the N columns handled here; chunk0: A-operand chunk (= column / 8) they are stored to;
     // c0s / c1s: per-column constants, already offset to the first column
     uint32_t v[2][32];
@@ -100,6 +101,12 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* a
         float y[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) y[q] = __uint_as_float(v[c & 1][q]);
+        if (MODE == 1 && h_out) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(h_out + c * 32 + 4 * q) =
+                    make_float4(fmaxf(y[4 * q], 0.f), fmaxf(y[4 * q + 1], 0.f), fmaxf(y[4 * q + 2], 0.f), fmaxf(y[4 * q + 3], 0.f));
+        }
         if (MODE == 1) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -615,7 +622,12 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             return;
         }
         if (l < 7) hidden_epilogue<0, W, kHiLo>(tcol, abuf, hf * (W / 8), m, nullptr, nullptr, X.abuf_lo);
-        else if (l == 7) raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo);
+        else if (l == 7) {
+            // train-mode recompute for the backward: the trunk output goes to memory so that the BatchNorm-reduction passes of
+            // pe_field_bwd_kernel start from it instead of recomputing bender, encoding and trunk
+            float* h_out = (kStats && A.h7_out && X.stat_phase == 0 && valid) ? A.h7_out + gs * 256 + hf * W : nullptr;
+            raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo, h_out);
+        }
         else if (l == 8) hidden_epilogue<2, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W, X.abuf_lo);
         else hidden_epilogue<2, W2, kHiLo>(taddr + hf * W2, abuf, hf * (W2 / 8), m, cst + CST_SC2 + hf * W2, cst + CST_SH2 + hf * W2, X.abuf_lo);
         if (l == 4) {
