@@ -237,6 +237,12 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
                 pre.tile_list = o.tile_list; pre.tile_count = o.tile_count;
                 int rc2;
+                if (s.training && phase != 1) {
+                    // statistics phase 2 / final pass of a train-mode call: positions, masks and the tile list of phase 1 are still valid
+                    PeFieldArgs tcargs = pre;
+                    tcargs.phase = phase;
+                    return pe_launch_field_tc(tcargs, none, sm_count, stream);
+                }
                 // The bender's output feeds 2^9-octave Fourier features (x2pi/size: an absolute error e of the normalised
                 // displacement becomes a phase error of 3217 e), so the tensor-core bender (hi/lo split, all four partial products,
                 // but the tensor core's own fp32 accumulation) lands at ~3e-4 of the reference on the rendered outputs: used in the
