@@ -1,6 +1,7 @@
 // Small kernels around the field evaluation: style prologue (AdaIn affine with folded BatchNorm),
 // parameter packing, ray generation, stand-alone positional encoding and the decoder hand-off fold.
 #include "pe_kernels.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -184,7 +185,10 @@ int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParam
     }
     if (L.tc_supported) {
         PE_TRY(pe_tc_pack(d, L, p, packed, stream));
-        PE_TRY(pe_tc2_pack(d, L, p, packed, stream));
+        // the CTA-pair layout only when the experimental kernel is selected (PE_TC_KERNEL=2, read per process): in training the
+        // parameters are re-packed after every optimizer step
+        const char* which = getenv("PE_TC_KERNEL");
+        if (which && atoi(which) == 2) PE_TRY(pe_tc2_pack(d, L, p, packed, stream));
     }
 #undef PE_TRY
     return PE_OK;
