@@ -89,3 +89,45 @@ def test_cpu_tensors_fail_loudly():
     comp.eval()
     with torch.no_grad(), pytest.raises(_cabi.PeError):
         comp(*[inputs[k] for k in INPUT_KEYS], False)
+
+
+def _shipped_desc(positional_bender: bool, positions: int):
+    from playableenvironments_b200 import _cabi
+    d = _cabi.PeObjectDesc()
+    d.nerf_kind, d.bender_kind = _cabi.NERF_ADAIN, (_cabi.BENDER_POSITIONAL if positional_bender else _cabi.BENDER_ZEROED)
+    d.width, d.layers, d.skip, d.octaves, d.features, d.positions = 256, 8, 4, 10, 192, positions
+    d.style_features, d.deformation_features = 64, 32
+    d.b_width, d.b_layers, d.b_skip, d.b_octaves = 128, 6, 3, 6
+    d.bbox[:] = [-1.0, 1.0, -1.0, 1.0, 0.0, 2.0]
+    d.z_near_min, d.z_far_max, d.empty_space_alpha = 0.1, 10.0, -3.5
+    d.packed = 256                                  # any non-null pointer: sizing never dereferences it
+    return d
+
+
+def test_workspace_and_blob_sizes_follow_the_chosen_path(lib):
+    """Host-side sizing (no GPU): the packed blob of a shipped-shape object holds the tensor-core weight streams (field: hi + lo passes
+    twice -- single-CTA and CTA-pair layout --, ray bender: hi + lo), and the forward workspace grows by the pre-pass hand-off (bent
+    positions, masks, tile list) exactly when a ray-bender object takes the tensor-core path."""
+    from playableenvironments_b200 import _cabi
+    plain, bent = _shipped_desc(False, 32), _shipped_desc(True, 32)
+    b_plain, b_bent = lib.pe_packed_bytes(ctypes.byref(plain)), lib.pe_packed_bytes(ctypes.byref(bent))
+    assert b_plain > 4 * 1_300_000                  # 2 layouts x 2 passes x 1.30 MB of fp16 slabs (+ the fp32 section)
+    assert b_bent - b_plain > 2 * 241_664           # + bender fp32 weights + its two slab passes
+    scene = _cabi.PeScene()
+    scene.images, scene.rays, scene.objects, scene.static_objects = 2, 1000, 1, 0
+    scene.object[0] = bent
+    sizes = {}
+    for name in ("fp32", "fp16x3"):
+        scene.precision = _cabi.PRECISIONS[name]
+        sizes[name] = lib.pe_workspace_bytes(ctypes.byref(scene))
+        assert sizes[name] > 0, lib.pe_last_error()
+    slots = 2 * 1000 * 32
+    assert sizes["fp16x3"] - sizes["fp32"] >= slots * 13            # 12 B position + 1 B mask per slot (+ tile list)
+    scene.training = 1
+    assert lib.pe_backward_workspace_bytes(ctypes.byref(scene)) > sizes["fp16x3"] + slots * 256 * 4      # + trunk-output hand-off
+
+
+def test_debug_entry_points_validate_their_arguments(lib):
+    assert lib.pe_debug_umma_gemm2(3, None, None, None, 128, 64, 0, 0, None) != 0
+    assert b"debug gemm2" in lib.pe_last_error()
+    assert lib.pe_debug_umma_gemm2(1, None, None, None, 100, 64, 128, 2048, None) != 0
