@@ -338,6 +338,7 @@ def run_b200(args):
                 diff = feats_main.reshape(rays, F).double()[stable] - ref
                 parity = {"reference": "fp16x3 mode (fp32-class: within 1e-5 of the fp32 CUDA path) on the same frame",
                           "rel_l2": float(diff.norm() / ref.norm()), "max_over_scale": float(diff.abs().max() / ref.abs().max()),
+                          "frac_of_values_within_1e-3_of_scale": float((diff.abs() <= 1e-3 * ref.abs().max()).double().mean()),
                           "rays_on_opacity_step_excluded": float(1.0 - stable.float().mean())}
         comp.precision = args.precision
 
