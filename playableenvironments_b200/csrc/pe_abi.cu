@@ -345,7 +345,16 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
 struct ObjBwdWorkspace {
     float *cw_obj, *cw_glob, *g_raw, *g_t, *g_dm, *g_pos, *g_od, *adain_sums, *bn_fix;
     double* bn_sums;
+    int32_t *slot_list, *slot_count, *tile_begin;      // compacted tiles of the field backward (NULL: dense tiles)
 };
+
+// The field backward walks tiles of 32 samples; with the in-box masks of the (tensor-core) forward recompute at hand it walks only the
+// samples inside the object's box, compacted per image (PE_BWD_COMPACT=0: tiles of 32 consecutive slots as in the all-fp32 path).
+static bool backward_compacts(const PeScene& s, int k) {
+    const char* env = getenv("PE_BWD_COMPACT");
+    if (env && atoi(env) == 0) return false;
+    return s.object[k].nerf_kind == PE_NERF_ADAIN && (object_uses_tc(s, k) || object_uses_prepass(s, k));
+}
 
 struct BwdWorkspace {
     void* fwd;
@@ -383,6 +392,10 @@ static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
         o.g_raw = (float*)take(n * 4); o.g_t = (float*)take(n * 4); o.g_dm = (float*)take(n * 4);
         o.g_pos = (float*)take(n * 12);
         o.g_od = d.nerf_kind == PE_NERF_SKYBOX_V3 ? (float*)take(n * 24) : nullptr;
+        const bool compact = backward_compacts(s, k);
+        o.slot_list = compact ? (int32_t*)take(n * 4) : nullptr;
+        o.slot_count = compact ? (int32_t*)take((size_t)s.images * 4) : nullptr;
+        o.tile_begin = compact ? (int32_t*)take(((size_t)s.images + 1) * 4) : nullptr;
     }
     const size_t z0 = off;
     w.zero_begin = base ? (char*)base + off : nullptr;
@@ -490,6 +503,14 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
         fb.g_deformation = grad_in->deformation[k];
         fb.stash = bw.stash; fb.stash_floats = bw.stash_floats;
         fb.h7_cache = o.h7; fb.inbox_in = o.h7 ? o.inbox : nullptr;
+        if (b.slot_list) {
+            // samples inside the box (outer mask: the ray bender's backward covers them all), from the forward recompute's masks
+            const uint8_t* mask_src = object_uses_prepass(s, k) ? o.flags : o.inbox;
+            rc = pe_launch_compact_slots(mask_src, 1, s.images, (int64_t)s.rays * d.positions, b.slot_list, b.slot_count, b.tile_begin, stream);
+            if (rc) return rc;
+            PE_CUDA_CHECK(cudaMemsetAsync(b.g_pos, 0, (size_t)s.images * s.rays * d.positions * 12, stream));     // slots outside the list
+            fb.slot_list = b.slot_list; fb.slot_count = b.slot_count; fb.tile_begin = b.tile_begin;
+        }
         if (!fb.w.head0_w || !fb.w.head3_w || !fb.w.head6_w) { pe_set_error("backward needs the fp32 parameters of object %d", k); return PE_ERR_INVALID; }
         if (s.training) {
             fb.bwd_phase = 1;

@@ -45,7 +45,7 @@ struct Smem {
     float* wS;                    // [KC][NPASS]
     float *pos, *bent, *aux;      // [3][TB], [3][TB], [9][TB] (object-space origin, direction, displacement)
     float *graw, *gdm;            // [TB] upstream gradients of the raw alpha / displacement magnitude of the slot
-    int *flags, *clampf;          // [TB]
+    int *flags, *clampf, *slot;   // [TB]
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         S.graw = p; p += TB;
         S.gdm = p; p += TB;
         S.flags = reinterpret_cast<int*>(p); p += TB;
-        S.clampf = reinterpret_cast<int*>(p);
+        S.clampf = reinterpret_cast<int*>(p); p += TB;
+        S.slot = reinterpret_cast<int*>(p);
     }
     const Stash ST = stash_layout(ob, L);
     float* stash = B.stash + (int64_t)blockIdx.x * B.stash_floats;
@@ -253,10 +254,31 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
     const float* k1_2 = B.bn_fix + 2 * W;
     const float* k2_2 = B.bn_fix + 2 * W + W / 2;
 
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int img = (int)(tile / tiles_per_image);
-        const int64_t slot0 = (tile - (int64_t)img * tiles_per_image) * TB;
-        const int64_t gs0 = (int64_t)img * slots_per_image + slot0;
+    const bool compact = B.slot_list != nullptr;
+    const int64_t num_tiles = compact ? (int64_t)B.tile_begin[A.images] : total_tiles;
+    int img_c = 0;                                   // compacted numbering: image of the current tile (tiles are visited in order)
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int img;
+        if (compact) {
+            while (tile >= B.tile_begin[img_c + 1]) ++img_c;
+            img = img_c;
+        } else {
+            img = (int)(tile / tiles_per_image);
+        }
+        const int64_t gsi = (int64_t)img * slots_per_image;        // first slot of the image
+        __syncthreads();
+        if (tid < TB) {
+            // slot (inside the image) handled by row tid of this tile, -1: none
+            int64_t s;
+            if (compact) {
+                const int64_t e = (tile - B.tile_begin[img]) * TB + tid;
+                s = e < B.slot_count[img] ? (int64_t)B.slot_list[gsi + e] : -1;
+            } else {
+                s = (tile - (int64_t)img * tiles_per_image) * TB + tid;
+                if (s >= slots_per_image) s = -1;
+            }
+            S.slot[tid] = (int)s;
+        }
         const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
         __syncthreads();
         float* bufs[2] = {S.bufA, S.bufB};
@@ -266,31 +288,31 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         const bool from_cache = !full && B.h7_cache != nullptr && B.inbox_in != nullptr;
         if (from_cache) {
             if (tid < TB) {
-                const int64_t s = slot0 + tid;
+                const int s = S.slot[tid];
                 int flag = 0;
-                if (s < slots_per_image) flag = 4 | (B.inbox_in[gs0 + tid] ? 3 : 0);
+                if (s >= 0) flag = 4 | (B.inbox_in[gsi + s] ? 3 : 0);
                 S.flags[tid] = flag;
             }
             const int any = __syncthreads_or(tid < TB ? (S.flags[tid] & 2) : 0);
             if (!any) continue;
             for (int idx = tid; idx < W * TB; idx += NT) {
                 const int m = idx / W, n = idx - m * W;                 // consecutive threads: consecutive features of one sample
-                bufs[0][n * TS + m] = (S.flags[m] & 2) ? B.h7_cache[(gs0 + m) * W + n] : 0.f;
+                bufs[0][n * TS + m] = (S.flags[m] & 2) ? B.h7_cache[(gsi + S.slot[m]) * W + n] : 0.f;
             }
             cur = bufs[0]; curK = W; which = 1;
             __syncthreads();
         } else {
         // ================================ forward recompute ================================
         if (tid < TB) {
-            const int64_t s = slot0 + tid;
+            const int64_t s = S.slot[tid];
             int flag = 0;
             float x[3] = {0.f, 0.f, 0.f};
             float graw = 0.f, gdm = 0.f;
             for (int a = 0; a < 9; ++a) S.aux[a * TB + tid] = 0.f;
-            if (s < slots_per_image) {
+            if (s >= 0) {
                 flag = 4;
                 const int r = (int)(s / P), p = (int)(s - (int64_t)r * P);
-                const int64_t gs = gs0 + tid;
+                const int64_t gs = gsi + s;
                 const PeRay ray = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3,
                                               A.dirs + ((int64_t)img * A.rays + r) * 3, in_scene);
                 const float u = A.perturb ? A.rand[gs] : 0.f;
@@ -310,8 +332,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         const int any_inbox = __syncthreads_or(tid < TB ? (S.flags[tid] & 1) : 0);
         if (!any_inbox) {
             if (full && tid < TB && (S.flags[tid] & 4)) {
-                for (int a = 0; a < 3; ++a) B.g_pos[(gs0 + tid) * 3 + a] = 0.f;
-                if (B.g_od) for (int a = 0; a < 6; ++a) B.g_od[(gs0 + tid) * 6 + a] = 0.f;
+                for (int a = 0; a < 3; ++a) B.g_pos[(gsi + S.slot[tid]) * 3 + a] = 0.f;
+                if (B.g_od) for (int a = 0; a < 6; ++a) B.g_od[(gsi + S.slot[tid]) * 6 + a] = 0.f;
             }
             continue;
         }
@@ -459,8 +481,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             const int m = idx / F, c = idx - m * F;
             float g = 0.f;
             if (S.flags[m] & 2) {
-                const int64_t gs = gs0 + m;
-                const int64_t ray = (int64_t)img * A.rays + (slot0 + m) / P;
+                const int64_t gs = gsi + S.slot[m];
+                const int64_t ray = (int64_t)img * A.rays + S.slot[m] / P;
                 if (B.g_feat_obj) g = B.cw_obj[gs] * __ldg(B.g_feat_obj + ray * F + c);
                 if (B.g_feat_glob) g = fmaf(B.cw_glob[gs], __ldg(B.g_feat_glob + ray * F + c), g);
                 if (A.apply_activation) {
@@ -560,8 +582,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
                     for (int a = 0; a < 6; ++a) gx[a] = (S.flags[m] & 2) ? enc_backward(S.enc + m, xin, 6, ob.octaves, a, nullptr) : 0.f;
                     const float dot = gx[3] * xin[3] + gx[4] * xin[4] + gx[5] * xin[5];
                     for (int a = 0; a < 3; ++a) {
-                        B.g_od[(gs0 + m) * 6 + a] = gx[a] / size[a];
-                        B.g_od[(gs0 + m) * 6 + 3 + a] = (gx[3 + a] - xin[3 + a] * dot) / nrm;      // d(d/|d|)
+                        B.g_od[(gsi + S.slot[m]) * 6 + a] = gx[a] / size[a];
+                        B.g_od[(gsi + S.slot[m]) * 6 + 3 + a] = (gx[3 + a] - xin[3 + a] * dot) / nrm;      // d(d/|d|)
                     }
                 }
             } else if (S.flags[m] & 2) {
@@ -638,15 +660,59 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         }
         if (tid < TB && (S.flags[tid] & 4)) {
             const bool use = (S.flags[tid] & 1) != 0;
-            for (int a = 0; a < 3; ++a) B.g_pos[(gs0 + tid) * 3 + a] = use ? gpos[a] : 0.f;
+            for (int a = 0; a < 3; ++a) B.g_pos[(gsi + S.slot[tid]) * 3 + a] = use ? gpos[a] : 0.f;
         }
+    }
+}
+
+// Per image: the slots whose flag has a bit of `mask`, in slot order (one block per image, ballot-based stream compaction).
+__global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* __restrict__ flags, int mask, int64_t slots_per_image,
+                                                                 int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint8_t* f = flags + (int64_t)img * slots_per_image;
+    int32_t* out = list + (int64_t)img * slots_per_image;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int64_t s0 = 0; s0 < slots_per_image; s0 += blockDim.x) {
+        const int64_t s = s0 + threadIdx.x;
+        const bool keep = s < slots_per_image && (f[s] & mask) != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_tot[warp] = __popc(b);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (keep) out[off + __popc(b & ((1u << lane) - 1))] = (int32_t)s;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w]; base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) count[img] = base;
+}
+
+__global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int images, int32_t* __restrict__ tile_begin) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < images; ++i) { tile_begin[i] = t; t += (count[i] + TB - 1) / TB; }
+        tile_begin[images] = t;
     }
 }
 
 }  // namespace
 
+int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
+                            int32_t* tile_begin, cudaStream_t stream) {
+    if (images == 0 || slots_per_image == 0) return PE_OK;
+    pe_compact_slots_kernel<<<images, 1024, 0, stream>>>(flags, flag_mask, slots_per_image, slot_list, slot_count);
+    PE_LAUNCH_CHECK("pe_compact_slots_kernel");
+    pe_tile_prefix_kernel<<<1, 32, 0, stream>>>(slot_count, images, tile_begin);
+    PE_LAUNCH_CHECK("pe_tile_prefix_kernel");
+    return PE_OK;
+}
+
 size_t pe_field_bwd_smem_bytes() {
-    return sizeof(float) * ((size_t)3 * CMAX * TS + (size_t)EMAX * TS + (size_t)KC * NPASS + 17 * TB) + sizeof(int) * 2 * TB;
+    return sizeof(float) * ((size_t)3 * CMAX * TS + (size_t)EMAX * TS + (size_t)KC * NPASS + 17 * TB) + sizeof(int) * 3 * TB;
 }
 
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L) { return (int64_t)stash_layout(ob, L).rows * TS; }

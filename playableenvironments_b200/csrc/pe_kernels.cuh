@@ -106,6 +106,11 @@ struct PeFieldBwdArgs {
     int64_t stash_floats;          // floats per block
     const float* h7_cache;         // [images][rays][P][W] trunk output written by the forward recompute (tensor-core path) or NULL:
     const uint8_t* inbox_in;       // ... with its evaluated-sample mask; the BatchNorm-reduction passes (bwd_phase 1, 2) start from them
+    // compacted tiles (or NULL: tiles of 32 consecutive slots): per image the slots inside the object's box, so that a tile holds
+    // 32 samples that need work instead of one ray's mostly empty samples
+    const int32_t* slot_list;      // [images][rays * P] slot index inside the image; the first slot_count[img] entries are valid
+    const int32_t* slot_count;     // [images]
+    const int32_t* tile_begin;     // [images + 1] first tile of every image in the compacted numbering; [images] = number of tiles
 };
 
 // Style / BatchNorm backward (pe_backward.cu)
@@ -137,6 +142,8 @@ size_t pe_field_bwd_smem_bytes();
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);
 int pe_field_bwd_grid(int sm_count);
 int pe_launch_field_bwd(const PeFieldBwdArgs& args, int sm_count, cudaStream_t stream);
+int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
+                            int32_t* tile_begin, cudaStream_t stream);
 int pe_launch_composite_bwd(const PeCompositeBwdArgs& args, cudaStream_t stream);
 int pe_launch_style_bwd(const PeStyleBwdArgs& args, cudaStream_t stream);
 int pe_launch_bn_fix(const double* fwd_stats, const double* bn_sums, int channels, float* bn_fix, cudaStream_t stream);
