@@ -665,7 +665,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
     }
 }
 
-// Per image: the slots whose flag has a bit of `mask`, in slot order (one block per image, ballot-based stream compaction).
+// Per image: the slots whose flag has a bit of `mask`, in slot order (one block per image, four slots per thread and iteration,
+// warp-shuffle scan + per-warp totals).
 __global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* __restrict__ flags, int mask, int64_t slots_per_image,
                                                                  int32_t* __restrict__ list, int32_t* __restrict__ count) {
     __shared__ int warp_tot[32];
@@ -675,15 +676,21 @@ __global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* _
     int32_t* out = list + (int64_t)img * slots_per_image;
     if (threadIdx.x == 0) base = 0;
     __syncthreads();
-    for (int64_t s0 = 0; s0 < slots_per_image; s0 += blockDim.x) {
-        const int64_t s = s0 + threadIdx.x;
-        const bool keep = s < slots_per_image && (f[s] & mask) != 0;
-        const unsigned b = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(b);
+    for (int64_t s0 = 0; s0 < slots_per_image; s0 += 4 * (int64_t)blockDim.x) {
+        const int64_t s = s0 + 4 * (int64_t)threadIdx.x;
+        bool keep[4];
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { keep[i] = s + i < slots_per_image && (f[s + i] & mask) != 0; c += keep[i] ? 1 : 0; }
+        int incl = c;                                   // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        int off = base;
+        int off = base + incl - c;
         for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        if (keep) out[off + __popc(b & ((1u << lane) - 1))] = (int32_t)s;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (keep[i]) out[off++] = (int32_t)(s + i);
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w]; base += t; }
         __syncthreads();
