@@ -358,6 +358,53 @@ class RayHelper:
         positions = ray_origins.unsqueeze(-2).unsqueeze(-2) + ray_directions.unsqueeze(-2) * t.unsqueeze(-1)
         return positions, t
 
+    # ------------------------------------------------------------------------------------------------------------------
+    # hierarchical ("fine") sampling helpers (reference :1284-1403).  No shipped config enables a fine model (``use_fine: False``
+    # everywhere) and the fused composer raises for one; the helpers keep the reference API for callers that use them.
+    # ------------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def transform_ray_positions(ray_origins, ray_directions, focal_normals, ray_positions, transformation_matrix):
+        """Reference :1284-1318 (broadcast instead of the per-sample matrix ``repeat``)."""
+        o, d, n = RayHelper.transform_rays(ray_origins, ray_directions, focal_normals, transformation_matrix)
+        p = RayHelper.transform_points(ray_positions, transformation_matrix.unsqueeze(-3).unsqueeze(-3))
+        return o, d, n, p
+
+    @staticmethod
+    def sample_pdf(bin_delimiters: torch.Tensor, weights: torch.Tensor, positions_count: int, perturb: bool,
+                   cdf_samples: torch.Tensor = None) -> torch.Tensor:
+        """Reference :1349-1403: inverse-CDF samples of a piecewise-constant density over the bins between ``bin_delimiters``
+        (..., B) with ``weights`` (..., B - 1).  (The reference adds its 1e-5 to ``weights`` in place; this version does not
+        modify its argument.)"""
+        weights = weights + 1e-5
+        pdf = weights / torch.sum(weights, dim=-1, keepdim=True)
+        cdf = torch.cumsum(pdf, dim=-1)
+        cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+        lead = list(cdf.shape[:-1])
+        if cdf_samples is None:
+            if not perturb:
+                cdf_samples = torch.linspace(0.0, 1.0, positions_count, device=cdf.device).expand(lead + [positions_count])
+            else:
+                cdf_samples = torch.rand(lead + [positions_count]).to(cdf.device)
+        cdf_samples = cdf_samples.contiguous()
+        idx = torch.searchsorted(cdf, cdf_samples, right=True)
+        below = torch.clamp(idx - 1, min=0)
+        above = torch.clamp(idx, max=cdf.size(-1) - 1)
+        cdf_lo, cdf_hi = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+        bin_lo, bin_hi = torch.gather(bin_delimiters, -1, below), torch.gather(bin_delimiters, -1, above)
+        norm = cdf_hi - cdf_lo
+        norm = torch.where(norm < 1e-5, torch.ones_like(norm), norm)
+        return bin_lo + (cdf_samples - cdf_lo) / norm * (bin_hi - bin_lo)
+
+    @staticmethod
+    def create_ray_positions_weighted(ray_origins, ray_directions, positions_count: int, reference_ray_positions_t, weights,
+                                      perturb: bool):
+        """Reference :1320-1347: ``positions_count`` new samples drawn from the coarse weights, merged (sorted) with the coarse ones."""
+        mid = (reference_ray_positions_t[..., 1:] + reference_ray_positions_t[..., :-1]) / 2
+        t_new = RayHelper.sample_pdf(mid, weights[..., 1:-1], positions_count, perturb).detach()
+        merged, _ = torch.sort(torch.cat([reference_ray_positions_t, t_new], dim=-1), dim=-1)
+        positions = ray_origins.unsqueeze(-2).unsqueeze(-2) + ray_directions.unsqueeze(-2) * merged.unsqueeze(-1)
+        return positions, merged
+
     @staticmethod
     def strided_patch_ray_samples_to_patch(samples: torch.Tensor):
         """Reference :185-204."""

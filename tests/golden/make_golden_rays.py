@@ -50,6 +50,17 @@ def ray_cases():
     return cases
 
 
+def fine_case():
+    """Inputs of create_ray_positions_weighted (reference :1320-1347): coarse t values and weights of 3 x 50 rays x 16 samples."""
+    rng = np.random.default_rng(21)
+    lead, R, P = [3], 50, 16
+    origins = torch.from_numpy(rng.standard_normal(lead + [3]).astype(np.float32))
+    dirs = torch.from_numpy(rng.standard_normal(lead + [R, 3]).astype(np.float32))
+    t = torch.from_numpy(np.sort(rng.random(lead + [R, P]).astype(np.float32) * 5.0 + 0.5, axis=-1))
+    w = torch.from_numpy((rng.random(lead + [R, P]) ** 4).astype(np.float32))
+    return origins, dirs, t, w
+
+
 def main():
     collections.Sequence = collections.abc.Sequence
     torch.Tensor.cuda = lambda self, *a, **k: self
@@ -63,6 +74,12 @@ def main():
         for i, t in enumerate(res):
             out[f"{name}/{i}"] = t.numpy()
         print(name, [tuple(t.shape) for t in res])
+    origins, dirs, t, w = fine_case()
+    for perturb in (False, True):
+        torch.manual_seed(33)
+        pos, merged = Ref.create_ray_positions_weighted(origins, dirs, 24, t, w.clone(), perturb)     # (the reference adds 1e-5 to w in place)
+        out[f"fine_{int(perturb)}/0"], out[f"fine_{int(perturb)}/1"] = pos.numpy(), merged.numpy()
+        print("fine", perturb, tuple(pos.shape))
     np.savez_compressed(os.path.join(HERE, "ray_selection.npz"), **out)
 
 

@@ -9,7 +9,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.dirname(HERE), os.path.join(HERE, "golden")]
-from make_golden_rays import ray_cases  # noqa: E402
+from make_golden_rays import fine_case, ray_cases  # noqa: E402
 from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper  # noqa: E402
 
 GOLDEN = np.load(os.path.join(HERE, "golden", "ray_selection.npz"))
@@ -68,3 +68,14 @@ def test_install_ray_selection_rebinds_a_reference_style_class():
     install_ray_selection(FakeReferenceRayHelper)
     for name in RAY_SELECTION_FUNCTIONS:
         assert getattr(FakeReferenceRayHelper, name) is getattr(RayHelper, name)
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_weighted_fine_sampling_matches_the_reference(perturb):
+    """create_ray_positions_weighted / sample_pdf (reference :1320-1403) for the same RNG state."""
+    origins, dirs, t, w = fine_case()
+    torch.manual_seed(33)
+    pos, merged = RayHelper.create_ray_positions_weighted(origins, dirs, 24, t, w, perturb)
+    np.testing.assert_allclose(merged.numpy(), GOLDEN[f"fine_{int(perturb)}/1"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(pos.numpy(), GOLDEN[f"fine_{int(perturb)}/0"], rtol=0, atol=2e-5)
+    assert torch.equal(w, fine_case()[3])          # the argument is left untouched
