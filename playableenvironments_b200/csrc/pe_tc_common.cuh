@@ -56,17 +56,20 @@ __device__ __forceinline__ void store_a8_relu(unsigned char* a_base, int chunk, 
     *reinterpret_cast<uint4*>(a_base + chunk * CHUNK_BYTES + m * 16) = q;
 }
 
-// fp16x3 mode: activations are kept as hi + lo fp16 pairs (hi = fp16(max(v,0)), lo = fp16(max(v,0) - hi)) in two operand buffers
+// fp16x3 mode: activations are kept as hi + lo fp16 pairs (hi = fp16(max(v,0)), lo = fp16(max(v,0) - hi)) in two operand buffers.
+// Packed conversions: one cvt(.relu).f16x2 per pair for hi, unpack, subtract, one cvt.f16x2 for lo.
 __device__ __forceinline__ void store_a8_hilo(unsigned char* a_hi, unsigned char* a_lo, int chunk, int m, const float* v, bool relu) {
-    float h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float x = relu ? fminf(fmaxf(v[i], 0.f), 65504.f) : v[i];
-        h[i] = __half2float(__float2half_rn(x));
-        l[i] = x - h[i];
+    for (int i = 0; i < 4; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        h[i] = relu ? relu_pack_half2(a, b) : pack_half2(a, b);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        l[i] = pack_half2(a - hf.x, b - hf.y);
     }
-    store_a8(a_hi, chunk, m, h);
-    store_a8(a_lo, chunk, m, l);
+    *reinterpret_cast<uint4*>(a_hi + chunk * CHUNK_BYTES + m * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + chunk * CHUNK_BYTES + m * 16) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // wait for outstanding tcgen05.ld; the registers are threaded through so no use can be scheduled above the wait
