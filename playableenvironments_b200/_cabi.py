@@ -18,8 +18,9 @@ PE_MAX_OCTAVES = 16
 
 NERF_ADAIN, NERF_SKYBOX_V3 = 0, 1
 BENDER_ZEROED, BENDER_POSITIONAL = 0, 1
-PRECISION_FP32, PRECISION_FP16, PRECISION_FP16X2, PRECISION_FP16X3 = 0, 1, 2, 3
-PRECISIONS = {"fp32": PRECISION_FP32, "fp16": PRECISION_FP16, "fp16x2": PRECISION_FP16X2, "fp16x3": PRECISION_FP16X3}
+PRECISION_FP32, PRECISION_FP16, PRECISION_FP16X2, PRECISION_FP16X3, PRECISION_MIXED = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": PRECISION_FP32, "fp16": PRECISION_FP16, "fp16x2": PRECISION_FP16X2, "fp16x3": PRECISION_FP16X3,
+              "mixed": PRECISION_MIXED}
 
 _f = C.POINTER(C.c_float)
 _u8 = C.POINTER(C.c_uint8)

@@ -7,7 +7,6 @@
 
 #include "pe_kernels.cuh"
 
-#define PE_TC_DEFAULT_PAIR false
 
 static thread_local char g_error[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -83,6 +82,14 @@ static bool tc_allowed(const PeScene& s) {
 static thread_local bool g_keep_samples = false;
 struct KeepSamples { bool prev; KeepSamples() : prev(g_keep_samples) { g_keep_samples = true; } ~KeepSamples() { g_keep_samples = prev; } };
 
+// Arithmetic of one object.  The mixed mode keeps objects with few samples per ray in the fp32-class mode: alpha = 1 - exp(-relu(raw) * delta)
+// amplifies an absolute raw-alpha error by the sample spacing delta (court P = 4: delta ~ 20, Minecraft ground in front of the skybox: ~85),
+// and their share of the frame's FLOPs is negligible.
+static int object_precision(const PeScene& s, int k) {
+    if (s.precision == PE_PRECISION_MIXED && s.object[k].positions < 32) return PE_PRECISION_FP16X3;
+    return s.precision;
+}
+
 static bool object_uses_tc(const PeScene& s, int k) { return tc_allowed(s) && pe_tc_shape_ok(s.object[k]); }
 
 // Objects with a positional ray bender: sampling + bender run as an exact fp32 pre-pass, the field runs on the tensor cores over
@@ -129,7 +136,7 @@ static Workspace carve(const PeScene& s, void* base) {
         o.fold_v = fold ? (float*)take((size_t)s.images * s.rays * 128 * 4) : nullptr;
         o.fold_s = fold ? (float*)take((size_t)s.images * s.rays * 4) : nullptr;
         const bool prepass = object_uses_prepass(s, k);
-        const size_t rpt = 128 / P, tiles = ((size_t)s.rays + rpt - 1) / rpt * (size_t)s.images;
+        const size_t rpt = prepass ? 128 / P : 1, tiles = ((size_t)s.rays + rpt - 1) / rpt * (size_t)s.images;   // pre-pass objects have P <= 128
         o.bent = prepass ? (float*)take(n * 12) : nullptr;
         o.flags = prepass ? (uint8_t*)take(n) : nullptr;
         o.tile_list = prepass ? (int32_t*)take(tiles * 4) : nullptr;
@@ -197,7 +204,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.ob = d; fa.L = L;
         fa.images = s.images; fa.rays = s.rays; fa.objects = s.objects; fa.k = k;
         fa.perturb = s.perturb; fa.explicit_positions = s.explicit_positions; fa.training = s.training;
-        fa.apply_activation = s.apply_activation; fa.precision = s.precision;
+        fa.apply_activation = s.apply_activation; fa.precision = object_precision(s, k);
         fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
         fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.positions = in->positions; fa.ois = in->object_in_scene;
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;
@@ -248,7 +255,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 // but the tensor core's own fp32 accumulation) lands at ~3e-4 of the reference on the rendered outputs: used in the
                 // performance modes (fp16, fp16x2); the parity-first mode (fp16x3) keeps the exact fp32 bender.  PE_TC_BENDER=0/1 forces.
                 const char* benv = getenv("PE_TC_BENDER");
-                const bool tc_bender = benv ? atoi(benv) != 0 : s.precision != PE_PRECISION_FP16X3;
+                const bool tc_bender = benv ? atoi(benv) != 0 : fa.precision != PE_PRECISION_FP16X3;
                 if (pe_tc_bender_ok(d) && tc_bender) {
                     // 1a. exact fp32 sampling: t, positions, outer mask; empty-space values everywhere
                     rc2 = pe_launch_sample(pre, sm_count, stream); if (rc2) return rc2;
@@ -269,10 +276,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
             }
             if (!tc) return pe_launch_field_fp32(fa, sm_count, stream);
             const PeIntegrated& gout = (s.objects == 1 && !s.perturb) ? out->global : none;
-            // PE_TC_KERNEL=1 selects the single-CTA lockstep kernel, 2 (default) the CTA-pair ping-pong kernel
-            const char* which = getenv("PE_TC_KERNEL");
-            const bool pair = (which ? atoi(which) == 2 : PE_TC_DEFAULT_PAIR) && s.precision != PE_PRECISION_FP16X3;
-            return pair ? pe_launch_field_tc2(fa, gout, sm_count, stream) : pe_launch_field_tc(fa, gout, sm_count, stream);
+            return pe_launch_field_tc(fa, gout, sm_count, stream);
         };
         if (s.training) {
             // train-mode BatchNorm (adain.py:47): statistics over all in-box samples of this object in this call.

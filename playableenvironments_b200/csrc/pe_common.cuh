@@ -60,9 +60,12 @@ struct PeLayout {
     // tcgen05 section
     int64_t tc_base;                // start of the fp16 slab stream (0 if the shape is unsupported)
     int64_t tc_bytes_per_pass;      // bytes of one weight pass (hi); lo pass follows at +tc_bytes_per_pass
-    int64_t tc2_base;               // same stream in the CTA-pair layout (pe_field_tc2.cu): [hi pass | lo pass]
     int64_t tcb_base;               // ray-bender slab stream [hi pass | lo pass] (0 if the bender shape is unsupported)
     int64_t tcb_bytes_per_pass;
+    int64_t tcT_base;               // TRANSPOSED slab stream of the field (dX = G W of the tensor-core backward, pe_bwd_tc.cu) [hi | lo]
+    int64_t tcT_bytes_per_pass;
+    int64_t tcbT_base;              // transposed slab stream of the ray bender [hi | lo]
+    int64_t tcbT_bytes_per_pass;
     int32_t tc_supported;
     int64_t total;
 };
@@ -90,6 +93,13 @@ __host__ __device__ inline bool pe_tc_bender_ok(const PeObjectDesc& d) {
 // bytes of one weight pass of the bender stream: L0 (K=96): 3 slabs; L1,2,4,5: 4; L3 (K=224): 7; out (N=16): 4; 6 bias slabs
 __host__ __device__ inline int64_t pe_tcb_pass_bytes() { return (3LL + 16 + 7) * 128 * 32 * 2 + 4LL * 16 * 32 * 2 + 6LL * 128 * 32; }
 
+// Transposed streams (backward): per chain step an [N' = layer inputs][K' = layer outputs] operand in K'=32 slabs.
+// field:  H6T (N'128,K'192) H3T (256,128) H0T L7T L6T L5T (256,256) L4encT (64,256) L4T L3T L2T L1T (256,256) L0T (64,256)
+__host__ __device__ inline int64_t pe_tcT_pass_bytes() { return 6LL * 128 * 64 + 4LL * 256 * 64 + 8LL * 8 * 256 * 64 + 2LL * 8 * 64 * 64; }
+// bender: OUTT (N'128,K'32) L5T L4T (128,128) L3encT (96,128) L3T L2T L1T (128,128) L0T (96,128)
+__host__ __device__ inline int64_t pe_tcbT_pass_bytes() { return 1LL * 128 * 64 + 5LL * 4 * 128 * 64 + 2LL * 4 * 96 * 64; }
+
+#define PE_TC_MIXED_MASK 0x3F0                // default two-pass layers of the mixed mode: L4-L7, head 0, head 3
 #define PE_TC_SLAB_K 32                       // K elements per streamed weight slab
 // number of K=32 slabs of one weight pass of the shipped field:
 // L0: 64/32=2; L1-3: 8 each; L4: 320/32=10; L5-7: 8 each; H0: 8; H3 (N=128): 8; H6 (K=128,N=192): 4
@@ -143,13 +153,21 @@ __host__ __device__ inline PeLayout pe_layout(const PeObjectDesc& d) {
         L.tc_bytes_per_pass = pe_tc_pass_bytes();
         L.tc_base = off;
         off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
-        L.tc2_base = off;
-        off = pe_align_up(off + 2 * L.tc_bytes_per_pass, 256);
     }
     if (L.tc_supported && pe_tc_bender_ok(d)) {
         L.tcb_bytes_per_pass = pe_tcb_pass_bytes();
         L.tcb_base = off;
         off = pe_align_up(off + 2 * L.tcb_bytes_per_pass, 256);
+    }
+    if (L.tc_supported) {
+        L.tcT_bytes_per_pass = pe_tcT_pass_bytes();
+        L.tcT_base = off;
+        off = pe_align_up(off + 2 * L.tcT_bytes_per_pass, 256);
+        if (pe_tc_bender_ok(d)) {
+            L.tcbT_bytes_per_pass = pe_tcbT_pass_bytes();
+            L.tcbT_base = off;
+            off = pe_align_up(off + 2 * L.tcbT_bytes_per_pass, 256);
+        }
     }
     L.total = off;
     return L;

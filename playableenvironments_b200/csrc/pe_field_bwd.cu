@@ -698,10 +698,10 @@ __global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* _
     if (threadIdx.x == 0) count[img] = base;
 }
 
-__global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int images, int32_t* __restrict__ tile_begin) {
+__global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int images, int32_t* __restrict__ tile_begin, int tile_rows) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int t = 0;
-        for (int i = 0; i < images; ++i) { tile_begin[i] = t; t += (count[i] + TB - 1) / TB; }
+        for (int i = 0; i < images; ++i) { tile_begin[i] = t; t += (count[i] + tile_rows - 1) / tile_rows; }
         tile_begin[images] = t;
     }
 }
@@ -709,11 +709,11 @@ __global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int ima
 }  // namespace
 
 int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
-                            int32_t* tile_begin, cudaStream_t stream) {
+                            int32_t* tile_begin, cudaStream_t stream, int tile_rows) {
     if (images == 0 || slots_per_image == 0) return PE_OK;
     pe_compact_slots_kernel<<<images, 1024, 0, stream>>>(flags, flag_mask, slots_per_image, slot_list, slot_count);
     PE_LAUNCH_CHECK("pe_compact_slots_kernel");
-    pe_tile_prefix_kernel<<<1, 32, 0, stream>>>(slot_count, images, tile_begin);
+    pe_tile_prefix_kernel<<<1, 32, 0, stream>>>(slot_count, images, tile_begin, tile_rows);
     PE_LAUNCH_CHECK("pe_tile_prefix_kernel");
     return PE_OK;
 }

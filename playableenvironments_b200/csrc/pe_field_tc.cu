@@ -24,125 +24,19 @@ using namespace pe_tc;
 
 constexpr int SPLIT = 1;                          // threads per tile row in the epilogue groups
 constexpr int THREADS = 128 + 2 * 128 * SPLIT;    // producer, MMA, TMEM-alloc, spare + 2 groups of 4*SPLIT epilogue warps
-constexpr int STAGE_BYTES = 16384;                // largest slab: 256 rows x 32 k x 2 B
-constexpr int NUM_STAGES = 4;
 constexpr int SMEM_BAR = 2 * A_BYTES + NUM_STAGES * STAGE_BYTES;
 constexpr int SMEM_ONES = SMEM_BAR + 256;         // 256-byte "ones" operand of the rank-1 bias update
 constexpr int SMEM_TOTAL = SMEM_ONES + 256;
 
-struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
-    uint64_t* acc_full;
-    uint64_t* a_ready;
-    uint32_t phase;
-    int lane;
-    uint64_t* h6_full;
-    uint64_t* h6_done;
-    uint32_t h6_phase;
-    __device__ __forceinline__ void wait_acc() { mbar_wait(acc_full, phase); phase ^= 1; tc_fence_after(); }
-    // every thread publishes its operand writes to the async proxy and orders its TMEM reads; ONE arrival per warp
-    // (128 serialized arrivals on one mbarrier cost several hundred cycles per layer)
-    __device__ __forceinline__ void arrive_ready() {
-        fence_proxy_async(); tc_fence_before(); __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
-    }
-    // folded-head mode: this warp's per-ray sums are in global memory (release: visible to the head-6 warp of the CTA)
-    // (two-way handshake: the head-6 warp must have consumed the previous tile's phase before it can complete again)
-    __device__ __forceinline__ void arrive_fold() {
-        __syncwarp();
-        if (lane == 0) { mbar_wait(h6_done, h6_phase ^ 1); mbar_arrive(h6_full); }
-        h6_phase ^= 1;
-    }
-};
-
-// State of the MMA-issuing thread that persists across layers: position in the weight ring, operand addresses.
-struct MmaRing {
-    uint64_t *full_bar, *empty_bar, *acc_full;
-    uint32_t a_addr[2], ring_addr, tmem_base;
-    int stage; uint32_t phase;
-    int num_passes, x3;
-};
-
-// Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
-// (D^T = W * A^T, folded-head mode, head layer 3) -- a separate instantiation so that the common loop stays branch-free.
-// kX3Mode: 0 = one A buffer per tile (fp16 / fp16x2), 1 = fp16x3 (hi and lo A buffers of one tile), 2 = all four partial products
-template <bool kSwap, int kMBlocks, int kX3Mode>
-__device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, int chunk0, bool has_bias, uint32_t idesc, uint32_t lbo_b) {
-    (void)l; (void)n;
-    // kSwap: D^T = W * A^T -- the weight slab is the M operand (blocks of 128 of its n rows: block b starts 2048 B into every K chunk and
-    // lands in accumulator columns 128 b ..), the tile's 128 samples are N; idesc must describe M = 128, N = 128
-    constexpr int mblocks = kMBlocks;                // 2: the 256-row slab of head layer 0 in the statistics phase
-    const int num_passes = R.num_passes;
-    for (int s = 0; s < slabs; ++s) {
-        for (int pass = 0; pass < num_passes; ++pass) {
-            mbar_wait(R.full_bar + R.stage, R.phase);
-            tc_fence_after();
-            const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
-            const uint32_t b_addr = R.ring_addr + R.stage * STAGE_BYTES;
-            if (kX3Mode != 0) {
-                // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
-                    const uint64_t da_hi = umma_smem_desc(R.a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
-                    const uint64_t da_lo = umma_smem_desc(R.a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
-                    const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
-#pragma unroll
-                    for (int b = 0; b < mblocks; ++b) {
-                        const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
-                        const uint32_t td = R.tmem_base + b * 128;
-                        umma_f16_ss(td, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
-                        // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
-                        if (pass == 0 || kX3Mode == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
-                    }
-                }
-                if (last) umma_commit(R.acc_full + 0);
-            } else if (kMBlocks == 1) {
-                // the common case, kept minimal (the issue loop shares its scheduler with two epilogue warps): descriptor words
-                // advanced by 32-bit adds
-                constexpr uint32_t hi = umma_desc_hi(128);
-                const uint32_t b_lo = umma_desc_lo(b_addr, lbo_b);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const uint32_t a_lo = umma_desc_lo(R.a_addr[g] + (chunk0 + 4 * s) * CHUNK_BYTES, CHUNK_BYTES);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t al = a_lo + j * (2 * CHUNK_BYTES >> 4), bl = b_lo + j * (2 * lbo_b >> 4);
-                        const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
-                        if (kSwap) umma_f16_ss_words(R.tmem_base + g * 256, bl, hi, al, hi, idesc, accum);
-                        else umma_f16_ss_words(R.tmem_base + g * 256, al, hi, bl, hi, idesc, accum);
-                    }
-                    if (last) umma_commit(R.acc_full + g);
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
-                        const uint64_t da = umma_smem_desc(R.a_addr[g] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
-#pragma unroll
-                        for (int b = 0; b < mblocks; ++b) {
-                            const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
-                            umma_f16_ss(R.tmem_base + g * 256 + b * 128, kSwap ? db : da, kSwap ? da : db, idesc, (s | pass | j) != 0 ? 1u : 0u);
-                        }
-                    }
-                    if (last) umma_commit(R.acc_full + g);
-                }
-            }
-            umma_commit(R.empty_bar + R.stage);
-            if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
-        }
-    }
-}
-
 // kStats: the train-mode instantiation (statistics phases of BatchNorm); the eval instantiation carries none of that code
 // kFoldOnly: the headline instantiation (folded head, sampling inside the kernel, eval)
 // kX3: the fp16x3 instantiation (one tile per iteration, both epilogue groups on its rows); the other modes do not carry its code
-// kPasses: weight passes per k-step known at compile time (1: fp16, 2: fp16x2 / fp16x3), 0: taken from the argument
+// kPasses: weight passes per k-step known at compile time (1: fp16, 2: fp16x2 / fp16x3), 0: per layer from `pass2_mask`
+// (bit l set: layer l runs hi + lo weight passes -- the "mixed" precision mode gives the late layers two passes)
 template <bool kStats, bool kFoldOnly, bool kX3, int kPasses>
-__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int num_passes_arg, const int x3_arg, const int fold, const int dbg) {
+__global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldArgs A, const PeIntegrated G2, const int pass2_mask, const int x3_arg, const int fold, const int dbg) {
     constexpr int x3 = kX3 ? 1 : 0;
-    const int num_passes = kPasses ? kPasses : num_passes_arg;
+    auto layer_passes = [&](int l) { return kPasses ? kPasses : (((pass2_mask >> l) & 1) ? 2 : 1); };
     (void)x3_arg;
     // fold: folded-head mode (pe_tc_common.cuh): head layer 6 is applied per ray by pe_head6_fold_kernel, 10 MMA layers per tile
     // x3: fp16x3 mode — ONE tile per iteration; buffer 0 holds the high halves of the activations, buffer 1 the low halves;
@@ -202,6 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
+                    const int num_passes = layer_passes(l);
                     for (int s = 0; s < slabs; ++s) {
                         for (int pass = 0; pass < num_passes; ++pass) {
                             mbar_wait(empty_bar + stage, phase ^ 1);
@@ -230,12 +125,13 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = x3;
+            R.stage = 0; R.phase = 0; R.num_passes = layer_passes(0); R.x3 = x3;
             const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
             for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
                 for (int l = 0; l < num_layers; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
+                    if (!kPasses) R.num_passes = layer_passes(l);
                     // transposed layers (folded head: head layer 3; statistics phases: the layer whose column sums are wanted)
                     const bool swap = (fold && l == 9) || (stat_phase != 0 && l == num_layers - 1);
                     const uint32_t idesc = umma_idesc_f16(TILE_M, swap ? TILE_M : n);
@@ -881,6 +777,12 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     }
     const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
     const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
+    // per-layer weight passes: bit l of the mask = layer l (0-7 trunk, 8 head 0, 9 head 3, 10 head 6) runs hi + lo.
+    // "mixed" (PE_PRECISION_MIXED): two passes where the systematic fp16 rounding of the weights matters most (the late trunk layers
+    // and the head, tests/emulate_precision.py), one pass for the early trunk; PE_TC_PASS2_MASK overrides the choice.
+    int pass2_mask = num_passes == 2 ? 0x7FF : 0;
+    const bool mixed = args.precision == PE_PRECISION_MIXED;
+    if (mixed) { const char* menv = getenv("PE_TC_PASS2_MASK"); pass2_mask = menv ? (int)strtol(menv, nullptr, 0) : PE_TC_MIXED_MASK; }
     const int fold = (args.fold_v != nullptr && args.phase == 0) ? 1 : 0;
     if (fold && (!args.fold_s || args.feat_out || args.apply_activation || args.ob.positions % 32)) {
         pe_set_error("tensor-core field kernel: folded head needs positions %% 32 == 0, no per-sample features, no output activation");
@@ -896,10 +798,10 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     using Kernel = void (*)(const PeFieldArgs, const PeIntegrated, const int, const int, const int, const int);
     Kernel kernel;
     if (args.training) kernel = x3 ? pe_field_tc_kernel<true, false, true, 2> : pe_field_tc_kernel<true, false, false, 0>;
-    else if (fold && !prepass) kernel = x3 ? pe_field_tc_kernel<false, true, true, 2> : (num_passes == 1 ? pe_field_tc_kernel<false, true, false, 1> : pe_field_tc_kernel<false, true, false, 2>);
+    else if (fold && !prepass) kernel = x3 ? pe_field_tc_kernel<false, true, true, 2> : (mixed ? pe_field_tc_kernel<false, true, false, 0> : (num_passes == 1 ? pe_field_tc_kernel<false, true, false, 1> : pe_field_tc_kernel<false, true, false, 2>));
     else kernel = x3 ? pe_field_tc_kernel<false, false, true, 2> : pe_field_tc_kernel<false, false, false, 0>;
     PE_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, num_passes, x3, fold, dbg);
+    kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, global_out, pass2_mask, x3, fold, dbg);
     PE_LAUNCH_CHECK("pe_field_tc_kernel");
     return PE_OK;
 }

@@ -138,12 +138,50 @@ struct PeGeometryBwdArgs {
     float* g_w2o;                  // accumulated [images][objects][12]
 };
 
+// Arguments of the tensor-core field backward (pe_bwd_tc.cu).  The samples inside the object's box are compacted per image into tiles of
+// 128 rows (slot_list / slot_count / tile_begin, TB = 128); every tile owns one block of the activation / gradient STASH in the
+// canonical K-major no-swizzle operand layout (chunk = 8 columns x 128 rows x fp16 = 2048 B), so that a whole operand of a tile is ONE
+// contiguous bulk copy, usable K-major (dX = G W: K = features) and MN-major (dW = G^T A: K = the tile's samples).
+struct PeBwdTcArgs {
+    PeFieldArgs f;                 // forward view: ob, L, images, rays, k, aff1/aff2, ois, deformation, bent, flags, raw_out, feat_out, inbox_out, ...
+    const int32_t* slot_list;      // [images][rays * P]
+    const int32_t* slot_count;     // [images]
+    const int32_t* tile_begin;     // [images + 1]
+    int32_t tile_capacity;         // tiles the stash holds (tiles beyond it are dropped and flagged in *overflow)
+    int32_t* overflow;             // device flag or NULL
+    unsigned char* stash;          // [tile][PE_BWD_FS_CHUNKS][2048] field stash
+    unsigned char* bstash;         // [tile][PE_BWD_BS_CHUNKS][2048] ray-bender stash or NULL
+    const float* cw_obj;           // [images][rays][P] from the compositing backward (pe_backward.cu)
+    const float* cw_glob;
+    const float* g_feat_obj;       // [images][rays][F] or NULL
+    const float* g_feat_glob;
+    const float* g_raw;            // [images][rays][P]
+    const float* g_dm;             // [images][rays][P]
+    const float* scale;            // device [2]: S (power of two applied to the fp16 gradient operands), 1 / S
+    const float* bn_fix;           // [2W + W]: k1, k2 of BatchNorm 1 then 2 (zeros in eval mode)
+    float* g_bent;                 // out [images][rays][P][3]: dL/d (bent) sample position, object space, unscaled
+    float* g_pos;                  // out [images][rays][P][3]: dL/d sample position (== g_bent without a ray bender)
+    PeObjectParamGrads gw;         // accumulated parameter gradients
+    float* adain_sums;             // accumulated [images][3W] (layout of PeFieldBwdArgs::adain_sums)
+    double* bn_sums;               // [3W] (layout of PeFieldBwdArgs::bn_sums)
+    float* g_deformation;          // accumulated [images][D] or NULL
+};
+#define PE_BWD_TILE 128
+#define PE_BWD_FS_CHUNKS 688       // field stash chunks per tile: activations 360 + gradients 328 (map in pe_bwd_tc.cu)
+#define PE_BWD_BS_CHUNKS 212       // ray-bender stash chunks per tile
+bool pe_bwd_tc_object_ok(const PeObjectDesc& ob);
+int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream);
+int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int precision, int sm_count, cudaStream_t stream);
+int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scratch, cudaStream_t stream);
+int pe_launch_bwd_chain(const PeBwdTcArgs& args, int training, const double* fwd_stats, int sm_count, cudaStream_t stream);
+int pe_launch_bwd_dw(const PeBwdTcArgs& args, int sm_count, cudaStream_t stream);
+
 size_t pe_field_bwd_smem_bytes();
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);
 int pe_field_bwd_grid(int sm_count);
 int pe_launch_field_bwd(const PeFieldBwdArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
-                            int32_t* tile_begin, cudaStream_t stream);
+                            int32_t* tile_begin, cudaStream_t stream, int tile_rows = 32);
 int pe_launch_composite_bwd(const PeCompositeBwdArgs& args, cudaStream_t stream);
 int pe_launch_style_bwd(const PeStyleBwdArgs& args, cudaStream_t stream);
 int pe_launch_bn_fix(const double* fwd_stats, const double* bn_sums, int channels, float* bn_fix, cudaStream_t stream);
@@ -155,7 +193,6 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
 int pe_launch_tile_list(const PeFieldArgs& args, int flag_mask, int32_t* tile_list, int32_t* tile_count, cudaStream_t stream);
 int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
 int pe_launch_sample(const PeFieldArgs& args, int sm_count, cudaStream_t stream);
-int pe_launch_field_tc2(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream);
 int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream);
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream);
 int pe_launch_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);

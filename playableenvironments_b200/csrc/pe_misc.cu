@@ -150,7 +150,6 @@ static int copy_to(const float* src, void* blob, int64_t off, int64_t n, cudaStr
 }
 
 int pe_tc_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);
-int pe_tc2_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);
 
 int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
     int rc;
@@ -185,10 +184,6 @@ int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParam
     }
     if (L.tc_supported) {
         PE_TRY(pe_tc_pack(d, L, p, packed, stream));
-        // the CTA-pair layout only when the experimental kernel is selected (PE_TC_KERNEL=2, read per process): in training the
-        // parameters are re-packed after every optimizer step
-        const char* which = getenv("PE_TC_KERNEL");
-        if (which && atoi(which) == 2) PE_TRY(pe_tc2_pack(d, L, p, packed, stream));
     }
 #undef PE_TRY
     return PE_OK;

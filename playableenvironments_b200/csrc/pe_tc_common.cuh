@@ -716,4 +716,113 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     named_bar_sync(bar_id, GROUP);        // scratch is dead before the next tile's encoding overwrites it
 }
 
+// ---- weight ring + MMA issue, shared by the forward kernel (pe_field_tc.cu) and the backward kernels (pe_bwd_tc.cu) ----
+constexpr int STAGE_BYTES = 16384;                // largest slab: 256 rows x 32 k x 2 B
+constexpr int NUM_STAGES = 4;
+
+struct Sync1 {        // epilogue <-> MMA handshakes inside one CTA
+    uint64_t* acc_full;
+    uint64_t* a_ready;
+    uint32_t phase;
+    int lane;
+    uint64_t* h6_full;
+    uint64_t* h6_done;
+    uint32_t h6_phase;
+    __device__ __forceinline__ void wait_acc() { mbar_wait(acc_full, phase); phase ^= 1; tc_fence_after(); }
+    // every thread publishes its operand writes to the async proxy and orders its TMEM reads; ONE arrival per warp
+    // (128 serialized arrivals on one mbarrier cost several hundred cycles per layer)
+    __device__ __forceinline__ void arrive_ready() {
+        fence_proxy_async(); tc_fence_before(); __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+    }
+    // folded-head mode: this warp's per-ray sums are in global memory (release: visible to the head-6 warp of the CTA)
+    // (two-way handshake: the head-6 warp must have consumed the previous tile's phase before it can complete again)
+    __device__ __forceinline__ void arrive_fold() {
+        __syncwarp();
+        if (lane == 0) { mbar_wait(h6_done, h6_phase ^ 1); mbar_arrive(h6_full); }
+        h6_phase ^= 1;
+    }
+};
+
+// State of the MMA-issuing thread that persists across layers: position in the weight ring, operand addresses.
+struct MmaRing {
+    uint64_t *full_bar, *empty_bar, *acc_full;
+    uint32_t a_addr[2], ring_addr, tmem_base;
+    int stage; uint32_t phase;
+    int num_passes, x3;
+};
+
+// Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
+// (D^T = W * A^T, folded-head mode, head layer 3) -- a separate instantiation so that the common loop stays branch-free.
+// kX3Mode: 0 = one A buffer per tile (fp16 / fp16x2), 1 = fp16x3 (hi and lo A buffers of one tile), 2 = all four partial products
+template <bool kSwap, int kMBlocks, int kX3Mode>
+__device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, int chunk0, bool has_bias, uint32_t idesc, uint32_t lbo_b) {
+    (void)l; (void)n;
+    // kSwap: D^T = W * A^T -- the weight slab is the M operand (blocks of 128 of its n rows: block b starts 2048 B into every K chunk and
+    // lands in accumulator columns 128 b ..), the tile's 128 samples are N; idesc must describe M = 128, N = 128
+    constexpr int mblocks = kMBlocks;                // 2: the 256-row slab of head layer 0 in the statistics phase
+    const int num_passes = R.num_passes;
+    for (int s = 0; s < slabs; ++s) {
+        for (int pass = 0; pass < num_passes; ++pass) {
+            mbar_wait(R.full_bar + R.stage, R.phase);
+            tc_fence_after();
+            const bool last = !has_bias && (s == slabs - 1) && (pass == num_passes - 1);
+            const uint32_t b_addr = R.ring_addr + R.stage * STAGE_BYTES;
+            if (kX3Mode != 0) {
+                // pass 0 (W_hi): A_hi and A_lo; pass 1 (W_lo): A_hi only
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
+                    const uint64_t da_hi = umma_smem_desc(R.a_addr[0] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+                    const uint64_t da_lo = umma_smem_desc(R.a_addr[1] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+                    const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
+#pragma unroll
+                    for (int b = 0; b < mblocks; ++b) {
+                        const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
+                        const uint32_t td = R.tmem_base + b * 128;
+                        umma_f16_ss(td, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
+                        // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
+                        if (pass == 0 || kX3Mode == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);
+                    }
+                }
+                if (last) umma_commit(R.acc_full + 0);
+            } else if (kMBlocks == 1) {
+                // the common case, kept minimal (the issue loop shares its scheduler with two epilogue warps): descriptor words
+                // advanced by 32-bit adds
+                constexpr uint32_t hi = umma_desc_hi(128);
+                const uint32_t b_lo = umma_desc_lo(b_addr, lbo_b);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t a_lo = umma_desc_lo(R.a_addr[g] + (chunk0 + 4 * s) * CHUNK_BYTES, CHUNK_BYTES);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t al = a_lo + j * (2 * CHUNK_BYTES >> 4), bl = b_lo + j * (2 * lbo_b >> 4);
+                        const uint32_t accum = (s | pass | j) != 0 ? 1u : 0u;
+                        if (kSwap) umma_f16_ss_words(R.tmem_base + g * 256, bl, hi, al, hi, idesc, accum);
+                        else umma_f16_ss_words(R.tmem_base + g * 256, al, hi, bl, hi, idesc, accum);
+                    }
+                    if (last) umma_commit(R.acc_full + g);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t a_chunk = chunk0 + 4 * s + 2 * j;
+                        const uint64_t da = umma_smem_desc(R.a_addr[g] + a_chunk * CHUNK_BYTES, CHUNK_BYTES, 128);
+#pragma unroll
+                        for (int b = 0; b < mblocks; ++b) {
+                            const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
+                            umma_f16_ss(R.tmem_base + g * 256 + b * 128, kSwap ? db : da, kSwap ? da : db, idesc, (s | pass | j) != 0 ? 1u : 0u);
+                        }
+                    }
+                    if (last) umma_commit(R.acc_full + g);
+                }
+            }
+            umma_commit(R.empty_bar + R.stage);
+            if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
+        }
+    }
+}
+
 }  // namespace pe_tc

@@ -56,17 +56,21 @@ def install_ray_selection(reference_ray_helper=None):
     return reference_ray_helper
 
 
-def install(environment_model, precision: str = "fp16x3", ray_selection: bool = False):
+def install(environment_model, precision: str = None, ray_selection: bool = False):
     """Replaces ``environment_model.object_composer`` (a reference ObjectComposer) by the B200 composer carrying the same
     parameters, and routes ``batchified_composer_call`` to the single-call version.  ``ray_selection=True`` also rebinds
-    the reference's ray-selection helpers (``install_ray_selection``)."""
+    the reference's ray-selection helpers (``install_ray_selection``).  ``precision=None`` keeps the configured
+    ``model.b200_precision`` (default: the composer's own).  Note: the rebound ``batchified_composer_call`` ignores
+    ``samples_per_image_batching``; in TRAIN mode the BatchNorm batch of the AdaIn layers is therefore the whole call instead of
+    one chunk (eval mode is chunk-invariant, bit for bit)."""
     if ray_selection:
         install_ray_selection()
     reference = environment_model.object_composer
     config = dict(environment_model.config)
     composer = ObjectComposer(config)
     composer.load_state_dict(reference.state_dict())
-    composer.precision = precision
+    if precision is not None:
+        composer.precision = precision
     composer.to(next(reference.parameters()).device)
     composer.train(reference.training)
     environment_model.object_composer = composer

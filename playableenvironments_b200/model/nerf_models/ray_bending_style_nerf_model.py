@@ -51,8 +51,19 @@ class RayBendingStyleNerfModel(nn.Module):
         return build_object_desc(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config, positions, is_static,
                                  canonical_pose, self.packed_parameters())
 
+    def state_tensors(self):
+        """Every tensor the packed blob is built from (learnable tensors + the BatchNorm running statistics), collected by
+        ATTRIBUTE access: nn.DataParallel replicas (train.py:61) carry their weights as plain attributes and have empty
+        ``_parameters`` / ``_buffers``, so ``.parameters()`` would yield nothing there."""
+        tensors = [t for _, _, t in self.parameter_slots()]
+        head = self.nerf_model.features_head
+        for layer in (head[1], head[4]):
+            bn = layer.ada_in.normalization
+            tensors += [bn.running_mean, bn.running_var]
+        return tensors
+
     def packed_parameters(self) -> torch.Tensor:
-        tensors = list(self.nerf_model.parameters()) + list(self.nerf_model.buffers()) + list(self.ray_bender.parameters())
+        tensors = self.state_tensors()
         key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
         if self._packed is None or key != self._packed_key:
             self._packed = pack_object(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config)
@@ -166,7 +177,7 @@ def build_object_desc(nerf, bender, bounding_box: BoundingBox, model_config: Dic
 
 def pack_object(nerf, bender, bounding_box: BoundingBox, model_config: Dict) -> torch.Tensor:
     """Packs the parameters into the kernel-side blob (pe_pack_object)."""
-    device = next(nerf.parameters()).device
+    device = nerf.backbone_layers[0].weight.device        # attribute access: valid on nn.DataParallel replicas too
     if device.type != "cuda":
         raise _cabi.PeError("parameters must live on a CUDA device: the render path has no CPU implementation")
     L = _cabi.lib()

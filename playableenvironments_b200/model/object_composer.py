@@ -53,6 +53,10 @@ class ObjectComposer(nn.Module):
             if current_object_model is not None:
                 current_object_model.set_step(current_step)
 
+    def _any_parameter_requires_grad(self) -> bool:
+        """Attribute walk instead of ``self.parameters()``: on nn.DataParallel replicas the weights are plain tensor attributes."""
+        return any(t.requires_grad for m in self.object_models_coarse for t in m.state_tensors())
+
     def _descs(self, canonical_pose: bool):
         helper = self.object_id_helper
         descs = []
@@ -74,7 +78,7 @@ class ObjectComposer(nn.Module):
         if self.precision not in _cabi.PRECISIONS:
             raise Exception(f"unknown b200_precision '{self.precision}'")
         needs_grad = torch.is_grad_enabled() and (
-            any(p.requires_grad for p in self.parameters())
+            self._any_parameter_requires_grad()
             or any(torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
         helper = self.object_id_helper
         models = None
@@ -115,7 +119,7 @@ class ObjectComposer(nn.Module):
         The samples (ray parameter t, displacement, compositing weights) come from the same kernels as ``forward`` in a single-object
         scene; the weighted average itself is three small tensor ops.  Forward only: the pose-consistency / keypoint losses that
         differentiate through it have weight 0 in every shipped config, so a call that would need a graph raises."""
-        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or any(
+        if torch.is_grad_enabled() and (self._any_parameter_requires_grad() or any(
                 torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation))):
             raise Exception("forward_expected_positions is forward-only in the B200 render path: call it under torch.no_grad()")
         from ..utils.lib_3d.ray_helper import RayHelper

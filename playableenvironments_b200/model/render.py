@@ -160,6 +160,9 @@ class RenderFunction(torch.autograd.Function):
         styles, deforms = list(flat[:K]), list(flat[K:2 * K])
         res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms)
         ctx.meta = meta
+        # the descs in ``meta`` hold RAW pointers into each model's packed blob: keep those tensors alive with the graph (a second
+        # forward before this node's backward may repack -- train-mode BatchNorm bumps the running statistics every call)
+        ctx.packed_keepalive = [m.packed_parameters() for m in meta["models"]] if meta.get("models") else []
         ctx.save_for_backward(origins, dirs, w2o, *styles, *deforms)
         names = [f"object_{k}" for k in range(K)] + ["global"]
         outs = [res[n][key] for n in names for key in DIFF_KEYS]

@@ -42,8 +42,13 @@ def all_gather_rays(local: torch.Tensor, rays: int, dim: int, group=None, multip
 
 def render_sharded(composer, ray_origins, ray_directions, focal_normals, w2o, style, deformation, object_in_scene, perturb: bool,
                    group=None, **kw):
-    """Renders this rank's ray shard and all-gathers the global feature grid (+ opacity/depth).  Returns
-    (full integrated_features (..., R, F), local results dict, (begin, end))."""
+    """Renders this rank's ray shard and all-gathers the global feature grid.  Returns
+    (full integrated_features (..., R, F), local results dict, (begin, end)).
+
+    INFERENCE ONLY: the all-gather is not autograd-aware (no gradient would reach the other ranks' shards) and train-mode
+    BatchNorm statistics would be per rank; training shards whole frames per rank instead (``sharding.allreduce_gradients``)."""
+    if torch.is_grad_enabled() and composer.training:
+        raise Exception("render_sharded is inference-only: call it under torch.no_grad() / composer.eval()")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     rays = ray_directions.size(-2)
