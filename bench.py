@@ -1,7 +1,7 @@
 """Benchmark of the per-frame NeRF render path (BASELINE.json metric: ray-samples/sec of the fused style-MLP ray-march
 at 256x256 rays x 128 samples/ray).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|fp16x2|fp32] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision mixed|fp16|fp16x2|fp16x3|fp32] [--impl b200|reference]
 
 A step = one pass of the hot path over one synthetic frame per GPU (BASELINE configs[1]: one static field, shipped
 8x256/192-feature architecture, camera inside the box so all 8 388 608 samples are in-box), followed for N > 1 by the
@@ -28,6 +28,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "
 
 FLOP_PER_SAMPLE = 2 * 614144          # matmul MACs of the shipped field x 2
 HEIGHT, WIDTH, POSITIONS = 256, 256, 128
+TRAFFIC_MIXED = None                 # dram bytes of one pe_field_tc_kernel launch in mixed mode (profiles/r2_*), set once captured
 WORKLOAD = "cfg2: 1 static field (W=256,L=8,skip=4,10 oct,F=192), 256x256 rays x 128 samples/ray, 100% in-box, forward"
 
 
@@ -125,7 +126,66 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def train_step_report(device, dense: bool, precision: str = "fp16x3"):
+def gpu_eager_reference(device, tennis_hw=(144, 256)):
+    """SURVEY 8(d) / BASELINE.md section 3: the reference's own eager PyTorch formulation of the path (the oracle port: the same
+    torch op sequence as upstream, pinned against it by tests/golden) timed ON THIS GPU, in plain fp32 and with TF32 matmuls:
+    cfg2 forward in chunks of 8192 rays (the reference bounds activation memory by chunking, environment_model.py:584) and the cfg3
+    Tennis train step (forward + backward through autograd, train-mode BatchNorm).  What the repo's kernels must beat on equal hardware."""
+    import scenes
+    from helpers import INPUT_KEYS
+    from oracle import render_oracle as O
+    out = {"kind": "port (oracle/render_oracle.py under torch.device(cuda): ATen / cuBLAS kernels, like the upstream eager path)"}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            fn()
+        e0.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(e0) / reps
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        with torch.device(device):
+            config, state, inputs = build_scene()
+            state_d = {k: v.to(device) for k, v in state.items()}
+            args = [inputs[k].to(device) for k in INPUT_KEYS]
+
+            def fwd():
+                with torch.no_grad():
+                    O.batchified_composer_call(config, state_d, *args, perturb=False, samples_per_image_batching=8192)
+
+            tscene = scenes.scene_tennis(seed=13, height=tennis_hw[0], width=tennis_hw[1], stride=1, lead=(1, 1, 1), dense=True)
+            tconfig, tstate, tinputs = tscene
+            tstate_d = {k: v.to(device).requires_grad_(v.is_floating_point() and "running_" not in k) for k, v in tstate.items()}
+            targs = [tinputs[k].to(device) for k in INPUT_KEYS]
+            targs = [a.requires_grad_(True) if (k in scenes.GRAD_INPUT_KEYS) else a for k, a in zip(INPUT_KEYS, targs)]
+            rays = tinputs["ray_directions"].size(-2)
+            cot = torch.randn(rays, 192)
+
+            def train():
+                for t in list(tstate_d.values()) + targs:
+                    t.grad = None
+                res = O.composer_forward(tconfig, tstate_d, *targs, perturb=False, training=True)["coarse"]["global"]
+                loss = (res["integrated_features"].reshape(rays, 192) * cot).sum() + res["opacity"].sum()
+                loss.backward()
+
+            for tf32 in (False, True):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                tag = "tf32" if tf32 else "fp32"
+                ms = timed(fwd, 2)
+                out[f"cfg2_fwd_{tag}_ms"] = ms
+                out[f"cfg2_fwd_{tag}_samples_per_s"] = HEIGHT * WIDTH * POSITIONS / (ms / 1e3)
+                out[f"cfg3_dense_train_step_{tag}_ms"] = timed(train, 2)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+def train_step_report(device, dense: bool, precision: str = "mixed", world: int = 1):
     """BASELINE configs[2]: Tennis scene (court + 2 players with positional ray benders, composed), 256x144 rays, forward and
     forward+backward through ObjectComposer with every parameter and every differentiable input requiring a gradient.
     Secondary figures (the headline stays configs[1]).  precision fp16x3 (the composer's default): train-mode forward and the
@@ -148,11 +208,16 @@ def train_step_report(device, dense: bool, precision: str = "fp16x3"):
         with torch.no_grad():
             return comp(*call, False)
 
+    from playableenvironments_b200 import sharding
+    params = list(comp.parameters())
+
     def fwd_bwd():
         comp.zero_grad(set_to_none=True)
         res = comp(*call, False)["coarse"]
         loss = (res["global"]["integrated_features"].reshape(rays, 192) * cot).sum() + res["global"]["opacity"].sum()
         loss.backward()
+        if world > 1:           # data-parallel step: one frame per rank, ONE all-reduce of the flat gradient bucket (train.py:61)
+            sharding.allreduce_gradients(params, average=True)
 
     def timed(fn, reps):
         fn()
@@ -175,7 +240,13 @@ def train_step_report(device, dense: bool, precision: str = "fp16x3"):
         inbox += int((ra != float(m["empty_space_alpha"])).sum().item())
     ms_f, ms_fb = timed(fwd, 3), timed(fwd_bwd, 3)
     os.environ.pop("PE_TC_BACKWARD_RECOMPUTE", None)
-    return {"workload": f"cfg3 Tennis{' (dense: camera on a player)' if dense else ''}: court P=4 + 2 players P=32 with ray benders, 256x144 rays, train-mode BatchNorm",
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_f, ms_fb], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_f, ms_fb = float(t[0]), float(t[1])
+        inbox *= world
+    return {"n_gpus": world, "gradient_allreduce_bytes": sum(p.numel() for p in params) * 4 if world > 1 else 0,"workload": f"cfg3 Tennis{' (dense: camera on a player)' if dense else ''}: court P=4 + 2 players P=32 with ray benders, 256x144 rays, train-mode BatchNorm",
             "sample_slots": slots, "in_box_samples": inbox, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
             "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3),
             "precision": "fp32 (CUDA cores only)" if precision == "fp32" else f"{precision} forward + recompute on tensor cores, fp32 field backward"}
@@ -205,7 +276,7 @@ def eval_frame_report(device, dense: bool):
         return s0.elapsed_time(e0) / reps
 
     out = {"workload": f"cfg3 Tennis{' (dense)' if dense else ''}, eval forward, 256x144 rays, court P=4 + 2 players P=32 with ray benders"}
-    for precision in ("fp16x3", "fp16"):
+    for precision in ("mixed", "fp16x3", "fp16"):
         out[f"{precision}_ms"] = timed(precision)
     os.environ["PE_TC_PREPASS"] = "0"
     try:
@@ -238,13 +309,17 @@ def run_b200(args):
     gathered = torch.empty((world, rays, F), dtype=torch.float32, device=device) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)     # > 126 MB L2
 
+    from playableenvironments_b200 import sharding
+    side = torch.cuda.Stream(device=device)
+
     def step():
         with torch.no_grad():
+            if world > 1:
+                # the frame renders in ray chunks; chunk i's grid is all-gathered (the single collective of the path) on a side
+                # stream while chunk i+1 renders: only the last chunk's transfer is exposed
+                return sharding.render_pipelined(comp, *call_args, False, chunks=args.chunks, gathered=gathered, side_stream=side)
             res = comp(*call_args, False)
-        feats = res["coarse"]["global"]["integrated_features"]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, feats.reshape(rays, F))     # the single collective of the path
-        return feats
+        return res["coarse"]["global"]["integrated_features"]
 
     def barrier():
         if world > 1:
@@ -283,12 +358,9 @@ def run_b200(args):
 
     def e2e_step():
         d = [host_in[k].to(device, non_blocking=True) for k in INPUT_KEYS]
-        with torch.no_grad():
-            res = comp(*d, False)
-        feats = res["coarse"]["global"]["integrated_features"].reshape(rays, F)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, feats)
-        host_out.copy_(feats, non_blocking=True)
+        with torch.no_grad():      # D2H of chunk i (and its all-gather) overlap the render of chunk i+1
+            sharding.render_pipelined(comp, *d, False, chunks=args.chunks, gathered=gathered if world > 1 else None, host_out=host_out,
+                                      side_stream=side)
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -305,11 +377,27 @@ def run_b200(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * samples_per_rank * e2e_steps / (float(e2e_ms.item()) / 1e3)
 
-    # ---- the other tensor-core modes on the same frame + live parity of the timed mode against the fp32-class mode ----
+    # ---- the other tensor-core modes on the same frame; live parity of the timed mode against the UPSTREAM reference's output on every
+    # 16th ray of this very frame (tests/golden/cfg2_subset.npz, written by tests/golden/make_golden_fullsize.py) ----
     modes, parity = {}, None
     if rank == 0 and world == 1 and not args.quick:
+        import numpy as np
+        from helpers import load_golden
         feats_main = step().clone()
-        for other in ("fp16x2", "fp16x3"):
+        g = load_golden("cfg2_subset")
+        stride = int(g["stride"])
+        # rays whose last-sample raw alpha sits on the opacity step (alpha jumps 0 -> 1 over a 1e10 interval,
+        # object_composer.py:172,197) are not resolvable below fp32: counted, and excluded from the bound
+        stable = torch.from_numpy(np.abs(g["raw_alpha_last"].reshape(-1)) > 4e-3).to(device)
+        ref = torch.from_numpy(g["integrated_features"].reshape(-1, F)).to(device).double()
+        got = feats_main.reshape(rays, F)[::stride].double()
+        diff = (got - ref)[stable]
+        parity = {"reference": "upstream ObjectComposer on every 16th ray of this frame (4096 rays, tests/golden/cfg2_subset.npz)",
+                  "rel_l2": float(diff.norm() / ref[stable].norm()), "max_over_scale": float(diff.abs().max() / ref.abs().max()),
+                  "max_over_scale_all_rays": float((got - ref).abs().max() / ref.abs().max()),
+                  "frac_of_values_within_1e-3_of_scale": float((diff.abs() <= 1e-3 * ref.abs().max()).double().mean()),
+                  "rays_on_opacity_step_excluded": float(1.0 - stable.float().mean())}
+        for other in ("fp16", "mixed", "fp16x2", "fp16x3"):
             if other == args.precision:
                 continue
             comp.precision = other
@@ -324,24 +412,15 @@ def run_b200(args):
             e0.record()
             torch.cuda.synchronize()
             ms = s0.elapsed_time(e0) / n_other
+            d_o = (out_other.reshape(rays, F)[::stride].double() - ref)[stable]
             modes[other] = {"ms_per_step": ms, "value": samples_per_rank / (ms / 1e3),
-                            "roofline_frac": samples_per_rank * FLOP_PER_SAMPLE / (ms / 1e3) / 1e12 / measured_peaks()["burst"]}
-            if other == "fp16x3":
-                # rays whose last-sample raw alpha sits on the opacity step (alpha jumps 0 -> 1 over a 1e10 interval,
-                # object_composer.py:172,197) are not resolvable at reduced precision: counted, and excluded from the bound
-                comp.return_raw_alphas = True
-                with torch.no_grad():
-                    res = comp(*call_args, False)["coarse"]
-                comp.return_raw_alphas = False
-                stable = (res["object_0"]["raw_alphas"][..., -1].reshape(-1).abs() > 4e-3)
-                ref = out_other.reshape(rays, F).double()[stable]
-                diff = feats_main.reshape(rays, F).double()[stable] - ref
-                parity = {"reference": "fp16x3 mode (fp32-class: within 1e-5 of the fp32 CUDA path) on the same frame",
-                          "rel_l2": float(diff.norm() / ref.norm()), "max_over_scale": float(diff.abs().max() / ref.abs().max()),
-                          "frac_of_values_within_1e-3_of_scale": float((diff.abs() <= 1e-3 * ref.abs().max()).double().mean()),
-                          "rays_on_opacity_step_excluded": float(1.0 - stable.float().mean())}
+                            "roofline_frac": samples_per_rank * FLOP_PER_SAMPLE / (ms / 1e3) / 1e12 / measured_peaks()["burst"],
+                            "max_over_scale_vs_reference": float(d_o.abs().max() / ref.abs().max())}
         comp.precision = args.precision
 
+    train_multi = None
+    if world > 1 and not args.quick:
+        train_multi = train_step_report(device, True, world=world)       # every rank takes part (collective inside)
     if rank == 0:
         peaks = measured_peaks()
         ms_per_step = total_s * 1e3 / args.steps
@@ -350,18 +429,19 @@ def run_b200(args):
         line = {
             "metric": "ray-samples/sec (style-MLP ray-march, fwd)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp16": "f16 operands, f32 accumulate", "fp16x2": "f16 operands (weights hi+lo), f32 accumulate",
+            "vs_baseline": None, "dtype": {"mixed": "f16 operands (weights hi+lo on layers L4-L7 and the head), f32 accumulate",
+                                           "fp16": "f16 operands, f32 accumulate", "fp16x2": "f16 operands (weights hi+lo), f32 accumulate",
                                            "fp16x3": "f16 operands (weights and activations hi+lo), f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MB memset)",
-                       "frames_per_s": world * args.steps / total_s, "collective": "all_gather(feature grid)" if world > 1 else "none"},
+                       "frames_per_s": world * args.steps / total_s, "collective": f"all_gather(feature grid) per ray chunk, {args.chunks} chunks, overlapped with the next chunk's render" if world > 1 else "none"},
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / peaks["burst"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one pe_field_tc_kernel launch on this workload
                          # (profiles/r1c_final_summary.md; fp16: 3.4 MB + 146.8 MB, fp16x2: 4.1 MB + 147.7 MB)
-                         "traffic": {"fp16": 150208768, "fp16x2": 151788032}.get(args.precision), "peak_source": peaks["source"] + " bf16 burst",
+                         "traffic": {"fp16": 150208768, "fp16x2": 151788032, "mixed": TRAFFIC_MIXED}.get(args.precision), "peak_source": peaks["source"] + " bf16 burst",
                          "frac_of_sustained": achieved_tflops / peaks["sustained"],
-                         "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0}[args.precision]},
+                         "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0, "mixed": "2 on L4-L7 + head, 1 on L0-L3"}[args.precision]},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
@@ -371,6 +451,9 @@ def run_b200(args):
             line["train_step"] = [train_step_report(device, False), train_step_report(device, True),
                                   train_step_report(device, False, "fp32"), train_step_report(device, True, "fp32")]
             line["eval_frame"] = [eval_frame_report(device, False), eval_frame_report(device, True)]
+            line["gpu_eager_baseline"] = gpu_eager_reference(device)
+        if train_multi:
+            line["train_step"] = [train_multi]
         if modes:
             line["other_modes"] = modes
         if parity:
@@ -391,7 +474,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "fp16"), choices=["fp16", "fp16x2", "fp16x3", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "mixed"), choices=["mixed", "fp16", "fp16x2", "fp16x3", "fp32"])
+    ap.add_argument("--chunks", type=int, default=4, help="ray chunks per frame of the pipelined render (N > 1 and the e2e figure)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the other precision modes and the live parity check")
     args = ap.parse_args()

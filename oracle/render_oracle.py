@@ -155,7 +155,7 @@ def positional_encoding(x: Tensor, octaves: int, append_original: bool = True, w
 def annealing_weights(current_step: int, octaves: int, num_steps: int) -> Tensor:
     """model/annealable_positional_encoder.py:54-58."""
     alpha = torch.tensor(float(current_step)) * octaves / num_steps
-    idx = torch.arange(octaves, dtype=torch.float32)
+    idx = torch.arange(octaves, dtype=torch.get_default_dtype())
     return (1 - torch.cos(math.pi * torch.clamp(alpha - idx, min=0.0, max=1.0))) / 2
 
 
@@ -225,8 +225,8 @@ def adain_style_nerf(sd: Dict[str, Tensor], prefix: str, cfg: dict, bbox: Tensor
     """model/nerf_models/adain_style_nerf_model.py:106-199 on flat (N,3)
     positions, including its own second bounding-box mask (lines 171-184)."""
     n = positions.size(0)
-    feats = torch.zeros((n, cfg["output_features"]), dtype=torch.float32)
-    alphas = torch.ones((n, 1), dtype=torch.float32) * cfg["empty_space_alpha"]
+    feats = torch.zeros((n, cfg["output_features"]), dtype=positions.dtype)
+    alphas = torch.ones((n, 1), dtype=positions.dtype) * cfg["empty_space_alpha"]
     mask = bounding_box_mask(positions, bbox)
     x = positions[mask] / (bbox[:, 1] - bbox[:, 0])
     enc = positional_encoding(x, cfg["position_encoder"]["octaves"], cfg["position_encoder"]["append_original"])
@@ -276,7 +276,7 @@ def ray_bending_style_nerf(sd: Dict[str, Tensor], cfg: dict, positions: Tensor, 
                            new_stats=None) -> Tuple[Tensor, Tensor, Tensor]:
     """model/nerf_models/ray_bending_style_nerf_model.py:137-219.
     positions (..., R, P, 3); origins/directions (..., R, 3); style (..., 1|R, S)."""
-    bbox = torch.as_tensor(cfg["bounding_box"], dtype=torch.float32)
+    bbox = torch.as_tensor(cfg["bounding_box"], dtype=positions.dtype)
     lead = list(positions.shape[:-1])
     P = positions.size(-2)
     flat_pos = positions.reshape(-1, 3)
@@ -288,9 +288,9 @@ def ray_bending_style_nerf(sd: Dict[str, Tensor], cfg: dict, positions: Tensor, 
     ncfg, bcfg = dict(cfg["nerf_model"]), dict(cfg["ray_bender_model"])
     for c in (ncfg, bcfg):                                    # :39-50
         c["empty_space_alpha"] = cfg["empty_space_alpha"]
-    out_f = torch.zeros((n, ncfg["output_features"]), dtype=torch.float32)
-    out_a = torch.ones((n,), dtype=torch.float32) * cfg["empty_space_alpha"]
-    out_d = torch.zeros((n, 3), dtype=torch.float32)
+    out_f = torch.zeros((n, ncfg["output_features"]), dtype=positions.dtype)
+    out_a = torch.ones((n,), dtype=positions.dtype) * cfg["empty_space_alpha"]
+    out_d = torch.zeros((n, 3), dtype=positions.dtype)
     mask = bounding_box_mask(flat_pos, bbox)
     pos, sty, dfm = flat_pos[mask], flat_style[mask], flat_def[mask]
 
@@ -444,7 +444,7 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
         cfg = m["object_models"][mi]
         prefix = f"object_models_coarse.{mi}."
         sd = {key[len(prefix):]: val for key, val in state.items() if key.startswith(prefix)}
-        bbox = torch.as_tensor(cfg["bounding_box"], dtype=torch.float32)
+        bbox = torch.as_tensor(cfg["bounding_box"], dtype=ray_directions.dtype)
         w2o = transformation_matrix_w2o[..., k]
         ois = object_in_scene[..., k]
         o, d, _ = transform_rays(ray_origins, ray_directions, focal_normals, w2o)

@@ -82,11 +82,12 @@ static bool tc_allowed(const PeScene& s) {
 static thread_local bool g_keep_samples = false;
 struct KeepSamples { bool prev; KeepSamples() : prev(g_keep_samples) { g_keep_samples = true; } ~KeepSamples() { g_keep_samples = prev; } };
 
-// Arithmetic of one object.  The mixed mode keeps objects with few samples per ray in the fp32-class mode: alpha = 1 - exp(-relu(raw) * delta)
-// amplifies an absolute raw-alpha error by the sample spacing delta (court P = 4: delta ~ 20, Minecraft ground in front of the skybox: ~85),
-// and their share of the frame's FLOPs is negligible.
+// Arithmetic of one object.  The mixed mode keeps objects with fewer than 64 samples per ray in the fp32-class mode: alpha = 1 - exp(-relu(raw) * delta)
+// amplifies an absolute raw-alpha error by the sample spacing delta (court P = 4: delta ~ 20, Minecraft ground in front of the skybox: ~85;
+// players P = 32: the fp16 rounding of the ACTIVATIONS alone leaves 2-3e-3 on the compositing weights, measured, profiles/r2_mixed_mode.md),
+// and their share of a frame's FLOPs is small.
 static int object_precision(const PeScene& s, int k) {
-    if (s.precision == PE_PRECISION_MIXED && s.object[k].positions < 32) return PE_PRECISION_FP16X3;
+    if (s.precision == PE_PRECISION_MIXED && s.object[k].positions < 64) return PE_PRECISION_FP16X3;
     return s.precision;
 }
 

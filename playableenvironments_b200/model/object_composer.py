@@ -29,7 +29,7 @@ class ObjectComposer(nn.Module):
         #   "fp16x3" tensor cores, weights and activations split hi+lo — fp32-class parity (default)
         #   "fp16x2" tensor cores, weights split hi+lo          "fp16" tensor cores, single pass (fastest)
         #   "fp32"   CUDA cores only
-        self.precision = self.config["model"].get("b200_precision", "fp16x3")
+        self.precision = self.config["model"].get("b200_precision", "mixed")
         # diagnostic switch: also return the per-sample raw alphas of every object under results["coarse"]["object_k"]["raw_alphas"]
         self.return_raw_alphas = False
 

@@ -46,7 +46,7 @@ def render_sharded(composer, ray_origins, ray_directions, focal_normals, w2o, st
     (full integrated_features (..., R, F), local results dict, (begin, end)).
 
     INFERENCE ONLY: the all-gather is not autograd-aware (no gradient would reach the other ranks' shards) and train-mode
-    BatchNorm statistics would be per rank; training shards whole frames per rank instead (``sharding.allreduce_gradients``)."""
+    BatchNorm statistics would be per rank; training shards whole frames per rank instead (``allreduce_gradients`` below)."""
     if torch.is_grad_enabled() and composer.training:
         raise Exception("render_sharded is inference-only: call it under torch.no_grad() / composer.eval()")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -57,3 +57,76 @@ def render_sharded(composer, ray_origins, ray_directions, focal_normals, w2o, st
     feats = local["coarse"]["global"]["integrated_features"]
     full = all_gather_rays(feats, rays, dim=-2, group=group) if world > 1 else feats
     return full, local, (begin, end)
+
+
+def render_pipelined(composer, ray_origins, ray_directions, focal_normals, w2o, style, deformation, object_in_scene, perturb: bool,
+                     chunks: int = 4, group=None, gathered: torch.Tensor = None, host_out: torch.Tensor = None, side_stream=None, **kw):
+    """Renders the local rays in ``chunks`` contiguous ray chunks and moves each chunk's feature grid off the compute stream while
+    the next chunk renders: chunk i is all-gathered across the ranks (``gathered``: (world, rays, F), every rank renders the same
+    number of rays -- one frame or one equal shard per rank) and/or copied to pinned host memory (``host_out``: (rays, F)) on
+    ``side_stream``; only the last chunk's transfer is exposed.  Rays are independent, so the chunks equal the single-launch
+    render bit for bit.  Inference only.  Returns the local feature grid (rays, F) (device)."""
+    if torch.is_grad_enabled() and composer.training:
+        raise Exception("render_pipelined is inference-only: call it under torch.no_grad() / composer.eval()")
+    world = dist.get_world_size(group) if (dist.is_initialized() and gathered is not None) else 1
+    rays = ray_directions.size(-2)
+    main = torch.cuda.current_stream()
+    side = side_stream if side_stream is not None else torch.cuda.Stream()
+    local, keep = None, []
+    for c in range(chunks):
+        begin, end = ray_shard(rays, c, chunks)
+        if end == begin:
+            continue
+        res = composer(ray_origins, ray_directions[..., begin:end, :], focal_normals, w2o, style, deformation, object_in_scene, perturb, **kw)
+        feats = res["coarse"]["global"]["integrated_features"]
+        feats = feats.reshape(end - begin, feats.size(-1))
+        if local is None:
+            local = feats.new_empty((rays, feats.size(-1))) if (gathered is None or world == 1) else None
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            if gathered is not None and world > 1:
+                dist.all_gather([gathered[r, begin:end] for r in range(world)], feats, group=group)
+            elif gathered is not None:
+                gathered[0, begin:end].copy_(feats, non_blocking=True)
+            if local is not None:
+                local[begin:end].copy_(feats, non_blocking=True)
+            if host_out is not None:
+                host_out[begin:end].copy_(feats, non_blocking=True)
+        keep.append(feats)                  # alive until the side stream has consumed it
+    done = torch.cuda.Event()
+    done.record(side)
+    main.wait_event(done)
+    for t in keep:
+        t.record_stream(side)
+    if local is None:
+        local = gathered[dist.get_rank(group)]
+    return local
+
+
+def allreduce_gradients(parameters, group=None, average: bool = True) -> int:
+    """Data-parallel training across the ranks (the reference: nn.DataParallel's replica-gradient reduction, train.py:61): every
+    rank renders whole frames, then ONE all-reduce of a single flat bucket holding every composer gradient (2.87 M parameters =
+    11.5 MB in the shipped Tennis configuration) -- sized for launch latency, not for link count (NVSwitch).  Parameters without a
+    gradient on this rank contribute zeros.  Train-mode BatchNorm statistics stay per rank, like the reference's replicas.
+    Returns the number of bytes reduced."""
+    params = [p for p in parameters if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    if world > 1:
+        dist.all_reduce(flat, group=group)
+        if average:
+            flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel() * flat.element_size()

@@ -26,7 +26,7 @@ pytestmark = pytest.mark.gpu
 
 GRAD_TOL = 2e-3
 GRAD_CASES = [("cfg1", False, 1e-4), ("toy_world", False, 1e-4), ("static_small", False, 8e-3), ("tennis_dense", False, 5e-2),
-              ("minecraft_small", False, 5e-2), ("cfg1", True, 1e-4), ("toy_world", True, 1e-4), ("tennis_dense", True, 5e-2)]
+              ("minecraft_small", False, 1e-2), ("cfg1", True, 1e-4), ("toy_world", True, 1e-4), ("tennis_dense", True, 5e-2)]
 
 
 def run_backward(name, training, precision="fp32"):

@@ -8,6 +8,8 @@ Tolerances (relative to the tensor's scale: max|got - ref| / max|ref|; BASELINE.
                                                                                      2e-3 scale-relative max (measured 1.2e-3 at 256x256)
   few-sample objects (P=4, P=16) amplify the fp16 activation rounding through exp(-relu(a) * delta) with delta ~ 20..85:
   fp16/fp16x2 are held to 6e-3 / 8e-2 there; fp16x3 and fp32 stay at 2e-4 (Numerics).
+  mixed  the composer's and bench.py's default (hi+lo weight passes on L4-L7 and the head for objects with >= 64 samples per ray,
+         fp16x3 for the others): 1e-3 on EVERY golden scene and on the 4096-ray golden of the full-size headline frame.
 """
 import os
 
@@ -140,6 +142,35 @@ def test_fp16x3_tensor_core_path_matches_reference(name):
     _, _, _, comp, dev = _build(name, "fp16x3")
     bad = compare(flatten(_run(comp, dev)), load_golden(name), FP32_TOL)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_mixed_mode_matches_reference_within_1e_3(name):
+    """The default mode against the upstream goldens: BASELINE.json's 1e-3, max norm relative to each tensor's scale, every output."""
+    _, _, _, comp, dev = _build(name, "mixed")
+    bad = compare(flatten(_run(comp, dev)), load_golden(name), 1e-3)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision,tol", [("mixed", 1e-3), ("fp16x3", 2e-4), ("fp16x2", 1e-3), ("fp16", 2e-3)])
+def test_full_size_frame_against_reference_golden(precision, tol):
+    """BASELINE configs[1] at FULL size (256x256 rays x 128 samples): every 16th ray of the rendered frame against the upstream
+    ObjectComposer's output on exactly those 4096 rays (tests/golden/make_golden_fullsize.py).  The reference's opacity is a step
+    function of the raw alpha of a ray's last sample (interval 1e10, object_composer.py:172,197): rays whose value lies within 4e-3 of
+    that step (0.8 % of the rays) are not resolvable below fp32 and are excluded -- except in the fp32-class mode, which must
+    reproduce all of them."""
+    from gpu_common import build_composer, run_composer
+    scene = scenes.scene_static(seed=12, height=256, width=256, P=128)
+    _, _, _, comp, dev = build_composer(scene, precision)
+    full = run_composer(comp, dev)["coarse"]["global"]
+    g = load_golden("cfg2_subset")
+    stride = int(g["stride"])
+    stable = np.abs(g["raw_alpha_last"].reshape(-1)) > (0.0 if precision == "fp16x3" else 4e-3)
+    assert stable.mean() > 0.99
+    for key in ("integrated_features", "opacity", "depth"):
+        got = full[key].reshape(65536, -1)[::stride].cpu().numpy()[stable]
+        want = g[key].reshape(4096, -1)[stable]
+        assert scale_rel_err(got, want) < tol, (key, scale_rel_err(got, want))
 
 
 @pytest.mark.parametrize("precision,tol", [("fp16x3", 2e-4), ("fp16x2", 1e-3), ("fp16", 3e-3)])

@@ -132,3 +132,30 @@ def test_all_gather_of_ray_shards_world_size_2(tmp_path, rays):
     port = 29500 + (os.getpid() + rays) % 2000
     mp.spawn(_gather_worker, args=(2, port, rays, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def _allreduce_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    params = [torch.nn.Parameter(torch.randn(5, 7)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.randn(3, 3)),
+              torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    grads = [[torch.full_like(p, float(r + 1)) * (i + 1) for i, p in enumerate(params)] for r in range(world)]
+    params[0].grad, params[1].grad = grads[rank][0].clone(), grads[rank][1].clone()      # params[2]: no gradient on any rank but rank 1
+    if rank == 1:
+        params[2].grad = grads[1][2].clone()
+    nbytes = sharding.allreduce_gradients(params, average=True)
+    want0 = sum(grads[r][0] for r in range(world)) / world
+    want1 = sum(grads[r][1] for r in range(world)) / world
+    want2 = grads[1][2] / world
+    ok = (nbytes == (35 + 11 + 9) * 4 and torch.allclose(params[0].grad, want0) and torch.allclose(params[1].grad, want1)
+          and torch.allclose(params[2].grad, want2) and params[3].grad is None)
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world_size_2(tmp_path):
+    """Data-parallel training step: one flat bucket, one all-reduce, averaged like nn.DataParallel's replica reduction (train.py:61)."""
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
