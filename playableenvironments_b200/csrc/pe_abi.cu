@@ -349,6 +349,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
 // ------------------------------------------------------------------------------------------------
 struct ObjBwdWorkspace {
     float *cw_obj, *cw_glob, *g_raw, *g_t, *g_dm, *g_pos, *g_od, *adain_sums, *bn_fix;
+    float *g_bent, *scale;                             // tensor-core field backward: dL/d bent position, gradient scale [S, 1/S] + scratch
     double* bn_sums;
     int32_t *slot_list, *slot_count, *tile_begin;      // compacted tiles of the field backward (NULL: dense tiles)
 };
@@ -361,7 +362,28 @@ static bool backward_compacts(const PeScene& s, int k) {
     return s.object[k].nerf_kind == PE_NERF_ADAIN && (object_uses_tc(s, k) || object_uses_prepass(s, k));
 }
 
+// The field backward of the shipped field shape runs on the tensor cores (pe_bwd_tc.cu) over tiles of 128 compacted samples; PE_BWD_TC=0
+// keeps it on the exact fp32 kernel.  Its activation / gradient stash holds `capacity` tiles (1.45 MB each); more tiles than that are
+// processed in batches (the number of in-box samples is only known on the device, so the batch count is the worst case and surplus
+// launches find no tile).
+static bool backward_on_tc(const PeScene& s, int k) {
+    return backward_compacts(s, k) && !s.apply_activation && pe_bwd_tc_object_ok(s.object[k]) && pe_layout(s.object[k]).tcT_base != 0;
+}
+static int64_t bwd_tc_tiles_upper_bound(const PeScene& s, int k) {
+    return (int64_t)s.images * (((int64_t)s.rays * s.object[k].positions + PE_BWD_TILE - 1) / PE_BWD_TILE);
+}
+static int64_t bwd_tc_capacity(const PeScene& s) {
+    int64_t ub = 0;
+    for (int k = 0; k < s.objects; ++k)
+        if (backward_on_tc(s, k)) ub = bwd_tc_tiles_upper_bound(s, k) > ub ? bwd_tc_tiles_upper_bound(s, k) : ub;
+    const char* env = getenv("PE_BWD_TC_MAX_TILES");
+    const int64_t cap = env ? atoll(env) : 8192;
+    return pe_min64(ub, cap > 0 ? cap : 1);
+}
+
 struct BwdWorkspace {
+    unsigned char* tc_stash;
+    int64_t tc_capacity;
     void* fwd;
     size_t fwd_bytes;
     ObjBwdWorkspace obj[PE_MAX_OBJECTS];
@@ -401,7 +423,12 @@ static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
         o.slot_list = compact ? (int32_t*)take(n * 4) : nullptr;
         o.slot_count = compact ? (int32_t*)take((size_t)s.images * 4) : nullptr;
         o.tile_begin = compact ? (int32_t*)take(((size_t)s.images + 1) * 4) : nullptr;
+        const bool tcb = backward_on_tc(s, k);
+        o.g_bent = (tcb && object_uses_prepass(s, k)) ? (float*)take(n * 12) : nullptr;
+        o.scale = tcb ? (float*)take(64) : nullptr;
     }
+    w.tc_capacity = bwd_tc_capacity(s);
+    w.tc_stash = w.tc_capacity ? (unsigned char*)take(pe_bwd_tc_stash_bytes(w.tc_capacity)) : nullptr;
     const size_t z0 = off;
     w.zero_begin = base ? (char*)base + off : nullptr;
     for (int k = 0; k < s.objects; ++k) {
@@ -508,15 +535,62 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
         fb.g_deformation = grad_in->deformation[k];
         fb.stash = bw.stash; fb.stash_floats = bw.stash_floats;
         fb.h7_cache = o.h7; fb.inbox_in = o.h7 ? o.inbox : nullptr;
+        const bool on_tc = bw.tc_capacity > 0 && backward_on_tc(s, k);
+        const bool prepass = object_uses_prepass(s, k);
         if (b.slot_list) {
             // samples inside the box (outer mask: the ray bender's backward covers them all), from the forward recompute's masks
-            const uint8_t* mask_src = object_uses_prepass(s, k) ? o.flags : o.inbox;
-            rc = pe_launch_compact_slots(mask_src, 1, s.images, (int64_t)s.rays * d.positions, b.slot_list, b.slot_count, b.tile_begin, stream);
+            const uint8_t* mask_src = prepass ? o.flags : o.inbox;
+            rc = pe_launch_compact_slots(mask_src, 1, s.images, (int64_t)s.rays * d.positions, b.slot_list, b.slot_count, b.tile_begin, stream,
+                                         on_tc ? PE_BWD_TILE : 32);
             if (rc) return rc;
             PE_CUDA_CHECK(cudaMemsetAsync(b.g_pos, 0, (size_t)s.images * s.rays * d.positions * 12, stream));     // slots outside the list
             fb.slot_list = b.slot_list; fb.slot_count = b.slot_count; fb.tile_begin = b.tile_begin;
         }
         if (!fb.w.head0_w || !fb.w.head3_w || !fb.w.head6_w) { pe_set_error("backward needs the fp32 parameters of object %d", k); return PE_ERR_INVALID; }
+        if (on_tc) {
+            // ---- field backward on the tensor cores (pe_bwd_tc.cu): recompute with stash -> dX chain -> dW, per batch of stash tiles ----
+            PeBwdTcArgs ta = {};
+            ta.f = fa;
+            if (prepass) { ta.f.bent = o.bent; ta.f.flags = o.flags; }
+            ta.slot_list = b.slot_list; ta.slot_count = b.slot_count; ta.tile_begin = b.tile_begin;
+            ta.tile_capacity = (int32_t)bw.tc_capacity; ta.stash = bw.tc_stash;
+            ta.cw_obj = b.cw_obj; ta.cw_glob = b.cw_glob;
+            ta.g_feat_obj = grad_out->object[k].integrated_features; ta.g_feat_glob = grad_out->global.integrated_features;
+            ta.g_raw = b.g_raw; ta.g_dm = b.g_dm;
+            ta.scale = b.scale; ta.bn_fix = b.bn_fix;
+            ta.g_pos = b.g_pos; ta.g_bent = prepass ? b.g_bent : nullptr;
+            ta.gw = grad_in->params[k];
+            ta.adain_sums = b.adain_sums; ta.bn_sums = b.bn_sums;
+            rc = pe_launch_bwd_scale(ta, b.scale, (unsigned int*)(b.scale + 4), stream); if (rc) return rc;
+            const int64_t ub = bwd_tc_tiles_upper_bound(s, k);
+            const int64_t batches = (ub + bw.tc_capacity - 1) / bw.tc_capacity;
+            if (s.training) {
+                // train-mode BatchNorm backward: two global reductions before the full pass (second, then first AdaIn layer of the head)
+                for (int64_t bt = 0; bt < batches; ++bt) {
+                    rc = pe_launch_bwd_fwd(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc;
+                    rc = pe_launch_bwd_chain(ta, bt * bw.tc_capacity, 1, sm_count, stream); if (rc) return rc;
+                }
+                rc = pe_launch_bn_fix(o.stats + 2 * W + 2, b.bn_sums + 2 * W, W / 2, b.bn_fix + 2 * W, stream); if (rc) return rc;
+                for (int64_t bt = 0; bt < batches; ++bt) {
+                    if (batches > 1) { rc = pe_launch_bwd_fwd(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc; }
+                    rc = pe_launch_bwd_chain(ta, bt * bw.tc_capacity, 2, sm_count, stream); if (rc) return rc;
+                }
+                rc = pe_launch_bn_fix(o.stats, b.bn_sums, W, b.bn_fix, stream); if (rc) return rc;
+            }
+            for (int64_t bt = 0; bt < batches; ++bt) {
+                if (batches > 1 || !s.training) { rc = pe_launch_bwd_fwd(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc; }
+                rc = pe_launch_bwd_chain(ta, bt * bw.tc_capacity, 0, sm_count, stream); if (rc) return rc;
+                rc = pe_launch_bwd_dw(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc;
+            }
+            if (prepass) {
+                // the ray bender's backward stays on the exact fp32 kernel (tiles of 32 listed slots): dL/d bent position -> bender -> g_pos
+                rc = pe_launch_compact_slots(o.flags, 1, s.images, (int64_t)s.rays * d.positions, b.slot_list, b.slot_count, b.tile_begin, stream, 32);
+                if (rc) return rc;
+                fb.g_bent_in = b.g_bent;
+                fb.bwd_phase = 0;
+                rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
+            }
+        } else {
         if (s.training) {
             fb.bwd_phase = 1;
             rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
@@ -527,6 +601,7 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
         }
         fb.bwd_phase = 0;
         rc = pe_launch_field_bwd(fb, sm_count, stream); if (rc) return rc;
+        }
 
         const unsigned char* blob = (const unsigned char*)d.packed;
         auto P32 = [&](int64_t off) { return (const float*)(blob + off); };

@@ -1,0 +1,986 @@
+// Backward of the shipped field (8x256 trunk, skip at 4, 10 octaves, AdaIn head, 192 features) on the 5th-generation tensor cores.
+// What autograd does for the reference by replaying model/nerf_models/adain_style_nerf_model.py:106-145, model/layers/adain.py:21-61 and
+// model/positional_encoder.py:41-65 op by op (training/trainer.py:643).
+//
+// The samples inside the object's box are compacted per image into tiles of 128 rows (pe_launch_compact_slots).  Three kernels walk them:
+//   pe_bwd_fwd_kernel    recomputes the field forward of a tile pair on tcgen05 (hi + lo weight passes) and writes every layer's
+//                        activations to the tile's STASH block in fp16, in the very K-major no-swizzle operand layout the MMAs read
+//                        (chunk = 8 columns x 128 rows = 2048 B), plus one ReLU-mask bit per activation;
+//   pe_bwd_chain_kernel  dX chain: G_{l-1} = (G_l W_l) * relu'(h_{l-1}) with the TRANSPOSED weight stream (PeLayout::tcT_base), AdaIn /
+//                        train-mode BatchNorm backward in the epilogues, down to the gradient of the sample position; every G_l goes to
+//                        the stash (fp16, scaled by a power of two S chosen per call);
+//   pe_bwd_dw_kernel     dW_l = G_l^T A_l, db_l = G_l^T 1: both operands MN-major straight from the stash (K = the tile's 128 samples,
+//                        form validated by tests/test_gpu_parity.py::test_umma_operand_forms), accumulated in TMEM over a range of
+//                        tiles, added once to the fp32 parameter gradients.
+#include "pe_tc_common.cuh"
+#include <stdlib.h>
+
+namespace {
+using namespace pe;
+using namespace pe_tc;
+
+// ---- stash map: chunk offsets inside a tile's block (PE_BWD_FS_CHUNKS chunks of 2048 B) ----
+__host__ __device__ constexpr int FS_H(int l) { return l < 4 ? 32 * l : 136 + 32 * (l - 4); }   // h0..h3 | enc | h4..h7: [h3 | enc] is contiguous
+constexpr int FS_ENC = 128, FS_Y1 = 264, FS_Y2 = 296, FS_X1 = 312, FS_X2 = 344;
+constexpr int FS_GF = 360;                                     // 24 chunks (192 columns); a 128-row block starting at column 128 over-reads into GP(0)
+__host__ __device__ constexpr int FS_GP(int l) { return 384 + 32 * l; }
+constexpr int FS_GX1 = 640, FS_GX2 = 672, FS_GRAW = 688, FS_MASK = 690;
+// mask words (uint32, [word][row]): h_l -> words 8l .. 8l+7, y1 -> 64..71, y2 -> 72..75
+constexpr int MASK_Y1 = 64, MASK_Y2 = 72, MASK_WORDS = 76;
+static_assert(FS_MASK * 2048 + MASK_WORDS * 512 <= PE_BWD_FS_CHUNKS * 2048, "stash block too small");
+constexpr int64_t FS_BYTES = (int64_t)PE_BWD_FS_CHUNKS * CHUNK_BYTES;
+
+constexpr int THREADS = 384;                      // producer, MMA, TMEM-alloc, spare + 2 epilogue groups of 4 warps
+constexpr int SMEM_BAR = 2 * A_BYTES + NUM_STAGES * STAGE_BYTES;
+constexpr int SMEM_ONES = SMEM_BAR + 256;
+constexpr int SMEM_TOTAL = SMEM_ONES + 256;
+// chain kernel: constants of the AdaIn / alpha steps live in the encoding columns of the A buffer (float offsets from CST_BASE) until
+// step 6 overwrites them with the encoding gradient of the skip layer
+constexpr int CC_SC1 = 0, CC_SC2 = 256, CC_AW = 384, CC_K11 = 640, CC_K21 = 896, CC_K12 = 1152, CC_K22 = 1280, CC_SUMA = 1408, CC_SUMB = 1664;
+
+// ---- per-row bookkeeping shared by the forward-recompute and the chain kernel ----
+struct BRow {
+    bool store;        // the tile exists (its stash block may be written)
+    bool listed;       // the row holds a sample of the compacted list
+    bool active;       // ... that the field evaluated (inner in-box mask)
+    bool in_scene;
+    int img, slot;
+    int64_t gs;        // global sample index img * rays * P + slot
+    float x[3];        // (bent) sample position, object space
+};
+
+__device__ __forceinline__ void load_row(const PeBwdTcArgs& B, int64_t tile, int64_t tile_end, int m, int& img_cursor, BRow& r) {
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    r.store = tile < tile_end;
+    r.listed = false; r.active = false; r.in_scene = true; r.img = 0; r.slot = -1; r.gs = 0;
+    r.x[0] = r.x[1] = r.x[2] = 0.f;
+    if (!r.store) return;
+    while (tile >= B.tile_begin[img_cursor + 1]) ++img_cursor;
+    r.img = img_cursor;
+    const int P = ob.positions;
+    const int64_t spi = (int64_t)A.rays * P;
+    const int64_t e = (tile - B.tile_begin[r.img]) * PE_BWD_TILE + m;
+    r.in_scene = A.ois ? A.ois[(int64_t)r.img * A.objects + A.k] != 0 : true;
+    if (e >= B.slot_count[r.img]) return;
+    r.slot = B.slot_list[(int64_t)r.img * spi + e];
+    r.gs = (int64_t)r.img * spi + r.slot;
+    r.listed = true;
+    if (A.bent) {                 // sampled and bent by the forward recompute's pre-pass
+        r.active = (A.flags[r.gs] & 2) != 0;
+        if (r.active) { r.x[0] = A.bent[r.gs * 3]; r.x[1] = A.bent[r.gs * 3 + 1]; r.x[2] = A.bent[r.gs * 3 + 2]; }
+    } else {
+        const int ray = r.slot / P, p = r.slot - ray * P;
+        const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)r.img * A.objects + A.k) * 12, A.origins + (int64_t)r.img * 3,
+                                     A.dirs + ((int64_t)r.img * A.rays + ray) * 3, r.in_scene);
+        const float u = A.perturb ? A.rand[r.gs] : 0.f;
+        const float t = pe_sample_t(pr, p, P, A.perturb != 0, u);
+        float x[3];
+        pe_position(pr, t, x);
+        r.active = pe_in_box(ob, x);
+        if (r.active) { r.x[0] = x[0]; r.x[1] = x[1]; r.x[2] = x[2]; }
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4 q, float* v) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint4 pack8_sat(const float* v) {
+    uint4 q;
+    q.x = pack_half2_sat(v[0], v[1]); q.y = pack_half2_sat(v[2], v[3]); q.z = pack_half2_sat(v[4], v[5]); q.w = pack_half2_sat(v[6], v[7]);
+    return q;
+}
+
+// lane j ends up with the sum over the warp's 32 lanes of v[j] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = upper ? v[i] : v[i + s];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+            v[i] = (upper ? v[i + s] : v[i]) + recv;
+        }
+    }
+    return v[0];
+}
+
+// weight producer of both kernels: streams `steps` operands ([n rows][32 k] slabs, `passes` weight passes each) per tile pair
+struct StepSpec { int n, slabs; };
+__device__ __forceinline__ StepSpec chain_step(int s) {
+    // H6T (N'128,K'192) H3T (256,128) H0T L7T L6T L5T (256,256) L4encT (64,256) L4T L3T L2T L1T (256,256) L0T (64,256)
+    StepSpec st; st.n = 256; st.slabs = 8;
+    if (s == 0) { st.n = 128; st.slabs = 6; }
+    else if (s == 1) { st.slabs = 4; }
+    else if (s == 6 || s == 11) { st.n = 64; }
+    return st;
+}
+
+// =====================================================================================================================
+// 1. forward recompute with stash
+// =====================================================================================================================
+// MODE 0: trunk layer  y = relu(acc);  MODE 2: AdaIn layer  x = acc (stashed), y = relu(x * sc + sh)
+template <int MODE, int N>
+__device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* abuf, int m, const float* __restrict__ c0s, const float* __restrict__ c1s,
+                                             unsigned char* st_y, unsigned char* st_x, uint32_t* mask_words, bool store) {
+    uint32_t v[2][32];
+    tmem_ld32(tcol, v[0]);
+#pragma unroll
+    for (int c = 0; c < N / 32; ++c) {
+        tmem_wait_ld_regs(v[c & 1]);
+        if (c + 1 < N / 32) tmem_ld32(tcol + (c + 1) * 32, v[(c + 1) & 1]);
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) y[q] = __uint_as_float(v[c & 1][q]);
+        if (MODE == 2) {
+            if (store) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(st_x + (c * 4 + cc) * CHUNK_BYTES + m * 16) = pack8_sat(y + 8 * cc);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 s4 = *reinterpret_cast<const float4*>(c0s + c * 32 + 4 * q);
+                const float4 b4 = *reinterpret_cast<const float4*>(c1s + c * 32 + 4 * q);
+                y[4 * q + 0] = fmaf(y[4 * q + 0], s4.x, b4.x);
+                y[4 * q + 1] = fmaf(y[4 * q + 1], s4.y, b4.y);
+                y[4 * q + 2] = fmaf(y[4 * q + 2], s4.z, b4.z);
+                y[4 * q + 3] = fmaf(y[4 * q + 3], s4.w, b4.w);
+            }
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) bits |= (y[q] > 0.f) ? (1u << q) : 0u;
+        if (store) mask_words[c * PE_BWD_TILE + m] = bits;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uint4 q;
+            q.x = relu_pack_half2(y[8 * cc + 0], y[8 * cc + 1]); q.y = relu_pack_half2(y[8 * cc + 2], y[8 * cc + 3]);
+            q.z = relu_pack_half2(y[8 * cc + 4], y[8 * cc + 5]); q.w = relu_pack_half2(y[8 * cc + 6], y[8 * cc + 7]);
+            if (abuf) *reinterpret_cast<uint4*>(abuf + (c * 4 + cc) * CHUNK_BYTES + m * 16) = q;
+            if (store) *reinterpret_cast<uint4*>(st_y + (c * 4 + cc) * CHUNK_BYTES + m * 16) = q;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArgs B, const int64_t tile0, const int num_passes) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* ring = smem + 2 * A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+    uint64_t* empty_bar = full_bar + NUM_STAGES;
+    uint64_t* acc_full = empty_bar + NUM_STAGES;     // [2]
+    uint64_t* a_ready = acc_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
+    unsigned char* ones = smem + SMEM_ONES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    const PeLayout& L = A.L;
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
+    const int64_t total = B.tile_begin[A.images];
+    const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
+    const int64_t pairs = tile_end > tile0 ? (tile_end - tile0 + 1) / 2 : 0;
+    constexpr int LAYERS = 10;                       // L0..L7, head 0, head 3
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, 4); }
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 128) {
+        const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+        reinterpret_cast<__half*>(ones)[threadIdx.x] = __float2half_rn((r < 8 && c < 2) ? 1.f : 0.f);
+    }
+    fence_proxy_async();
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+                const unsigned char* src = blob + L.tc_base;
+                for (int l = 0; l < LAYERS; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
+                    for (int s = 0; s < slabs; ++s) {
+                        for (int pass = 0; pass < num_passes; ++pass) {
+                            mbar_wait(empty_bar + stage, phase ^ 1);
+                            mbar_arrive_expect_tx(full_bar + stage, bytes);
+                            bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tc_bytes_per_pass, bytes, full_bar + stage);
+                            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        src += bytes;
+                    }
+                    if (has_bias) {
+                        const uint32_t bbytes = (uint32_t)n * 32;
+                        mbar_wait(empty_bar + stage, phase ^ 1);
+                        mbar_arrive_expect_tx(full_bar + stage, bbytes);
+                        bulk_copy_g2s(ring + stage * STAGE_BYTES, src, bbytes, full_bar + stage);
+                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        src += bbytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = 0;
+            const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
+            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+                for (int l = 0; l < LAYERS; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, n);
+                    const uint32_t lbo_b = (uint32_t)n * 16;
+                    mbar_wait(a_ready + 0, ready_phase);
+                    mbar_wait(a_ready + 1, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    mma_layer<false, 1, 0>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    if (has_bias) {
+                        mbar_wait(full_bar + R.stage, R.phase);
+                        tc_fence_after();
+                        const uint64_t db = umma_smem_desc(R.ring_addr + R.stage * STAGE_BYTES, lbo_b, 128);
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            umma_f16_ss(tmem_base + g * 256, ones_desc, db, idesc, 1u);
+                            umma_commit(acc_full + g);
+                        }
+                        umma_commit(empty_bar + R.stage);
+                        if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int g = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const int m = (wq << 5) | lane;
+        unsigned char* abuf = smem + g * A_BYTES;
+        float* cst = reinterpret_cast<float*>(abuf + CST_BASE);
+        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16) + g * 256;
+        const uint32_t bar_id = 1 + g;
+        TileCtx X = {};
+        X.abuf = abuf; X.m = m; X.lane = lane; X.half = 0;
+        X.size[0] = ob.bbox[1] - ob.bbox[0]; X.size[1] = ob.bbox[3] - ob.bbox[2]; X.size[2] = ob.bbox[5] - ob.bbox[4];
+        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, nullptr, nullptr, 0u};
+        int img_cursor = 0;
+        for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            const int64_t tile = tile0 + pair * 2 + g;
+            BRow r;
+            load_row(B, tile, tile_end, m, img_cursor, r);
+            unsigned char* st = B.stash + (tile - tile0) * FS_BYTES;
+            uint32_t* mask = reinterpret_cast<uint32_t*>(st + (int64_t)FS_MASK * CHUNK_BYTES);
+            uint4 enc[8];
+            encode_row<1, false>(X, r.x, enc);
+            store_enc<1, false>(X, enc);
+            if (r.store) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(st + (FS_ENC + c) * CHUNK_BYTES + m * 16) = enc[c];
+            }
+            sync.arrive_ready();
+            float4 pre[2];
+#pragma unroll 1
+            for (int l = 0; l < LAYERS; ++l) {
+                sync.wait_acc();
+                if (l == 4) {
+                    // the encoding columns are dead once L4 has run: they take this image's AdaIn scale / shift (sc1|sh1 512, sc2|sh2 256)
+                    const float* a1 = A.aff1 + (int64_t)r.img * 512;
+                    const float* a2 = A.aff2 + (int64_t)r.img * 256;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int i0 = (j * 128 + m) * 4;
+                        pre[j] = i0 < 512 ? __ldg(reinterpret_cast<const float4*>(a1 + i0))
+                                          : (i0 < 768 ? __ldg(reinterpret_cast<const float4*>(a2 + (i0 - 512))) : make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                }
+                if (l == 7) named_bar_sync(bar_id, 128);
+                if (l < 8) fwd_epilogue<0, 256>(taddr, abuf, m, nullptr, nullptr, st + FS_H(l) * CHUNK_BYTES, nullptr, mask + 8 * l * PE_BWD_TILE, r.store);
+                else if (l == 8) fwd_epilogue<2, 256>(taddr, abuf, m, cst + CST_SC1, cst + CST_SH1, st + FS_Y1 * CHUNK_BYTES, st + FS_X1 * CHUNK_BYTES,
+                                                      mask + MASK_Y1 * PE_BWD_TILE, r.store);
+                else fwd_epilogue<2, 128>(taddr, nullptr, m, cst + CST_SC2, cst + CST_SH2, st + FS_Y2 * CHUNK_BYTES, st + FS_X2 * CHUNK_BYTES,
+                                          mask + MASK_Y2 * PE_BWD_TILE, r.store);
+                if (l == 4) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) *reinterpret_cast<float4*>(cst + (j * 128 + m) * 4) = pre[j];
+                }
+                if (l < LAYERS - 1) sync.arrive_ready();
+            }
+            tc_fence_before();
+            named_bar_sync(bar_id, 128);      // the constants are dead before the next tile's encoding overwrites them
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// 2. dX chain
+// =====================================================================================================================
+struct ChainCtx {
+    unsigned char* abuf;
+    float* cst;
+    uint32_t taddr, bar_id;
+    int m, lane, wq;
+    float S, invS;
+};
+
+// KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
+template <int KIND>
+__device__ __forceinline__ void chain_epilogue_plain(const ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw_s,
+                                                     bool store) {
+    uint32_t bits[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
+    uint32_t v[2][32];
+    tmem_ld32(C.taddr, v[0]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        tmem_wait_ld_regs(v[c & 1]);
+        if (c + 1 < 8) tmem_ld32(C.taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            float a = __uint_as_float(v[c & 1][q]);
+            if (KIND == 2) a = fmaf(graw_s, C.cst[CC_AW + c * 32 + q], a);
+            y[q] = ((bits[c] >> q) & 1u) ? a : 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint4 q = pack8_sat(y + 8 * cc);
+            *reinterpret_cast<uint4*>(C.abuf + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+            if (store) *reinterpret_cast<uint4*>(st_g + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+        }
+    }
+}
+
+// AdaIn step (adain.py:51-61 backward): g = mask ? acc : 0;  per image A[c] += sum g, Bx[c] += sum g x;  G = g sc - k1 - x k2 on the rows the
+// field evaluated (k1 = k2 = 0 in eval mode).  sums: accumulate A / Bx into the tile's shared sums.
+template <int N>
+__device__ __forceinline__ void chain_epilogue_adain(const ChainCtx& C, const uint32_t* __restrict__ mask_words, const unsigned char* st_x,
+                                                     unsigned char* st_g, const float* sc, const float* k1s, const float* k2, bool active,
+                                                     bool sums, bool store) {
+    uint32_t bits[N / 32];
+#pragma unroll
+    for (int w = 0; w < N / 32; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
+    float* sumA = C.cst + CC_SUMA;
+    float* sumB = C.cst + CC_SUMB;
+    uint32_t v[32];
+#pragma unroll 1
+    for (int c = 0; c < N / 32; ++c) {
+        uint4 xq[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) xq[cc] = *reinterpret_cast<const uint4*>(st_x + (c * 4 + cc) * CHUNK_BYTES + C.m * 16);
+        tmem_ld32(C.taddr + c * 32, v);
+        tmem_wait_ld_regs(v);
+        float x[32], g[32];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) unpack8(xq[cc], x + 8 * cc);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) g[q] = ((bits[c] >> q) & 1u) ? __uint_as_float(v[q]) : 0.f;
+        if (sums) {
+            float a[32], b[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { a[q] = g[q]; b[q] = g[q] * x[q]; }
+            const float sa = warp_transpose_sum(a, C.lane);
+            const float sb = warp_transpose_sum(b, C.lane);
+            atomicAdd(sumA + c * 32 + C.lane, sa);
+            atomicAdd(sumB + c * 32 + C.lane, sb);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const int col = c * 32 + q;
+            g[q] = active ? fmaf(g[q], sc[col], -fmaf(x[q], k2[col], k1s[col])) : 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint4 q = pack8_sat(g + 8 * cc);
+            *reinterpret_cast<uint4*>(C.abuf + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+            if (store) *reinterpret_cast<uint4*>(st_g + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+        }
+    }
+}
+
+// phase 0: full chain (+ per-image AdaIn sums for the style backward); phase 1 / 2 (train mode): stop after the second / first AdaIn
+// layer of the head (walking backwards) and accumulate the cross-sample sums of its BatchNorm backward
+__global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase, const int num_passes) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* ring = smem + 2 * A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+    uint64_t* empty_bar = full_bar + NUM_STAGES;
+    uint64_t* acc_full = empty_bar + NUM_STAGES;
+    uint64_t* a_ready = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    const PeLayout& L = A.L;
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
+    const int64_t total = B.tile_begin[A.images];
+    const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
+    const int64_t pairs = tile_end > tile0 ? (tile_end - tile0 + 1) / 2 : 0;
+    const int steps = phase == 1 ? 1 : (phase == 2 ? 2 : 12);
+    constexpr int W = 256;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, 4); }
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t ph = 0;
+            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+                const unsigned char* src = blob + L.tcT_base;
+                for (int s = 0; s < steps; ++s) {
+                    const StepSpec st = chain_step(s);
+                    const uint32_t bytes = (uint32_t)st.n * PE_TC_SLAB_K * 2;
+                    for (int k = 0; k < st.slabs; ++k) {
+                        for (int pass = 0; pass < num_passes; ++pass) {
+                            mbar_wait(empty_bar + stage, ph ^ 1);
+                            mbar_arrive_expect_tx(full_bar + stage, bytes);
+                            bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcT_bytes_per_pass, bytes, full_bar + stage);
+                            if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
+                        }
+                        src += bytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = 0;
+            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+                for (int s = 0; s < steps; ++s) {
+                    const StepSpec st = chain_step(s);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, st.n);
+                    const uint32_t lbo_b = (uint32_t)st.n * 16;
+                    mbar_wait(a_ready + 0, ready_phase);
+                    mbar_wait(a_ready + 1, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    mma_layer<false, 1, 0>(R, s, st.n, st.slabs, 0, false, idesc, lbo_b);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int g = (warp - 4) >> 2;
+        ChainCtx C;
+        C.wq = warp & 3; C.lane = lane;
+        C.m = (C.wq << 5) | lane;
+        C.abuf = smem + g * A_BYTES;
+        C.cst = reinterpret_cast<float*>(C.abuf + CST_BASE);
+        C.taddr = tmem_base + (((uint32_t)C.wq * 32u) << 16) + g * 256;
+        C.bar_id = 1 + g;
+        C.S = B.scale[0]; C.invS = B.scale[1];
+        const int m = C.m;
+        float* cst = C.cst;
+        const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
+        const float* alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
+        const int P = ob.positions, F = ob.features;
+        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, nullptr, nullptr, 0u};
+        int img_cursor = 0;
+        for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            const int64_t tile = tile0 + pair * 2 + g;
+            BRow r;
+            load_row(B, tile, tile_end, m, img_cursor, r);
+            unsigned char* st = B.stash + (tile - tile0) * FS_BYTES;
+            const uint32_t* mask = reinterpret_cast<const uint32_t*>(st + (int64_t)FS_MASK * CHUNK_BYTES);
+            const bool store = r.store && phase == 0;
+            // ---- constants of this image: AdaIn scales, BatchNorm fix terms (k1 pre-scaled by S), alpha-head weights; zeroed sums ----
+            {
+                const float* sc1 = A.aff1 + (int64_t)r.img * 2 * W;
+                const float* sc2 = A.aff2 + (int64_t)r.img * W;
+                for (int i = m; i < W; i += 128) {
+                    cst[CC_SC1 + i] = sc1[i];
+                    cst[CC_AW + i] = __ldg(alpha_w + i);
+                    cst[CC_K11 + i] = B.bn_fix[i] * C.S;
+                    cst[CC_K21 + i] = B.bn_fix[W + i];
+                    cst[CC_SUMA + i] = 0.f; cst[CC_SUMB + i] = 0.f;
+                }
+                cst[CC_SC2 + m] = sc2[m];
+                cst[CC_K12 + m] = B.bn_fix[2 * W + m] * C.S;
+                cst[CC_K22 + m] = B.bn_fix[2 * W + W / 2 + m];
+            }
+            // ---- upstream gradient of the per-sample features: S * (cw_obj dL/dF_obj[ray] + cw_glob dL/dF_glob[ray]) -> operand + stash ----
+            float graw = 0.f;
+            {
+                float cwo = 0.f, cwg = 0.f;
+                const float* gfo = nullptr;
+                const float* gfg = nullptr;
+                if (r.active) {
+                    const int64_t ray = (int64_t)r.img * A.rays + r.slot / P;
+                    if (B.g_feat_obj) { cwo = B.cw_obj[r.gs] * C.S; gfo = B.g_feat_obj + ray * F; }
+                    if (B.g_feat_glob) { cwg = B.cw_glob[r.gs] * C.S; gfg = B.g_feat_glob + ray * F; }
+                    if (r.in_scene) graw = B.g_raw[r.gs];
+                }
+#pragma unroll 2
+                for (int c = 0; c < 24; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                    if (gfo) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(gfo + c * 8)), b = __ldg(reinterpret_cast<const float4*>(gfo + c * 8 + 4));
+                        v[0] = cwo * a.x; v[1] = cwo * a.y; v[2] = cwo * a.z; v[3] = cwo * a.w; v[4] = cwo * b.x; v[5] = cwo * b.y; v[6] = cwo * b.z; v[7] = cwo * b.w;
+                    }
+                    if (gfg) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(gfg + c * 8)), b = __ldg(reinterpret_cast<const float4*>(gfg + c * 8 + 4));
+                        v[0] = fmaf(cwg, a.x, v[0]); v[1] = fmaf(cwg, a.y, v[1]); v[2] = fmaf(cwg, a.z, v[2]); v[3] = fmaf(cwg, a.w, v[3]);
+                        v[4] = fmaf(cwg, b.x, v[4]); v[5] = fmaf(cwg, b.y, v[5]); v[6] = fmaf(cwg, b.z, v[6]); v[7] = fmaf(cwg, b.w, v[7]);
+                    }
+                    const uint4 q = pack8_sat(v);
+                    *reinterpret_cast<uint4*>(C.abuf + c * CHUNK_BYTES + m * 16) = q;
+                    if (store) *reinterpret_cast<uint4*>(st + (FS_GF + c) * CHUNK_BYTES + m * 16) = q;
+                }
+                if (store) {          // column 0 of a 16-column operand: S * dL/d raw alpha (d alpha_head.weight = h7^T graw in the dW kernel)
+                    float v[8] = {graw * C.S, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    *reinterpret_cast<uint4*>(st + FS_GRAW * CHUNK_BYTES + m * 16) = pack8_sat(v);
+                    *reinterpret_cast<uint4*>(st + (FS_GRAW + 1) * CHUNK_BYTES + m * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            if (phase == 0 && B.gw.alpha_b) {            // d alpha_head.bias = sum graw
+                float s = graw;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && s != 0.f) atomicAdd(B.gw.alpha_b, s);
+            }
+            sync.arrive_ready();
+            named_bar_sync(C.bar_id, 128);                // constants visible to the group
+            float* asum = B.adain_sums + (int64_t)r.img * 3 * W;
+
+            auto flush_sums = [&](int N, int off_a, int off_b, const float* sc, double* bn, bool to_bn) {
+                named_bar_sync(C.bar_id, 128);
+                for (int c = m; c < N; c += 128) {
+                    const float a = cst[CC_SUMA + c] * C.invS, b = cst[CC_SUMB + c] * C.invS;
+                    if (r.store) {
+                        if (to_bn) {            // cross-sample terms of the train-mode BatchNorm backward: S1 = sum g sc, S2 = sum g sc x
+                            atomicAdd(bn + c, (double)(a * sc[c]));
+                            atomicAdd(bn + N + c, (double)(b * sc[c]));
+                        } else {
+                            if (a != 0.f) atomicAdd(asum + off_a + c, a);
+                            if (b != 0.f) atomicAdd(asum + off_b + c, b);
+                        }
+                    }
+                    cst[CC_SUMA + c] = 0.f; cst[CC_SUMB + c] = 0.f;
+                }
+                named_bar_sync(C.bar_id, 128);
+            };
+
+            // ---- step 0: gy2 = gF H6 -> AdaIn 2 ----
+            sync.wait_acc();
+            chain_epilogue_adain<128>(C, mask + MASK_Y2 * PE_BWD_TILE, st + FS_X2 * CHUNK_BYTES, st + FS_GX2 * CHUNK_BYTES, cst + CC_SC2, cst + CC_K12,
+                                      cst + CC_K22, r.active, phase != 2, store);
+            if (phase != 2) flush_sums(W / 2, 2 * W, 2 * W + W / 2, cst + CC_SC2, B.bn_sums + 2 * W, phase == 1);
+            if (phase == 1) { tc_fence_before(); named_bar_sync(C.bar_id, 128); continue; }
+            sync.arrive_ready();
+            // ---- step 1: gy1 = gx2 H3 -> AdaIn 1 ----
+            sync.wait_acc();
+            chain_epilogue_adain<256>(C, mask + MASK_Y1 * PE_BWD_TILE, st + FS_X1 * CHUNK_BYTES, st + FS_GX1 * CHUNK_BYTES, cst + CC_SC1, cst + CC_K11,
+                                      cst + CC_K21, r.active, true, store);
+            flush_sums(W, 0, W, cst + CC_SC1, B.bn_sums, phase == 2);
+            if (phase == 2) { tc_fence_before(); named_bar_sync(C.bar_id, 128); continue; }
+            sync.arrive_ready();
+            // ---- step 2: gh7 = gx1 H0 + graw alpha_w -> relu'(h7) ----
+            sync.wait_acc();
+            chain_epilogue_plain<2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw * C.S, store);
+            sync.arrive_ready();
+            // ---- steps 3-5: trunk layers 7, 6, 5 -> gradients of the pre-activations of layers 6, 5, 4 ----
+#pragma unroll 1
+            for (int l = 6; l >= 4; --l) {
+                sync.wait_acc();
+                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, store);
+                sync.arrive_ready();
+            }
+            // ---- step 6: the encoding half of the skip layer's input gradient (fp16, parked in the encoding columns) ----
+            sync.wait_acc();
+            {
+                uint32_t v[2][32];
+                tmem_ld32(C.taddr, v[0]);
+                tmem_ld32(C.taddr + 32, v[1]);
+                tmem_wait_ld_regs(v[0]);
+                tmem_wait_ld_regs(v[1]);
+                named_bar_sync(C.bar_id, 128);            // every reader of the constants is done
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float y[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]);
+                        *reinterpret_cast<uint4*>(C.abuf + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16) = pack8_sat(y);
+                    }
+            }
+            sync.arrive_ready();
+            // ---- steps 7-10: trunk layers 4 (hidden half), 3, 2, 1 -> gradients of the pre-activations of layers 3, 2, 1, 0 ----
+#pragma unroll 1
+            for (int l = 3; l >= 0; --l) {
+                sync.wait_acc();
+                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, store);
+                sync.arrive_ready();
+            }
+            // ---- step 11: encoding gradient = layer 0's input gradient + the parked half; positional_encoder.py:59-64 backward ----
+            sync.wait_acc();
+            {
+                uint32_t v[2][32];
+                tmem_ld32(C.taddr, v[0]);
+                tmem_ld32(C.taddr + 32, v[1]);
+                tmem_wait_ld_regs(v[0]);
+                tmem_wait_ld_regs(v[1]);
+                float ge[64];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float part[8];
+                        unpack8(*reinterpret_cast<const uint4*>(C.abuf + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), part);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ge[c * 32 + cc * 8 + i] = __uint_as_float(v[c][8 * cc + i]) + part[i];
+                    }
+                float gx[3] = {0.f, 0.f, 0.f};
+                if (r.active) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float xn = __fdiv_rn(r.x[a], size[a]);
+                        float gsum = ge[a];
+#pragma unroll
+                        for (int o = 0; o < 10; ++o) {
+                            const float f = (float)(1 << o);
+                            float s, c;
+                            sincosf(__fmul_rn(f, xn), &s, &c);
+                            gsum = fmaf(f, c * ge[3 + 6 * o + a] - s * ge[3 + 6 * o + 3 + a], gsum);
+                        }
+                        gx[a] = gsum / size[a] * C.invS;
+                    }
+                }
+                if (r.listed) {
+                    float* dst = (B.g_bent ? B.g_bent : B.g_pos) + r.gs * 3;
+                    dst[0] = gx[0]; dst[1] = gx[1]; dst[2] = gx[2];
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(C.bar_id, 128);        // the parked gradient is dead before the next tile's constants overwrite it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// 3. dW / db
+// =====================================================================================================================
+struct DwItem {
+    int32_t g_chunk;       // stash chunk of the 128-column block of the M operand (the gradient; the trunk output for the alpha head)
+    int32_t a_chunk;       // stash chunk of the N operand
+    int32_t n;             // N operand columns (multiple of 16, <= 256)
+    int32_t rows, cols;    // valid rows / columns of the 128 x n product
+    int32_t ld;            // row stride of the output
+    float* out;            // fp32 gradient, accumulated
+    float* bias;           // fp32 bias gradient of the block's rows (column sums of the M operand) or NULL
+};
+constexpr int DW_MAX_ITEMS = 32;
+struct DwArgs {
+    const unsigned char* stash;
+    const int32_t* tile_begin;
+    int32_t images, tile_capacity;
+    int64_t tile0;
+    const float* scale;
+    int32_t items, splits;
+    DwItem item[DW_MAX_ITEMS];
+};
+constexpr int DW_THREADS = 192;                                // producer, MMA + TMEM, 4 epilogue warps
+constexpr int DW_G_BYTES = 16 * CHUNK_BYTES, DW_A_BYTES = 32 * CHUNK_BYTES, DW_STAGE = DW_G_BYTES + DW_A_BYTES;
+constexpr int DW_SMEM_ONES = 2 * DW_STAGE, DW_SMEM_BAR = DW_SMEM_ONES + 2 * CHUNK_BYTES, DW_SMEM_TOTAL = DW_SMEM_BAR + 128;
+
+__global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + DW_SMEM_BAR);    // [2]
+    uint64_t* empty_bar = full_bar + 2;                                      // [2]
+    uint64_t* acc_full = empty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    unsigned char* ones = smem + DW_SMEM_ONES;                               // 128 rows x 16 columns, column 0 = 1
+    const int warp = threadIdx.x >> 5;
+    const DwItem& it = D.item[blockIdx.x];
+    const int64_t total = D.tile_begin[D.images];
+    const int64_t tile_end = pe_min64(total, D.tile0 + D.tile_capacity);
+    const int64_t count = tile_end > D.tile0 ? tile_end - D.tile0 : 0;
+    const int64_t per = (count + D.splits - 1) / D.splits;
+    const int64_t t0 = pe_min64((int64_t)blockIdx.y * per, count), t1 = pe_min64(t0 + per, count);
+    if (t0 >= t1) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < 128 * 16; i += DW_THREADS) {
+        const int row = i >> 4, col = i & 15;
+        reinterpret_cast<__half*>(ones + (col >> 3) * CHUNK_BYTES + row * 16)[col & 7] = __float2half_rn(col == 0 ? 1.f : 0.f);
+    }
+    fence_proxy_async();
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_bytes = (uint32_t)(it.n / 8) * CHUNK_BYTES;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = t0; t < t1; ++t) {
+                const unsigned char* st = D.stash + t * FS_BYTES;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                mbar_arrive_expect_tx(full_bar + stage, DW_G_BYTES + a_bytes);
+                bulk_copy_g2s(smem + stage * DW_STAGE, st + (int64_t)it.g_chunk * CHUNK_BYTES, DW_G_BYTES, full_bar + stage);
+                bulk_copy_g2s(smem + stage * DW_STAGE + DW_G_BYTES, st + (int64_t)it.a_chunk * CHUNK_BYTES, a_bytes, full_bar + stage);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t idesc = umma_idesc_f16_major(128, it.n, 1, 1);
+            const uint32_t idesc_b = umma_idesc_f16_major(128, 16, 1, 1);
+            for (int64_t t = t0; t < t1; ++t) {
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint32_t g_addr = smem_u32(smem + stage * DW_STAGE), a_addr = g_addr + DW_G_BYTES;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                 // K = the tile's 128 samples: 16 rows (2 row groups of 128 B) per MMA
+                    const uint64_t dg = umma_smem_desc(g_addr + j * 256, 128, CHUNK_BYTES);
+                    const uint64_t da = umma_smem_desc(a_addr + j * 256, 128, CHUNK_BYTES);
+                    const uint32_t accum = (t != t0 || j != 0) ? 1u : 0u;
+                    umma_f16_ss(tmem_base, dg, da, idesc, accum);
+                    if (it.bias) umma_f16_ss(tmem_base + 256, dg, umma_smem_desc(smem_u32(ones) + j * 256, 128, CHUNK_BYTES), idesc_b, accum);
+                }
+                umma_commit(empty_bar + stage);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int wq = warp & 3;
+        const int lane = threadIdx.x & 31;
+        const int row = (wq << 5) | lane;
+        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16);
+        const float invS = D.scale[1];
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < it.n; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_wait_ld_regs16(v);
+            if (row < it.rows) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float val = __uint_as_float(v[q]) * invS;
+                    if (c0 + q < it.cols && val != 0.f) atomicAdd(it.out + (int64_t)row * it.ld + c0 + q, val);
+                }
+            }
+        }
+        if (it.bias) {
+            uint32_t v[16];
+            tmem_ld16(taddr + 256, v);
+            tmem_wait_ld_regs16(v);
+            const float val = __uint_as_float(v[0]) * invS;
+            if (row < it.rows && val != 0.f) atomicAdd(it.bias + row, val);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================================
+// gradient scale: S = 2^k with S * (largest upstream gradient magnitude) ~ 256 (fp16 operands: 256 x headroom below overflow,
+// 2^-32 of it above the smallest subnormal)
+// =====================================================================================================================
+__global__ void pe_bwd_absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+    float mx = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(x[i]);
+        if (v == v && v < INFINITY) mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out, __float_as_uint(mx));
+}
+
+__global__ void pe_bwd_scale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ scale) {
+    // mx: [0] |dL/dF_obj|, [1] |dL/dF_glob|, [2] |dL/d raw alpha|, [3] |alpha_head.weight|
+    const float m = fmaxf(__uint_as_float(mx[0]) + __uint_as_float(mx[1]), __uint_as_float(mx[2]) * __uint_as_float(mx[3]));
+    float S = 1.f;
+    if (m > 0.f) {
+        int e = (int)floorf(log2f(256.f / m));
+        e = max(-60, min(60, e));
+        S = exp2f((float)e);
+    }
+    scale[0] = S;
+    scale[1] = 1.f / S;
+}
+
+// transposed operand of one chain step: element (n, k) = w[k * ld + col0 + n] (nn.Linear weight [out][in], n = input, k = output)
+__global__ void pe_tcT_pack_kernel(const float* __restrict__ w, int ld, int col0, int n_real, int N, int K, unsigned char* __restrict__ hi,
+                                   unsigned char* __restrict__ lo) {
+    const int total = N * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / N, n = i - k * N;
+        const float v = n < n_real ? w[(int64_t)k * ld + col0 + n] : 0.f;
+        const __half h = __float2half_rn(v);
+        const int slab = k / PE_TC_SLAB_K, kk = k - slab * PE_TC_SLAB_K;
+        const int64_t off = (int64_t)slab * N * PE_TC_SLAB_K * 2 + (int64_t)(kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(hi + off) = h;
+        *reinterpret_cast<__half*>(lo + off) = __float2half_rn(v - __half2float(h));
+    }
+}
+
+}  // namespace
+
+bool pe_bwd_tc_object_ok(const PeObjectDesc& ob) {
+    const char* env = getenv("PE_BWD_TC");
+    if (env && atoi(env) == 0) return false;
+    return pe_tc_field_ok(ob);
+}
+
+int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
+    (void)d;
+    if (!L.tcT_base) return PE_OK;
+    unsigned char* hi = (unsigned char*)packed + L.tcT_base;
+    unsigned char* lo = hi + L.tcT_bytes_per_pass;
+    struct Item { const float* w; int ld, col0, n_real, N, K; };
+    const Item items[12] = {
+        {p.head6_w, 128, 0, 128, 128, 192},          {p.head3_w, 256, 0, 256, 256, 128},          {p.head0_w, 256, 0, 256, 256, 256},
+        {p.backbone_w[7], 256, 0, 256, 256, 256},    {p.backbone_w[6], 256, 0, 256, 256, 256},    {p.backbone_w[5], 256, 0, 256, 256, 256},
+        {p.backbone_w[4], 319, 256, 63, 64, 256},    {p.backbone_w[4], 319, 0, 256, 256, 256},    {p.backbone_w[3], 256, 0, 256, 256, 256},
+        {p.backbone_w[2], 256, 0, 256, 256, 256},    {p.backbone_w[1], 256, 0, 256, 256, 256},    {p.backbone_w[0], 63, 0, 63, 64, 256}};
+    int64_t off = 0;
+    for (int s = 0; s < 12; ++s) {
+        const Item& it = items[s];
+        if (!it.w) { pe_set_error("missing parameter tensor for the transposed weight stream (step %d)", s); return PE_ERR_INVALID; }
+        pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, hi + off, lo + off);
+        PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
+        off += (int64_t)it.N * it.K * 2;
+    }
+    if (off != L.tcT_bytes_per_pass) { pe_set_error("internal: transposed weight stream size mismatch"); return PE_ERR_INVALID; }
+    return PE_OK;
+}
+
+static int bwd_passes() {
+    const char* env = getenv("PE_BWD_TC_PASSES");
+    const int p = env ? atoi(env) : 2;
+    return p == 1 ? 1 : 2;
+}
+
+int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    const int grid = (int)pe_min64(((int64_t)args.tile_capacity + 1) / 2, sm_count);
+    if (grid <= 0) return PE_OK;
+    pe_bwd_fwd_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, tile0, 2);
+    PE_LAUNCH_CHECK("pe_bwd_fwd_kernel");
+    return PE_OK;
+}
+
+int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int sm_count, cudaStream_t stream) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    const int grid = (int)pe_min64(((int64_t)args.tile_capacity + 1) / 2, sm_count);
+    if (grid <= 0) return PE_OK;
+    pe_bwd_chain_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase, bwd_passes());
+    PE_LAUNCH_CHECK("pe_bwd_chain_kernel");
+    return PE_OK;
+}
+
+int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scratch, cudaStream_t stream) {
+    const PeFieldArgs& A = args.f;
+    PE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(unsigned int), stream));
+    const int64_t nf = (int64_t)A.images * A.rays * A.ob.features, ns = (int64_t)A.images * A.rays * A.ob.positions;
+    auto absmax = [&](const float* x, int64_t n, unsigned int* out) {
+        if (!x || n == 0) return PE_OK;
+        pe_bwd_absmax_kernel<<<(int)pe_min64((n + 255) / 256, 1024), 256, 0, stream>>>(x, n, out);
+        PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
+        return PE_OK;
+    };
+    int rc;
+    if ((rc = absmax(args.g_feat_obj, nf, scratch + 0))) return rc;
+    if ((rc = absmax(args.g_feat_glob, nf, scratch + 1))) return rc;
+    if ((rc = absmax(args.g_raw, ns, scratch + 2))) return rc;
+    if ((rc = absmax(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(A.ob.packed) + A.L.alpha_w), A.ob.width, scratch + 3))) return rc;
+    pe_bwd_scale_kernel<<<1, 1, 0, stream>>>(scratch, scale);
+    PE_LAUNCH_CHECK("pe_bwd_scale_kernel");
+    return PE_OK;
+}
+
+int pe_launch_bwd_dw(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
+    const PeObjectParamGrads& gw = args.gw;
+    DwArgs D = {};
+    D.stash = args.stash; D.tile_begin = args.tile_begin; D.images = args.f.images; D.tile_capacity = args.tile_capacity;
+    D.tile0 = tile0; D.scale = args.scale;
+    int n = 0;
+    auto add = [&](int g_chunk, int a_chunk, int cols_n, int rows, int cols, int ld, float* out, float* bias) {
+        if (!out && !bias) return;
+        DwItem& it = D.item[n++];
+        it.g_chunk = g_chunk; it.a_chunk = a_chunk; it.n = cols_n; it.rows = rows; it.cols = out ? cols : 0; it.ld = ld;
+        it.out = out ? out : bias;           // (never dereferenced with cols == 0)
+        it.bias = bias;
+    };
+    for (int l = 0; l < 8; ++l) {
+        const int ld = l == 0 ? 63 : (l == 4 ? 319 : 256);
+        for (int mb = 0; mb < 2; ++mb) {
+            float* w = gw.backbone_w[l] ? gw.backbone_w[l] + (int64_t)mb * 128 * ld : nullptr;
+            float* b = gw.backbone_b[l] ? gw.backbone_b[l] + mb * 128 : nullptr;
+            if (l == 0) add(FS_GP(0) + 16 * mb, FS_ENC, 64, 128, 63, ld, w, b);
+            else add(FS_GP(l) + 16 * mb, FS_H(l - 1), 256, 128, 256, ld, w, b);
+            if (l == 4 && w) add(FS_GP(4) + 16 * mb, FS_ENC, 64, 128, 63, ld, w + 256, nullptr);
+        }
+    }
+    for (int mb = 0; mb < 2; ++mb) add(FS_GX1 + 16 * mb, FS_H(7), 256, 128, 256, 256, gw.head0_w ? gw.head0_w + (int64_t)mb * 128 * 256 : nullptr, nullptr);
+    add(FS_GX2, FS_Y1, 256, 128, 256, 256, gw.head3_w, nullptr);
+    add(FS_GF, FS_Y2, 128, 128, 128, 128, gw.head6_w, gw.head6_b);
+    add(FS_GF + 16, FS_Y2, 128, 64, 128, 128, gw.head6_w ? gw.head6_w + 128 * 128 : nullptr, gw.head6_b ? gw.head6_b + 128 : nullptr);
+    for (int mb = 0; mb < 2; ++mb) add(FS_H(7) + 16 * mb, FS_GRAW, 16, 128, 1, 1, gw.alpha_w ? gw.alpha_w + mb * 128 : nullptr, nullptr);
+    if (n == 0) return PE_OK;
+    D.items = n;
+    D.splits = (int)pe_min64(pe_min64(args.tile_capacity, 65535), (2 * sm_count + n - 1) / n);
+    if (D.splits < 1) D.splits = 1;
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_TOTAL));
+    pe_bwd_dw_kernel<<<dim3(n, D.splits), DW_THREADS, DW_SMEM_TOTAL, stream>>>(D);
+    PE_LAUNCH_CHECK("pe_bwd_dw_kernel");
+    return PE_OK;
+}
+
+size_t pe_bwd_tc_stash_bytes(int64_t tiles) { return (size_t)tiles * FS_BYTES; }

@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
     const float* k1_2 = B.bn_fix + 2 * W;
     const float* k2_2 = B.bn_fix + 2 * W + W / 2;
 
+    // ray-bender-only mode: the field's backward ran on the tensor cores (pe_bwd_tc.cu) and left dL/d bent position in g_bent_in
+    const bool bender_only = B.g_bent_in != nullptr;
     const bool compact = B.slot_list != nullptr;
     const int64_t num_tiles = compact ? (int64_t)B.tile_begin[A.images] : total_tiles;
     int img_c = 0;                                   // compacted numbering: image of the current tile (tiles are visited in order)
@@ -400,6 +402,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             if (!(f & 2) || !in_scene || skybox) S.graw[tid] = 0.f;
         }
         __syncthreads();
+        if (!bender_only) {
         // ---- positional encoding ----
         for (int idx = tid; idx < L.enc * TB; idx += NT) {
             const int e = idx / TB, m = idx - e * TB;
@@ -432,7 +435,13 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             });
             cur = nxt; curK = W; which ^= 1;
         }
+        }   // !bender_only
         }   // !from_cache
+        float* gA = S.bufA;
+        float* gB = S.bufB;
+        float* gcur = gB;
+        float* gnext = gA;
+        if (!bender_only) {
         // ---- feature head with AdaIn ----
         const float* sc1 = A.aff1 + (int64_t)img * 2 * W;
         const float* sh1 = sc1 + W;
@@ -475,8 +484,6 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
 
         // ================================ backward ================================
         // upstream gradient of the per-sample features: w_obj * dL/dF_obj[ray] + w_glob * dL/dF_glob[ray]
-        float* gA = S.bufA;
-        float* gB = S.bufB;
         for (int idx = tid; idx < F * TB; idx += NT) {
             const int m = idx / F, c = idx - m * F;
             float g = 0.f;
@@ -547,8 +554,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         }
         // ---- trunk, last layer first; gcur = dL/d(pre-activation of layer l) ----
         for (int idx = tid; idx < L.enc * TS; idx += NT) S.enc[idx] = 0.f;       // becomes the gradient of the encoding
-        float* gcur = gB;
-        float* gnext = gA;
+        gcur = gB;
+        gnext = gA;
         for (int l = ob.layers - 1; l >= 0; --l) {
             const int first = l == 0 ? L.enc : W;                   // rows of the first input segment
             const int Kl = L.k_in[l];
@@ -568,9 +575,15 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
             });
             float* tsw = gcur; gcur = gnext; gnext = tsw;
         }
+        }   // !bender_only
         // ---- positional encoding backward -> gradient of the (bent) position, or of origin / direction for the skybox ----
         float gbent[3] = {0.f, 0.f, 0.f};
-        if (tid < TB) {
+        if (bender_only) {
+            if (tid < TB && (S.flags[tid] & 2)) {
+                const float* g = B.g_bent_in + (gsi + S.slot[tid]) * 3;
+                gbent[0] = g[0]; gbent[1] = g[1]; gbent[2] = g[2];
+            }
+        } else if (tid < TB) {
             const int m = tid;
             if (skybox) {
                 if (B.g_od && (S.flags[m] & 4)) {

@@ -111,6 +111,9 @@ struct PeFieldBwdArgs {
     const int32_t* slot_list;      // [images][rays * P] slot index inside the image; the first slot_count[img] entries are valid
     const int32_t* slot_count;     // [images]
     const int32_t* tile_begin;     // [images + 1] first tile of every image in the compacted numbering; [images] = number of tiles
+    // ray-bender-only mode (objects whose field backward ran on the tensor cores, pe_bwd_tc.cu): dL/d bent position of every listed
+    // slot; the kernel recomputes the bender of a tile, back-propagates through it and writes g_pos
+    const float* g_bent_in;        // [images][rays][P][3] or NULL
 };
 
 // Style / BatchNorm backward (pe_backward.cu)
@@ -167,14 +170,16 @@ struct PeBwdTcArgs {
     float* g_deformation;          // accumulated [images][D] or NULL
 };
 #define PE_BWD_TILE 128
-#define PE_BWD_FS_CHUNKS 688       // field stash chunks per tile: activations 360 + gradients 328 (map in pe_bwd_tc.cu)
+#define PE_BWD_FS_CHUNKS 709       // field stash chunks per tile: activations 360 + gradients 330 + ReLU-mask words (19) (map in pe_bwd_tc.cu)
 #define PE_BWD_BS_CHUNKS 212       // ray-bender stash chunks per tile
 bool pe_bwd_tc_object_ok(const PeObjectDesc& ob);
 int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream);
-int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int precision, int sm_count, cudaStream_t stream);
+// every launch covers the tiles [tile0, tile0 + args.tile_capacity) of the compacted numbering (one stash batch)
+int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream);
 int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scratch, cudaStream_t stream);
-int pe_launch_bwd_chain(const PeBwdTcArgs& args, int training, const double* fwd_stats, int sm_count, cudaStream_t stream);
-int pe_launch_bwd_dw(const PeBwdTcArgs& args, int sm_count, cudaStream_t stream);
+int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int sm_count, cudaStream_t stream);
+int pe_launch_bwd_dw(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream);
+size_t pe_bwd_tc_stash_bytes(int64_t tiles);
 
 size_t pe_field_bwd_smem_bytes();
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);

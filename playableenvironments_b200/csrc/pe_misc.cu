@@ -184,6 +184,7 @@ int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParam
     }
     if (L.tc_supported) {
         PE_TRY(pe_tc_pack(d, L, p, packed, stream));
+        PE_TRY(pe_tcT_pack(d, L, p, packed, stream));
     }
 #undef PE_TRY
     return PE_OK;
