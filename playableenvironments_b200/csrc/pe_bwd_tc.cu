@@ -20,16 +20,24 @@ using namespace pe;
 using namespace pe_tc;
 
 // ---- stash map: chunk offsets inside a tile's block (PE_BWD_FS_CHUNKS chunks of 2048 B) ----
+// Every activation / gradient is kept as a hi + lo fp16 pair (the gradient sums cancel heavily: the backward needs fp32-class operands
+// throughout, see "Numerics" below); the lo copies live FS_ALO / FS_GLO chunks above the hi ones.
 __host__ __device__ constexpr int FS_H(int l) { return l < 4 ? 32 * l : 136 + 32 * (l - 4); }   // h0..h3 | enc | h4..h7: [h3 | enc] is contiguous
-constexpr int FS_ENC = 128, FS_Y1 = 264, FS_Y2 = 296, FS_X1 = 312, FS_X2 = 344;
-constexpr int FS_GF = 360;                                     // 24 chunks (192 columns); a 128-row block starting at column 128 over-reads into GP(0)
-__host__ __device__ constexpr int FS_GP(int l) { return 384 + 32 * l; }
-constexpr int FS_GX1 = 640, FS_GX2 = 672, FS_GRAW = 688, FS_MASK = 690;
+constexpr int FS_ENC = 128, FS_Y1 = 264, FS_Y2 = 296;          // activations hi: [0, 312)
+constexpr int FS_ALO = 312;                                    // activations lo: [312, 624)
+constexpr int FS_X1 = 624, FS_X2 = 656;                        // AdaIn inputs (hi only): [624, 672)
+constexpr int FS_GF = 672;                                     // 24 chunks (192 columns); a 128-row block starting at column 128 over-reads into GP(0)
+__host__ __device__ constexpr int FS_GP(int l) { return FS_GF + 24 + 32 * l; }
+constexpr int FS_GX1 = FS_GF + 24 + 256, FS_GX2 = FS_GX1 + 32;  // gradients hi: [672, 1000)
+constexpr int FS_GLO = 328;                                    // gradients lo: [1000, 1328)
+constexpr int FS_GRAW = 1328, FS_MASK = 1330;                  // 16-column operand [graw hi | graw lo | 0 ...]; ReLU-mask words
 // mask words (uint32, [word][row]): h_l -> words 8l .. 8l+7, y1 -> 64..71, y2 -> 72..75
 constexpr int MASK_Y1 = 64, MASK_Y2 = 72, MASK_WORDS = 76;
+static_assert(FS_GX2 + 16 == 1000 && FS_GX2 + 16 + FS_GLO == FS_GRAW, "stash map");
 static_assert(FS_MASK * 2048 + MASK_WORDS * 512 <= PE_BWD_FS_CHUNKS * 2048, "stash block too small");
 constexpr int64_t FS_BYTES = (int64_t)PE_BWD_FS_CHUNKS * CHUNK_BYTES;
 
+constexpr int TCT_WEXP = 10;                      // the transposed weight stream holds 2^10 * W (hi + lo)
 constexpr int THREADS = 384;                      // producer, MMA, TMEM-alloc, spare + 2 epilogue groups of 4 warps
 constexpr int SMEM_BAR = 2 * A_BYTES + NUM_STAGES * STAGE_BYTES;
 constexpr int SMEM_ONES = SMEM_BAR + 256;
@@ -130,10 +138,28 @@ __device__ __forceinline__ StepSpec chain_step(int s) {
 // =====================================================================================================================
 // 1. forward recompute with stash
 // =====================================================================================================================
+// fp16x3 form (activations and weights as hi + lo pairs, three MMAs per k-step), ONE tile per iteration: ReLU masks and activations
+// agree with an fp32 evaluation to ~1e-6 -- the gradients' sums cancel so heavily that fp16-level differences of the recompute alone
+// show up at the 1e-2 .. 1e-1 level on the position gradients (measured, profiles/r2_bwd_tc.md).
+__device__ __forceinline__ void split_store8(unsigned char* hi_dst, unsigned char* lo_dst, const float* v, bool relu) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float a = v[2 * i], b = v[2 * i + 1];
+        h[i] = relu ? relu_pack_half2(a, b) : pack_half2_sat(a, b);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+        l[i] = pack_half2_sat(a - hf.x, b - hf.y);
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo_dst) *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // MODE 0: trunk layer  y = relu(acc);  MODE 2: AdaIn layer  x = acc (stashed), y = relu(x * sc + sh)
+// smem: hi / lo operand buffers (or NULL: last layer); st_y: stash chunk base of the layer's hi copy (lo copy FS_ALO chunks above)
 template <int MODE, int N>
-__device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* abuf, int m, const float* __restrict__ c0s, const float* __restrict__ c1s,
-                                             unsigned char* st_y, unsigned char* st_x, uint32_t* mask_words, bool store) {
+__device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* a_hi, unsigned char* a_lo, int m, const float* __restrict__ c0s,
+                                             const float* __restrict__ c1s, unsigned char* st_y, unsigned char* st_x, uint32_t* mask_words, bool store) {
     uint32_t v[2][32];
     tmem_ld32(tcol, v[0]);
 #pragma unroll
@@ -164,22 +190,23 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* abuf,
         if (store) mask_words[c * PE_BWD_TILE + m] = bits;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            uint4 q;
-            q.x = relu_pack_half2(y[8 * cc + 0], y[8 * cc + 1]); q.y = relu_pack_half2(y[8 * cc + 2], y[8 * cc + 3]);
-            q.z = relu_pack_half2(y[8 * cc + 4], y[8 * cc + 5]); q.w = relu_pack_half2(y[8 * cc + 6], y[8 * cc + 7]);
-            if (abuf) *reinterpret_cast<uint4*>(abuf + (c * 4 + cc) * CHUNK_BYTES + m * 16) = q;
-            if (store) *reinterpret_cast<uint4*>(st_y + (c * 4 + cc) * CHUNK_BYTES + m * 16) = q;
+            const int off = (c * 4 + cc) * CHUNK_BYTES + m * 16;
+            if (a_hi) split_store8(a_hi + off, a_lo + off, y + 8 * cc, true);
+            if (store) split_store8(st_y + off, st_y + (int64_t)FS_ALO * CHUNK_BYTES + off, y + 8 * cc, true);
         }
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArgs B, const int64_t tile0, const int num_passes) {
+constexpr int CHAIN_THREADS = 256;       // producer, MMA, TMEM-alloc, spare + 4 epilogue warps
+constexpr uint32_t CHAIN_BAR = 1;
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArgs B, const int64_t tile0) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
     uint64_t* empty_bar = full_bar + NUM_STAGES;
-    uint64_t* acc_full = empty_bar + NUM_STAGES;     // [2]
-    uint64_t* a_ready = acc_full + 2;                // [2]
+    uint64_t* acc_full = empty_bar + NUM_STAGES;
+    uint64_t* a_ready = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 2);
     unsigned char* ones = smem + SMEM_ONES;
 
@@ -190,12 +217,12 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
     const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
     const int64_t total = B.tile_begin[A.images];
     const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
-    const int64_t pairs = tile_end > tile0 ? (tile_end - tile0 + 1) / 2 : 0;
+    const int64_t tiles = tile_end > tile0 ? tile_end - tile0 : 0;
     constexpr int LAYERS = 10;                       // L0..L7, head 0, head 3
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, 4); }
+        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
         mbar_fence_init();
     }
     if (threadIdx.x < 128) {
@@ -203,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
         reinterpret_cast<__half*>(ones)[threadIdx.x] = __float2half_rn((r < 8 && c < 2) ? 1.f : 0.f);
     }
     fence_proxy_async();
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -212,14 +239,14 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const unsigned char* src = blob + L.tc_base;
                 for (int l = 0; l < LAYERS; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
                     for (int s = 0; s < slabs; ++s) {
-                        for (int pass = 0; pass < num_passes; ++pass) {
+                        for (int pass = 0; pass < 2; ++pass) {
                             mbar_wait(empty_bar + stage, phase ^ 1);
                             mbar_arrive_expect_tx(full_bar + stage, bytes);
                             bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tc_bytes_per_pass, bytes, full_bar + stage);
@@ -245,28 +272,24 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = 0;
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 1;
             const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
-            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 for (int l = 0; l < LAYERS; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t idesc = umma_idesc_f16(TILE_M, n);
                     const uint32_t lbo_b = (uint32_t)n * 16;
-                    mbar_wait(a_ready + 0, ready_phase);
-                    mbar_wait(a_ready + 1, ready_phase);
+                    mbar_wait(a_ready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
-                    mma_layer<false, 1, 0>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    mma_layer<false, 1, 1>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {
                         mbar_wait(full_bar + R.stage, R.phase);
                         tc_fence_after();
                         const uint64_t db = umma_smem_desc(R.ring_addr + R.stage * STAGE_BYTES, lbo_b, 128);
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            umma_f16_ss(tmem_base + g * 256, ones_desc, db, idesc, 1u);
-                            umma_commit(acc_full + g);
-                        }
+                        umma_f16_ss(tmem_base, ones_desc, db, idesc, 1u);
+                        umma_commit(acc_full);
                         umma_commit(empty_bar + R.stage);
                         if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
                     }
@@ -274,30 +297,42 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
             }
         }
     } else if (warp >= 4) {
-        const int g = (warp - 4) >> 2;
         const int wq = warp & 3;
         const int m = (wq << 5) | lane;
-        unsigned char* abuf = smem + g * A_BYTES;
-        float* cst = reinterpret_cast<float*>(abuf + CST_BASE);
-        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16) + g * 256;
-        const uint32_t bar_id = 1 + g;
-        TileCtx X = {};
-        X.abuf = abuf; X.m = m; X.lane = lane; X.half = 0;
-        X.size[0] = ob.bbox[1] - ob.bbox[0]; X.size[1] = ob.bbox[3] - ob.bbox[2]; X.size[2] = ob.bbox[5] - ob.bbox[4];
-        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, nullptr, nullptr, 0u};
+        unsigned char* a_hi = smem;
+        unsigned char* a_lo = smem + A_BYTES;
+        float* cst = reinterpret_cast<float*>(a_hi + CST_BASE);
+        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16);
+        const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
+        Sync1 sync{acc_full, a_ready, 0u, lane, nullptr, nullptr, 0u};
         int img_cursor = 0;
-        for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-            const int64_t tile = tile0 + pair * 2 + g;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int64_t tile = tile0 + t;
             BRow r;
             load_row(B, tile, tile_end, m, img_cursor, r);
-            unsigned char* st = B.stash + (tile - tile0) * FS_BYTES;
+            unsigned char* st = B.stash + t * FS_BYTES;
             uint32_t* mask = reinterpret_cast<uint32_t*>(st + (int64_t)FS_MASK * CHUNK_BYTES);
-            uint4 enc[8];
-            encode_row<1, false>(X, r.x, enc);
-            store_enc<1, false>(X, enc);
-            if (r.store) {
+            {
+                // Fourier features (positional_encoder.py:59-64): exact argument reduction + SFU, like the forward kernels; hi + lo operand
+                const float xn[3] = {__fdiv_rn(r.x[0], size[0]), __fdiv_rn(r.x[1], size[1]), __fdiv_rn(r.x[2], size[2])};
+                float tp[3], tl[3];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(st + (FS_ENC + c) * CHUNK_BYTES + m * 16) = enc[c];
+                for (int a = 0; a < 3; ++a) {
+                    const float c_hi = 0.15915494f, c_lo = 6.4206382e-9f;
+                    tp[a] = xn[a] * c_hi;
+                    tl[a] = fmaf(xn[a], c_lo, fmaf(xn[a], c_hi, -tp[a]));
+                }
+                float enc[32];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 0) encode_half<0>(xn, tp, tl, enc); else encode_half<1>(xn, tp, tl, enc);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int off = (4 * h + c) * CHUNK_BYTES + m * 16;
+                        split_store8(a_hi + PE_CHUNK0 * CHUNK_BYTES + off, a_lo + PE_CHUNK0 * CHUNK_BYTES + off, enc + 8 * c, false);
+                        if (r.store) split_store8(st + FS_ENC * CHUNK_BYTES + off, st + (int64_t)(FS_ENC + FS_ALO) * CHUNK_BYTES + off, enc + 8 * c, false);
+                    }
+                }
             }
             sync.arrive_ready();
             float4 pre[2];
@@ -315,11 +350,11 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
                                           : (i0 < 768 ? __ldg(reinterpret_cast<const float4*>(a2 + (i0 - 512))) : make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
-                if (l == 7) named_bar_sync(bar_id, 128);
-                if (l < 8) fwd_epilogue<0, 256>(taddr, abuf, m, nullptr, nullptr, st + FS_H(l) * CHUNK_BYTES, nullptr, mask + 8 * l * PE_BWD_TILE, r.store);
-                else if (l == 8) fwd_epilogue<2, 256>(taddr, abuf, m, cst + CST_SC1, cst + CST_SH1, st + FS_Y1 * CHUNK_BYTES, st + FS_X1 * CHUNK_BYTES,
+                if (l == 7) named_bar_sync(CHAIN_BAR, 128);
+                if (l < 8) fwd_epilogue<0, 256>(taddr, a_hi, a_lo, m, nullptr, nullptr, st + FS_H(l) * CHUNK_BYTES, nullptr, mask + 8 * l * PE_BWD_TILE, r.store);
+                else if (l == 8) fwd_epilogue<2, 256>(taddr, a_hi, a_lo, m, cst + CST_SC1, cst + CST_SH1, st + FS_Y1 * CHUNK_BYTES, st + FS_X1 * CHUNK_BYTES,
                                                       mask + MASK_Y1 * PE_BWD_TILE, r.store);
-                else fwd_epilogue<2, 128>(taddr, nullptr, m, cst + CST_SC2, cst + CST_SH2, st + FS_Y2 * CHUNK_BYTES, st + FS_X2 * CHUNK_BYTES,
+                else fwd_epilogue<2, 128>(taddr, nullptr, nullptr, m, cst + CST_SC2, cst + CST_SH2, st + FS_Y2 * CHUNK_BYTES, st + FS_X2 * CHUNK_BYTES,
                                           mask + MASK_Y2 * PE_BWD_TILE, r.store);
                 if (l == 4) {
 #pragma unroll
@@ -328,33 +363,63 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArg
                 if (l < LAYERS - 1) sync.arrive_ready();
             }
             tc_fence_before();
-            named_bar_sync(bar_id, 128);      // the constants are dead before the next tile's encoding overwrites them
+            named_bar_sync(CHAIN_BAR, 128);      // the constants are dead before the next tile's encoding overwrites them
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 // =====================================================================================================================
 // 2. dX chain
 // =====================================================================================================================
+// Numerics.  Gradients are badly scaled (compositing weights span many decades) and their sums over samples cancel heavily (d sin(512 x)/dx),
+// so the chain runs in the fp32-class form of the forward's fp16x3 mode: every gradient operand is kept as a hi + lo fp16 pair (two operand
+// buffers, ONE tile per iteration), weights as hi + lo slabs, three MMAs per k-step (G_hi W_hi + G_lo W_hi + G_hi W_lo), and every ROW is
+// normalised by its own power of two s_m (the chain is linear per row) so that its values sit at ~2^8 whatever the sample's weight.
+// The stash copy of G (the M operand of dW, summed over rows) carries the call-wide scale S instead: G_norm * S / s_m, fp16 hi only.
 struct ChainCtx {
-    unsigned char* abuf;
+    unsigned char *a_hi, *a_lo;
     float* cst;
-    uint32_t taddr, bar_id;
-    int m, lane, wq;
-    float S, invS;
+    uint32_t taddr;
+    int m, lane;
+    int kS;            // S = 2^kS
+    int km;            // exponent of the row's scale: the operand currently stored in the A buffers holds (true gradient) * 2^km
+    float mop;         // largest magnitude of that stored row
 };
+// power of two that brings a row whose largest magnitude is `mx` to [128, 256), keeping the row exponent within +-100
+__device__ __forceinline__ int renorm_exp(float mx, int km) {
+    if (!(mx > 0.f) || !(mx < INFINITY)) return 0;
+    int e;
+    frexpf(mx, &e);
+    return max(-100 - km, min(100 - km, 8 - e));
+}
+
+// gradient operand (hi + lo fp16 pair) of 8 consecutive columns of row m, saturating
+__device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char* a_lo, int chunk, int m, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack_half2_sat(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        l[i] = pack_half2_sat(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    }
+    *reinterpret_cast<uint4*>(a_hi + chunk * CHUNK_BYTES + m * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + chunk * CHUNK_BYTES + m * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
 template <int KIND>
-__device__ __forceinline__ void chain_epilogue_plain(const ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw_s,
-                                                     bool store) {
+__device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw, bool store) {
+    const int fexp = renorm_exp(C.mop, C.km);
+    const int km = C.km + fexp;
+    const float f = ldexpf(1.f, fexp - TCT_WEXP), r_stash = ldexpf(1.f, C.kS - km), graw_n = ldexpf(graw, km);
     uint32_t bits[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
     uint32_t v[2][32];
+    float mx = 0.f;
     tmem_ld32(C.taddr, v[0]);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -363,69 +428,94 @@ __device__ __forceinline__ void chain_epilogue_plain(const ChainCtx& C, const ui
         float y[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-            float a = __uint_as_float(v[c & 1][q]);
-            if (KIND == 2) a = fmaf(graw_s, C.cst[CC_AW + c * 32 + q], a);
+            float a = __uint_as_float(v[c & 1][q]) * f;
+            if (KIND == 2) a = fmaf(graw_n, C.cst[CC_AW + c * 32 + q], a);
             y[q] = ((bits[c] >> q) & 1u) ? a : 0.f;
+            mx = fmaxf(mx, fabsf(y[q]));
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            const uint4 q = pack8_sat(y + 8 * cc);
-            *reinterpret_cast<uint4*>(C.abuf + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
-            if (store) *reinterpret_cast<uint4*>(st_g + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+            store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, y + 8 * cc);
+            if (store) {
+                float z[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = y[8 * cc + i] * r_stash;
+                const int off = (c * 4 + cc) * CHUNK_BYTES + C.m * 16;
+                split_store8(st_g + off, st_g + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+            }
         }
     }
+    C.km = km; C.mop = mx;
 }
 
 // AdaIn step (adain.py:51-61 backward): g = mask ? acc : 0;  per image A[c] += sum g, Bx[c] += sum g x;  G = g sc - k1 - x k2 on the rows the
-// field evaluated (k1 = k2 = 0 in eval mode).  sums: accumulate A / Bx into the tile's shared sums.
+// field evaluated (k1 = k2 = 0 in eval mode).  Two passes over the accumulators: the first finds the row's largest output (the BatchNorm
+// terms are the same for every row, so a row with a tiny own gradient can grow by many decades here), the second stores it re-normalised.
+// sums: accumulate A / Bx (true units) into the tile's shared sums.
 template <int N>
-__device__ __forceinline__ void chain_epilogue_adain(const ChainCtx& C, const uint32_t* __restrict__ mask_words, const unsigned char* st_x,
-                                                     unsigned char* st_g, const float* sc, const float* k1s, const float* k2, bool active,
+__device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t* __restrict__ mask_words, const unsigned char* st_x,
+                                                     unsigned char* st_g, const float* sc, const float* k1, const float* k2, bool active,
                                                      bool sums, bool store) {
     uint32_t bits[N / 32];
 #pragma unroll
     for (int w = 0; w < N / 32; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
     float* sumA = C.cst + CC_SUMA;
     float* sumB = C.cst + CC_SUMB;
-    uint32_t v[32];
+    int km = C.km + renorm_exp(C.mop, C.km);
+    float mx = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < N / 32; ++c) {
-        uint4 xq[4];
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) { km += renorm_exp(mx, km); mx = 0.f; }
+        const float f = ldexpf(1.f, km - C.km - TCT_WEXP), s_row = ldexpf(1.f, km), inv_s_row = ldexpf(1.f, -km), r_stash = ldexpf(1.f, C.kS - km);
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c = 0; c < N / 32; ++c) {
+            uint4 xq[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) xq[cc] = *reinterpret_cast<const uint4*>(st_x + (c * 4 + cc) * CHUNK_BYTES + C.m * 16);
-        tmem_ld32(C.taddr + c * 32, v);
-        tmem_wait_ld_regs(v);
-        float x[32], g[32];
+            for (int cc = 0; cc < 4; ++cc) xq[cc] = *reinterpret_cast<const uint4*>(st_x + (c * 4 + cc) * CHUNK_BYTES + C.m * 16);
+            tmem_ld32(C.taddr + c * 32, v);
+            tmem_wait_ld_regs(v);
+            float x[32], g[32];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) unpack8(xq[cc], x + 8 * cc);
+            for (int cc = 0; cc < 4; ++cc) unpack8(xq[cc], x + 8 * cc);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) g[q] = ((bits[c] >> q) & 1u) ? __uint_as_float(v[q]) : 0.f;
-        if (sums) {
-            float a[32], b[32];
+            for (int q = 0; q < 32; ++q) g[q] = ((bits[c] >> q) & 1u) ? __uint_as_float(v[q]) * f : 0.f;
+            if (sums && pass == 1) {
+                float a[32], b[32];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) { a[q] = g[q]; b[q] = g[q] * x[q]; }
-            const float sa = warp_transpose_sum(a, C.lane);
-            const float sb = warp_transpose_sum(b, C.lane);
-            atomicAdd(sumA + c * 32 + C.lane, sa);
-            atomicAdd(sumB + c * 32 + C.lane, sb);
-        }
+                for (int q = 0; q < 32; ++q) { a[q] = g[q] * inv_s_row; b[q] = a[q] * x[q]; }
+                const float sa = warp_transpose_sum(a, C.lane);
+                const float sb = warp_transpose_sum(b, C.lane);
+                atomicAdd(sumA + c * 32 + C.lane, sa);
+                atomicAdd(sumB + c * 32 + C.lane, sb);
+            }
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            const int col = c * 32 + q;
-            g[q] = active ? fmaf(g[q], sc[col], -fmaf(x[q], k2[col], k1s[col])) : 0.f;
-        }
+            for (int q = 0; q < 32; ++q) {
+                const int col = c * 32 + q;
+                g[q] = active ? fmaf(g[q], sc[col], -s_row * fmaf(x[q], k2[col], k1[col])) : 0.f;
+                mx = fmaxf(mx, fabsf(g[q]));
+            }
+            if (pass == 1) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const uint4 q = pack8_sat(g + 8 * cc);
-            *reinterpret_cast<uint4*>(C.abuf + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
-            if (store) *reinterpret_cast<uint4*>(st_g + (c * 4 + cc) * CHUNK_BYTES + C.m * 16) = q;
+                for (int cc = 0; cc < 4; ++cc) {
+                    store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, g + 8 * cc);
+                    if (store) {
+                        float z[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) z[i] = g[8 * cc + i] * r_stash;
+                        const int off = (c * 4 + cc) * CHUNK_BYTES + C.m * 16;
+                        split_store8(st_g + off, st_g + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+                    }
+                }
+            }
         }
     }
+    C.km = km; C.mop = mx;
 }
 
 // phase 0: full chain (+ per-image AdaIn sums for the style backward); phase 1 / 2 (train mode): stop after the second / first AdaIn
 // layer of the head (walking backwards) and accumulate the cross-sample sums of its BatchNorm backward
-__global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase, const int num_passes) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -441,17 +531,17 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
     const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
     const int64_t total = B.tile_begin[A.images];
     const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
-    const int64_t pairs = tile_end > tile0 ? (tile_end - tile0 + 1) / 2 : 0;
+    const int64_t tiles = tile_end > tile0 ? tile_end - tile0 : 0;
     const int steps = phase == 1 ? 1 : (phase == 2 ? 2 : 12);
     constexpr int W = 256;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(acc_full + g, 1); mbar_init(a_ready + g, 4); }
+        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
         mbar_fence_init();
     }
     fence_proxy_async();
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -460,13 +550,13 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
     if (warp == 0) {
         if (elect_one()) {
             int stage = 0; uint32_t ph = 0;
-            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const unsigned char* src = blob + L.tcT_base;
                 for (int s = 0; s < steps; ++s) {
                     const StepSpec st = chain_step(s);
                     const uint32_t bytes = (uint32_t)st.n * PE_TC_SLAB_K * 2;
                     for (int k = 0; k < st.slabs; ++k) {
-                        for (int pass = 0; pass < num_passes; ++pass) {
+                        for (int pass = 0; pass < 2; ++pass) {
                             mbar_wait(empty_bar + stage, ph ^ 1);
                             mbar_arrive_expect_tx(full_bar + stage, bytes);
                             bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcT_bytes_per_pass, bytes, full_bar + stage);
@@ -484,60 +574,64 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = num_passes; R.x3 = 0;
-            for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 1;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 for (int s = 0; s < steps; ++s) {
                     const StepSpec st = chain_step(s);
                     const uint32_t idesc = umma_idesc_f16(TILE_M, st.n);
                     const uint32_t lbo_b = (uint32_t)st.n * 16;
-                    mbar_wait(a_ready + 0, ready_phase);
-                    mbar_wait(a_ready + 1, ready_phase);
+                    mbar_wait(a_ready, ready_phase);
                     ready_phase ^= 1;
                     tc_fence_after();
-                    mma_layer<false, 1, 0>(R, s, st.n, st.slabs, 0, false, idesc, lbo_b);
+                    mma_layer<false, 1, 1>(R, s, st.n, st.slabs, 0, false, idesc, lbo_b);
                 }
             }
         }
     } else if (warp >= 4) {
-        const int g = (warp - 4) >> 2;
         ChainCtx C;
-        C.wq = warp & 3; C.lane = lane;
-        C.m = (C.wq << 5) | lane;
-        C.abuf = smem + g * A_BYTES;
-        C.cst = reinterpret_cast<float*>(C.abuf + CST_BASE);
-        C.taddr = tmem_base + (((uint32_t)C.wq * 32u) << 16) + g * 256;
-        C.bar_id = 1 + g;
-        C.S = B.scale[0]; C.invS = B.scale[1];
+        C.lane = lane;
+        C.m = ((warp & 3) << 5) | lane;
+        C.a_hi = smem; C.a_lo = smem + A_BYTES;
+        C.cst = reinterpret_cast<float*>(smem + CST_BASE);
+        C.taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+        const float S = B.scale[0];
+        const float max_aw = B.scale[2];
+        {
+            int e;
+            frexpf(S, &e);               // S = 2^(e - 1)
+            C.kS = e - 1;
+        }
         const int m = C.m;
         float* cst = C.cst;
         const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
         const float* alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
         const int P = ob.positions, F = ob.features;
-        Sync1 sync{acc_full + g, a_ready + g, 0u, lane, nullptr, nullptr, 0u};
+        Sync1 sync{acc_full, a_ready, 0u, lane, nullptr, nullptr, 0u};
         int img_cursor = 0;
-        for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-            const int64_t tile = tile0 + pair * 2 + g;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int64_t tile = tile0 + t;
             BRow r;
             load_row(B, tile, tile_end, m, img_cursor, r);
-            unsigned char* st = B.stash + (tile - tile0) * FS_BYTES;
+            unsigned char* st = B.stash + t * FS_BYTES;
             const uint32_t* mask = reinterpret_cast<const uint32_t*>(st + (int64_t)FS_MASK * CHUNK_BYTES);
-            const bool store = r.store && phase == 0;
-            // ---- constants of this image: AdaIn scales, BatchNorm fix terms (k1 pre-scaled by S), alpha-head weights; zeroed sums ----
+            const bool store = phase == 0;
+            // ---- constants of this image: AdaIn scales, BatchNorm fix terms, alpha-head weights; zeroed sums ----
             {
                 const float* sc1 = A.aff1 + (int64_t)r.img * 2 * W;
                 const float* sc2 = A.aff2 + (int64_t)r.img * W;
                 for (int i = m; i < W; i += 128) {
                     cst[CC_SC1 + i] = sc1[i];
                     cst[CC_AW + i] = __ldg(alpha_w + i);
-                    cst[CC_K11 + i] = B.bn_fix[i] * C.S;
+                    cst[CC_K11 + i] = B.bn_fix[i];
                     cst[CC_K21 + i] = B.bn_fix[W + i];
                     cst[CC_SUMA + i] = 0.f; cst[CC_SUMB + i] = 0.f;
                 }
                 cst[CC_SC2 + m] = sc2[m];
-                cst[CC_K12 + m] = B.bn_fix[2 * W + m] * C.S;
+                cst[CC_K12 + m] = B.bn_fix[2 * W + m];
                 cst[CC_K22 + m] = B.bn_fix[2 * W + W / 2 + m];
             }
-            // ---- upstream gradient of the per-sample features: S * (cw_obj dL/dF_obj[ray] + cw_glob dL/dF_glob[ray]) -> operand + stash ----
+            // ---- upstream gradient of the per-sample features: cw_obj dL/dF_obj[ray] + cw_glob dL/dF_glob[ray], row-normalised -> operand,
+            //      call-scaled -> stash ----
             float graw = 0.f;
             {
                 float cwo = 0.f, cwg = 0.f;
@@ -545,13 +639,11 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                 const float* gfg = nullptr;
                 if (r.active) {
                     const int64_t ray = (int64_t)r.img * A.rays + r.slot / P;
-                    if (B.g_feat_obj) { cwo = B.cw_obj[r.gs] * C.S; gfo = B.g_feat_obj + ray * F; }
-                    if (B.g_feat_glob) { cwg = B.cw_glob[r.gs] * C.S; gfg = B.g_feat_glob + ray * F; }
+                    if (B.g_feat_obj) { cwo = B.cw_obj[r.gs]; gfo = B.g_feat_obj + ray * F; }
+                    if (B.g_feat_glob) { cwg = B.cw_glob[r.gs]; gfg = B.g_feat_glob + ray * F; }
                     if (r.in_scene) graw = B.g_raw[r.gs];
                 }
-#pragma unroll 2
-                for (int c = 0; c < 24; ++c) {
-                    float v[8];
+                auto feature_grad8 = [&](int c, float* v) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = 0.f;
                     if (gfo) {
@@ -563,12 +655,34 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                         v[0] = fmaf(cwg, a.x, v[0]); v[1] = fmaf(cwg, a.y, v[1]); v[2] = fmaf(cwg, a.z, v[2]); v[3] = fmaf(cwg, a.w, v[3]);
                         v[4] = fmaf(cwg, b.x, v[4]); v[5] = fmaf(cwg, b.y, v[5]); v[6] = fmaf(cwg, b.z, v[6]); v[7] = fmaf(cwg, b.w, v[7]);
                     }
-                    const uint4 q = pack8_sat(v);
-                    *reinterpret_cast<uint4*>(C.abuf + c * CHUNK_BYTES + m * 16) = q;
-                    if (store) *reinterpret_cast<uint4*>(st + (FS_GF + c) * CHUNK_BYTES + m * 16) = q;
+                };
+                float mx = fabsf(graw) * max_aw;
+#pragma unroll 2
+                for (int c = 0; c < 24; ++c) {
+                    float v[8];
+                    feature_grad8(c, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const float av = fabsf(v[i]); if (av < INFINITY) mx = fmaxf(mx, av); }
                 }
-                if (store) {          // column 0 of a 16-column operand: S * dL/d raw alpha (d alpha_head.weight = h7^T graw in the dW kernel)
-                    float v[8] = {graw * C.S, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                C.km = renorm_exp(mx, 0);                  // mx * 2^km in [128, 256)
+                C.mop = ldexpf(mx, C.km);
+                const float s_row = ldexpf(1.f, C.km);
+#pragma unroll 2
+                for (int c = 0; c < 24; ++c) {
+                    float v[8], z[8];
+                    feature_grad8(c, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { z[i] = v[i] * S; v[i] *= s_row; }
+                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
+                    if (store && r.store) {
+                        const int off = (FS_GF + c) * CHUNK_BYTES + m * 16;
+                        split_store8(st + off, st + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+                    }
+                }
+                if (store && r.store) {          // columns 0, 1 of a 16-column operand: S * dL/d raw alpha as hi, lo (d alpha_head.weight = h7^T graw)
+                    const float gs = graw * S;
+                    const float hi = __half2float(__float2half_rn(fminf(fmaxf(gs, -65504.f), 65504.f)));
+                    float v[8] = {hi, gs - hi, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     *reinterpret_cast<uint4*>(st + FS_GRAW * CHUNK_BYTES + m * 16) = pack8_sat(v);
                     *reinterpret_cast<uint4*>(st + (FS_GRAW + 1) * CHUNK_BYTES + m * 16) = make_uint4(0u, 0u, 0u, 0u);
                 }
@@ -580,13 +694,14 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                 if (lane == 0 && s != 0.f) atomicAdd(B.gw.alpha_b, s);
             }
             sync.arrive_ready();
-            named_bar_sync(C.bar_id, 128);                // constants visible to the group
+            named_bar_sync(CHAIN_BAR, 128);                // constants visible to the group
             float* asum = B.adain_sums + (int64_t)r.img * 3 * W;
+            const bool st_ok = store && r.store;
 
             auto flush_sums = [&](int N, int off_a, int off_b, const float* sc, double* bn, bool to_bn) {
-                named_bar_sync(C.bar_id, 128);
+                named_bar_sync(CHAIN_BAR, 128);
                 for (int c = m; c < N; c += 128) {
-                    const float a = cst[CC_SUMA + c] * C.invS, b = cst[CC_SUMB + c] * C.invS;
+                    const float a = cst[CC_SUMA + c], b = cst[CC_SUMB + c];
                     if (r.store) {
                         if (to_bn) {            // cross-sample terms of the train-mode BatchNorm backward: S1 = sum g sc, S2 = sum g sc x
                             atomicAdd(bn + c, (double)(a * sc[c]));
@@ -598,35 +713,36 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                     }
                     cst[CC_SUMA + c] = 0.f; cst[CC_SUMB + c] = 0.f;
                 }
-                named_bar_sync(C.bar_id, 128);
+                named_bar_sync(CHAIN_BAR, 128);
             };
 
             // ---- step 0: gy2 = gF H6 -> AdaIn 2 ----
             sync.wait_acc();
             chain_epilogue_adain<128>(C, mask + MASK_Y2 * PE_BWD_TILE, st + FS_X2 * CHUNK_BYTES, st + FS_GX2 * CHUNK_BYTES, cst + CC_SC2, cst + CC_K12,
-                                      cst + CC_K22, r.active, phase != 2, store);
+                                      cst + CC_K22, r.active, phase != 2, st_ok);
             if (phase != 2) flush_sums(W / 2, 2 * W, 2 * W + W / 2, cst + CC_SC2, B.bn_sums + 2 * W, phase == 1);
-            if (phase == 1) { tc_fence_before(); named_bar_sync(C.bar_id, 128); continue; }
+            if (phase == 1) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 128); continue; }
             sync.arrive_ready();
             // ---- step 1: gy1 = gx2 H3 -> AdaIn 1 ----
             sync.wait_acc();
             chain_epilogue_adain<256>(C, mask + MASK_Y1 * PE_BWD_TILE, st + FS_X1 * CHUNK_BYTES, st + FS_GX1 * CHUNK_BYTES, cst + CC_SC1, cst + CC_K11,
-                                      cst + CC_K21, r.active, true, store);
+                                      cst + CC_K21, r.active, true, st_ok);
             flush_sums(W, 0, W, cst + CC_SC1, B.bn_sums, phase == 2);
-            if (phase == 2) { tc_fence_before(); named_bar_sync(C.bar_id, 128); continue; }
+            if (phase == 2) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 128); continue; }
             sync.arrive_ready();
             // ---- step 2: gh7 = gx1 H0 + graw alpha_w -> relu'(h7) ----
             sync.wait_acc();
-            chain_epilogue_plain<2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw * C.S, store);
+            chain_epilogue_plain<2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw, st_ok);
             sync.arrive_ready();
             // ---- steps 3-5: trunk layers 7, 6, 5 -> gradients of the pre-activations of layers 6, 5, 4 ----
 #pragma unroll 1
             for (int l = 6; l >= 4; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, store);
+                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
                 sync.arrive_ready();
             }
-            // ---- step 6: the encoding half of the skip layer's input gradient (fp16, parked in the encoding columns) ----
+            // ---- step 6: the encoding half of the skip layer's input gradient, parked (hi + lo) in the encoding columns ----
+            int km_parked = 0;
             sync.wait_acc();
             {
                 uint32_t v[2][32];
@@ -634,15 +750,18 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                 tmem_ld32(C.taddr + 32, v[1]);
                 tmem_wait_ld_regs(v[0]);
                 tmem_wait_ld_regs(v[1]);
-                named_bar_sync(C.bar_id, 128);            // every reader of the constants is done
+                named_bar_sync(CHAIN_BAR, 128);            // every reader of the constants is done
+                const int fexp = renorm_exp(C.mop, C.km);  // (the operand stays: the next step reads it again with the same factor)
+                km_parked = C.km + fexp;
+                const float f = ldexpf(1.f, fexp - TCT_WEXP);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         float y[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]);
-                        *reinterpret_cast<uint4*>(C.abuf + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16) = pack8_sat(y);
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]) * f;
+                        store_g8_hilo(C.a_hi, C.a_lo, PE_CHUNK0 + c * 4 + cc, m, y);
                     }
             }
             sync.arrive_ready();
@@ -650,7 +769,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
 #pragma unroll 1
             for (int l = 3; l >= 0; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, store);
+                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
                 sync.arrive_ready();
             }
             // ---- step 11: encoding gradient = layer 0's input gradient + the parked half; positional_encoder.py:59-64 backward ----
@@ -661,15 +780,18 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                 tmem_ld32(C.taddr + 32, v[1]);
                 tmem_wait_ld_regs(v[0]);
                 tmem_wait_ld_regs(v[1]);
+                // true gradient = accumulator / 2^km + parked / 2^km_parked
+                const float fa = ldexpf(1.f, -C.km - TCT_WEXP), fp = ldexpf(1.f, -km_parked);
                 float ge[64];
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
-                        float part[8];
-                        unpack8(*reinterpret_cast<const uint4*>(C.abuf + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), part);
+                        float ph[8], pl[8];
+                        unpack8(*reinterpret_cast<const uint4*>(C.a_hi + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), ph);
+                        unpack8(*reinterpret_cast<const uint4*>(C.a_lo + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), pl);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) ge[c * 32 + cc * 8 + i] = __uint_as_float(v[c][8 * cc + i]) + part[i];
+                        for (int i = 0; i < 8; ++i) ge[c * 32 + cc * 8 + i] = fmaf(__uint_as_float(v[c][8 * cc + i]), fa, (ph[i] + pl[i]) * fp);
                     }
                 float gx[3] = {0.f, 0.f, 0.f};
                 if (r.active) {
@@ -684,7 +806,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                             sincosf(__fmul_rn(f, xn), &s, &c);
                             gsum = fmaf(f, c * ge[3 + 6 * o + a] - s * ge[3 + 6 * o + 3 + a], gsum);
                         }
-                        gx[a] = gsum / size[a] * C.invS;
+                        gx[a] = gsum / size[a];
                     }
                 }
                 if (r.listed) {
@@ -693,12 +815,12 @@ __global__ void __launch_bounds__(THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcA
                 }
             }
             tc_fence_before();
-            named_bar_sync(C.bar_id, 128);        // the parked gradient is dead before the next tile's constants overwrite it
+            named_bar_sync(CHAIN_BAR, 128);        // the parked gradient is dead before the next tile's constants overwrite it
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 // =====================================================================================================================
@@ -710,19 +832,65 @@ struct DwItem {
     int32_t n;             // N operand columns (multiple of 16, <= 256)
     int32_t rows, cols;    // valid rows / columns of the 128 x n product
     int32_t ld;            // row stride of the output
+    int32_t fold;          // add the valid columns of a row into one output element (alpha head: the N operand is [graw hi | graw lo])
     float* out;            // fp32 gradient, accumulated
     float* bias;           // fp32 bias gradient of the block's rows (column sums of the M operand) or NULL
 };
-constexpr int DW_MAX_ITEMS = 32;
 struct DwArgs {
     const unsigned char* stash;
     const int32_t* tile_begin;
     int32_t images, tile_capacity;
     int64_t tile0;
     const float* scale;
-    int32_t items, splits;
-    DwItem item[DW_MAX_ITEMS];
+    int32_t splits;
+    PeObjectParamGrads gw;
 };
+constexpr int DW_BASE_ITEMS = 25, DW_ITEMS = 3 * DW_BASE_ITEMS;
+
+// Work item `idx` = (base product, term): every product G^T A runs as three fp16 products G_hi A_hi + G_lo A_hi + G_hi A_lo.
+//   base 0-15: trunk layer l = base / 2, output rows 128 (base % 2) ..;  16-17: the encoding columns of the skip layer;  18-19: head layer 0;
+//   20: head layer 3;  21-22: head layer 6 (192 rows);  23-24: alpha head (M operand = trunk output, N operand = [graw hi | graw lo])
+__device__ __forceinline__ bool dw_item(int idx, const PeObjectParamGrads& gw, DwItem& it) {
+    const int base = idx / 3, term = idx - 3 * base;
+    it.rows = 128; it.fold = 0; it.bias = nullptr; it.out = nullptr;
+    float* bias = nullptr;
+    if (base < 16) {
+        const int l = base >> 1, mb = base & 1;
+        it.ld = l == 0 ? 63 : (l == 4 ? 319 : 256);
+        it.g_chunk = FS_GP(l) + 16 * mb;
+        it.a_chunk = l == 0 ? FS_ENC : FS_H(l - 1);
+        it.n = l == 0 ? 64 : 256; it.cols = l == 0 ? 63 : 256;
+        if (gw.backbone_w[l]) it.out = gw.backbone_w[l] + (int64_t)mb * 128 * it.ld;
+        if (gw.backbone_b[l]) bias = gw.backbone_b[l] + mb * 128;
+    } else if (base < 18) {
+        const int mb = base - 16;
+        it.ld = 319; it.g_chunk = FS_GP(4) + 16 * mb; it.a_chunk = FS_ENC; it.n = 64; it.cols = 63;
+        if (gw.backbone_w[4]) it.out = gw.backbone_w[4] + (int64_t)mb * 128 * 319 + 256;
+    } else if (base < 20) {
+        const int mb = base - 18;
+        it.ld = 256; it.g_chunk = FS_GX1 + 16 * mb; it.a_chunk = FS_H(7); it.n = 256; it.cols = 256;
+        if (gw.head0_w) it.out = gw.head0_w + (int64_t)mb * 128 * 256;
+    } else if (base == 20) {
+        it.ld = 256; it.g_chunk = FS_GX2; it.a_chunk = FS_Y1; it.n = 256; it.cols = 256;
+        it.out = gw.head3_w;
+    } else if (base < 23) {
+        const int mb = base - 21;
+        it.ld = 128; it.g_chunk = FS_GF + 16 * mb; it.a_chunk = FS_Y2; it.n = 128; it.cols = 128; it.rows = mb ? 64 : 128;
+        if (gw.head6_w) it.out = gw.head6_w + (int64_t)mb * 128 * 128;
+        if (gw.head6_b) bias = gw.head6_b + mb * 128;
+    } else {
+        const int mb = base - 23;
+        if (term == 2) return false;
+        it.ld = 1; it.g_chunk = FS_H(7) + 16 * mb + (term == 1 ? FS_ALO : 0); it.a_chunk = FS_GRAW; it.n = 16; it.cols = 2; it.fold = 1;
+        if (gw.alpha_w) it.out = gw.alpha_w + mb * 128;
+        return it.out != nullptr;
+    }
+    if (term == 1) it.g_chunk += FS_GLO;
+    if (term == 2) it.a_chunk += FS_ALO;
+    if (term != 2) it.bias = bias;          // column sums of G_hi and of G_lo
+    if (!it.out) it.cols = 0;
+    return it.out != nullptr || it.bias != nullptr;
+}
 constexpr int DW_THREADS = 192;                                // producer, MMA + TMEM, 4 epilogue warps
 constexpr int DW_G_BYTES = 16 * CHUNK_BYTES, DW_A_BYTES = 32 * CHUNK_BYTES, DW_STAGE = DW_G_BYTES + DW_A_BYTES;
 constexpr int DW_SMEM_ONES = 2 * DW_STAGE, DW_SMEM_BAR = DW_SMEM_ONES + 2 * CHUNK_BYTES, DW_SMEM_TOTAL = DW_SMEM_BAR + 128;
@@ -735,7 +903,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     unsigned char* ones = smem + DW_SMEM_ONES;                               // 128 rows x 16 columns, column 0 = 1
     const int warp = threadIdx.x >> 5;
-    const DwItem& it = D.item[blockIdx.x];
+    DwItem it;
+    if (!dw_item(blockIdx.x, D.gw, it)) return;
     const int64_t total = D.tile_begin[D.images];
     const int64_t tile_end = pe_min64(total, D.tile0 + D.tile_capacity);
     const int64_t count = tile_end > D.tile0 ? tile_end - D.tile0 : 0;
@@ -807,10 +976,18 @@ __global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D
             tmem_ld16(taddr + c0, v);
             tmem_wait_ld_regs16(v);
             if (row < it.rows) {
+                if (it.fold) {
+                    float val = 0.f;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float val = __uint_as_float(v[q]) * invS;
-                    if (c0 + q < it.cols && val != 0.f) atomicAdd(it.out + (int64_t)row * it.ld + c0 + q, val);
+                    for (int q = 0; q < 16; ++q) if (c0 + q < it.cols) val += __uint_as_float(v[q]);
+                    val *= invS;
+                    if (c0 == 0 && val != 0.f) atomicAdd(it.out + (int64_t)row * it.ld, val);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float val = __uint_as_float(v[q]) * invS;
+                        if (c0 + q < it.cols && val != 0.f) atomicAdd(it.out + (int64_t)row * it.ld + c0 + q, val);
+                    }
                 }
             }
         }
@@ -853,6 +1030,7 @@ __global__ void pe_bwd_scale_kernel(const unsigned int* __restrict__ mx, float* 
     }
     scale[0] = S;
     scale[1] = 1.f / S;
+    scale[2] = __uint_as_float(mx[3]);
 }
 
 // transposed operand of one chain step: element (n, k) = w[k * ld + col0 + n] (nn.Linear weight [out][in], n = input, k = output)
@@ -861,8 +1039,10 @@ __global__ void pe_tcT_pack_kernel(const float* __restrict__ w, int ld, int col0
     const int total = N * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i / N, n = i - k * N;
-        const float v = n < n_real ? w[(int64_t)k * ld + col0 + n] : 0.f;
-        const __half h = __float2half_rn(v);
+        // scaled by 2^TCT_WEXP: the lo half of a weight of typical size 0.03 would otherwise be a SUBNORMAL fp16 (quantum 6e-8 = 2e-6 of the
+        // weight -- a systematic error the cancelling gradient sums amplify); the chain's epilogues fold the factor into the row exponent
+        const float v = n < n_real ? ldexpf(w[(int64_t)k * ld + col0 + n], TCT_WEXP) : 0.f;
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
         const int slab = k / PE_TC_SLAB_K, kk = k - slab * PE_TC_SLAB_K;
         const int64_t off = (int64_t)slab * N * PE_TC_SLAB_K * 2 + (int64_t)(kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
         *reinterpret_cast<__half*>(hi + off) = h;
@@ -901,26 +1081,20 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
     return PE_OK;
 }
 
-static int bwd_passes() {
-    const char* env = getenv("PE_BWD_TC_PASSES");
-    const int p = env ? atoi(env) : 2;
-    return p == 1 ? 1 : 2;
-}
-
 int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    const int grid = (int)pe_min64(((int64_t)args.tile_capacity + 1) / 2, sm_count);
+    const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
     if (grid <= 0) return PE_OK;
-    pe_bwd_fwd_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, tile0, 2);
+    pe_bwd_fwd_kernel<<<grid, CHAIN_THREADS, SMEM_TOTAL, stream>>>(args, tile0);
     PE_LAUNCH_CHECK("pe_bwd_fwd_kernel");
     return PE_OK;
 }
 
 int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int sm_count, cudaStream_t stream) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    const int grid = (int)pe_min64(((int64_t)args.tile_capacity + 1) / 2, sm_count);
+    const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
     if (grid <= 0) return PE_OK;
-    pe_bwd_chain_kernel<<<grid, THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase, bwd_passes());
+    pe_bwd_chain_kernel<<<grid, CHAIN_THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase);
     PE_LAUNCH_CHECK("pe_bwd_chain_kernel");
     return PE_OK;
 }
@@ -946,39 +1120,13 @@ int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scr
 }
 
 int pe_launch_bwd_dw(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
-    const PeObjectParamGrads& gw = args.gw;
     DwArgs D = {};
     D.stash = args.stash; D.tile_begin = args.tile_begin; D.images = args.f.images; D.tile_capacity = args.tile_capacity;
-    D.tile0 = tile0; D.scale = args.scale;
-    int n = 0;
-    auto add = [&](int g_chunk, int a_chunk, int cols_n, int rows, int cols, int ld, float* out, float* bias) {
-        if (!out && !bias) return;
-        DwItem& it = D.item[n++];
-        it.g_chunk = g_chunk; it.a_chunk = a_chunk; it.n = cols_n; it.rows = rows; it.cols = out ? cols : 0; it.ld = ld;
-        it.out = out ? out : bias;           // (never dereferenced with cols == 0)
-        it.bias = bias;
-    };
-    for (int l = 0; l < 8; ++l) {
-        const int ld = l == 0 ? 63 : (l == 4 ? 319 : 256);
-        for (int mb = 0; mb < 2; ++mb) {
-            float* w = gw.backbone_w[l] ? gw.backbone_w[l] + (int64_t)mb * 128 * ld : nullptr;
-            float* b = gw.backbone_b[l] ? gw.backbone_b[l] + mb * 128 : nullptr;
-            if (l == 0) add(FS_GP(0) + 16 * mb, FS_ENC, 64, 128, 63, ld, w, b);
-            else add(FS_GP(l) + 16 * mb, FS_H(l - 1), 256, 128, 256, ld, w, b);
-            if (l == 4 && w) add(FS_GP(4) + 16 * mb, FS_ENC, 64, 128, 63, ld, w + 256, nullptr);
-        }
-    }
-    for (int mb = 0; mb < 2; ++mb) add(FS_GX1 + 16 * mb, FS_H(7), 256, 128, 256, 256, gw.head0_w ? gw.head0_w + (int64_t)mb * 128 * 256 : nullptr, nullptr);
-    add(FS_GX2, FS_Y1, 256, 128, 256, 256, gw.head3_w, nullptr);
-    add(FS_GF, FS_Y2, 128, 128, 128, 128, gw.head6_w, gw.head6_b);
-    add(FS_GF + 16, FS_Y2, 128, 64, 128, 128, gw.head6_w ? gw.head6_w + 128 * 128 : nullptr, gw.head6_b ? gw.head6_b + 128 : nullptr);
-    for (int mb = 0; mb < 2; ++mb) add(FS_H(7) + 16 * mb, FS_GRAW, 16, 128, 1, 1, gw.alpha_w ? gw.alpha_w + mb * 128 : nullptr, nullptr);
-    if (n == 0) return PE_OK;
-    D.items = n;
-    D.splits = (int)pe_min64(pe_min64(args.tile_capacity, 65535), (2 * sm_count + n - 1) / n);
+    D.tile0 = tile0; D.scale = args.scale; D.gw = args.gw;
+    D.splits = (int)pe_min64(pe_min64(args.tile_capacity, 65535), (3 * sm_count + DW_ITEMS - 1) / DW_ITEMS);
     if (D.splits < 1) D.splits = 1;
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_TOTAL));
-    pe_bwd_dw_kernel<<<dim3(n, D.splits), DW_THREADS, DW_SMEM_TOTAL, stream>>>(D);
+    pe_bwd_dw_kernel<<<dim3(DW_ITEMS, D.splits), DW_THREADS, DW_SMEM_TOTAL, stream>>>(D);
     PE_LAUNCH_CHECK("pe_bwd_dw_kernel");
     return PE_OK;
 }

@@ -170,7 +170,7 @@ struct PeBwdTcArgs {
     float* g_deformation;          // accumulated [images][D] or NULL
 };
 #define PE_BWD_TILE 128
-#define PE_BWD_FS_CHUNKS 709       // field stash chunks per tile: activations 360 + gradients 330 + ReLU-mask words (19) (map in pe_bwd_tc.cu)
+#define PE_BWD_FS_CHUNKS 1349      // field stash chunks per tile: activations hi + lo (624) + AdaIn inputs (48) + gradients hi + lo (658) + ReLU-mask words (19)
 #define PE_BWD_BS_CHUNKS 212       // ray-bender stash chunks per tile
 bool pe_bwd_tc_object_ok(const PeObjectDesc& ob);
 int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream);

@@ -28,6 +28,13 @@ pytestmark = pytest.mark.gpu
 GRAD_TOL = 2e-3
 GRAD_CASES = [("cfg1", False, 1e-4), ("toy_world", False, 1e-4), ("static_small", False, 8e-3), ("tennis_dense", False, 5e-2),
               ("minecraft_small", False, 2e-2), ("cfg1", True, 1e-4), ("toy_world", True, 1e-4), ("tennis_dense", True, 5e-2)]
+# The same scenes with the field backward of the shipped shape on the TENSOR CORES (pe_bwd_tc.cu, the default).  Every operand is a hi + lo
+# fp16 pair (fp32-class), but the recomputed pre-activations carry the tensor core's own accumulation error (~1e-5, like the fp16x3
+# forward), so the ReLU masks of the ~3e-5 of the units whose pre-activation lies that close to zero may differ from an fp32 evaluation's.
+# A ReLU network's input gradient depends on the forward ONLY through those masks: on the small golden scenes single flips show up at the
+# 1e-2 level on per-ray input gradients (measured: static_small 2.1e-2 on ray_directions, parameters <= 2.7e-3; tennis_dense 4.8e-2;
+# minecraft_small and tennis_dense/train: equal to the fp32 path).  The exact fp32 CUDA-core path stays pinned above (PE_BWD_TC=0).
+TC_GRAD_CASES = [("static_small", False, 3e-2), ("tennis_dense", False, 8e-2), ("minecraft_small", False, 2e-2), ("tennis_dense", True, 5e-2)]
 
 
 def run_backward(name, training, precision="fp32"):
@@ -46,16 +53,34 @@ def run_backward(name, training, precision="fp32"):
     return golden, float(loss.item()), got_in, got_par
 
 
+@pytest.mark.parametrize("name,training,tol", TC_GRAD_CASES)
+def test_tensor_core_backward_matches_reference_autograd(name, training, tol, monkeypatch):
+    monkeypatch.setenv("PE_BWD_TC", "1")
+    golden, loss, got_in, got_par = run_backward(name, training)
+    assert abs(loss - float(golden["loss"])) <= 2e-4 * max(1.0, abs(float(golden["loss"])))
+    bad = compare_grads(got_in, got_par, golden, tol)
+    assert not bad, bad
+    # parameter gradients (sums over all samples) are far better conditioned than per-ray input gradients: held to 1e-2 of the fp32 path
+    monkeypatch.setenv("PE_BWD_TC", "0")
+    _, _, _, ref_par = run_backward(name, training)
+    for k, v in got_par.items():
+        if "nerf_model" in k:
+            scale = float(np.abs(ref_par[k]).max())
+            assert float(np.abs(v - ref_par[k]).max()) <= (1e-2 if name != "tennis_dense" or training else 5e-2) * max(scale, 1e-12), k
+
+
 @pytest.mark.parametrize("name,training,tol", GRAD_CASES)
-def test_backward_matches_reference_autograd(name, training, tol):
+def test_backward_matches_reference_autograd(name, training, tol, monkeypatch):
+    monkeypatch.setenv("PE_BWD_TC", "0")          # the exact fp32 CUDA-core backward
     golden, loss, got_in, got_par = run_backward(name, training)
     assert abs(loss - float(golden["loss"])) <= 2e-4 * max(1.0, abs(float(golden["loss"])))
     bad = compare_grads(got_in, got_par, golden, tol)
     assert not bad, bad
 
 
-def test_backward_after_tensor_core_forward():
+def test_backward_after_tensor_core_forward(monkeypatch):
     """Forward on the tcgen05 path (fp16x3), backward recomputes in fp32: same gradients within the forward's own precision."""
+    monkeypatch.setenv("PE_BWD_TC", "0")
     golden, loss, got_in, got_par = run_backward("static_small", False, precision="fp16x3")
     bad = compare_grads(got_in, got_par, golden, 8e-3)
     assert not bad, bad
