@@ -80,6 +80,8 @@ static bool tc_allowed(const PeScene& s) {
 // Set while pe_render_backward recomputes the forward: every per-sample tensor must land in the workspace (the compositing backward
 // reads t / raw alpha / features / masks), so the self-contained and folded-head shortcuts are off.
 static thread_local bool g_keep_samples = false;
+// ... and whether that recompute may run the ray bender on the tensor cores (the forward it mirrors did: a performance mode)
+static thread_local bool g_recompute_tc_bender = false;
 struct KeepSamples { bool prev; KeepSamples() : prev(g_keep_samples) { g_keep_samples = true; } ~KeepSamples() { g_keep_samples = prev; } };
 
 // Arithmetic of one object.  The mixed mode keeps objects with fewer than 64 samples per ray in the fp32-class mode: alpha = 1 - exp(-relu(raw) * delta)
@@ -254,9 +256,9 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 // The bender's output feeds 2^9-octave Fourier features (x2pi/size: an absolute error e of the normalised
                 // displacement becomes a phase error of 3217 e), so the tensor-core bender (hi/lo split, all four partial products,
                 // but the tensor core's own fp32 accumulation) lands at ~3e-4 of the reference on the rendered outputs: used in the
-                // performance modes (fp16, fp16x2); the parity-first mode (fp16x3) keeps the exact fp32 bender.  PE_TC_BENDER=0/1 forces.
+                // performance modes (mixed, fp16, fp16x2); the parity-first mode (fp16x3) keeps the exact fp32 bender.  PE_TC_BENDER=0/1 forces.
                 const char* benv = getenv("PE_TC_BENDER");
-                const bool tc_bender = benv ? atoi(benv) != 0 : fa.precision != PE_PRECISION_FP16X3;
+                const bool tc_bender = benv ? atoi(benv) != 0 : (g_keep_samples ? g_recompute_tc_bender : s.precision != PE_PRECISION_FP16X3);
                 if (pe_tc_bender_ok(d) && tc_bender) {
                     // 1a. exact fp32 sampling: t, positions, outer mask; empty-space values everywhere
                     rc2 = pe_launch_sample(pre, sm_count, stream); if (rc2) return rc2;
@@ -363,7 +365,7 @@ static bool backward_compacts(const PeScene& s, int k) {
 }
 
 // The field backward of the shipped field shape runs on the tensor cores (pe_bwd_tc.cu) over tiles of 128 compacted samples; PE_BWD_TC=0
-// keeps it on the exact fp32 kernel.  Its activation / gradient stash holds `capacity` tiles (1.45 MB each); more tiles than that are
+// keeps it on the exact fp32 kernel.  Its activation / gradient stash holds `capacity` tiles (2.76 MB each: every operand as a hi + lo fp16 pair); more tiles than that are
 // processed in batches (the number of in-box samples is only known on the device, so the batch count is the worst case and surplus
 // launches find no tile).
 static bool backward_on_tc(const PeScene& s, int k) {
@@ -377,7 +379,7 @@ static int64_t bwd_tc_capacity(const PeScene& s) {
     for (int k = 0; k < s.objects; ++k)
         if (backward_on_tc(s, k)) ub = bwd_tc_tiles_upper_bound(s, k) > ub ? bwd_tc_tiles_upper_bound(s, k) : ub;
     const char* env = getenv("PE_BWD_TC_MAX_TILES");
-    const int64_t cap = env ? atoll(env) : 8192;
+    const int64_t cap = env ? atoll(env) : 12288;
     return pe_min64(ub, cap > 0 ? cap : 1);
 }
 
@@ -482,6 +484,7 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
     // 1. recompute the forward: per-sample t / raw alpha / features / |displacement| / in-box flags, AdaIn scale-shift, BatchNorm sums
     const PeOutputs none = {};
     KeepSamples keep;
+    g_recompute_tc_bender = scene->precision == PE_PRECISION_MIXED || scene->precision == PE_PRECISION_FP16 || scene->precision == PE_PRECISION_FP16X2;
     rc = pe_render_forward(&s, in, &none, bw.fwd, bw.fwd_bytes, stream_);
     if (rc != PE_OK) return rc;
     const Workspace ws = carve(s, bw.fwd);
@@ -553,7 +556,10 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
             ta.f = fa;
             if (prepass) { ta.f.bent = o.bent; ta.f.flags = o.flags; }
             ta.slot_list = b.slot_list; ta.slot_count = b.slot_count; ta.tile_begin = b.tile_begin;
-            ta.tile_capacity = (int32_t)bw.tc_capacity; ta.stash = bw.tc_stash;
+            ta.tile_capacity = (int32_t)bw.tc_capacity; ta.stash = bw.tc_stash; ta.bstash = bw.tc_stash;
+            ta.g_deformation = grad_in->deformation[k];
+            const bool bender_tc = prepass && pe_bwd_tc_bender_ok(d, L);
+            if (prepass) PE_CUDA_CHECK(cudaMemsetAsync(b.g_bent, 0, (size_t)s.images * s.rays * d.positions * 12, stream));
             ta.cw_obj = b.cw_obj; ta.cw_glob = b.cw_glob;
             ta.g_feat_obj = grad_out->object[k].integrated_features; ta.g_feat_glob = grad_out->global.integrated_features;
             ta.g_raw = b.g_raw; ta.g_dm = b.g_dm;
@@ -561,7 +567,7 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
             ta.g_pos = b.g_pos; ta.g_bent = prepass ? b.g_bent : nullptr;
             ta.gw = grad_in->params[k];
             ta.adain_sums = b.adain_sums; ta.bn_sums = b.bn_sums;
-            rc = pe_launch_bwd_scale(ta, b.scale, (unsigned int*)(b.scale + 4), stream); if (rc) return rc;
+            rc = pe_launch_bwd_scale(ta, b.scale, (unsigned int*)(b.scale + 8), stream); if (rc) return rc;
             const int64_t ub = bwd_tc_tiles_upper_bound(s, k);
             const int64_t batches = (ub + bw.tc_capacity - 1) / bw.tc_capacity;
             if (s.training) {
@@ -581,8 +587,13 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
                 if (batches > 1 || !s.training) { rc = pe_launch_bwd_fwd(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc; }
                 rc = pe_launch_bwd_chain(ta, bt * bw.tc_capacity, 0, sm_count, stream); if (rc) return rc;
                 rc = pe_launch_bwd_dw(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc;
+                if (bender_tc) {
+                    // the ray bender of this batch's tiles, on the same stash memory: dL/d bent position -> bender -> g_pos, parameter gradients
+                    rc = pe_launch_bwd_scale_bender(ta, b.scale, (unsigned int*)(b.scale + 8), stream); if (rc) return rc;
+                    rc = pe_launch_bwd_bender(ta, bt * bw.tc_capacity, sm_count, stream); if (rc) return rc;
+                }
             }
-            if (prepass) {
+            if (prepass && !bender_tc) {
                 // the ray bender's backward stays on the exact fp32 kernel (tiles of 32 listed slots): dL/d bent position -> bender -> g_pos
                 rc = pe_launch_compact_slots(o.flags, 1, s.images, (int64_t)s.rays * d.positions, b.slot_list, b.slot_count, b.tile_begin, stream, 32);
                 if (rc) return rc;

@@ -410,21 +410,21 @@ __device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char
 }
 
 // KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
-template <int KIND>
+template <int KIND, int NB = 8, int LO_CHUNKS = FS_GLO>
 __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw, bool store) {
     const int fexp = renorm_exp(C.mop, C.km);
     const int km = C.km + fexp;
     const float f = ldexpf(1.f, fexp - TCT_WEXP), r_stash = ldexpf(1.f, C.kS - km), graw_n = ldexpf(graw, km);
-    uint32_t bits[8];
+    uint32_t bits[NB];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
+    for (int w = 0; w < NB; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
     uint32_t v[2][32];
     float mx = 0.f;
     tmem_ld32(C.taddr, v[0]);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < NB; ++c) {
         tmem_wait_ld_regs(v[c & 1]);
-        if (c + 1 < 8) tmem_ld32(C.taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        if (c + 1 < NB) tmem_ld32(C.taddr + (c + 1) * 32, v[(c + 1) & 1]);
         float y[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -441,7 +441,7 @@ __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[i] = y[8 * cc + i] * r_stash;
                 const int off = (c * 4 + cc) * CHUNK_BYTES + C.m * 16;
-                split_store8(st_g + off, st_g + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+                split_store8(st_g + off, st_g + (int64_t)LO_CHUNKS * CHUNK_BYTES + off, z, false);
             }
         }
     }
@@ -824,6 +824,485 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
 }
 
 // =====================================================================================================================
+// 2b. ray bender (model/nerf_models/positional_ray_bender_model.py:81-163), shipped shape: 6 x 128, skip at 3, 6 annealed octaves + 32
+//     deformation features.  Same three-kernel scheme on its own stash block (PE_BWD_BS_CHUNKS chunks per tile):
+//     recompute (fp16x3 with all four partial products, like pe_bender_tc_kernel) -> dX chain (from dL/d bent position, left by the
+//     field's chain, and dL/d |displacement|) -> dW through pe_bwd_dw_kernel with the bender's item table.
+// =====================================================================================================================
+__host__ __device__ constexpr int BS_H(int l) { return l < 3 ? 16 * l : 60 + 16 * (l - 3); }     // bh0..bh2 | input (12) | bh3..bh5: [bh2 | input] contiguous
+constexpr int BS_ENC = 48, BS_ALO = 108;                       // activations hi [0, 108), lo [108, 216)
+constexpr int BS_GOUT = 216;                                   // 4 chunks (3 real columns); a 128-row block over-reads into GP(0)
+__host__ __device__ constexpr int BS_GP(int l) { return 220 + 16 * l; }
+constexpr int BS_GLO = 100;                                    // gradients hi [216, 316), lo [316, 416)
+constexpr int BS_MASK = 416, BS_AUX = 422;                     // mask words [layer][4][row]; per row: clamp bits, displacement xyz (fp32)
+static_assert(BS_AUX + 1 == PE_BWD_BS_CHUNKS, "bender stash map");
+constexpr int64_t BS_BYTES = (int64_t)PE_BWD_BS_CHUNKS * CHUNK_BYTES;
+constexpr int BB_A_CHUNKS = 28, BB_ENC_CHUNK0 = 16;            // operand buffers: K columns 0..127 activations, 128..223 the bender's input
+constexpr int BB_A_BYTES = BB_A_CHUNKS * CHUNK_BYTES;
+constexpr int BB_SMEM_BAR = 2 * BB_A_BYTES + NUM_STAGES * STAGE_BYTES;
+constexpr int BB_SMEM_ONES = BB_SMEM_BAR + 128;
+constexpr int BB_SMEM_TOTAL = BB_SMEM_ONES + 256;
+
+__host__ __device__ __forceinline__ void bb_layer_spec(int l, int& n, int& slabs, int& chunk0, bool& has_bias) {
+    n = 128; slabs = 4; chunk0 = 0; has_bias = true;
+    if (l == 0) { slabs = 3; chunk0 = BB_ENC_CHUNK0; }
+    else if (l == 3) { slabs = 7; }
+    else if (l == 6) { n = 16; has_bias = false; }
+}
+// chain steps: OUTT (N'128,K'32) L5T L4T (128,128) L3encT (96,128) L3T L2T L1T (128,128) L0T (96,128)
+__device__ __forceinline__ StepSpec bb_chain_step(int s) {
+    StepSpec st; st.n = 128; st.slabs = 4;
+    if (s == 0) st.slabs = 1;
+    else if (s == 3 || s == 7) st.n = 96;
+    return st;
+}
+
+// row of a bender tile: the sample BEFORE bending (the list holds exactly the samples inside the box)
+__device__ __forceinline__ void load_row_prebend(const PeBwdTcArgs& B, int64_t tile, int64_t tile_end, int m, int& img_cursor, BRow& r) {
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    r.store = tile < tile_end;
+    r.listed = false; r.active = false; r.in_scene = true; r.img = 0; r.slot = -1; r.gs = 0;
+    r.x[0] = r.x[1] = r.x[2] = 0.f;
+    if (!r.store) return;
+    while (tile >= B.tile_begin[img_cursor + 1]) ++img_cursor;
+    r.img = img_cursor;
+    const int P = ob.positions;
+    const int64_t spi = (int64_t)A.rays * P;
+    const int64_t e = (tile - B.tile_begin[r.img]) * PE_BWD_TILE + m;
+    r.in_scene = A.ois ? A.ois[(int64_t)r.img * A.objects + A.k] != 0 : true;
+    if (e >= B.slot_count[r.img]) return;
+    r.slot = B.slot_list[(int64_t)r.img * spi + e];
+    r.gs = (int64_t)r.img * spi + r.slot;
+    r.listed = true;
+    const int ray = r.slot / P, p = r.slot - ray * P;
+    const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)r.img * A.objects + A.k) * 12, A.origins + (int64_t)r.img * 3,
+                                 A.dirs + ((int64_t)r.img * A.rays + ray) * 3, r.in_scene);
+    const float u = A.perturb ? A.rand[r.gs] : 0.f;
+    const float t = pe_sample_t(pr, p, P, A.perturb != 0, u);
+    pe_position(pr, t, r.x);
+    r.active = pe_in_box(ob, r.x);
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bfwd_kernel(const PeBwdTcArgs B, const int64_t tile0) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = smem + BB_A_BYTES;
+    unsigned char* ring = smem + 2 * BB_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BB_SMEM_BAR);
+    uint64_t* empty_bar = full_bar + NUM_STAGES;
+    uint64_t* acc_full = empty_bar + NUM_STAGES;
+    uint64_t* a_ready = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+    unsigned char* ones = smem + BB_SMEM_ONES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    const PeLayout& L = A.L;
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
+    const int64_t total = B.tile_begin[A.images];
+    const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
+    const int64_t tiles = tile_end > tile0 ? tile_end - tile0 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 128) {
+        const int r = threadIdx.x >> 3, c = threadIdx.x & 7;
+        reinterpret_cast<__half*>(ones)[threadIdx.x] = __float2half_rn((r < 8 && c < 2) ? 1.f : 0.f);
+    }
+    fence_proxy_async();
+    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const unsigned char* src = blob + L.tcb_base;
+                for (int l = 0; l < 7; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    bb_layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
+                    for (int s = 0; s < slabs; ++s) {
+                        for (int pass = 0; pass < 2; ++pass) {
+                            mbar_wait(empty_bar + stage, phase ^ 1);
+                            mbar_arrive_expect_tx(full_bar + stage, bytes);
+                            bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcb_bytes_per_pass, bytes, full_bar + stage);
+                            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        src += bytes;
+                    }
+                    if (has_bias) {
+                        const uint32_t bbytes = (uint32_t)n * 32;
+                        mbar_wait(empty_bar + stage, phase ^ 1);
+                        mbar_arrive_expect_tx(full_bar + stage, bbytes);
+                        bulk_copy_g2s(ring + stage * STAGE_BYTES, src, bbytes, full_bar + stage);
+                        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                        src += bbytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(a_hi); R.a_addr[1] = smem_u32(a_lo);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 2;
+            const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                for (int l = 0; l < 7; ++l) {
+                    int n, slabs, chunk0; bool has_bias;
+                    bb_layer_spec(l, n, slabs, chunk0, has_bias);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, n);
+                    const uint32_t lbo_b = (uint32_t)n * 16;
+                    mbar_wait(a_ready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    mma_layer<false, 1, 2>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    if (has_bias) {
+                        mbar_wait(full_bar + R.stage, R.phase);
+                        tc_fence_after();
+                        const uint64_t db = umma_smem_desc(R.ring_addr + R.stage * STAGE_BYTES, lbo_b, 128);
+                        umma_f16_ss(tmem_base, ones_desc, db, idesc, 1u);
+                        umma_commit(acc_full);
+                        umma_commit(empty_bar + R.stage);
+                        if (++R.stage == NUM_STAGES) { R.stage = 0; R.phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int wq = warp & 3;
+        const int m = (wq << 5) | lane;
+        const uint32_t taddr = tmem_base + (((uint32_t)wq * 32u) << 16);
+        Sync1 sync{acc_full, a_ready, 0u, lane, nullptr, nullptr, 0u};
+        const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
+        int img_cursor = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            BRow r;
+            load_row_prebend(B, tile0 + t, tile_end, m, img_cursor, r);
+            unsigned char* st = B.bstash + t * BS_BYTES;
+            uint32_t* mask = reinterpret_cast<uint32_t*>(st + (int64_t)BS_MASK * CHUNK_BYTES);
+            const bool use = r.listed && r.active;
+            {
+                // the bender's input: annealed Fourier features of x / size (positional_ray_bender_model.py:96-100) | deformation code
+                const float xn[3] = {__fdiv_rn(r.x[0], size[0]), __fdiv_rn(r.x[1], size[1]), __fdiv_rn(r.x[2], size[2])};
+                const float* dfm = A.deformation + (int64_t)r.img * 32;
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int e = 8 * c + i;
+                        v[i] = !use ? 0.f : (e < 39 ? pe_encoding_value(xn, 3, e, ob.b_anneal) : (e < 71 ? __ldg(dfm + (e - 39)) : 0.f));
+                    }
+                    const int off = c * CHUNK_BYTES + m * 16;
+                    split_store8(a_hi + BB_ENC_CHUNK0 * CHUNK_BYTES + off, a_lo + BB_ENC_CHUNK0 * CHUNK_BYTES + off, v, false);
+                    if (r.store) split_store8(st + BS_ENC * CHUNK_BYTES + off, st + (int64_t)(BS_ENC + BS_ALO) * CHUNK_BYTES + off, v, false);
+                }
+            }
+            sync.arrive_ready();
+#pragma unroll 1
+            for (int l = 0; l < 6; ++l) {
+                sync.wait_acc();
+                uint32_t v[2][32];
+                tmem_ld32(taddr, v[0]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    tmem_wait_ld_regs(v[c & 1]);
+                    if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    float y[32];
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) { y[q] = __uint_as_float(v[c & 1][q]); bits |= (y[q] > 0.f) ? (1u << q) : 0u; }
+                    if (r.store) mask[(l * 4 + c) * PE_BWD_TILE + m] = bits;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int off = (c * 4 + cc) * CHUNK_BYTES + m * 16;
+                        split_store8(a_hi + off, a_lo + off, y + 8 * cc, true);
+                        if (r.store) split_store8(st + BS_H(l) * CHUNK_BYTES + off, st + (int64_t)(BS_H(l) + BS_ALO) * CHUNK_BYTES + off, y + 8 * cc, true);
+                    }
+                }
+                sync.arrive_ready();
+            }
+            sync.wait_acc();
+            uint32_t v[16];
+            tmem_ld16(taddr, v);
+            tmem_wait_ld_regs16(v);
+            tc_fence_before();
+            // displacement = clamp(out * size) into the box (clamp_output :116-140): remember which axes the network output still moves
+            int cf = 0;
+            float dsp[3] = {0.f, 0.f, 0.f};
+            if (use) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float raw = __fmul_rn(__uint_as_float(v[a]), size[a]);
+                    const float lo = __fsub_rn(ob.bbox[2 * a], r.x[a]), hi = __fsub_rn(ob.bbox[2 * a + 1], r.x[a]);
+                    float d = fmaxf(raw, lo);
+                    const bool pass = !(raw < lo) && !(d > hi);
+                    d = fminf(d, hi);
+                    if (ob.canonical_pose) d = __fmul_rn(d, 0.f);
+                    if (pass) cf |= 1 << a;
+                    dsp[a] = d;
+                }
+            }
+            if (r.store)
+                *reinterpret_cast<float4*>(st + (int64_t)BS_AUX * CHUNK_BYTES + m * 16) = make_float4(__int_as_float(cf), dsp[0], dsp[1], dsp[2]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const PeBwdTcArgs B, const int64_t tile0) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* ring = smem + 2 * BB_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BB_SMEM_BAR);
+    uint64_t* empty_bar = full_bar + NUM_STAGES;
+    uint64_t* acc_full = empty_bar + NUM_STAGES;
+    uint64_t* a_ready = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PeFieldArgs& A = B.f;
+    const PeObjectDesc& ob = A.ob;
+    const PeLayout& L = A.L;
+    const unsigned char* blob = reinterpret_cast<const unsigned char*>(ob.packed);
+    const int64_t total = B.tile_begin[A.images];
+    const int64_t tile_end = pe_min64(total, tile0 + B.tile_capacity);
+    const int64_t tiles = tile_end > tile0 ? tile_end - tile0 : 0;
+    constexpr int STEPS = 8;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0; uint32_t ph = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const unsigned char* src = blob + L.tcbT_base;
+                for (int s = 0; s < STEPS; ++s) {
+                    const StepSpec st = bb_chain_step(s);
+                    const uint32_t bytes = (uint32_t)st.n * PE_TC_SLAB_K * 2;
+                    for (int k = 0; k < st.slabs; ++k) {
+                        for (int pass = 0; pass < 2; ++pass) {
+                            mbar_wait(empty_bar + stage, ph ^ 1);
+                            mbar_arrive_expect_tx(full_bar + stage, bytes);
+                            bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcbT_bytes_per_pass, bytes, full_bar + stage);
+                            if (++stage == NUM_STAGES) { stage = 0; ph ^= 1; }
+                        }
+                        src += bytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t ready_phase = 0;
+            MmaRing R;
+            R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
+            R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + BB_A_BYTES);
+            R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 1;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                for (int s = 0; s < STEPS; ++s) {
+                    const StepSpec st = bb_chain_step(s);
+                    const uint32_t idesc = umma_idesc_f16(TILE_M, st.n);
+                    const uint32_t lbo_b = (uint32_t)st.n * 16;
+                    mbar_wait(a_ready, ready_phase);
+                    ready_phase ^= 1;
+                    tc_fence_after();
+                    mma_layer<false, 1, 1>(R, s, st.n, st.slabs, 0, false, idesc, lbo_b);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        ChainCtx C;
+        C.lane = lane;
+        C.m = ((warp & 3) << 5) | lane;
+        C.a_hi = smem; C.a_lo = smem + BB_A_BYTES;
+        C.cst = nullptr;
+        C.taddr = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16);
+        const float S = B.scale[4];                      // the bender's own call-wide scale (pe_launch_bwd_scale_bender)
+        {
+            int e;
+            frexpf(S, &e);
+            C.kS = e - 1;
+        }
+        const int m = C.m;
+        const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
+        Sync1 sync{acc_full, a_ready, 0u, lane, nullptr, nullptr, 0u};
+        int img_cursor = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            BRow r;
+            load_row_prebend(B, tile0 + t, tile_end, m, img_cursor, r);
+            unsigned char* st = B.bstash + t * BS_BYTES;
+            const uint32_t* mask = reinterpret_cast<const uint32_t*>(st + (int64_t)BS_MASK * CHUNK_BYTES);
+            const bool use = r.listed && r.active;
+            // ---- dL/d displacement -> dL/d network output (inside the clamp) or -> dL/d position (clamped to a box face) ----
+            float gpos[3] = {0.f, 0.f, 0.f}, gout[3] = {0.f, 0.f, 0.f};
+            if (r.listed) {
+                const float* gb = B.g_bent + r.gs * 3;
+                gpos[0] = gb[0]; gpos[1] = gb[1]; gpos[2] = gb[2];
+            }
+            if (use) {
+                const float4 aux = *reinterpret_cast<const float4*>(st + (int64_t)BS_AUX * CHUNK_BYTES + m * 16);
+                const int cf = __float_as_int(aux.x);
+                const float d[3] = {aux.y, aux.z, aux.w};
+                const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                const float gdm = B.g_dm[r.gs];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    float gd = 0.f;
+                    if (!ob.canonical_pose) {
+                        gd = gpos[a];
+                        if (nrm > 0.f) gd = fmaf(gdm, d[a] / nrm, gd);       // torch.norm backward, 0 at the origin
+                    }
+                    if ((cf >> a) & 1) gout[a] = gd * size[a];
+                    else gpos[a] -= gd;
+                }
+            }
+            {
+                const float mx = fmaxf(fabsf(gout[0]), fmaxf(fabsf(gout[1]), fabsf(gout[2])));
+                C.km = renorm_exp(mx, 0);
+                C.mop = ldexpf(mx, C.km);
+                const float s_row = ldexpf(1.f, C.km);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (c == 0) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { v[a] = gout[a] * s_row; z[a] = gout[a] * S; }
+                    }
+                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
+                    if (r.store) {
+                        const int off = (BS_GOUT + c) * CHUNK_BYTES + m * 16;
+                        split_store8(st + off, st + (int64_t)BS_GLO * CHUNK_BYTES + off, z, false);
+                    }
+                }
+            }
+            sync.arrive_ready();
+            // ---- step 0: output head; steps 1, 2: layers 5, 4 -> gradients of the pre-activations of layers 5, 4, 3 ----
+#pragma unroll 1
+            for (int l = 5; l >= 3; --l) {
+                sync.wait_acc();
+                chain_epilogue_plain<0, 4, BS_GLO>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                sync.arrive_ready();
+            }
+            // ---- step 3: the input half of the skip layer's input gradient, parked (hi + lo) behind the activations ----
+            int km_parked = 0;
+            sync.wait_acc();
+            {
+                uint32_t v[3][32];
+                tmem_ld32(C.taddr, v[0]);
+                tmem_ld32(C.taddr + 32, v[1]);
+                tmem_ld32(C.taddr + 64, v[2]);
+                tmem_wait_ld_regs(v[0]);
+                tmem_wait_ld_regs(v[1]);
+                tmem_wait_ld_regs(v[2]);
+                const int fexp = renorm_exp(C.mop, C.km);
+                km_parked = C.km + fexp;
+                const float f = ldexpf(1.f, fexp - TCT_WEXP);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float y[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]) * f;
+                        store_g8_hilo(C.a_hi, C.a_lo, BB_ENC_CHUNK0 + c * 4 + cc, m, y);
+                    }
+            }
+            sync.arrive_ready();
+            // ---- steps 4-6: layers 3 (hidden half), 2, 1 -> gradients of the pre-activations of layers 2, 1, 0 ----
+#pragma unroll 1
+            for (int l = 2; l >= 0; --l) {
+                sync.wait_acc();
+                chain_epilogue_plain<0, 4, BS_GLO>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                sync.arrive_ready();
+            }
+            // ---- step 7: gradient of the bender's input = layer 0's input gradient + the parked half ----
+            sync.wait_acc();
+            {
+                uint32_t v[3][32];
+                tmem_ld32(C.taddr, v[0]);
+                tmem_ld32(C.taddr + 32, v[1]);
+                tmem_ld32(C.taddr + 64, v[2]);
+                tmem_wait_ld_regs(v[0]);
+                tmem_wait_ld_regs(v[1]);
+                tmem_wait_ld_regs(v[2]);
+                const float fa = ldexpf(1.f, -C.km - TCT_WEXP), fp = ldexpf(1.f, -km_parked);
+                float ge[3][32];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float ph[8], pl[8];
+                        unpack8(*reinterpret_cast<const uint4*>(C.a_hi + (BB_ENC_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), ph);
+                        unpack8(*reinterpret_cast<const uint4*>(C.a_lo + (BB_ENC_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), pl);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) ge[c][cc * 8 + i] = use ? fmaf(__uint_as_float(v[c][8 * cc + i]), fa, (ph[i] + pl[i]) * fp) : 0.f;
+                    }
+                if (use) {
+                    // annealed positional encoding backward (annealable_positional_encoder.py:54-76): columns [x | sin, cos per octave] * weight
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float xn = __fdiv_rn(r.x[a], size[a]);
+                        float gsum = ge[0][a];
+#pragma unroll
+                        for (int o = 0; o < 6; ++o) {
+                            const float f = (float)(1 << o);
+                            float s, c;
+                            sincosf(__fmul_rn(f, xn), &s, &c);
+                            const int is = 3 + 6 * o + a, ic = is + 3;
+                            gsum = fmaf(ob.b_anneal[o] * f, c * ge[is >> 5][is & 31] - s * ge[ic >> 5][ic & 31], gsum);
+                        }
+                        gpos[a] += gsum / size[a];
+                    }
+                }
+                if (B.g_deformation) {
+                    // the deformation code is replicated over the samples of its image: column sums of input columns 39 .. 70
+                    float* gd = B.g_deformation + (int64_t)r.img * 32;
+#pragma unroll
+                    for (int c = 1; c < 3; ++c) {
+                        const float sum = warp_transpose_sum(ge[c], lane);
+                        const int col = c * 32 + lane;
+                        if (r.store && col >= 39 && col < 71 && sum != 0.f) atomicAdd(gd + (col - 39), sum);
+                    }
+                }
+                if (r.listed) {
+                    float* dst = B.g_pos + r.gs * 3;
+                    dst[0] = gpos[0]; dst[1] = gpos[1]; dst[2] = gpos[2];
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(CHAIN_BAR, 128);        // the parked gradient is dead before the next tile's operand overwrites it
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 128);
+}
+
+// =====================================================================================================================
 // 3. dW / db
 // =====================================================================================================================
 struct DwItem {
@@ -840,9 +1319,9 @@ struct DwArgs {
     const unsigned char* stash;
     const int32_t* tile_begin;
     int32_t images, tile_capacity;
-    int64_t tile0;
-    const float* scale;
-    int32_t splits;
+    int64_t tile0, tile_bytes;
+    const float* scale;            // [S, 1 / S] of the stash's gradients
+    int32_t splits, bender;
     PeObjectParamGrads gw;
 };
 constexpr int DW_BASE_ITEMS = 25, DW_ITEMS = 3 * DW_BASE_ITEMS;
@@ -891,6 +1370,32 @@ __device__ __forceinline__ bool dw_item(int idx, const PeObjectParamGrads& gw, D
     if (!it.out) it.cols = 0;
     return it.out != nullptr || it.bias != nullptr;
 }
+// the ray bender's products: base 0-5: layer l (128 rows; the skip layer's N operand is [bh2 | input], contiguous in the stash); 6: output head
+constexpr int DW_BENDER_ITEMS = 3 * 7;
+__device__ __forceinline__ bool dw_item_bender(int idx, const PeObjectParamGrads& gw, DwItem& it) {
+    const int base = idx / 3, term = idx - 3 * base;
+    it.rows = 128; it.fold = 0; it.bias = nullptr; it.out = nullptr;
+    float* bias = nullptr;
+    if (base < 6) {
+        const int l = base;
+        it.g_chunk = BS_GP(l);
+        it.a_chunk = l == 0 ? BS_ENC : BS_H(l - 1);
+        it.n = l == 0 ? 96 : (l == 3 ? 224 : 128);
+        it.cols = l == 0 ? 71 : (l == 3 ? 199 : 128);
+        it.ld = it.cols;
+        it.out = gw.bender_w[l];
+        bias = gw.bender_b[l];
+    } else {
+        it.g_chunk = BS_GOUT; it.a_chunk = BS_H(5); it.n = 128; it.cols = 128; it.ld = 128; it.rows = 3;
+        it.out = gw.bender_out_w;
+    }
+    if (term == 1) it.g_chunk += BS_GLO;
+    if (term == 2) it.a_chunk += BS_ALO;
+    if (term != 2) it.bias = bias;
+    if (!it.out) it.cols = 0;
+    return it.out != nullptr || it.bias != nullptr;
+}
+
 constexpr int DW_THREADS = 192;                                // producer, MMA + TMEM, 4 epilogue warps
 constexpr int DW_G_BYTES = 16 * CHUNK_BYTES, DW_A_BYTES = 32 * CHUNK_BYTES, DW_STAGE = DW_G_BYTES + DW_A_BYTES;
 constexpr int DW_SMEM_ONES = 2 * DW_STAGE, DW_SMEM_BAR = DW_SMEM_ONES + 2 * CHUNK_BYTES, DW_SMEM_TOTAL = DW_SMEM_BAR + 128;
@@ -904,7 +1409,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D
     unsigned char* ones = smem + DW_SMEM_ONES;                               // 128 rows x 16 columns, column 0 = 1
     const int warp = threadIdx.x >> 5;
     DwItem it;
-    if (!dw_item(blockIdx.x, D.gw, it)) return;
+    if (!(D.bender ? dw_item_bender(blockIdx.x, D.gw, it) : dw_item(blockIdx.x, D.gw, it))) return;
     const int64_t total = D.tile_begin[D.images];
     const int64_t tile_end = pe_min64(total, D.tile0 + D.tile_capacity);
     const int64_t count = tile_end > D.tile0 ? tile_end - D.tile0 : 0;
@@ -933,7 +1438,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int64_t t = t0; t < t1; ++t) {
-                const unsigned char* st = D.stash + t * FS_BYTES;
+                const unsigned char* st = D.stash + t * D.tile_bytes;
                 mbar_wait(empty_bar + stage, phase ^ 1);
                 mbar_arrive_expect_tx(full_bar + stage, DW_G_BYTES + a_bytes);
                 bulk_copy_g2s(smem + stage * DW_STAGE, st + (int64_t)it.g_chunk * CHUNK_BYTES, DW_G_BYTES, full_bar + stage);
@@ -1033,15 +1538,27 @@ __global__ void pe_bwd_scale_kernel(const unsigned int* __restrict__ mx, float* 
     scale[2] = __uint_as_float(mx[3]);
 }
 
+__global__ void pe_bwd_scale_bender_kernel(const unsigned int* __restrict__ mx, float msize, float* __restrict__ scale) {
+    const float m = (__uint_as_float(mx[0]) + __uint_as_float(mx[1])) * msize;
+    float S = 1.f;
+    if (m > 0.f) {
+        int e = (int)floorf(log2f(256.f / m));
+        e = max(-60, min(60, e));
+        S = exp2f((float)e);
+    }
+    scale[4] = S;
+    scale[5] = 1.f / S;
+}
+
 // transposed operand of one chain step: element (n, k) = w[k * ld + col0 + n] (nn.Linear weight [out][in], n = input, k = output)
-__global__ void pe_tcT_pack_kernel(const float* __restrict__ w, int ld, int col0, int n_real, int N, int K, unsigned char* __restrict__ hi,
-                                   unsigned char* __restrict__ lo) {
+__global__ void pe_tcT_pack_kernel(const float* __restrict__ w, int ld, int col0, int n_real, int N, int K, int k_real,
+                                   unsigned char* __restrict__ hi, unsigned char* __restrict__ lo) {
     const int total = N * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i / N, n = i - k * N;
         // scaled by 2^TCT_WEXP: the lo half of a weight of typical size 0.03 would otherwise be a SUBNORMAL fp16 (quantum 6e-8 = 2e-6 of the
         // weight -- a systematic error the cancelling gradient sums amplify); the chain's epilogues fold the factor into the row exponent
-        const float v = n < n_real ? ldexpf(w[(int64_t)k * ld + col0 + n], TCT_WEXP) : 0.f;
+        const float v = (n < n_real && k < k_real) ? ldexpf(w[(int64_t)k * ld + col0 + n], TCT_WEXP) : 0.f;
         const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
         const int slab = k / PE_TC_SLAB_K, kk = k - slab * PE_TC_SLAB_K;
         const int64_t off = (int64_t)slab * N * PE_TC_SLAB_K * 2 + (int64_t)(kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
@@ -1073,11 +1590,30 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
     for (int s = 0; s < 12; ++s) {
         const Item& it = items[s];
         if (!it.w) { pe_set_error("missing parameter tensor for the transposed weight stream (step %d)", s); return PE_ERR_INVALID; }
-        pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, hi + off, lo + off);
+        pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.K, hi + off, lo + off);
         PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
         off += (int64_t)it.N * it.K * 2;
     }
     if (off != L.tcT_bytes_per_pass) { pe_set_error("internal: transposed weight stream size mismatch"); return PE_ERR_INVALID; }
+    if (L.tcbT_base) {
+        // ray bender: OUTT (N'128,K'32) L5T L4T (128,128) L3encT (96,128) L3T L2T L1T (128,128) L0T (96,128)
+        unsigned char* bhi = (unsigned char*)packed + L.tcbT_base;
+        unsigned char* blo = bhi + L.tcbT_bytes_per_pass;
+        struct BItem { const float* w; int ld, col0, n_real, N, K, k_real; };
+        const BItem bitems[8] = {
+            {p.bender_out_w, 128, 0, 128, 128, 32, 3},   {p.bender_w[5], 128, 0, 128, 128, 128, 128}, {p.bender_w[4], 128, 0, 128, 128, 128, 128},
+            {p.bender_w[3], 199, 128, 71, 96, 128, 128}, {p.bender_w[3], 199, 0, 128, 128, 128, 128}, {p.bender_w[2], 128, 0, 128, 128, 128, 128},
+            {p.bender_w[1], 128, 0, 128, 128, 128, 128}, {p.bender_w[0], 71, 0, 71, 96, 128, 128}};
+        int64_t boff = 0;
+        for (int s = 0; s < 8; ++s) {
+            const BItem& it = bitems[s];
+            if (!it.w) { pe_set_error("missing ray-bender parameter tensor for the transposed weight stream (step %d)", s); return PE_ERR_INVALID; }
+            pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.k_real, bhi + boff, blo + boff);
+            PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
+            boff += (int64_t)it.N * it.K * 2;
+        }
+        if (boff != L.tcbT_bytes_per_pass) { pe_set_error("internal: transposed ray-bender weight stream size mismatch"); return PE_ERR_INVALID; }
+    }
     return PE_OK;
 }
 
@@ -1122,11 +1658,55 @@ int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scr
 int pe_launch_bwd_dw(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
     DwArgs D = {};
     D.stash = args.stash; D.tile_begin = args.tile_begin; D.images = args.f.images; D.tile_capacity = args.tile_capacity;
-    D.tile0 = tile0; D.scale = args.scale; D.gw = args.gw;
+    D.tile0 = tile0; D.scale = args.scale; D.gw = args.gw; D.tile_bytes = FS_BYTES;
     D.splits = (int)pe_min64(pe_min64(args.tile_capacity, 65535), (3 * sm_count + DW_ITEMS - 1) / DW_ITEMS);
     if (D.splits < 1) D.splits = 1;
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_TOTAL));
     pe_bwd_dw_kernel<<<dim3(DW_ITEMS, D.splits), DW_THREADS, DW_SMEM_TOTAL, stream>>>(D);
+    PE_LAUNCH_CHECK("pe_bwd_dw_kernel");
+    return PE_OK;
+}
+
+// ---- ray bender ----
+bool pe_bwd_tc_bender_ok(const PeObjectDesc& ob, const PeLayout& L) {
+    const char* env = getenv("PE_BWD_TC_BENDER");
+    if (env && atoi(env) == 0) return false;
+    return pe_tc_bender_ok(ob) && L.tcb_base != 0 && L.tcbT_base != 0;
+}
+
+// call-wide scale of the bender's gradient stash from |dL/d bent position| (left by the field's chain) and |dL/d |displacement||
+int pe_launch_bwd_scale_bender(const PeBwdTcArgs& args, float* scale, unsigned int* scratch, cudaStream_t stream) {
+    const PeFieldArgs& A = args.f;
+    PE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(unsigned int), stream));
+    const int64_t ns = (int64_t)A.images * A.rays * A.ob.positions;
+    if (ns == 0) return PE_OK;
+    pe_bwd_absmax_kernel<<<(int)pe_min64((3 * ns + 255) / 256, 1024), 256, 0, stream>>>(args.g_bent, 3 * ns, scratch + 0);
+    PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
+    pe_bwd_absmax_kernel<<<(int)pe_min64((ns + 255) / 256, 1024), 256, 0, stream>>>(args.g_dm, ns, scratch + 1);
+    PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
+    const PeObjectDesc& ob = A.ob;
+    const float msize = fmaxf(ob.bbox[1] - ob.bbox[0], fmaxf(ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]));
+    pe_bwd_scale_bender_kernel<<<1, 1, 0, stream>>>(scratch, msize, scale);
+    PE_LAUNCH_CHECK("pe_bwd_scale_bender_kernel");
+    return PE_OK;
+}
+
+int pe_launch_bwd_bender(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
+    const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
+    if (grid <= 0) return PE_OK;
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_bfwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_SMEM_TOTAL));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_bchain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_SMEM_TOTAL));
+    pe_bwd_bfwd_kernel<<<grid, CHAIN_THREADS, BB_SMEM_TOTAL, stream>>>(args, tile0);
+    PE_LAUNCH_CHECK("pe_bwd_bfwd_kernel");
+    pe_bwd_bchain_kernel<<<grid, CHAIN_THREADS, BB_SMEM_TOTAL, stream>>>(args, tile0);
+    PE_LAUNCH_CHECK("pe_bwd_bchain_kernel");
+    DwArgs D = {};
+    D.stash = args.bstash; D.tile_begin = args.tile_begin; D.images = args.f.images; D.tile_capacity = args.tile_capacity;
+    D.tile0 = tile0; D.scale = args.scale + 4; D.gw = args.gw; D.tile_bytes = BS_BYTES; D.bender = 1;
+    D.splits = (int)pe_min64(pe_min64(args.tile_capacity, 65535), (2 * sm_count + DW_BENDER_ITEMS - 1) / DW_BENDER_ITEMS);
+    if (D.splits < 1) D.splits = 1;
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_TOTAL));
+    pe_bwd_dw_kernel<<<dim3(DW_BENDER_ITEMS, D.splits), DW_THREADS, DW_SMEM_TOTAL, stream>>>(D);
     PE_LAUNCH_CHECK("pe_bwd_dw_kernel");
     return PE_OK;
 }

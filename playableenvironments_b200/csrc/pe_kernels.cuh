@@ -171,7 +171,7 @@ struct PeBwdTcArgs {
 };
 #define PE_BWD_TILE 128
 #define PE_BWD_FS_CHUNKS 1349      // field stash chunks per tile: activations hi + lo (624) + AdaIn inputs (48) + gradients hi + lo (658) + ReLU-mask words (19)
-#define PE_BWD_BS_CHUNKS 212       // ray-bender stash chunks per tile
+#define PE_BWD_BS_CHUNKS 423       // ray-bender stash chunks per tile (activations, gradients as hi + lo, masks, clamp state)
 bool pe_bwd_tc_object_ok(const PeObjectDesc& ob);
 int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream);
 // every launch covers the tiles [tile0, tile0 + args.tile_capacity) of the compacted numbering (one stash batch)
@@ -180,6 +180,9 @@ int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scr
 int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int sm_count, cudaStream_t stream);
 int pe_launch_bwd_dw(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream);
 size_t pe_bwd_tc_stash_bytes(int64_t tiles);
+bool pe_bwd_tc_bender_ok(const PeObjectDesc& ob, const PeLayout& L);
+int pe_launch_bwd_scale_bender(const PeBwdTcArgs& args, float* scale, unsigned int* scratch, cudaStream_t stream);
+int pe_launch_bwd_bender(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream);   // recompute + chain + dW of the ray bender
 
 size_t pe_field_bwd_smem_bytes();
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);
