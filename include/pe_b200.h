@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 2
+#define PE_ABI_VERSION 3
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -87,6 +87,8 @@ typedef struct PeScene {
     int32_t apply_activation;  /* sigmoid on features (object_composer.py:548-549)           */
     int32_t precision;         /* PePrecision                                                */
     int32_t explicit_positions;/* 0: sample along rays; 1: field evaluation on given points  */
+    int32_t keep_samples;      /* 1: the forward leaves every per-sample tensor, AdaIn constant and BatchNorm sum in its workspace,
+                                  which the caller keeps and hands to pe_render_backward_saved (no forward recompute there) */
     PeObjectDesc object[PE_MAX_OBJECTS];
 } PeScene;
 
@@ -194,6 +196,12 @@ size_t pe_backward_workspace_bytes(const PeScene* scene);
 int    pe_render_backward(const PeScene* scene, const PeInputs* in, const PeObjectParams* params,
                           const PeOutGrads* grad_out, const PeInGrads* grad_in,
                           void* workspace, size_t workspace_bytes, pe_stream_t stream);
+/* Same, on top of the workspace a pe_render_forward call with scene->keep_samples = 1 filled (`saved_forward`, untouched since;
+ * the scene must be that call's scene): what autograd's saved tensors are to the reference (training/trainer.py:643).         */
+int    pe_render_backward_saved(const PeScene* scene, const PeInputs* in, const PeObjectParams* params,
+                                const PeOutGrads* grad_out, const PeInGrads* grad_in,
+                                const void* saved_forward, size_t saved_forward_bytes,
+                                void* workspace, size_t workspace_bytes, pe_stream_t stream);
 
 /* -- stand-alone operators (module-level API of the reference) ---------------------------------- */
 /* PositionalEncoder.forward / AnnealablePositionalEncoder.forward

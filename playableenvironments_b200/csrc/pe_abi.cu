@@ -82,7 +82,11 @@ static bool tc_allowed(const PeScene& s) {
 static thread_local bool g_keep_samples = false;
 // ... and whether that recompute may run the ray bender on the tensor cores (the forward it mirrors did: a performance mode)
 static thread_local bool g_recompute_tc_bender = false;
-struct KeepSamples { bool prev; KeepSamples() : prev(g_keep_samples) { g_keep_samples = true; } ~KeepSamples() { g_keep_samples = prev; } };
+struct KeepSamples {
+    bool prev;
+    explicit KeepSamples(bool on = true) : prev(g_keep_samples) { g_keep_samples = on; }
+    ~KeepSamples() { g_keep_samples = prev; }
+};
 
 // Arithmetic of one object.  The mixed mode keeps objects with fewer than 64 samples per ray in the fp32-class mode: alpha = 1 - exp(-relu(raw) * delta)
 // amplifies an absolute raw-alpha error by the sample spacing delta (court P = 4: delta ~ 20, Minecraft ground in front of the skybox: ~85;
@@ -121,6 +125,8 @@ static bool object_folds_head(const PeScene& s, int k) {
     return object_uses_tc(s, k) && !needs_feature_buffer(s, k) && !s.apply_activation && s.object[k].positions % 32 == 0;
 }
 
+static bool backward_on_tc(const PeScene& s, int k);
+
 static Workspace carve(const PeScene& s, void* base) {
     Workspace w = {};
     size_t off = 0;
@@ -147,7 +153,8 @@ static Workspace carve(const PeScene& s, void* base) {
         // train-mode recompute for the backward on the tensor cores: the trunk output of every evaluated sample, so that the two
         // BatchNorm-reduction passes of the field backward start from it (PE_BWD_TRUNK_CACHE=0 disables)
         const char* cenv = getenv("PE_BWD_TRUNK_CACHE");
-        const bool cache = g_keep_samples && s.training && (object_uses_tc(s, k) || prepass) && !(cenv && atoi(cenv) == 0);
+        const bool cache = g_keep_samples && s.training && (object_uses_tc(s, k) || prepass) && !(cenv && atoi(cenv) == 0) &&
+                           !backward_on_tc(s, k);      // (only the fp32 field backward reads it)
         o.h7 = cache ? (float*)take(n * d.width * 4) : nullptr;
         o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
         o.aff2 = (float*)take((size_t)s.images * d.width * 4);
@@ -173,6 +180,7 @@ static int validate_scene(const PeScene& s) {
 
 extern "C" size_t pe_workspace_bytes(const PeScene* scene) {
     if (!scene || validate_scene(*scene) != PE_OK) return 0;
+    if (scene->keep_samples) { KeepSamples keep; return carve(*scene, nullptr).bytes + 256; }
     return carve(*scene, nullptr).bytes + 256;
 }
 
@@ -184,6 +192,8 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     if (rc != PE_OK) return rc;
     cudaStream_t stream = (cudaStream_t)stream_;
     if ((size_t)workspace % 256) { pe_set_error("workspace must be 256-byte aligned"); return PE_ERR_WORKSPACE; }
+    // keep_samples: every per-sample tensor lands in the (caller-kept) workspace, like the backward's own forward recompute
+    KeepSamples keep_guard(s.keep_samples != 0 || g_keep_samples);
     const Workspace ws = carve(s, workspace);
     if (ws.bytes > workspace_bytes) { pe_set_error("workspace too small: %zu < %zu", workspace_bytes, ws.bytes); return PE_ERR_WORKSPACE; }
     if (s.perturb && !s.explicit_positions) {
@@ -258,7 +268,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
                 // but the tensor core's own fp32 accumulation) lands at ~3e-4 of the reference on the rendered outputs: used in the
                 // performance modes (mixed, fp16, fp16x2); the parity-first mode (fp16x3) keeps the exact fp32 bender.  PE_TC_BENDER=0/1 forces.
                 const char* benv = getenv("PE_TC_BENDER");
-                const bool tc_bender = benv ? atoi(benv) != 0 : (g_keep_samples ? g_recompute_tc_bender : s.precision != PE_PRECISION_FP16X3);
+                const bool tc_bender = benv ? atoi(benv) != 0 : ((g_keep_samples && !s.keep_samples) ? g_recompute_tc_bender : s.precision != PE_PRECISION_FP16X3);
                 if (pe_tc_bender_ok(d) && tc_bender) {
                     // 1a. exact fp32 sampling: t, positions, outer mask; empty-space values everywhere
                     rc2 = pe_launch_sample(pre, sm_count, stream); if (rc2) return rc2;
@@ -411,7 +421,7 @@ static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? (char*)base + off : nullptr; off = (off + bytes + 255) / 256 * 256; return p; };
     KeepSamples keep;
-    w.fwd_bytes = carve(s, nullptr).bytes;
+    w.fwd_bytes = s.keep_samples ? 0 : carve(s, nullptr).bytes;       // (a saved forward lives in the caller's buffer)
     w.fwd = take(w.fwd_bytes);
     for (int k = 0; k < s.objects; ++k) {
         const PeObjectDesc& d = s.object[k];
@@ -458,19 +468,32 @@ static int backward_grid() {
     return pe_field_bwd_grid(sm);
 }
 
+// With a saved forward (scene.keep_samples) the backward takes its path decisions from the scene itself -- the saved workspace was carved
+// for it -- instead of the recompute's fp32-class scene.
+static PeScene backward_scene_for(const PeScene& scene) { return scene.keep_samples ? scene : backward_scene(scene); }
+
 extern "C" size_t pe_backward_workspace_bytes(const PeScene* scene) {
     if (!scene || validate_scene(*scene) != PE_OK) return 0;
     if (scene->explicit_positions) { pe_set_error("backward on explicit positions is not supported"); return 0; }
-    return carve_backward(backward_scene(*scene), nullptr, backward_grid()).bytes + 256;
+    return carve_backward(backward_scene_for(*scene), nullptr, backward_grid()).bytes + 256;
 }
 
 extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, const PeObjectParams* params, const PeOutGrads* grad_out,
                                   const PeInGrads* grad_in, void* workspace, size_t workspace_bytes, pe_stream_t stream_) {
+    if (scene && scene->keep_samples) { pe_set_error("scene.keep_samples is set: call pe_render_backward_saved with the kept forward workspace"); return PE_ERR_INVALID; }
+    return pe_render_backward_saved(scene, in, params, grad_out, grad_in, nullptr, 0, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int pe_render_backward_saved(const PeScene* scene, const PeInputs* in, const PeObjectParams* params, const PeOutGrads* grad_out,
+                                        const PeInGrads* grad_in, const void* saved_forward, size_t saved_forward_bytes, void* workspace,
+                                        size_t workspace_bytes, pe_stream_t stream_) {
     if (!scene || !in || !params || !grad_out || !grad_in) { pe_set_error("null argument"); return PE_ERR_INVALID; }
     int rc = validate_scene(*scene);
     if (rc != PE_OK) return rc;
     if (scene->explicit_positions) { pe_set_error("backward on explicit positions is not supported"); return PE_ERR_UNSUPPORTED; }
-    const PeScene s = backward_scene(*scene);
+    if ((saved_forward != nullptr) != (scene->keep_samples != 0)) { pe_set_error("a saved forward workspace goes with scene.keep_samples = 1, and only with it"); return PE_ERR_INVALID; }
+    if (saved_forward && scene->precision == PE_PRECISION_FP32) { pe_set_error("the saved-forward backward needs a tensor-core precision mode (compacted sample lists come from its masks)"); return PE_ERR_UNSUPPORTED; }
+    const PeScene s = backward_scene_for(*scene);
     cudaStream_t stream = (cudaStream_t)stream_;
     if ((size_t)workspace % 256) { pe_set_error("workspace must be 256-byte aligned"); return PE_ERR_WORKSPACE; }
     int sm_count = 148;
@@ -481,13 +504,18 @@ extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, cons
     if (bw.bytes > workspace_bytes) { pe_set_error("backward workspace too small: %zu < %zu", workspace_bytes, bw.bytes); return PE_ERR_WORKSPACE; }
     if (s.images == 0 || s.rays == 0) return PE_OK;
 
-    // 1. recompute the forward: per-sample t / raw alpha / features / |displacement| / in-box flags, AdaIn scale-shift, BatchNorm sums
+    // 1. the forward's per-sample t / raw alpha / features / |displacement| / in-box flags, AdaIn scale-shift, BatchNorm sums: kept by the
+    //    caller's forward, or recomputed here
     const PeOutputs none = {};
     KeepSamples keep;
-    g_recompute_tc_bender = scene->precision == PE_PRECISION_MIXED || scene->precision == PE_PRECISION_FP16 || scene->precision == PE_PRECISION_FP16X2;
-    rc = pe_render_forward(&s, in, &none, bw.fwd, bw.fwd_bytes, stream_);
-    if (rc != PE_OK) return rc;
-    const Workspace ws = carve(s, bw.fwd);
+    if (saved_forward) {
+        if ((size_t)saved_forward % 256 || carve(s, nullptr).bytes > saved_forward_bytes) { pe_set_error("saved forward workspace: misaligned or too small"); return PE_ERR_WORKSPACE; }
+    } else {
+        g_recompute_tc_bender = scene->precision == PE_PRECISION_MIXED || scene->precision == PE_PRECISION_FP16 || scene->precision == PE_PRECISION_FP16X2;
+        rc = pe_render_forward(&s, in, &none, bw.fwd, bw.fwd_bytes, stream_);
+        if (rc != PE_OK) return rc;
+    }
+    const Workspace ws = carve(s, saved_forward ? const_cast<void*>(saved_forward) : bw.fwd);
     PE_CUDA_CHECK(cudaMemsetAsync(bw.zero_begin, 0, bw.zero_bytes, stream));
 
     // 2. compositing backward

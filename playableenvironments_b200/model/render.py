@@ -107,7 +107,16 @@ def _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep) 
     return ins
 
 
-def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms) -> Dict:
+def _save_forward(meta) -> bool:
+    """Training calls in a tensor-core mode keep the forward's workspace (per-sample tensors, masks, BatchNorm sums) for the
+    backward instead of recomputing the forward there (PE_SAVE_FORWARD=0: recompute; the exact fp32 mode always recomputes,
+    in the fp32-class tensor-core mode)."""
+    import os
+    return meta["precision"] != _cabi.PRECISION_FP32 and os.environ.get("PE_SAVE_FORWARD", "1") != "0"
+
+
+def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Optional[List] = None) -> Dict:
+    """``saved``: a list that receives the kept forward workspace (autograd path, see ``_save_forward``)."""
     device = dirs.device
     L = _cabi.lib()
     descs = meta["descs"]
@@ -139,10 +148,16 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms) -> Dict:
     _fill(outs.global_, g)
     results["global"] = g
     with torch.cuda.device(device):
+        if saved is not None:
+            scene.keep_samples = 1
         nbytes = L.pe_workspace_bytes(C.byref(scene))
         if nbytes == 0:
             raise _cabi.PeError(f"pe_workspace_bytes: {L.pe_last_error().decode()}")
-        ws = _Workspace.get(device, nbytes)
+        if saved is not None:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)       # lives with the autograd node, not in the call cache
+            saved.append(ws)
+        else:
+            ws = _Workspace.get(device, nbytes)
         _cabi.check(L.pe_render_forward(C.byref(scene), C.byref(ins), C.byref(outs), _cabi.ptr(ws), ws.numel(),
                                         _cabi.current_stream(device)))
     del keep
@@ -158,7 +173,9 @@ class RenderFunction(torch.autograd.Function):
     def forward(ctx, meta, origins, dirs, w2o, *flat):
         K = len(meta["descs"])
         styles, deforms = list(flat[:K]), list(flat[K:2 * K])
-        res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms)
+        saved = [] if _save_forward(meta) else None
+        res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms, saved)
+        ctx.saved_forward = saved[0] if saved else None
         ctx.meta = meta
         # the descs in ``meta`` hold RAW pointers into each model's packed blob: keep those tensors alive with the graph (a second
         # forward before this node's backward may repack -- train-mode BatchNorm bumps the running statistics every call)
@@ -223,12 +240,18 @@ class RenderFunction(torch.autograd.Function):
                     else:
                         getattr(gin.params[k], field)[i] = _cabi.ptr(g)
         with torch.cuda.device(device):
+            fwd_ws = ctx.saved_forward
+            scene.keep_samples = 1 if fwd_ws is not None else 0
             nbytes = L.pe_backward_workspace_bytes(C.byref(scene))
             if nbytes == 0:
                 raise _cabi.PeError(f"pe_backward_workspace_bytes: {L.pe_last_error().decode()}")
             ws = _Workspace.get(device, nbytes)
-            _cabi.check(L.pe_render_backward(C.byref(scene), C.byref(ins), params, C.byref(gout), C.byref(gin), _cabi.ptr(ws), ws.numel(),
-                                             _cabi.current_stream(device)))
+            if fwd_ws is not None:
+                _cabi.check(L.pe_render_backward_saved(C.byref(scene), C.byref(ins), params, C.byref(gout), C.byref(gin), _cabi.ptr(fwd_ws),
+                                                       fwd_ws.numel(), _cabi.ptr(ws), ws.numel(), _cabi.current_stream(device)))
+            else:
+                _cabi.check(L.pe_render_backward(C.byref(scene), C.byref(ins), params, C.byref(gout), C.byref(gin), _cabi.ptr(ws), ws.numel(),
+                                                 _cabi.current_stream(device)))
         del keep
         return (None, g_origins, g_dirs, g_w2o, *g_styles, *g_deforms, *g_params)
 

@@ -53,15 +53,19 @@ def run_backward(name, training, precision="fp32"):
     return golden, float(loss.item()), got_in, got_par
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 @pytest.mark.parametrize("name,training,tol", TC_GRAD_CASES)
-def test_tensor_core_backward_matches_reference_autograd(name, training, tol, monkeypatch):
+def test_tensor_core_backward_matches_reference_autograd(name, training, tol, precision, monkeypatch):
+    """precision fp32: exact forward, the backward recomputes it (fp32-class tensor-core mode); fp16x3: the forward keeps its workspace
+    for the backward (pe_render_backward_saved, what every tensor-core mode does in training)."""
     monkeypatch.setenv("PE_BWD_TC", "1")
-    golden, loss, got_in, got_par = run_backward(name, training)
+    golden, loss, got_in, got_par = run_backward(name, training, precision=precision)
     assert abs(loss - float(golden["loss"])) <= 2e-4 * max(1.0, abs(float(golden["loss"])))
     bad = compare_grads(got_in, got_par, golden, tol)
     assert not bad, bad
     # parameter gradients (sums over all samples) are far better conditioned than per-ray input gradients: held to 1e-2 of the fp32 path
     monkeypatch.setenv("PE_BWD_TC", "0")
+    monkeypatch.setenv("PE_SAVE_FORWARD", "0")
     _, _, _, ref_par = run_backward(name, training)
     for k, v in got_par.items():
         if "nerf_model" in k:
