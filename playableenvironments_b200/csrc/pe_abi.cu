@@ -375,7 +375,7 @@ static bool backward_compacts(const PeScene& s, int k) {
 }
 
 // The field backward of the shipped field shape runs on the tensor cores (pe_bwd_tc.cu) over tiles of 128 compacted samples; PE_BWD_TC=0
-// keeps it on the exact fp32 kernel.  Its activation / gradient stash holds `capacity` tiles (2.76 MB each: every operand as a hi + lo fp16 pair); more tiles than that are
+// keeps it on the exact fp32 kernel.  Its activation / gradient stash holds `capacity` tiles (1.45 MB each); more tiles than that are
 // processed in batches (the number of in-box samples is only known on the device, so the batch count is the worst case and surplus
 // launches find no tile).
 static bool backward_on_tc(const PeScene& s, int k) {

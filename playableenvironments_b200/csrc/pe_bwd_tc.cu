@@ -20,20 +20,19 @@ using namespace pe;
 using namespace pe_tc;
 
 // ---- stash map: chunk offsets inside a tile's block (PE_BWD_FS_CHUNKS chunks of 2048 B) ----
-// Every activation / gradient is kept as a hi + lo fp16 pair (the gradient sums cancel heavily: the backward needs fp32-class operands
-// throughout, see "Numerics" below); the lo copies live FS_ALO / FS_GLO chunks above the hi ones.
+// The stash feeds dW = G^T A, a sum over ~10^5..10^6 samples: plain fp16 copies are enough there (measured: adding the lo halves of G and A
+// as two more products changes no parameter gradient by more than 1e-4 of its scale) -- unlike the operands of the recompute and of the dX
+// chain, which stay hi + lo pairs in shared memory (see "Numerics" below).
 __host__ __device__ constexpr int FS_H(int l) { return l < 4 ? 32 * l : 136 + 32 * (l - 4); }   // h0..h3 | enc | h4..h7: [h3 | enc] is contiguous
-constexpr int FS_ENC = 128, FS_Y1 = 264, FS_Y2 = 296;          // activations hi: [0, 312)
-constexpr int FS_ALO = 312;                                    // activations lo: [312, 624)
-constexpr int FS_X1 = 624, FS_X2 = 656;                        // AdaIn inputs (hi only): [624, 672)
-constexpr int FS_GF = 672;                                     // 24 chunks (192 columns); a 128-row block starting at column 128 over-reads into GP(0)
+constexpr int FS_ENC = 128, FS_Y1 = 264, FS_Y2 = 296;          // activations: [0, 312)
+constexpr int FS_X1 = 312, FS_X2 = 344;                        // AdaIn inputs: [312, 360)
+constexpr int FS_GF = 360;                                     // 24 chunks (192 columns); a 128-row block starting at column 128 over-reads into GP(0)
 __host__ __device__ constexpr int FS_GP(int l) { return FS_GF + 24 + 32 * l; }
-constexpr int FS_GX1 = FS_GF + 24 + 256, FS_GX2 = FS_GX1 + 32;  // gradients hi: [672, 1000)
-constexpr int FS_GLO = 328;                                    // gradients lo: [1000, 1328)
-constexpr int FS_GRAW = 1328, FS_MASK = 1330;                  // 16-column operand [graw hi | graw lo | 0 ...]; ReLU-mask words
+constexpr int FS_GX1 = FS_GF + 24 + 256, FS_GX2 = FS_GX1 + 32;  // gradients: [360, 688)
+constexpr int FS_GRAW = 688, FS_MASK = 690;                    // 16-column operand [graw hi | graw lo | 0 ...]; ReLU-mask words
 // mask words (uint32, [word][row]): h_l -> words 8l .. 8l+7, y1 -> 64..71, y2 -> 72..75
 constexpr int MASK_Y1 = 64, MASK_Y2 = 72, MASK_WORDS = 76;
-static_assert(FS_GX2 + 16 == 1000 && FS_GX2 + 16 + FS_GLO == FS_GRAW, "stash map");
+static_assert(FS_GX2 + 16 == FS_GRAW, "stash map");
 static_assert(FS_MASK * 2048 + MASK_WORDS * 512 <= PE_BWD_FS_CHUNKS * 2048, "stash block too small");
 constexpr int64_t FS_BYTES = (int64_t)PE_BWD_FS_CHUNKS * CHUNK_BYTES;
 
@@ -156,7 +155,7 @@ __device__ __forceinline__ void split_store8(unsigned char* hi_dst, unsigned cha
 }
 
 // MODE 0: trunk layer  y = relu(acc);  MODE 2: AdaIn layer  x = acc (stashed), y = relu(x * sc + sh)
-// smem: hi / lo operand buffers (or NULL: last layer); st_y: stash chunk base of the layer's hi copy (lo copy FS_ALO chunks above)
+// smem: hi / lo operand buffers (or NULL: last layer); st_y: stash chunk base of the layer (plain fp16 copy)
 template <int MODE, int N>
 __device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* a_hi, unsigned char* a_lo, int m, const float* __restrict__ c0s,
                                              const float* __restrict__ c1s, unsigned char* st_y, unsigned char* st_x, uint32_t* mask_words, bool store) {
@@ -192,7 +191,7 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* a_hi,
         for (int cc = 0; cc < 4; ++cc) {
             const int off = (c * 4 + cc) * CHUNK_BYTES + m * 16;
             if (a_hi) split_store8(a_hi + off, a_lo + off, y + 8 * cc, true);
-            if (store) split_store8(st_y + off, st_y + (int64_t)FS_ALO * CHUNK_BYTES + off, y + 8 * cc, true);
+            if (store) split_store8(st_y + off, nullptr, y + 8 * cc, true);
         }
     }
 }
@@ -330,7 +329,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_fwd_kernel(const PeBw
                     for (int c = 0; c < 4; ++c) {
                         const int off = (4 * h + c) * CHUNK_BYTES + m * 16;
                         split_store8(a_hi + PE_CHUNK0 * CHUNK_BYTES + off, a_lo + PE_CHUNK0 * CHUNK_BYTES + off, enc + 8 * c, false);
-                        if (r.store) split_store8(st + FS_ENC * CHUNK_BYTES + off, st + (int64_t)(FS_ENC + FS_ALO) * CHUNK_BYTES + off, enc + 8 * c, false);
+                        if (r.store) split_store8(st + FS_ENC * CHUNK_BYTES + off, nullptr, enc + 8 * c, false);
                     }
                 }
             }
@@ -410,7 +409,7 @@ __device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char
 }
 
 // KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
-template <int KIND, int NB = 8, int LO_CHUNKS = FS_GLO>
+template <int KIND, int NB = 8>
 __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw, bool store) {
     const int fexp = renorm_exp(C.mop, C.km);
     const int km = C.km + fexp;
@@ -441,7 +440,7 @@ __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[i] = y[8 * cc + i] * r_stash;
                 const int off = (c * 4 + cc) * CHUNK_BYTES + C.m * 16;
-                split_store8(st_g + off, st_g + (int64_t)LO_CHUNKS * CHUNK_BYTES + off, z, false);
+                split_store8(st_g + off, nullptr, z, false);
             }
         }
     }
@@ -504,7 +503,7 @@ __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t
 #pragma unroll
                         for (int i = 0; i < 8; ++i) z[i] = g[8 * cc + i] * r_stash;
                         const int off = (c * 4 + cc) * CHUNK_BYTES + C.m * 16;
-                        split_store8(st_g + off, st_g + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+                        split_store8(st_g + off, nullptr, z, false);
                     }
                 }
             }
@@ -676,7 +675,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                     store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
                     if (store && r.store) {
                         const int off = (FS_GF + c) * CHUNK_BYTES + m * 16;
-                        split_store8(st + off, st + (int64_t)FS_GLO * CHUNK_BYTES + off, z, false);
+                        split_store8(st + off, nullptr, z, false);
                     }
                 }
                 if (store && r.store) {          // columns 0, 1 of a 16-column operand: S * dL/d raw alpha as hi, lo (d alpha_head.weight = h7^T graw)
@@ -830,11 +829,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
 //     field's chain, and dL/d |displacement|) -> dW through pe_bwd_dw_kernel with the bender's item table.
 // =====================================================================================================================
 __host__ __device__ constexpr int BS_H(int l) { return l < 3 ? 16 * l : 60 + 16 * (l - 3); }     // bh0..bh2 | input (12) | bh3..bh5: [bh2 | input] contiguous
-constexpr int BS_ENC = 48, BS_ALO = 108;                       // activations hi [0, 108), lo [108, 216)
-constexpr int BS_GOUT = 216;                                   // 4 chunks (3 real columns); a 128-row block over-reads into GP(0)
-__host__ __device__ constexpr int BS_GP(int l) { return 220 + 16 * l; }
-constexpr int BS_GLO = 100;                                    // gradients hi [216, 316), lo [316, 416)
-constexpr int BS_MASK = 416, BS_AUX = 422;                     // mask words [layer][4][row]; per row: clamp bits, displacement xyz (fp32)
+constexpr int BS_ENC = 48;                                     // activations [0, 108)
+constexpr int BS_GOUT = 108;                                   // 4 chunks (3 real columns); a 128-row block over-reads into GP(0)
+__host__ __device__ constexpr int BS_GP(int l) { return 112 + 16 * l; }   // gradients [108, 208)
+constexpr int BS_MASK = 208, BS_AUX = 214;                     // mask words [layer][4][row]; per row: clamp bits, displacement xyz (fp32)
 static_assert(BS_AUX + 1 == PE_BWD_BS_CHUNKS, "bender stash map");
 constexpr int64_t BS_BYTES = (int64_t)PE_BWD_BS_CHUNKS * CHUNK_BYTES;
 constexpr int BB_A_CHUNKS = 28, BB_ENC_CHUNK0 = 16;            // operand buffers: K columns 0..127 activations, 128..223 the bender's input
@@ -1007,7 +1005,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bfwd_kernel(const PeB
                     }
                     const int off = c * CHUNK_BYTES + m * 16;
                     split_store8(a_hi + BB_ENC_CHUNK0 * CHUNK_BYTES + off, a_lo + BB_ENC_CHUNK0 * CHUNK_BYTES + off, v, false);
-                    if (r.store) split_store8(st + BS_ENC * CHUNK_BYTES + off, st + (int64_t)(BS_ENC + BS_ALO) * CHUNK_BYTES + off, v, false);
+                    if (r.store) split_store8(st + BS_ENC * CHUNK_BYTES + off, nullptr, v, false);
                 }
             }
             sync.arrive_ready();
@@ -1029,7 +1027,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bfwd_kernel(const PeB
                     for (int cc = 0; cc < 4; ++cc) {
                         const int off = (c * 4 + cc) * CHUNK_BYTES + m * 16;
                         split_store8(a_hi + off, a_lo + off, y + 8 * cc, true);
-                        if (r.store) split_store8(st + BS_H(l) * CHUNK_BYTES + off, st + (int64_t)(BS_H(l) + BS_ALO) * CHUNK_BYTES + off, y + 8 * cc, true);
+                        if (r.store) split_store8(st + BS_H(l) * CHUNK_BYTES + off, nullptr, y + 8 * cc, true);
                     }
                 }
                 sync.arrive_ready();
@@ -1195,7 +1193,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
                     store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
                     if (r.store) {
                         const int off = (BS_GOUT + c) * CHUNK_BYTES + m * 16;
-                        split_store8(st + off, st + (int64_t)BS_GLO * CHUNK_BYTES + off, z, false);
+                        split_store8(st + off, nullptr, z, false);
                     }
                 }
             }
@@ -1204,7 +1202,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
 #pragma unroll 1
             for (int l = 5; l >= 3; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0, 4, BS_GLO>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                chain_epilogue_plain<0, 4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
                 sync.arrive_ready();
             }
             // ---- step 3: the input half of the skip layer's input gradient, parked (hi + lo) behind the activations ----
@@ -1236,7 +1234,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
 #pragma unroll 1
             for (int l = 2; l >= 0; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0, 4, BS_GLO>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                chain_epilogue_plain<0, 4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
                 sync.arrive_ready();
             }
             // ---- step 7: gradient of the bender's input = layer 0's input gradient + the parked half ----
@@ -1324,13 +1322,12 @@ struct DwArgs {
     int32_t splits, bender;
     PeObjectParamGrads gw;
 };
-constexpr int DW_BASE_ITEMS = 25, DW_ITEMS = 3 * DW_BASE_ITEMS;
+constexpr int DW_ITEMS = 25;
 
-// Work item `idx` = (base product, term): every product G^T A runs as three fp16 products G_hi A_hi + G_lo A_hi + G_hi A_lo.
+// Work item `base`:
 //   base 0-15: trunk layer l = base / 2, output rows 128 (base % 2) ..;  16-17: the encoding columns of the skip layer;  18-19: head layer 0;
 //   20: head layer 3;  21-22: head layer 6 (192 rows);  23-24: alpha head (M operand = trunk output, N operand = [graw hi | graw lo])
-__device__ __forceinline__ bool dw_item(int idx, const PeObjectParamGrads& gw, DwItem& it) {
-    const int base = idx / 3, term = idx - 3 * base;
+__device__ __forceinline__ bool dw_item(int base, const PeObjectParamGrads& gw, DwItem& it) {
     it.rows = 128; it.fold = 0; it.bias = nullptr; it.out = nullptr;
     float* bias = nullptr;
     if (base < 16) {
@@ -1359,21 +1356,17 @@ __device__ __forceinline__ bool dw_item(int idx, const PeObjectParamGrads& gw, D
         if (gw.head6_b) bias = gw.head6_b + mb * 128;
     } else {
         const int mb = base - 23;
-        if (term == 2) return false;
-        it.ld = 1; it.g_chunk = FS_H(7) + 16 * mb + (term == 1 ? FS_ALO : 0); it.a_chunk = FS_GRAW; it.n = 16; it.cols = 2; it.fold = 1;
+        it.ld = 1; it.g_chunk = FS_H(7) + 16 * mb; it.a_chunk = FS_GRAW; it.n = 16; it.cols = 2; it.fold = 1;
         if (gw.alpha_w) it.out = gw.alpha_w + mb * 128;
         return it.out != nullptr;
     }
-    if (term == 1) it.g_chunk += FS_GLO;
-    if (term == 2) it.a_chunk += FS_ALO;
-    if (term != 2) it.bias = bias;          // column sums of G_hi and of G_lo
+    it.bias = bias;
     if (!it.out) it.cols = 0;
     return it.out != nullptr || it.bias != nullptr;
 }
 // the ray bender's products: base 0-5: layer l (128 rows; the skip layer's N operand is [bh2 | input], contiguous in the stash); 6: output head
-constexpr int DW_BENDER_ITEMS = 3 * 7;
-__device__ __forceinline__ bool dw_item_bender(int idx, const PeObjectParamGrads& gw, DwItem& it) {
-    const int base = idx / 3, term = idx - 3 * base;
+constexpr int DW_BENDER_ITEMS = 7;
+__device__ __forceinline__ bool dw_item_bender(int base, const PeObjectParamGrads& gw, DwItem& it) {
     it.rows = 128; it.fold = 0; it.bias = nullptr; it.out = nullptr;
     float* bias = nullptr;
     if (base < 6) {
@@ -1389,9 +1382,7 @@ __device__ __forceinline__ bool dw_item_bender(int idx, const PeObjectParamGrads
         it.g_chunk = BS_GOUT; it.a_chunk = BS_H(5); it.n = 128; it.cols = 128; it.ld = 128; it.rows = 3;
         it.out = gw.bender_out_w;
     }
-    if (term == 1) it.g_chunk += BS_GLO;
-    if (term == 2) it.a_chunk += BS_ALO;
-    if (term != 2) it.bias = bias;
+    it.bias = bias;
     if (!it.out) it.cols = 0;
     return it.out != nullptr || it.bias != nullptr;
 }

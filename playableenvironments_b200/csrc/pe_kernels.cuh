@@ -170,8 +170,8 @@ struct PeBwdTcArgs {
     float* g_deformation;          // accumulated [images][D] or NULL
 };
 #define PE_BWD_TILE 128
-#define PE_BWD_FS_CHUNKS 1349      // field stash chunks per tile: activations hi + lo (624) + AdaIn inputs (48) + gradients hi + lo (658) + ReLU-mask words (19)
-#define PE_BWD_BS_CHUNKS 423       // ray-bender stash chunks per tile (activations, gradients as hi + lo, masks, clamp state)
+#define PE_BWD_FS_CHUNKS 709       // field stash chunks per tile: activations (312) + AdaIn inputs (48) + gradients (330) + ReLU-mask words (19)
+#define PE_BWD_BS_CHUNKS 215       // ray-bender stash chunks per tile: activations (108), gradients (100), masks (6), clamp state (1)
 bool pe_bwd_tc_object_ok(const PeObjectDesc& ob);
 int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream);
 // every launch covers the tiles [tile0, tile0 + args.tile_capacity) of the compacted numbering (one stash batch)
