@@ -144,6 +144,19 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     // samples as N) so that its epilogue can sum over a ray's samples inside one thread; both operands are
                     // K-major in the same canonical layout, so the two descriptors simply swap roles
                     if (kStats && swap && n == 256) mma_layer<true, 2, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                    else if (!kPasses && kFoldOnly) {
+                        // mixed mode, headline instantiation: one copy of the issue loop per pass count, so that both run with a
+                        // compile-time trip count like the single-mode instantiations
+                        if (R.num_passes == 2) {
+                            R.num_passes = 2;
+                            if (swap) mma_layer<true, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                            else mma_layer<false, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                        } else {
+                            R.num_passes = 1;
+                            if (swap) mma_layer<true, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                            else mma_layer<false, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
+                        }
+                    }
                     else if (swap) mma_layer<true, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     else mma_layer<false, 1, x3>(R, l, n, slabs, chunk0, has_bias, idesc, lbo_b);
                     if (has_bias) {          // D += ones(128x16) * [bias_hi | bias_lo | 0..]^T : the bias, at fp32-class accuracy
