@@ -188,15 +188,17 @@ def gpu_eager_reference(device, tennis_hw=(144, 256)):
 def train_step_report(device, dense: bool, precision: str = "mixed", world: int = 1):
     """BASELINE configs[2]: Tennis scene (court + 2 players with positional ray benders, composed), 256x144 rays, forward and
     forward+backward through ObjectComposer with every parameter and every differentiable input requiring a gradient.
-    Secondary figures (the headline stays configs[1]).  precision fp16x3 (the composer's default): train-mode forward and the
-    backward's forward recompute on the tensor cores (fp32-class mode), field backward on the exact fp32 CUDA-core kernel;
-    precision fp32: everything on the CUDA cores."""
+    Secondary figures (the headline stays configs[1]).  precision mixed (the composer's default): train-mode forward on the tensor
+    cores, kept for the backward; field and ray-bender backward on the tensor cores (recompute with stash -> dX chain -> dW);
+    precision fp32: everything on the CUDA cores (round 1's path).  world > 1: one frame per rank + ONE all-reduce of the flat
+    gradient bucket (data-parallel step, train.py:61)."""
     import scenes
     from helpers import INPUT_KEYS
     from gpu_common import build_composer
     scene = scenes.scene_tennis(seed=13, height=144, width=256, stride=1, lead=(1, 1, 1), dense=dense)
     if precision == "fp32":
         os.environ["PE_TC_BACKWARD_RECOMPUTE"] = "0"
+        os.environ["PE_BWD_TC"] = "0"
     config, state, inputs, comp, dev = build_composer(scene, precision, device=device, training=True)
     comp.allow_forward_without_grad = False
     dev = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in dev.items()}
@@ -240,6 +242,7 @@ def train_step_report(device, dense: bool, precision: str = "mixed", world: int 
         inbox += int((ra != float(m["empty_space_alpha"])).sum().item())
     ms_f, ms_fb = timed(fwd, 3), timed(fwd_bwd, 3)
     os.environ.pop("PE_TC_BACKWARD_RECOMPUTE", None)
+    os.environ.pop("PE_BWD_TC", None)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms_f, ms_fb], dtype=torch.float64, device=device)
@@ -249,7 +252,8 @@ def train_step_report(device, dense: bool, precision: str = "mixed", world: int 
     return {"n_gpus": world, "gradient_allreduce_bytes": sum(p.numel() for p in params) * 4 if world > 1 else 0,"workload": f"cfg3 Tennis{' (dense: camera on a player)' if dense else ''}: court P=4 + 2 players P=32 with ray benders, 256x144 rays, train-mode BatchNorm",
             "sample_slots": slots, "in_box_samples": inbox, "fwd_ms": ms_f, "fwd_bwd_ms": ms_fb,
             "in_box_samples_per_s_fwd_bwd": inbox / (ms_fb / 1e3),
-            "precision": "fp32 (CUDA cores only)" if precision == "fp32" else f"{precision} forward + recompute on tensor cores, fp32 field backward"}
+            "precision": "fp32 (CUDA cores only; the backward recomputes the forward)" if precision == "fp32"
+            else f"{precision} forward, its workspace kept for the backward; field and ray-bender backward on the tensor cores (pe_bwd_tc.cu)"}
 
 
 def eval_frame_report(device, dense: bool):
@@ -283,6 +287,54 @@ def eval_frame_report(device, dense: bool):
         out["players_on_fp32_field_ms"] = timed("fp16x3")
     finally:
         del os.environ["PE_TC_PREPASS"]
+    return out
+
+
+def t_frame_report(device):
+    """What play.py renders per frame ("T-frame"): the Tennis full frame 288x512 sampled on the strided grids of the
+    multiresolution decoder (strides 4 and 8: 9216 + 2304 = 11 520 rays), 4 object instances (2 static boxes with 4 samples per ray, 2
+    players with 32 samples per ray and positional ray benders: 72 samples per ray, 829 440 sample slots), eval mode, followed by the
+    hand-off fold into the decoder's per-stride CHW grids.  ONE composer call per frame (the reference: 12 chunks of 1000 rays)."""
+    import numpy as np
+    import scenes
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+    from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper
+    H, W, strides = 288, 512, [4, 8]
+    court = scenes.object_cfg([[-30, 30], [-40, 20.585], [-0.5, 0.0]], 4, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
+    stands = scenes.object_cfg([[-40, 40], [20.585, 45.0], [0.0, 12.0]], 4, 5.0, 120.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
+    player = lambda: scenes.object_cfg([[-0.75, 0.75], [-0.5, 0.5], [0.0, 2.15]], 32, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("positional"))
+    config = scenes.scene_config([court, stands, player(), player()], 2, [1, 1, 1, 1], True)
+    lead = (1, 1, 1)
+    focal = 1700.0 * 0.51417 * 0.5 * (W / 256.0)
+    parts = [scenes.camera_rays(lead, H, W, focal, scenes.tennis_camera(), st) for st in strides]
+    orig, norm = parts[0][0], parts[0][2]
+    dirs = torch.cat([p[1] for p in parts], dim=-2)
+    p1 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(0.3), [2.0, -11.0, 0.01]))
+    p2 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(-0.2), [-2.0, 11.0, 0.01]))
+    inputs = scenes.build_inputs(17, config, lead, orig, dirs, norm, [np.eye(4), np.eye(4), p1, p2])
+    scene = (config, scenes.scene_state(17, config), inputs)
+    out = {"workload": "T-frame: Tennis 288x512 on the stride-4 + stride-8 grids = 11520 rays, 2 static objects (P=4) + 2 players (P=32, ray benders), "
+                       "eval forward + fold into the decoder's CHW grids, one composer call", "rays": int(dirs.size(-2)), "sample_slots": int(dirs.size(-2)) * 72}
+    for precision in ("mixed", "fp16x3", "fp16"):
+        _, _, _, comp, dev = build_composer(scene, precision, device=device)
+        call = [dev[k] for k in INPUT_KEYS]
+
+        def frame():
+            with torch.no_grad():
+                feats = comp(*call, False)["coarse"]["global"]["integrated_features"]
+                return RayHelper.fold_feature_grids(feats, strides, (H, W), [64, 128])
+
+        frame()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(10):
+            grids = frame()
+        e0.record()
+        torch.cuda.synchronize()
+        out[f"{precision}_ms"] = s0.elapsed_time(e0) / 10
+    out["grids"] = [list(g.shape) for g in grids]
     return out
 
 
@@ -451,6 +503,7 @@ def run_b200(args):
             line["train_step"] = [train_step_report(device, False), train_step_report(device, True),
                                   train_step_report(device, False, "fp32"), train_step_report(device, True, "fp32")]
             line["eval_frame"] = [eval_frame_report(device, False), eval_frame_report(device, True)]
+            line["t_frame"] = t_frame_report(device)
             line["gpu_eager_baseline"] = gpu_eager_reference(device)
         if train_multi:
             line["train_step"] = [train_multi]

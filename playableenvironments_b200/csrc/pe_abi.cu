@@ -346,6 +346,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     auto wants = [](const PeIntegrated& o) {
         return o.integrated_features || o.opacity || o.weights || o.depth || o.disparity || o.integrated_displacements_magnitude || o.integrated_divergence;
     };
+    if (!wants(ca.global)) ca.do_global = 0;      // (inference, single object: the caller aliases the scene's outputs to the object's)
     bool any_out = wants(ca.global);
     for (int k = 0; k < s.objects; ++k) any_out = any_out || wants(ca.object[k]);
     if ((ca.do_objects || ca.do_global) && any_out) {

@@ -384,6 +384,7 @@ struct ChainCtx {
     uint32_t taddr;
     int m, lane;
     int kS;            // S = 2^kS
+    int lo_on;         // 0: diagnostic -- the lo halves of the gradient operands are zeroed (plain fp16 chain)
     int km;            // exponent of the row's scale: the operand currently stored in the A buffers holds (true gradient) * 2^km
     float mop;         // largest magnitude of that stored row
 };
@@ -396,13 +397,13 @@ __device__ __forceinline__ int renorm_exp(float mx, int km) {
 }
 
 // gradient operand (hi + lo fp16 pair) of 8 consecutive columns of row m, saturating
-__device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char* a_lo, int chunk, int m, const float* v) {
+__device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char* a_lo, int chunk, int m, const float* v, int lo_on = 1) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         h[i] = pack_half2_sat(v[2 * i], v[2 * i + 1]);
         const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
-        l[i] = pack_half2_sat(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        l[i] = lo_on ? pack_half2_sat(v[2 * i] - hf.x, v[2 * i + 1] - hf.y) : 0u;
     }
     *reinterpret_cast<uint4*>(a_hi + chunk * CHUNK_BYTES + m * 16) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(a_lo + chunk * CHUNK_BYTES + m * 16) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -434,7 +435,7 @@ __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t
         }
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, y + 8 * cc);
+            store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, y + 8 * cc, C.lo_on);
             if (store) {
                 float z[8];
 #pragma unroll
@@ -497,7 +498,7 @@ __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t
             if (pass == 1) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
-                    store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, g + 8 * cc);
+                    store_g8_hilo(C.a_hi, C.a_lo, c * 4 + cc, C.m, g + 8 * cc, C.lo_on);
                     if (store) {
                         float z[8];
 #pragma unroll
@@ -514,7 +515,7 @@ __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t
 
 // phase 0: full chain (+ per-image AdaIn sums for the style backward); phase 1 / 2 (train mode): stop after the second / first AdaIn
 // layer of the head (walking backwards) and accumulate the cross-sample sums of its BatchNorm backward
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase, const int lo_on) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
         }
     } else if (warp >= 4) {
         ChainCtx C;
-        C.lane = lane;
+        C.lane = lane; C.lo_on = lo_on;
         C.m = ((warp & 3) << 5) | lane;
         C.a_hi = smem; C.a_lo = smem + A_BYTES;
         C.cst = reinterpret_cast<float*>(smem + CST_BASE);
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                     feature_grad8(c, v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { z[i] = v[i] * S; v[i] *= s_row; }
-                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
+                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v, C.lo_on);
                     if (store && r.store) {
                         const int off = (FS_GF + c) * CHUNK_BYTES + m * 16;
                         split_store8(st + off, nullptr, z, false);
@@ -1062,7 +1063,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bfwd_kernel(const PeB
     if (warp == 2) tmem_dealloc(tmem_base, 128);
 }
 
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const PeBwdTcArgs B, const int64_t tile0) {
+__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int lo_on) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * BB_A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BB_SMEM_BAR);
@@ -1134,7 +1135,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
         }
     } else if (warp >= 4) {
         ChainCtx C;
-        C.lane = lane;
+        C.lane = lane; C.lo_on = lo_on;
         C.m = ((warp & 3) << 5) | lane;
         C.a_hi = smem; C.a_lo = smem + BB_A_BYTES;
         C.cst = nullptr;
@@ -1190,7 +1191,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
 #pragma unroll
                         for (int a = 0; a < 3; ++a) { v[a] = gout[a] * s_row; z[a] = gout[a] * S; }
                     }
-                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v);
+                    store_g8_hilo(C.a_hi, C.a_lo, c, m, v, C.lo_on);
                     if (r.store) {
                         const int off = (BS_GOUT + c) * CHUNK_BYTES + m * 16;
                         split_store8(st + off, nullptr, z, false);
@@ -1608,6 +1609,12 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
     return PE_OK;
 }
 
+// PE_BWD_CHAIN_LO=0 (diagnostic): the dX chains carry plain fp16 gradient operands (lo halves zeroed)
+static int chain_lo_on() {
+    const char* env = getenv("PE_BWD_CHAIN_LO");
+    return (env && atoi(env) == 0) ? 0 : 1;
+}
+
 int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
@@ -1621,7 +1628,7 @@ int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int s
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
     if (grid <= 0) return PE_OK;
-    pe_bwd_chain_kernel<<<grid, CHAIN_THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase);
+    pe_bwd_chain_kernel<<<grid, CHAIN_THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase, chain_lo_on());
     PE_LAUNCH_CHECK("pe_bwd_chain_kernel");
     return PE_OK;
 }
@@ -1689,7 +1696,7 @@ int pe_launch_bwd_bender(const PeBwdTcArgs& args, int64_t tile0, int sm_count, c
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_bchain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BB_SMEM_TOTAL));
     pe_bwd_bfwd_kernel<<<grid, CHAIN_THREADS, BB_SMEM_TOTAL, stream>>>(args, tile0);
     PE_LAUNCH_CHECK("pe_bwd_bfwd_kernel");
-    pe_bwd_bchain_kernel<<<grid, CHAIN_THREADS, BB_SMEM_TOTAL, stream>>>(args, tile0);
+    pe_bwd_bchain_kernel<<<grid, CHAIN_THREADS, BB_SMEM_TOTAL, stream>>>(args, tile0, chain_lo_on());
     PE_LAUNCH_CHECK("pe_bwd_bchain_kernel");
     DwArgs D = {};
     D.stash = args.bstash; D.tile_begin = args.tile_begin; D.images = args.f.images; D.tile_capacity = args.tile_capacity;

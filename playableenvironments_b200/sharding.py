@@ -70,6 +70,9 @@ def render_pipelined(composer, ray_origins, ray_directions, focal_normals, w2o, 
         raise Exception("render_pipelined is inference-only: call it under torch.no_grad() / composer.eval()")
     world = dist.get_world_size(group) if (dist.is_initialized() and gathered is not None) else 1
     rays = ray_directions.size(-2)
+    if ray_directions.numel() != rays * 3:
+        raise Exception("render_pipelined renders ONE image per call (leading dims of size 1): ray chunks of several images are not "
+                        "contiguous in the gathered grid; call it per image")
     main = torch.cuda.current_stream()
     side = side_stream if side_stream is not None else torch.cuda.Stream()
     local, keep = None, []

@@ -1,6 +1,6 @@
 """Multi-GPU product path on NCCL (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`):
 `sharding.render_sharded` / `render_pipelined` against the single-GPU render of the same frame, bit for bit (rays are independent),
-and the data-parallel gradient all-reduce against the single-GPU gradients of the two frames."""
+and the data-parallel gradient all-reduce (one flat bucket) against a per-tensor reduction."""
 import os
 import sys
 
@@ -28,7 +28,8 @@ def _worker(rank, world, port, tmp):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     ok = []
     try:
-        for scene, precision in ((scenes.scene_static(seed=12, height=40, width=50, P=128), "mixed"), ("tennis_small", "fp16x3")):
+        for scene, precision in ((scenes.scene_static(seed=12, height=40, width=50, P=128), "mixed"),
+                                 (scenes.scene_tennis(seed=13, stride=8, lead=(1, 1, 1)), "fp16x3")):
             _, _, _, comp, dev = build_composer(scene, precision, device=device)
             args = [dev[k] for k in INPUT_KEYS]
             rays = dev["ray_directions"].size(-2)
