@@ -41,7 +41,7 @@ enum PePrecision  { PE_PRECISION_FP32 = 0,  /* CUDA-core fp32 FMA path, any shap
                     PE_PRECISION_FP16 = 1,  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate     */
                     PE_PRECISION_FP16X2 = 2,/* tcgen05, weights split hi+lo fp16 (2 MMA passes)      */
                     PE_PRECISION_FP16X3 = 3,/* tcgen05, weights AND activations split hi+lo (3 MMAs per k-step): fp32-class accuracy */
-                    PE_PRECISION_MIXED = 4  /* tcgen05, hi+lo weights on the late trunk layers and the head only; objects with fewer
+                    PE_PRECISION_MIXED = 4  /* tcgen05, hi+lo weights on the late trunk layers (L3-L7) only; objects with fewer
                                                than 64 samples per ray (large sample spacing amplifies raw-alpha error) run as FP16X3 */ };
 enum PeError      { PE_OK = 0, PE_ERR_INVALID = -1, PE_ERR_UNSUPPORTED = -2, PE_ERR_CUDA = -3, PE_ERR_WORKSPACE = -4 };
 

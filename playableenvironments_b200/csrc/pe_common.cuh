@@ -99,7 +99,7 @@ __host__ __device__ inline int64_t pe_tcT_pass_bytes() { return 6LL * 128 * 64 +
 // bender: OUTT (N'128,K'32) L5T L4T (128,128) L3encT (96,128) L3T L2T L1T (128,128) L0T (96,128)
 __host__ __device__ inline int64_t pe_tcbT_pass_bytes() { return 1LL * 128 * 64 + 5LL * 4 * 128 * 64 + 2LL * 4 * 96 * 64; }
 
-#define PE_TC_MIXED_MASK 0x3F0                // default two-pass layers of the mixed mode: L4-L7, head 0, head 3
+#define PE_TC_MIXED_MASK 0x0F8                // two-pass layers of the mixed mode: trunk layers L3-L7 (the head gains nothing, profiles/r2_mixed_mode.md)
 #define PE_TC_SLAB_K 32                       // K elements per streamed weight slab
 // number of K=32 slabs of one weight pass of the shipped field:
 // L0: 64/32=2; L1-3: 8 each; L4: 320/32=10; L5-7: 8 each; H0: 8; H3 (N=128): 8; H6 (K=128,N=192): 4

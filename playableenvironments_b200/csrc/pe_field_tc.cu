@@ -791,8 +791,8 @@ int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, 
     const int x3 = args.precision == PE_PRECISION_FP16X3 ? 1 : 0;
     const int num_passes = args.precision == PE_PRECISION_FP16 ? 1 : 2;
     // per-layer weight passes: bit l of the mask = layer l (0-7 trunk, 8 head 0, 9 head 3, 10 head 6) runs hi + lo.
-    // "mixed" (PE_PRECISION_MIXED): two passes where the systematic fp16 rounding of the weights matters most (the late trunk layers
-    // and the head, tests/emulate_precision.py), one pass for the early trunk; PE_TC_PASS2_MASK overrides the choice.
+    // "mixed" (PE_PRECISION_MIXED): two passes where the systematic fp16 rounding of the weights matters most (trunk layers L3-L7,
+    // measured: profiles/r2_mixed_mode.md), one pass for the early trunk and the head; PE_TC_PASS2_MASK overrides the choice.
     int pass2_mask = num_passes == 2 ? 0x7FF : 0;
     const bool mixed = args.precision == PE_PRECISION_MIXED;
     if (mixed) { const char* menv = getenv("PE_TC_PASS2_MASK"); pass2_mask = menv ? (int)strtol(menv, nullptr, 0) : PE_TC_MIXED_MASK; }

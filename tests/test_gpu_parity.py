@@ -8,7 +8,7 @@ Tolerances (relative to the tensor's scale: max|got - ref| / max|ref|; BASELINE.
                                                                                      2e-3 scale-relative max (measured 1.2e-3 at 256x256)
   few-sample objects (P=4, P=16) amplify the fp16 activation rounding through exp(-relu(a) * delta) with delta ~ 20..85:
   fp16/fp16x2 are held to 6e-3 / 8e-2 there; fp16x3 and fp32 stay at 2e-4 (Numerics).
-  mixed  the composer's and bench.py's default (hi+lo weight passes on L4-L7 and the head for objects with >= 64 samples per ray,
+  mixed  the composer's and bench.py's default (hi+lo weight passes on the trunk layers L3-L7 for objects with >= 64 samples per ray,
          fp16x3 for the others): 1e-3 on EVERY golden scene and on the 4096-ray golden of the full-size headline frame.
 """
 import os

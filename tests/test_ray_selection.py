@@ -79,3 +79,28 @@ def test_weighted_fine_sampling_matches_the_reference(perturb):
     np.testing.assert_allclose(merged.numpy(), GOLDEN[f"fine_{int(perturb)}/1"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(pos.numpy(), GOLDEN[f"fine_{int(perturb)}/0"], rtol=0, atol=2e-5)
     assert torch.equal(w, fine_case()[3])          # the argument is left untouched
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_the_reference_on_the_device(name, monkeypatch):
+    """The same selection with every tensor on the GPU.  torch's CUDA generator is a different stream than the CPU one the goldens were
+    drawn from, so the random numbers are drawn on the host exactly as above and moved: everything downstream (cdf inversion,
+    searchsorted, index arithmetic, gathers) runs on the device and must reproduce the upstream results bit for bit."""
+    fn, seed, kwargs = CASES[name]
+    rand, randperm = torch.rand, torch.randperm
+
+    def host_rand(*size, device=None, **kw):
+        return rand(*size, **kw).to(device) if device is not None else rand(*size, **kw)
+
+    def host_randperm(n, device=None, **kw):
+        return randperm(n, **kw).to(device) if device is not None else randperm(n, **kw)
+
+    monkeypatch.setattr(torch, "rand", host_rand)
+    monkeypatch.setattr(torch, "randperm", host_randperm)
+    dev_kwargs = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+    torch.manual_seed(seed)
+    res = getattr(RayHelper, fn)(**dev_kwargs)
+    for i, t in enumerate(res):
+        assert t.is_cuda, (name, i)
+        np.testing.assert_array_equal(t.cpu().numpy(), GOLDEN[f"{name}/{i}"], err_msg=f"{name} output {i}")
