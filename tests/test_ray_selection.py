@@ -86,7 +86,9 @@ def test_weighted_fine_sampling_matches_the_reference(perturb):
 def test_matches_the_reference_on_the_device(name, monkeypatch):
     """The same selection with every tensor on the GPU.  torch's CUDA generator is a different stream than the CPU one the goldens were
     drawn from, so the random numbers are drawn on the host exactly as above and moved: everything downstream (cdf inversion,
-    searchsorted, index arithmetic, gathers) runs on the device and must reproduce the upstream results bit for bit."""
+    searchsorted, index arithmetic, gathers) runs on the device and must reproduce the upstream results: bit for bit where the output is
+    a gather of the inputs or an index, to 1 ulp for the normalised pixel positions (ATen's CUDA kernel divides by a scalar as a
+    multiplication with its reciprocal)."""
     fn, seed, kwargs = CASES[name]
     rand, randperm = torch.rand, torch.randperm
 
@@ -103,4 +105,8 @@ def test_matches_the_reference_on_the_device(name, monkeypatch):
     res = getattr(RayHelper, fn)(**dev_kwargs)
     for i, t in enumerate(res):
         assert t.is_cuda, (name, i)
-        np.testing.assert_array_equal(t.cpu().numpy(), GOLDEN[f"{name}/{i}"], err_msg=f"{name} output {i}")
+        got, want = t.cpu().numpy(), GOLDEN[f"{name}/{i}"]
+        if got.dtype.kind == "f" and got.shape[-1] == 2 and float(np.abs(want).max()) <= 1.0:      # normalised (row, column) positions
+            np.testing.assert_allclose(got, want, rtol=2.5e-7, atol=0, err_msg=f"{name} output {i}")
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=f"{name} output {i}")
