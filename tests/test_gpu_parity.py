@@ -391,3 +391,19 @@ def test_launch_accounting_and_no_fallback():
     render.take_launch_count()
     _run(comp, dev)
     assert render.take_launch_count() == 3          # two style prologues + ONE fused field kernel
+
+
+def test_composer_runs_as_a_dataparallel_replica():
+    """nn.DataParallel (train.py:61, every generate_*/evaluate_* script) calls replicas whose `_parameters` are EMPTY: the weights are
+    plain tensor attributes.  The composer reads its tensors by attribute, so a replica renders the same frame bit for bit."""
+    from torch.nn.parallel import replicate
+    _, _, _, comp, dev = _build("tennis_small", "mixed")
+    want = flatten(_run(comp, dev))
+    replica = replicate(comp, [torch.cuda.current_device()], detach=True)[0]
+    assert len(list(replica.parameters())) == 0
+    replica.allow_forward_without_grad = True
+    replica.precision = "mixed"
+    got = flatten(_run(replica, dev))
+    assert set(got) == set(want)
+    for k in want:
+        np.testing.assert_array_equal(got[k], want[k], err_msg=k)
