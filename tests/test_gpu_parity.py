@@ -399,7 +399,7 @@ def test_composer_runs_as_a_dataparallel_replica():
     from torch.nn.parallel import replicate
     _, _, _, comp, dev = _build("tennis_small", "mixed")
     want = flatten(_run(comp, dev))
-    replica = replicate(comp, [torch.cuda.current_device()], detach=True)[0]
+    replica = replicate(comp, [torch.cuda.current_device()], detach=False)[0]      # what DataParallel does with autograd on
     assert len(list(replica.parameters())) == 0
     replica.allow_forward_without_grad = True
     replica.precision = "mixed"
