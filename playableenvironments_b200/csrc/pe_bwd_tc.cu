@@ -14,6 +14,7 @@
 //                        tiles, added once to the fp32 parameter gradients.
 #include "pe_tc_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 using namespace pe;
@@ -197,6 +198,8 @@ __device__ __forceinline__ void fwd_epilogue(uint32_t tcol, unsigned char* a_hi,
 }
 
 constexpr int CHAIN_THREADS = 256;       // producer, MMA, TMEM-alloc, spare + 4 epilogue warps
+constexpr int FCHAIN_THREADS = 384;      // field chain: two epilogue groups (column halves of the same rows)
+constexpr int FCHAIN_XCH = SMEM_BAR + 256, FCHAIN_SMEM = FCHAIN_XCH + 2048;     // + the halves' exchange area
 constexpr uint32_t CHAIN_BAR = 1;
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_fwd_kernel(const PeBwdTcArgs B, const int64_t tile0) {
@@ -385,6 +388,9 @@ struct ChainCtx {
     int m, lane;
     int kS;            // S = 2^kS
     int lo_on;         // 0: diagnostic -- the lo halves of the gradient operands are zeroed (plain fp16 chain)
+    int h;             // column half handled by this thread (field chain: two epilogue groups share every row), 0 otherwise
+    int par;           // parity of the row-maximum exchange slots
+    float* xch;        // [2][2][128] exchange area of the two halves of a row
     int km;            // exponent of the row's scale: the operand currently stored in the A buffers holds (true gradient) * 2^km
     float mop;         // largest magnitude of that stored row
 };
@@ -394,6 +400,17 @@ __device__ __forceinline__ int renorm_exp(float mx, int km) {
     int e;
     frexpf(mx, &e);
     return max(-100 - km, min(100 - km, 8 - e));
+}
+
+// the two threads of a row agree on the row's largest magnitude (NH == 1: one thread per row, nothing to do)
+template <int NH>
+__device__ __forceinline__ float row_max_exchange(ChainCtx& C, float mx) {
+    if (NH == 1) return mx;
+    float* slot = C.xch + C.par * 256;
+    slot[C.h * 128 + C.m] = mx;
+    named_bar_sync(CHAIN_BAR, 256);
+    C.par ^= 1;
+    return fmaxf(slot[C.m], slot[128 + C.m]);
 }
 
 // gradient operand (hi + lo fp16 pair) of 8 consecutive columns of row m, saturating
@@ -410,27 +427,31 @@ __device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char
 }
 
 // KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
-template <int KIND, int NB = 8>
+template <int KIND, int NB = 8, int NH = 1>
 __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw, bool store) {
+    // NH == 2: this thread handles the NB / 2 column blocks of half C.h; C.mop leaves as this half's maximum (the caller exchanges it)
+    constexpr int MB = NB / NH;
+    const int c0 = NH == 1 ? 0 : C.h * MB;
     const int fexp = renorm_exp(C.mop, C.km);
     const int km = C.km + fexp;
     const float f = ldexpf(1.f, fexp - TCT_WEXP), r_stash = ldexpf(1.f, C.kS - km), graw_n = ldexpf(graw, km);
-    uint32_t bits[NB];
+    uint32_t bits[MB];
 #pragma unroll
-    for (int w = 0; w < NB; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
+    for (int w = 0; w < MB; ++w) bits[w] = mask_words[(c0 + w) * PE_BWD_TILE + C.m];
     uint32_t v[2][32];
     float mx = 0.f;
-    tmem_ld32(C.taddr, v[0]);
+    tmem_ld32(C.taddr + c0 * 32, v[0]);
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        tmem_wait_ld_regs(v[c & 1]);
-        if (c + 1 < NB) tmem_ld32(C.taddr + (c + 1) * 32, v[(c + 1) & 1]);
+    for (int cb = 0; cb < MB; ++cb) {
+        const int c = c0 + cb;
+        tmem_wait_ld_regs(v[cb & 1]);
+        if (cb + 1 < MB) tmem_ld32(C.taddr + (c + 1) * 32, v[(cb + 1) & 1]);
         float y[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-            float a = __uint_as_float(v[c & 1][q]) * f;
+            float a = __uint_as_float(v[cb & 1][q]) * f;
             if (KIND == 2) a = fmaf(graw_n, C.cst[CC_AW + c * 32 + q], a);
-            y[q] = ((bits[c] >> q) & 1u) ? a : 0.f;
+            y[q] = ((bits[cb] >> q) & 1u) ? a : 0.f;
             mx = fmaxf(mx, fabsf(y[q]));
         }
 #pragma unroll
@@ -452,24 +473,27 @@ __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t
 // field evaluated (k1 = k2 = 0 in eval mode).  Two passes over the accumulators: the first finds the row's largest output (the BatchNorm
 // terms are the same for every row, so a row with a tiny own gradient can grow by many decades here), the second stores it re-normalised.
 // sums: accumulate A / Bx (true units) into the tile's shared sums.
-template <int N>
+template <int N, int NH = 1>
 __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t* __restrict__ mask_words, const unsigned char* st_x,
                                                      unsigned char* st_g, const float* sc, const float* k1, const float* k2, bool active,
                                                      bool sums, bool store) {
-    uint32_t bits[N / 32];
+    constexpr int MB = N / 32 / NH;
+    const int c0 = NH == 1 ? 0 : C.h * MB;
+    uint32_t bits[MB];
 #pragma unroll
-    for (int w = 0; w < N / 32; ++w) bits[w] = mask_words[w * PE_BWD_TILE + C.m];
+    for (int w = 0; w < MB; ++w) bits[w] = mask_words[(c0 + w) * PE_BWD_TILE + C.m];
     float* sumA = C.cst + CC_SUMA;
     float* sumB = C.cst + CC_SUMB;
     int km = C.km + renorm_exp(C.mop, C.km);
     float mx = 0.f;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) { km += renorm_exp(mx, km); mx = 0.f; }
+        if (pass == 1) { km += renorm_exp(row_max_exchange<NH>(C, mx), km); mx = 0.f; }
         const float f = ldexpf(1.f, km - C.km - TCT_WEXP), s_row = ldexpf(1.f, km), inv_s_row = ldexpf(1.f, -km), r_stash = ldexpf(1.f, C.kS - km);
         uint32_t v[32];
 #pragma unroll 1
-        for (int c = 0; c < N / 32; ++c) {
+        for (int cb = 0; cb < MB; ++cb) {
+            const int c = c0 + cb;
             uint4 xq[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) xq[cc] = *reinterpret_cast<const uint4*>(st_x + (c * 4 + cc) * CHUNK_BYTES + C.m * 16);
@@ -479,7 +503,7 @@ __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) unpack8(xq[cc], x + 8 * cc);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) g[q] = ((bits[c] >> q) & 1u) ? __uint_as_float(v[q]) * f : 0.f;
+            for (int q = 0; q < 32; ++q) g[q] = ((bits[cb] >> q) & 1u) ? __uint_as_float(v[q]) * f : 0.f;
             if (sums && pass == 1) {
                 float a[32], b[32];
 #pragma unroll
@@ -515,7 +539,7 @@ __device__ __forceinline__ void chain_epilogue_adain(ChainCtx& C, const uint32_t
 
 // phase 0: full chain (+ per-image AdaIn sums for the style backward); phase 1 / 2 (train mode): stop after the second / first AdaIn
 // layer of the head (walking backwards) and accumulate the cross-sample sums of its BatchNorm backward
-__global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase, const int lo_on) {
+__global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const PeBwdTcArgs B, const int64_t tile0, const int phase, const int lo_on) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* ring = smem + 2 * A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -537,7 +561,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-        mbar_init(acc_full, 1); mbar_init(a_ready, 4);
+        mbar_init(acc_full, 1); mbar_init(a_ready, 8);
         mbar_fence_init();
     }
     fence_proxy_async();
@@ -588,8 +612,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
             }
         }
     } else if (warp >= 4) {
+        // two epilogue groups of 4 warps share every row: group h handles half of the columns of each step
         ChainCtx C;
         C.lane = lane; C.lo_on = lo_on;
+        C.h = (warp - 4) >> 2; C.par = 0;
+        C.xch = reinterpret_cast<float*>(smem + FCHAIN_XCH);
         C.m = ((warp & 3) << 5) | lane;
         C.a_hi = smem; C.a_lo = smem + A_BYTES;
         C.cst = reinterpret_cast<float*>(smem + CST_BASE);
@@ -601,7 +628,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
             frexpf(S, &e);               // S = 2^(e - 1)
             C.kS = e - 1;
         }
-        const int m = C.m;
+        const int m = C.m, h = C.h, tid = h * 128 + m;
         float* cst = C.cst;
         const float size[3] = {ob.bbox[1] - ob.bbox[0], ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]};
         const float* alpha_w = reinterpret_cast<const float*>(blob + L.alpha_w);
@@ -619,16 +646,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
             {
                 const float* sc1 = A.aff1 + (int64_t)r.img * 2 * W;
                 const float* sc2 = A.aff2 + (int64_t)r.img * W;
-                for (int i = m; i < W; i += 128) {
+                {
+                    const int i = tid;          // 256 threads, W = 256
                     cst[CC_SC1 + i] = sc1[i];
                     cst[CC_AW + i] = __ldg(alpha_w + i);
                     cst[CC_K11 + i] = B.bn_fix[i];
                     cst[CC_K21 + i] = B.bn_fix[W + i];
                     cst[CC_SUMA + i] = 0.f; cst[CC_SUMB + i] = 0.f;
                 }
-                cst[CC_SC2 + m] = sc2[m];
-                cst[CC_K12 + m] = B.bn_fix[2 * W + m];
-                cst[CC_K22 + m] = B.bn_fix[2 * W + W / 2 + m];
+                if (h == 0) {
+                    cst[CC_SC2 + m] = sc2[m];
+                    cst[CC_K12 + m] = B.bn_fix[2 * W + m];
+                    cst[CC_K22 + m] = B.bn_fix[2 * W + W / 2 + m];
+                }
             }
             // ---- upstream gradient of the per-sample features: cw_obj dL/dF_obj[ray] + cw_glob dL/dF_glob[ray], row-normalised -> operand,
             //      call-scaled -> stash ----
@@ -658,17 +688,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                 };
                 float mx = fabsf(graw) * max_aw;
 #pragma unroll 2
-                for (int c = 0; c < 24; ++c) {
+                for (int c = 12 * h; c < 12 * h + 12; ++c) {
                     float v[8];
                     feature_grad8(c, v);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { const float av = fabsf(v[i]); if (av < INFINITY) mx = fmaxf(mx, av); }
                 }
+                mx = row_max_exchange<2>(C, mx);
                 C.km = renorm_exp(mx, 0);                  // mx * 2^km in [128, 256)
                 C.mop = ldexpf(mx, C.km);
                 const float s_row = ldexpf(1.f, C.km);
 #pragma unroll 2
-                for (int c = 0; c < 24; ++c) {
+                for (int c = 12 * h; c < 12 * h + 12; ++c) {
                     float v[8], z[8];
                     feature_grad8(c, v);
 #pragma unroll
@@ -679,7 +710,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                         split_store8(st + off, nullptr, z, false);
                     }
                 }
-                if (store && r.store) {          // columns 0, 1 of a 16-column operand: S * dL/d raw alpha as hi, lo (d alpha_head.weight = h7^T graw)
+                if (store && r.store && h == 0) {          // columns 0, 1 of a 16-column operand: S * dL/d raw alpha as hi, lo (d alpha_head.weight = h7^T graw)
                     const float gs = graw * S;
                     const float hi = __half2float(__float2half_rn(fminf(fmaxf(gs, -65504.f), 65504.f)));
                     float v[8] = {hi, gs - hi, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -687,20 +718,20 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                     *reinterpret_cast<uint4*>(st + (FS_GRAW + 1) * CHUNK_BYTES + m * 16) = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
-            if (phase == 0 && B.gw.alpha_b) {            // d alpha_head.bias = sum graw
+            if (phase == 0 && B.gw.alpha_b && h == 0) {            // d alpha_head.bias = sum graw
                 float s = graw;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == 0 && s != 0.f) atomicAdd(B.gw.alpha_b, s);
             }
             sync.arrive_ready();
-            named_bar_sync(CHAIN_BAR, 128);                // constants visible to the group
+            named_bar_sync(CHAIN_BAR, 256);                // constants visible to the group
             float* asum = B.adain_sums + (int64_t)r.img * 3 * W;
             const bool st_ok = store && r.store;
 
             auto flush_sums = [&](int N, int off_a, int off_b, const float* sc, double* bn, bool to_bn) {
-                named_bar_sync(CHAIN_BAR, 128);
-                for (int c = m; c < N; c += 128) {
+                named_bar_sync(CHAIN_BAR, 256);
+                for (int c = tid; c < N; c += 256) {
                     const float a = cst[CC_SUMA + c], b = cst[CC_SUMB + c];
                     if (r.store) {
                         if (to_bn) {            // cross-sample terms of the train-mode BatchNorm backward: S1 = sum g sc, S2 = sum g sc x
@@ -713,109 +744,118 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_chain_kernel(const Pe
                     }
                     cst[CC_SUMA + c] = 0.f; cst[CC_SUMB + c] = 0.f;
                 }
-                named_bar_sync(CHAIN_BAR, 128);
+                named_bar_sync(CHAIN_BAR, 256);
             };
 
             // ---- step 0: gy2 = gF H6 -> AdaIn 2 ----
             sync.wait_acc();
-            chain_epilogue_adain<128>(C, mask + MASK_Y2 * PE_BWD_TILE, st + FS_X2 * CHUNK_BYTES, st + FS_GX2 * CHUNK_BYTES, cst + CC_SC2, cst + CC_K12,
+            chain_epilogue_adain<128, 2>(C, mask + MASK_Y2 * PE_BWD_TILE, st + FS_X2 * CHUNK_BYTES, st + FS_GX2 * CHUNK_BYTES, cst + CC_SC2, cst + CC_K12,
                                       cst + CC_K22, r.active, phase != 2, st_ok);
             if (phase != 2) flush_sums(W / 2, 2 * W, 2 * W + W / 2, cst + CC_SC2, B.bn_sums + 2 * W, phase == 1);
-            if (phase == 1) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 128); continue; }
+            if (phase == 1) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 256); continue; }
             sync.arrive_ready();
+            C.mop = row_max_exchange<2>(C, C.mop);
             // ---- step 1: gy1 = gx2 H3 -> AdaIn 1 ----
             sync.wait_acc();
-            chain_epilogue_adain<256>(C, mask + MASK_Y1 * PE_BWD_TILE, st + FS_X1 * CHUNK_BYTES, st + FS_GX1 * CHUNK_BYTES, cst + CC_SC1, cst + CC_K11,
+            chain_epilogue_adain<256, 2>(C, mask + MASK_Y1 * PE_BWD_TILE, st + FS_X1 * CHUNK_BYTES, st + FS_GX1 * CHUNK_BYTES, cst + CC_SC1, cst + CC_K11,
                                       cst + CC_K21, r.active, true, st_ok);
             flush_sums(W, 0, W, cst + CC_SC1, B.bn_sums, phase == 2);
-            if (phase == 2) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 128); continue; }
+            if (phase == 2) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 256); continue; }
             sync.arrive_ready();
+            C.mop = row_max_exchange<2>(C, C.mop);
             // ---- step 2: gh7 = gx1 H0 + graw alpha_w -> relu'(h7) ----
             sync.wait_acc();
-            chain_epilogue_plain<2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw, st_ok);
+            chain_epilogue_plain<2, 8, 2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw, st_ok);
             sync.arrive_ready();
+            C.mop = row_max_exchange<2>(C, C.mop);
             // ---- steps 3-5: trunk layers 7, 6, 5 -> gradients of the pre-activations of layers 6, 5, 4 ----
 #pragma unroll 1
             for (int l = 6; l >= 4; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
+                chain_epilogue_plain<0, 8, 2>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
                 sync.arrive_ready();
+                C.mop = row_max_exchange<2>(C, C.mop);
             }
             // ---- step 6: the encoding half of the skip layer's input gradient, parked (hi + lo) in the encoding columns ----
             int km_parked = 0;
             sync.wait_acc();
             {
-                uint32_t v[2][32];
-                tmem_ld32(C.taddr, v[0]);
-                tmem_ld32(C.taddr + 32, v[1]);
-                tmem_wait_ld_regs(v[0]);
-                tmem_wait_ld_regs(v[1]);
-                named_bar_sync(CHAIN_BAR, 128);            // every reader of the constants is done
+                uint32_t v[32];
+                tmem_ld32(C.taddr + 32 * h, v);
+                tmem_wait_ld_regs(v);
+                named_bar_sync(CHAIN_BAR, 256);            // every reader of the constants is done
                 const int fexp = renorm_exp(C.mop, C.km);  // (the operand stays: the next step reads it again with the same factor)
                 km_parked = C.km + fexp;
                 const float f = ldexpf(1.f, fexp - TCT_WEXP);
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int cc = 0; cc < 4; ++cc) {
+                    float y[8];
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float y[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]) * f;
-                        store_g8_hilo(C.a_hi, C.a_lo, PE_CHUNK0 + c * 4 + cc, m, y);
-                    }
+                    for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[8 * cc + i]) * f;
+                    store_g8_hilo(C.a_hi, C.a_lo, PE_CHUNK0 + h * 4 + cc, m, y);
+                }
             }
             sync.arrive_ready();
             // ---- steps 7-10: trunk layers 4 (hidden half), 3, 2, 1 -> gradients of the pre-activations of layers 3, 2, 1, 0 ----
 #pragma unroll 1
             for (int l = 3; l >= 0; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
+                chain_epilogue_plain<0, 8, 2>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
                 sync.arrive_ready();
+                C.mop = row_max_exchange<2>(C, C.mop);
             }
             // ---- step 11: encoding gradient = layer 0's input gradient + the parked half; positional_encoder.py:59-64 backward ----
             sync.wait_acc();
             {
-                uint32_t v[2][32];
-                tmem_ld32(C.taddr, v[0]);
-                tmem_ld32(C.taddr + 32, v[1]);
-                tmem_wait_ld_regs(v[0]);
-                tmem_wait_ld_regs(v[1]);
-                // true gradient = accumulator / 2^km + parked / 2^km_parked
+                uint32_t v[32];
+                tmem_ld32(C.taddr + 32 * h, v);
+                tmem_wait_ld_regs(v);
+                // true gradient = accumulator / 2^km + parked / 2^km_parked; this thread holds encoding columns 32 h .. 32 h + 31
                 const float fa = ldexpf(1.f, -C.km - TCT_WEXP), fp = ldexpf(1.f, -km_parked);
-                float ge[64];
+                float ge[32];
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int cc = 0; cc < 4; ++cc) {
+                    float ph[8], pl[8];
+                    unpack8(*reinterpret_cast<const uint4*>(C.a_hi + (PE_CHUNK0 + h * 4 + cc) * CHUNK_BYTES + m * 16), ph);
+                    unpack8(*reinterpret_cast<const uint4*>(C.a_lo + (PE_CHUNK0 + h * 4 + cc) * CHUNK_BYTES + m * 16), pl);
 #pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float ph[8], pl[8];
-                        unpack8(*reinterpret_cast<const uint4*>(C.a_hi + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), ph);
-                        unpack8(*reinterpret_cast<const uint4*>(C.a_lo + (PE_CHUNK0 + c * 4 + cc) * CHUNK_BYTES + m * 16), pl);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) ge[c * 32 + cc * 8 + i] = fmaf(__uint_as_float(v[c][8 * cc + i]), fa, (ph[i] + pl[i]) * fp);
-                    }
+                    for (int i = 0; i < 8; ++i) ge[cc * 8 + i] = fmaf(__uint_as_float(v[8 * cc + i]), fa, (ph[i] + pl[i]) * fp);
+                }
+                // positional_encoder.py:59-64 backward over this thread's columns: [x | sin, cos per octave], column e = 3 + 6 o + 3 fn + a
                 float gx[3] = {0.f, 0.f, 0.f};
                 if (r.active) {
+                    const float xn[3] = {__fdiv_rn(r.x[0], size[0]), __fdiv_rn(r.x[1], size[1]), __fdiv_rn(r.x[2], size[2])};
+                    auto columns = [&](auto half) {
+                        constexpr int H = decltype(half)::value;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const float xn = __fdiv_rn(r.x[a], size[a]);
-                        float gsum = ge[a];
-#pragma unroll
-                        for (int o = 0; o < 10; ++o) {
-                            const float f = (float)(1 << o);
-                            float s, c;
-                            sincosf(__fmul_rn(f, xn), &s, &c);
-                            gsum = fmaf(f, c * ge[3 + 6 * o + a] - s * ge[3 + 6 * o + 3 + a], gsum);
+                        for (int i = 0; i < 32; ++i) {
+                            constexpr int dummy = 0; (void)dummy;
+                            const int e = 32 * H + i;
+                            if (e < 3) gx[e] += ge[i];
+                            else if (e < 63) {
+                                const int o = (e - 3) / 6, rr = (e - 3) % 6, fn = rr / 3, a = rr % 3;
+                                const float f = (float)(1 << o);
+                                float sn, cs;
+                                sincosf(__fmul_rn(f, xn[a]), &sn, &cs);
+                                gx[a] = fmaf(f * (fn ? -sn : cs), ge[i], gx[a]);
+                            }
                         }
-                        gx[a] = gsum / size[a];
-                    }
+                    };
+                    if (h == 0) columns(std::integral_constant<int, 0>{}); else columns(std::integral_constant<int, 1>{});
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) gx[a] /= size[a];
                 }
-                if (r.listed) {
+                // the two halves of the row meet in the exchange area (barrier: a slow thread may still be reading the last row maximum)
+                named_bar_sync(CHAIN_BAR, 256);
+                if (h == 1) { C.xch[m * 3] = gx[0]; C.xch[m * 3 + 1] = gx[1]; C.xch[m * 3 + 2] = gx[2]; }
+                named_bar_sync(CHAIN_BAR, 256);
+                if (h == 0 && r.listed) {
                     float* dst = (B.g_bent ? B.g_bent : B.g_pos) + r.gs * 3;
-                    dst[0] = gx[0]; dst[1] = gx[1]; dst[2] = gx[2];
+                    dst[0] = gx[0] + C.xch[m * 3]; dst[1] = gx[1] + C.xch[m * 3 + 1]; dst[2] = gx[2] + C.xch[m * 3 + 2];
                 }
             }
             tc_fence_before();
-            named_bar_sync(CHAIN_BAR, 128);        // the parked gradient is dead before the next tile's constants overwrite it
+            named_bar_sync(CHAIN_BAR, 256);        // the parked gradient is dead before the next tile's constants overwrite it
         }
     }
     tc_fence_before();
@@ -1625,10 +1665,10 @@ int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cuda
 }
 
 int pe_launch_bwd_chain(const PeBwdTcArgs& args, int64_t tile0, int phase, int sm_count, cudaStream_t stream) {
-    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(pe_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FCHAIN_SMEM));
     const int grid = (int)pe_min64((int64_t)args.tile_capacity, sm_count);
     if (grid <= 0) return PE_OK;
-    pe_bwd_chain_kernel<<<grid, CHAIN_THREADS, SMEM_TOTAL, stream>>>(args, tile0, phase, chain_lo_on());
+    pe_bwd_chain_kernel<<<grid, FCHAIN_THREADS, FCHAIN_SMEM, stream>>>(args, tile0, phase, chain_lo_on());
     PE_LAUNCH_CHECK("pe_bwd_chain_kernel");
     return PE_OK;
 }
