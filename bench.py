@@ -364,11 +364,19 @@ def run_b200(args):
     from playableenvironments_b200 import sharding
     side = torch.cuda.Stream(device=device)
 
+    fused = world > 1 and args.gather == "fused"
+    pg = sharding.PeerGather(rays, F, device) if fused else None
+
     def step():
         with torch.no_grad():
+            if fused:
+                # the all-gather (the single collective of the path) is FUSED into the render kernel: every ray's features are stored
+                # to all ranks' grids over NVLink as they are produced (sharding.PeerGather); a device-side barrier orders the readers
+                comp(*call_args, False, peer_features=pg.destinations())
+                return pg.sync()[rank]
             if world > 1:
-                # the frame renders in ray chunks; chunk i's grid is all-gathered (the single collective of the path) on a side
-                # stream while chunk i+1 renders: only the last chunk's transfer is exposed
+                # --gather nccl: the frame renders in ray chunks; chunk i's grid is all-gathered by NCCL on a side stream while chunk
+                # i+1 renders
                 return sharding.render_pipelined(comp, *call_args, False, chunks=args.chunks, gathered=gathered, side_stream=side)
             res = comp(*call_args, False)
         return res["coarse"]["global"]["integrated_features"]
@@ -411,8 +419,8 @@ def run_b200(args):
     def e2e_step():
         d = [host_in[k].to(device, non_blocking=True) for k in INPUT_KEYS]
         with torch.no_grad():      # D2H of chunk i (and its all-gather) overlap the render of chunk i+1
-            sharding.render_pipelined(comp, *d, False, chunks=args.chunks, gathered=gathered if world > 1 else None, host_out=host_out,
-                                      side_stream=side)
+            sharding.render_pipelined(comp, *d, False, chunks=args.chunks, gathered=gathered if (world > 1 and not fused) else None,
+                                      host_out=host_out, side_stream=side, peer_gather=pg)
 
     for _ in range(min(args.warmup, 3)):
         e2e_step()
@@ -486,7 +494,8 @@ def run_b200(args):
                                            "fp16x3": "f16 operands (weights and activations hi+lo), f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MB memset)",
-                       "frames_per_s": world * args.steps / total_s, "collective": f"all_gather(feature grid) per ray chunk, {args.chunks} chunks, overlapped with the next chunk's render" if world > 1 else "none"},
+                       "frames_per_s": world * args.steps / total_s, "collective": ("none" if world == 1 else "all-gather of the feature grid fused into the render kernel (P2P stores over NVLink into symmetric memory, sharding.PeerGather) + one signal-pad barrier"
+                                      if fused else f"NCCL all_gather(feature grid) per ray chunk, {args.chunks} chunks, on a side stream")},
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / peaks["burst"],
                          # dram__bytes_read.sum + dram__bytes_write.sum of one pe_field_tc_kernel launch on this workload
@@ -529,6 +538,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("PE_PRECISION", "mixed"), choices=["mixed", "fp16", "fp16x2", "fp16x3", "fp32"])
     ap.add_argument("--chunks", type=int, default=4, help="ray chunks per frame of the pipelined render (N > 1 and the e2e figure)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: all-gather fused into the render kernel, or NCCL per ray chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the other precision modes and the live parity check")
     args = ap.parse_args()

@@ -26,11 +26,12 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 3
+#define PE_ABI_VERSION 4
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
 
+#define PE_MAX_PEERS 8
 typedef void* pe_stream_t;    /* cudaStream_t */
 
 enum PeNerfKind   { PE_NERF_ADAIN = 0,      /* model/nerf_models/adain_style_nerf_model.py          */
@@ -129,6 +130,13 @@ typedef struct PeOutputs {
      * caller applies the momentum update to its running buffers                                  */
     float* bn1_running[PE_MAX_OBJECTS];
     float* bn2_running[PE_MAX_OBJECTS];
+    /* fused all-gather of the rendered feature grid (the one collective of the path): `peers` extra destinations of the
+     * composed scene's integrated_features, [images][rays][features] each -- buffers of the OTHER GPUs of the box mapped into this
+     * process (CUDA virtual-memory handles: cuMemImportFromShareableHandle + cuMemMap, e.g. torch symmetric memory) or local ones.  The fused field kernel stores every ray's features to all of them as it produces
+     * them (P2P stores over NVLink, no separate collective and no SM taken from the render); other paths copy after their last kernel.
+     * The caller orders the peers' reads after this call with its own cross-rank synchronisation.                                   */
+    int32_t peers;
+    float* peer_features[PE_MAX_PEERS];
 } PeOutputs;
 
 /* -- library ------------------------------------------------------------------------------- */

@@ -11,10 +11,11 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 3
+PE_ABI_VERSION = 4
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
+PE_MAX_PEERS = 8
 
 NERF_ADAIN, NERF_SKYBOX_V3 = 0, 1
 BENDER_ZEROED, BENDER_POSITIONAL = 0, 1
@@ -86,6 +87,7 @@ class PeOutputs(C.Structure):
         ("raw_features", C.c_void_p * PE_MAX_OBJECTS), ("raw_alphas", C.c_void_p * PE_MAX_OBJECTS),
         ("displacements", C.c_void_p * PE_MAX_OBJECTS), ("positions_t", C.c_void_p * PE_MAX_OBJECTS),
         ("bn1_running", C.c_void_p * PE_MAX_OBJECTS), ("bn2_running", C.c_void_p * PE_MAX_OBJECTS),
+        ("peers", C.c_int32), ("peer_features", C.c_void_p * PE_MAX_PEERS),
     ]
 
 

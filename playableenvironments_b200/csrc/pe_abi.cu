@@ -98,6 +98,8 @@ static int object_precision(const PeScene& s, int k) {
 }
 
 static bool object_uses_tc(const PeScene& s, int k) { return tc_allowed(s) && pe_tc_shape_ok(s.object[k]); }
+static bool object_uses_prepass(const PeScene& s, int k);
+static bool prepass_object(const PeScene& s, int k) { return object_uses_prepass(s, k); }
 
 // Objects with a positional ray bender: sampling + bender run as an exact fp32 pre-pass, the field runs on the tensor cores over
 // the non-empty tiles only, the compositor integrates the object.  PE_TC_PREPASS=0 sends them to the fp32 field kernel instead.
@@ -205,6 +207,8 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     rc = pe_device_sm_count(&sm_count);
     if (rc != PE_OK) return rc;
 
+    if (out->peers < 0 || out->peers > PE_MAX_PEERS) { pe_set_error("peers must be in [0,%d]", PE_MAX_PEERS); return PE_ERR_INVALID; }
+    bool peers_fused = false;
     for (int k = 0; k < s.objects; ++k) {
         const PeObjectDesc& d = s.object[k];
         const PeLayout L = pe_layout(d);
@@ -235,6 +239,11 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.integ = out->object[k];
         fa.noise = s.perturb ? in->noise[k] : nullptr;
         if (tc && !fa.feat_out && o.fold_v) { fa.fold_v = o.fold_v; fa.fold_s = o.fold_s; }
+        if (fa.fold_v && s.objects == 1 && !s.training && !prepass_object(s, k)) {      // the fused kernel produces the scene's grid itself
+            fa.peers = out->peers;
+            for (int q = 0; q < out->peers; ++q) fa.peer_features[q] = out->peer_features[q];
+            peers_fused = true;
+        }
         fa.h7_out = o.h7;
         if (!tc && !fa.feat_out) { pe_set_error("internal: no feature buffer for object %d", k); return PE_ERR_INVALID; }
         if (d.bender_kind == PE_BENDER_POSITIONAL && !fa.deformation) { pe_set_error("object %d needs a deformation code", k); return PE_ERR_INVALID; }
@@ -352,6 +361,13 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     if ((ca.do_objects || ca.do_global) && any_out) {
         rc = pe_launch_composite(ca, stream);
         if (rc) return rc;
+    }
+    if (out->peers > 0 && !peers_fused) {
+        // paths whose grid comes out of the compositor (or of the general field kernel): one copy per destination after the last kernel
+        const float* src = out->global.integrated_features ? out->global.integrated_features : (s.objects == 1 ? out->object[0].integrated_features : nullptr);
+        if (!src) { pe_set_error("peer_features needs the composed scene's integrated_features as an output"); return PE_ERR_INVALID; }
+        const size_t bytes = (size_t)s.images * s.rays * s.object[0].features * sizeof(float);
+        for (int q = 0; q < out->peers; ++q) PE_CUDA_CHECK(cudaMemcpyAsync(out->peer_features[q], src, bytes, cudaMemcpyDefault, stream));
     }
     return PE_OK;
 }

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                         const int64_t o = (gr0 + r) * 192 + lane + 32 * j;
                         if (out0) out0[o] = acc[r][j];
                         if (out1) out1[o] = acc[r][j];
+                        // fused all-gather: the same 128-byte warp store to every peer's copy of the grid (P2P over NVLink)
+                        for (int q = 0; q < A.peers; ++q) A.peer_features[q][o] = acc[r][j];
                     }
                 }
             }

@@ -38,6 +38,9 @@ struct PeFieldArgs {
     const int32_t* tile_list;    // [*tile_count] tiles (of floor(128/P) rays) that hold at least one sample with bit 1
     const int32_t* tile_count;
     float* h7_out;               // [images][rays][P][W] trunk output of the evaluated samples (train-mode recompute for the backward) or NULL
+    // fused all-gather (folded-head path, the object is the scene): extra destinations of integrated_features, peer-mapped or local
+    int32_t peers;
+    float* peer_features[PE_MAX_PEERS];
 };
 
 // Arguments of the compositing kernel (model/object_composer.py:399-447, 724-784).

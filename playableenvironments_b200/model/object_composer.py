@@ -68,9 +68,11 @@ class ObjectComposer(nn.Module):
 
     def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
                 transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
-                perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None) -> Dict:
+                perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None,
+                peer_features=None) -> Dict:
         """Same contract as the reference (:786-812).  ``rand`` / ``noise`` optionally supply the perturbation tensors
-        (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample."""
+        (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample.  ``peer_features`` (inference):
+        extra destinations of the composed scene's feature grid -- the fused all-gather of ``sharding.PeerGather``."""
         objects_count = self.object_id_helper.objects_count
         if transformation_matrix_w2o.size(-1) != objects_count:
             raise Exception(f"Transformation matrix must specifies transformations for"
@@ -89,7 +91,7 @@ class ObjectComposer(nn.Module):
                                   ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
                                   self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
                                   _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running,
-                                  return_raw_alphas=self.return_raw_alphas, models=models)
+                                  return_raw_alphas=self.return_raw_alphas, models=models, peer_features=peer_features)
         if self.training:
             with torch.no_grad():
                 self._update_running_statistics(bn_running)

@@ -156,6 +156,16 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Opti
         g = _alloc_integrated(lead, rays, sum(d.positions for d in descs), F, device)
         _fill(outs.global_, g)
         results["global"] = g
+    peers = meta.get("peer_features") or []
+    if peers:
+        # fused all-gather: extra destinations of the scene's feature grid (peer-mapped buffers of the other GPUs, sharding.PeerGather)
+        if len(peers) > _cabi.PE_MAX_PEERS:
+            raise _cabi.PeError(f"at most {_cabi.PE_MAX_PEERS} peer destinations")
+        outs.peers = len(peers)
+        for i, t in enumerate(peers):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != images * rays * F:
+                raise _cabi.PeError("peer_features: contiguous fp32 tensors of images * rays * features elements")
+            outs.peer_features[i] = t.data_ptr()
     with torch.cuda.device(device):
         if saved is not None:
             scene.keep_samples = 1
@@ -270,7 +280,7 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
                  rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
                  bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
-                 return_samples: bool = False) -> Dict:
+                 return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
     With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node."""
     device = ray_directions.device
@@ -289,7 +299,9 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
     meta = {"descs": descs, "static_objects": static_objects, "perturb": perturb, "training": training,
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
-            "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples}
+            "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features}
+    if peer_features and models is not None and torch.is_grad_enabled():
+        raise _cabi.PeError("peer_features (fused all-gather of the feature grid) is an inference feature: call under torch.no_grad()")
     if models is not None and torch.is_grad_enabled():
         flat_params = [t for mdl in models for _, _, t in mdl.parameter_slots()]
         flat = RenderFunction.apply(meta, origins, dirs, m, *styles, *deforms, *flat_params)

@@ -59,13 +59,55 @@ def render_sharded(composer, ray_origins, ray_directions, focal_normals, w2o, st
     return full, local, (begin, end)
 
 
+class PeerGather:
+    """The all-gather of the rendered feature grid FUSED into the render kernel (the one collective of the path).
+
+    Every rank owns ``buffer`` (world, rays, F) in symmetric memory (CUDA virtual-memory allocations exchanged once at construction:
+    torch.distributed._symmetric_memory) and maps the buffers of the other ranks of the box into its own address space.  Handing
+    ``destinations()`` to ``ObjectComposer.forward(peer_features=...)`` makes the field kernel store each ray's features into slot
+    ``rank`` of EVERY rank's buffer as it produces them: P2P stores over NVLink / NVSwitch, no NCCL kernel competing for the SMs (the
+    persistent render kernel leaves none free) and nothing exposed after the render but ``sync()``, a device-side barrier on the
+    symmetric memory's signal pads.  (Legacy cudaIpc mappings fault under kernel stores from the importing device; measured.)
+    Inference only; one image per call."""
+
+    def __init__(self, rays: int, features: int, device: torch.device, group=None):
+        self.group, self.rays, self.features = group, rays, features
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        shape = (self.world, rays, features)
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buffer = symm_mem.empty(shape, dtype=torch.float32, device=device)
+            self._handle = symm_mem.rendezvous(self.buffer, group=group if group is not None else dist.group.WORLD)
+            self._peers = [self.buffer if r == self.rank else self._handle.get_buffer(r, shape, torch.float32) for r in range(self.world)]
+            self.buffer.zero_()
+            torch.cuda.synchronize(device)
+            dist.barrier(group=group)
+        else:
+            self.buffer = torch.zeros(shape, dtype=torch.float32, device=device)
+            self._handle, self._peers = None, [self.buffer]
+
+    def destinations(self, begin: int = 0, end: int = None) -> List[torch.Tensor]:
+        """Slot ``rank`` (rays ``begin:end``) of every rank's buffer, the local one included."""
+        end = self.rays if end is None else end
+        return [self._peers[r][self.rank, begin:end] for r in range(self.world)]
+
+    def sync(self):
+        """Orders every rank's reads of ``buffer`` after every rank's render (stream-ordered, on the current stream)."""
+        if self._handle is not None:
+            self._handle.barrier()
+        return self.buffer
+
+
 def render_pipelined(composer, ray_origins, ray_directions, focal_normals, w2o, style, deformation, object_in_scene, perturb: bool,
-                     chunks: int = 4, group=None, gathered: torch.Tensor = None, host_out: torch.Tensor = None, side_stream=None, **kw):
+                     chunks: int = 4, group=None, gathered: torch.Tensor = None, host_out: torch.Tensor = None, side_stream=None,
+                     peer_gather: "PeerGather" = None, **kw):
     """Renders the local rays in ``chunks`` contiguous ray chunks and moves each chunk's feature grid off the compute stream while
     the next chunk renders: chunk i is all-gathered across the ranks (``gathered``: (world, rays, F), every rank renders the same
     number of rays -- one frame or one equal shard per rank) and/or copied to pinned host memory (``host_out``: (rays, F)) on
-    ``side_stream``; only the last chunk's transfer is exposed.  Rays are independent, so the chunks equal the single-launch
-    render bit for bit.  Inference only.  Returns the local feature grid (rays, F) (device)."""
+    ``side_stream``; only the last chunk's transfer is exposed.  With ``peer_gather`` the all-gather is fused into the render kernel
+    instead (P2P stores, ``PeerGather``) and only the host copy rides the side stream.  Rays are independent, so the chunks equal the
+    single-launch render bit for bit.  Inference only.  Returns the local feature grid (rays, F) (device)."""
     if torch.is_grad_enabled() and composer.training:
         raise Exception("render_pipelined is inference-only: call it under torch.no_grad() / composer.eval()")
     world = dist.get_world_size(group) if (dist.is_initialized() and gathered is not None) else 1
@@ -80,9 +122,14 @@ def render_pipelined(composer, ray_origins, ray_directions, focal_normals, w2o, 
         begin, end = ray_shard(rays, c, chunks)
         if end == begin:
             continue
+        if peer_gather is not None:
+            kw["peer_features"] = peer_gather.destinations(begin, end)
         res = composer(ray_origins, ray_directions[..., begin:end, :], focal_normals, w2o, style, deformation, object_in_scene, perturb, **kw)
         feats = res["coarse"]["global"]["integrated_features"]
         feats = feats.reshape(end - begin, feats.size(-1))
+        if peer_gather is not None and host_out is None:
+            local = peer_gather.buffer[peer_gather.rank]
+            continue
         if local is None:
             local = feats.new_empty((rays, feats.size(-1))) if (gathered is None or world == 1) else None
         ready = torch.cuda.Event()
@@ -103,6 +150,9 @@ def render_pipelined(composer, ray_origins, ray_directions, focal_normals, w2o, 
     main.wait_event(done)
     for t in keep:
         t.record_stream(side)
+    if peer_gather is not None:
+        peer_gather.sync()
+        return peer_gather.buffer[peer_gather.rank]
     if local is None:
         local = gathered[dist.get_rank(group)]
     return local

@@ -47,6 +47,19 @@ def _worker(rank, world, port, tmp):
                 ok.append(torch.equal(mine, single.reshape(rays, F)))
                 ok.append(all(torch.equal(gathered[r], single.reshape(rays, F)) for r in range(world)))
                 ok.append(torch.equal(host, single.reshape(rays, F).cpu()))
+                # the all-gather fused into the render kernel (P2P stores into every rank's grid), single launch and pipelined with D2H
+                pg = sharding.PeerGather(rays, F, device)
+                comp(*args, False, peer_features=pg.destinations())
+                grid = pg.sync()
+                torch.cuda.synchronize()
+                ok.append(all(torch.equal(grid[r], single.reshape(rays, F)) for r in range(world)))
+                pg.buffer.zero_()
+                dist.barrier()
+                host.zero_()
+                sharding.render_pipelined(comp, *args, False, chunks=3, host_out=host, peer_gather=pg)
+                torch.cuda.synchronize()
+                ok.append(all(torch.equal(pg.buffer[r], single.reshape(rays, F)) for r in range(world)))
+                ok.append(torch.equal(host, single.reshape(rays, F).cpu()))
         # data-parallel training: rank r differentiates its own frame; the single flat-bucket all-reduce must equal a per-tensor reduction
         _, _, _, mine_comp, dev = build_composer(scenes.scene_static(seed=40 + rank, height=8, width=8, P=64), "fp32", device=device)
         mine_comp.allow_forward_without_grad = False
