@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 4
+#define PE_ABI_VERSION 5
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -90,6 +90,10 @@ typedef struct PeScene {
     int32_t explicit_positions;/* 0: sample along rays; 1: field evaluation on given points  */
     int32_t keep_samples;      /* 1: the forward leaves every per-sample tensor, AdaIn constant and BatchNorm sum in its workspace,
                                   which the caller keeps and hands to pe_render_backward_saved (no forward recompute there) */
+    int32_t explicit_t;        /* 1: hierarchical ("fine") pass -- every object is sampled at PeInputs.sample_t[k] (all non-NULL).  The
+                                  backward of such a call runs the exact fp32 kernels: on the resampled (clustered) ray parameters the
+                                  tensor-core backward deviates by 5-10 % on the fine model's trunk gradients (measured on the
+                                  static_fine golden, tests/gpu_fine_diag.py; cause not isolated), the fp32 one by 1e-2              */
     PeObjectDesc object[PE_MAX_OBJECTS];
 } PeScene;
 
@@ -104,6 +108,10 @@ typedef struct PeInputs {
     const float* noise[PE_MAX_OBJECTS];        /* [images][rays][P_k] normal, replaces torch.randn (object_composer.py:194) in the per-object integrate */
     const float* noise_global;       /* [images][rays][sum P]     same, for the composed scene */
     const float* positions;          /* explicit_positions: [images][rays][3] object space   */
+    /* hierarchical ("fine") pass, model/object_composer.py:563-578: explicit ray parameters [images][rays][P_k] of object k (sorted
+     * along P: RayHelper.create_ray_positions_weighted, utils/lib_3d/ray_helper.py:1320-1347) instead of the stratified samples of
+     * create_ray_positions; NULL = stratified.  rand[k] is not read for such an object.                                          */
+    const float* sample_t[PE_MAX_OBJECTS];
 } PeInputs;
 
 /* Result of ObjectComposer.integrate (model/object_composer.py:724-784). Any pointer may be NULL. */
@@ -196,6 +204,7 @@ typedef struct PeInGrads {
     float* style[PE_MAX_OBJECTS];              /* [images][style_features]                                   */
     float* deformation[PE_MAX_OBJECTS];        /* [images][deformation_features]                             */
     PeObjectParamGrads params[PE_MAX_OBJECTS]; /* per object instance                                        */
+    float* sample_t[PE_MAX_OBJECTS];           /* [images][rays][P_k] dL/dt of PeInputs.sample_t[k] (written, not accumulated) or NULL */
 } PeInGrads;
 
 size_t pe_backward_workspace_bytes(const PeScene* scene);

@@ -134,6 +134,38 @@ def create_ray_positions(origins: Tensor, directions: Tensor, z_near: Tensor, z_
     return positions, t
 
 
+def sample_pdf(bin_delimiters: Tensor, weights: Tensor, positions_count: int, perturb: bool, rand: Optional[Tensor] = None) -> Tensor:
+    """utils/lib_3d/ray_helper.py:1349-1403: inverse-CDF samples of the piecewise-constant density ``weights`` (..., B-1) over the
+    bins delimited by ``bin_delimiters`` (..., B).  ``rand`` replaces the ``torch.rand`` of :1379."""
+    weights = weights + 1e-5                                                        # :1365
+    pdf = weights / torch.sum(weights, dim=-1, keepdim=True)
+    cdf = torch.cumsum(pdf, dim=-1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    lead = list(cdf.shape[:-1])
+    if not perturb:
+        u = torch.linspace(0.0, 1.0, positions_count).expand(lead + [positions_count]).contiguous()   # :1371-1377
+    else:
+        u = torch.rand(lead + [positions_count]) if rand is None else rand
+    idx = torch.searchsorted(cdf, u, right=True)                                    # :1382
+    below = torch.clamp(idx - 1, min=0)
+    above = torch.clamp(idx, max=cdf.size(-1) - 1)
+    cdf_lo, cdf_hi = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    bin_lo, bin_hi = torch.gather(bin_delimiters, -1, below), torch.gather(bin_delimiters, -1, above)
+    norm = cdf_hi - cdf_lo
+    norm = torch.where(norm < 1e-5, torch.ones_like(norm), norm)                    # :1398
+    return bin_lo + (u - cdf_lo) / norm * (bin_hi - bin_lo)
+
+
+def create_ray_positions_weighted(origins: Tensor, directions: Tensor, positions_count: int, reference_t: Tensor, weights: Tensor,
+                                  perturb: bool, rand: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """utils/lib_3d/ray_helper.py:1320-1347: new samples from the coarse weights, merged with the coarse ones and sorted."""
+    mid = (reference_t[..., 1:] + reference_t[..., :-1]) / 2
+    t_new = sample_pdf(mid, weights[..., 1:-1], positions_count, perturb, rand).detach()
+    merged, _ = torch.sort(torch.cat([reference_t, t_new], dim=-1), dim=-1)
+    positions = origins.unsqueeze(-2).unsqueeze(-2) + directions.unsqueeze(-2) * merged.unsqueeze(-1)
+    return positions, merged
+
+
 # ----------------------------------------------------------------------------
 # Encoders (model/positional_encoder.py, model/annealable_positional_encoder.py)
 # ----------------------------------------------------------------------------
@@ -182,6 +214,10 @@ def affine_adain(sd: Dict[str, Tensor], prefix: str, x: Tensor, style: Tensor, t
     scale, bias = enc.chunk(2, 1)
     rm = sd[prefix + ".ada_in.normalization.running_mean"]
     rv = sd[prefix + ".ada_in.normalization.running_var"]
+    if training and new_stats is not None:
+        # a model shared by several object instances is called once per instance: each call updates the statistics the previous one left
+        rm = new_stats.get(prefix + ".ada_in.normalization.running_mean", rm)
+        rv = new_stats.get(prefix + ".ada_in.normalization.running_var", rv)
     if training:
         if x.size(0) == 1:
             raise ValueError("Expected more than 1 value per channel when training")
@@ -425,7 +461,8 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
                      object_in_scene: Tensor, perturb: bool, canonical_pose: bool = False, training: bool = False,
                      rand: Optional[List[Tensor]] = None, noise: Optional[Dict[str, Tensor]] = None,
                      new_stats: Optional[Dict[str, Tensor]] = None) -> Dict:
-    """model/object_composer.py:786-892 (+ forward_object :486-580), coarse pass.
+    """model/object_composer.py:786-892 (+ forward_object :486-580); with ``use_fine`` object models also the fine pass (:561-578:
+    ``object_models_fine.{m}.<param>`` on the coarse samples merged with inverse-CDF samples of the coarse weights).
 
     ``state`` holds ``object_models_coarse.{m}.<param>`` tensors.  ``rand[k]``
     (uniform, shape (..., R, P_k)) and ``noise["object_k"|"global"]`` (normal)
@@ -439,6 +476,8 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
         raise Exception(f"Transformation matrix must specifies transformations for({transformation_matrix_w2o.size(-1)}) objects instead of ({objects_count})")
     R = ray_directions.size(-2)
     per_obj = []
+    per_obj_fine = []
+    use_fine = m["object_models"][model_of[0]].get("use_fine", True)
     for k in range(objects_count):
         mi = model_of[k]
         cfg = m["object_models"][mi]
@@ -461,19 +500,35 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
         if m["apply_activation"]:
             f = torch.sigmoid(f)
         per_obj.append((f, a, t, pos, disp, torch.zeros_like(a)))
+        if use_fine:
+            # :552-578 -- coarse weights of THIS object (no raw-alpha noise here: the fine goldens are unperturbed), resampling, fine model
+            w_c = compute_weights(compute_alphas(a, position_distances(t, d), None))
+            fprefix = f"object_models_fine.{mi}."
+            fsd = {key[len(fprefix):]: val for key, val in state.items() if key.startswith(fprefix)}
+            fpos, ft = create_ray_positions_weighted(o, d, cfg["positions_count_fine"], t, w_c, perturb)
+            ff, fa, fdisp = ray_bending_style_nerf(fsd, cfg, fpos, o_exp, d, style[..., k].unsqueeze(-2), deformation[..., k].unsqueeze(-2),
+                                                   canonical_pose, training, None if new_stats is None else _Prefixed(new_stats, fprefix))
+            fa = torch.where(absent.reshape(list(absent.shape) + [1] * (fa.dim() - absent.dim())), torch.full_like(fa, cfg["empty_space_alpha"]), fa)
+            if m["apply_activation"]:
+                ff = torch.sigmoid(ff)
+            per_obj_fine.append((ff, fa, ft, fpos, fdisp, torch.zeros_like(fa)))
 
-    results: Dict = {"coarse": {}}
-    for k, (f, a, t, pos, disp, div) in enumerate(per_obj):
-        nz = None if (noise is None or not perturb) else noise[f"object_{k}"]
-        r = integrate(f, a, ray_directions, t, disp, div, nz)
-        r["extra_outputs"] = {}
-        results["coarse"][f"object_{k}"] = r
+    results: Dict = {}
     exp_origins = ray_origins.unsqueeze(-2).expand(list(ray_directions.shape))
-    cf, ca, ct, cp, cd, cv = compose(m.get("fix_object_overlaps", True), static_count, exp_origins,
-                                     [x[0] for x in per_obj], [x[1] for x in per_obj], [x[2] for x in per_obj],
-                                     [x[3] for x in per_obj], [x[4] for x in per_obj], [x[5] for x in per_obj])
-    nz = None if (noise is None or not perturb) else noise["global"]
-    results["coarse"]["global"] = integrate(cf, ca, ray_directions, ct, cd, cv, nz)
+    for model_type, objs in (("coarse", per_obj), ("fine", per_obj_fine)):
+        if not objs:
+            continue
+        results[model_type] = {}
+        for k, (f, a, t, pos, disp, div) in enumerate(objs):
+            nz = None if (noise is None or not perturb or model_type == "fine") else noise[f"object_{k}"]
+            r = integrate(f, a, ray_directions, t, disp, div, nz)
+            r["extra_outputs"] = {}
+            results[model_type][f"object_{k}"] = r
+        cf, ca, ct, cp, cd, cv = compose(m.get("fix_object_overlaps", True), static_count, exp_origins,
+                                         [x[0] for x in objs], [x[1] for x in objs], [x[2] for x in objs],
+                                         [x[3] for x in objs], [x[4] for x in objs], [x[5] for x in objs])
+        nz = None if (noise is None or not perturb or model_type == "fine") else noise["global"]
+        results[model_type]["global"] = integrate(cf, ca, ray_directions, ct, cd, cv, nz)
     results["pytorch_hook"] = torch.zeros((1,) * 9)
     return results
 
@@ -515,6 +570,9 @@ class _Prefixed(dict):
 
     def __setitem__(self, key, value):
         self._parent[self._prefix + key] = value
+
+    def get(self, key, default=None):
+        return self._parent.get(self._prefix + key, default)
 
 
 # ----------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 4
+PE_ABI_VERSION = 5
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -60,6 +60,7 @@ class PeScene(C.Structure):
         ("images", C.c_int32), ("rays", C.c_int32), ("objects", C.c_int32), ("static_objects", C.c_int32),
         ("perturb", C.c_int32), ("training", C.c_int32), ("fix_object_overlaps", C.c_int32), ("apply_activation", C.c_int32),
         ("precision", C.c_int32), ("explicit_positions", C.c_int32), ("keep_samples", C.c_int32),
+        ("explicit_t", C.c_int32),
         ("object", PeObjectDesc * PE_MAX_OBJECTS),
     ]
 
@@ -70,7 +71,7 @@ class PeInputs(C.Structure):
         ("style", C.c_void_p * PE_MAX_OBJECTS), ("deformation", C.c_void_p * PE_MAX_OBJECTS),
         ("object_in_scene", C.c_void_p),
         ("rand", C.c_void_p * PE_MAX_OBJECTS), ("noise", C.c_void_p * PE_MAX_OBJECTS), ("noise_global", C.c_void_p),
-        ("positions", C.c_void_p),
+        ("positions", C.c_void_p), ("sample_t", C.c_void_p * PE_MAX_OBJECTS),
     ]
 
 
@@ -120,7 +121,7 @@ class PeInGrads(C.Structure):
     _fields_ = [
         ("ray_origins", C.c_void_p), ("ray_directions", C.c_void_p), ("w2o", C.c_void_p),
         ("style", C.c_void_p * PE_MAX_OBJECTS), ("deformation", C.c_void_p * PE_MAX_OBJECTS),
-        ("params", PeObjectParamGrads * PE_MAX_OBJECTS),
+        ("params", PeObjectParamGrads * PE_MAX_OBJECTS), ("sample_t", C.c_void_p * PE_MAX_OBJECTS),
     ]
 
 

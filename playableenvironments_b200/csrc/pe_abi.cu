@@ -200,8 +200,11 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     if (ws.bytes > workspace_bytes) { pe_set_error("workspace too small: %zu < %zu", workspace_bytes, ws.bytes); return PE_ERR_WORKSPACE; }
     if (s.perturb && !s.explicit_positions) {
         for (int k = 0; k < s.objects; ++k)
-            if (!in->rand[k]) { pe_set_error("perturb needs rand[%d]", k); return PE_ERR_INVALID; }
+            if (!in->rand[k] && !in->sample_t[k]) { pe_set_error("perturb needs rand[%d]", k); return PE_ERR_INVALID; }
     }
+    for (int k = 0; k < s.objects; ++k)
+        if ((s.explicit_t != 0) != (in->sample_t[k] != nullptr)) { pe_set_error("scene.explicit_t and sample_t[%d] disagree", k); return PE_ERR_INVALID; }
+    if (s.explicit_t && s.explicit_positions) { pe_set_error("explicit_t and explicit_positions are exclusive"); return PE_ERR_INVALID; }
     if (s.images == 0 || s.rays == 0) return PE_OK;
     int sm_count = 148;
     rc = pe_device_sm_count(&sm_count);
@@ -223,7 +226,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.perturb = s.perturb; fa.explicit_positions = s.explicit_positions; fa.training = s.training;
         fa.apply_activation = s.apply_activation; fa.precision = object_precision(s, k);
         fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
-        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.positions = in->positions; fa.ois = in->object_in_scene;
+        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.t_in = in->sample_t[k]; fa.positions = in->positions; fa.ois = in->object_in_scene;
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;
         fa.t_out = out->positions_t[k] ? out->positions_t[k] : o.t;
         fa.raw_out = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
@@ -396,6 +399,7 @@ static bool backward_compacts(const PeScene& s, int k) {
 // processed in batches (the number of in-box samples is only known on the device, so the batch count is the worst case and surplus
 // launches find no tile).
 static bool backward_on_tc(const PeScene& s, int k) {
+    if (s.explicit_t) return false;          // fine pass: exact fp32 backward (see PeScene.explicit_t)
     return backward_compacts(s, k) && !s.apply_activation && pe_bwd_tc_object_ok(s.object[k]) && pe_layout(s.object[k]).tcT_base != 0;
 }
 static int64_t bwd_tc_tiles_upper_bound(const PeScene& s, int k) {
@@ -570,7 +574,7 @@ extern "C" int pe_render_backward_saved(const PeScene* scene, const PeInputs* in
         fa.images = s.images; fa.rays = s.rays; fa.objects = s.objects; fa.k = k;
         fa.perturb = s.perturb; fa.training = s.training; fa.apply_activation = s.apply_activation; fa.precision = s.precision;
         fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
-        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.ois = in->object_in_scene;
+        fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.t_in = in->sample_t[k]; fa.ois = in->object_in_scene;
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;
         fb.w = params[k];
         fb.gw = grad_in->params[k];
@@ -672,10 +676,11 @@ extern "C" int pe_render_backward_saved(const PeScene* scene, const PeInputs* in
         sb.g_aff_w = grad_in->params[k].affine2_w; sb.g_aff_b = grad_in->params[k].affine2_b;
         rc = pe_launch_style_bwd(sb, stream); if (rc) return rc;
 
-        if (grad_in->ray_origins || grad_in->ray_directions || grad_in->w2o) {
+        if (grad_in->ray_origins || grad_in->ray_directions || grad_in->w2o || (in->sample_t[k] && grad_in->sample_t[k])) {
             PeGeometryBwdArgs gb = {};
             gb.ob = d; gb.images = s.images; gb.rays = s.rays; gb.objects = s.objects; gb.k = k; gb.perturb = s.perturb;
             gb.origins = in->ray_origins; gb.dirs = in->ray_directions; gb.w2o = in->w2o; gb.ois = in->object_in_scene; gb.rand = in->rand[k];
+            gb.t_in = in->sample_t[k]; gb.g_t_in = in->sample_t[k] ? grad_in->sample_t[k] : nullptr;
             gb.g_pos = b.g_pos; gb.g_t = b.g_t; gb.g_od = b.g_od;
             gb.g_origins = grad_in->ray_origins; gb.g_dirs = grad_in->ray_directions; gb.g_w2o = grad_in->w2o;
             rc = pe_launch_geometry_bwd(gb, stream); if (rc) return rc;

@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(128) pe_geometry_bwd_kernel(const PeGeometryBw
         float g_o[3] = {0.f, 0.f, 0.f}, g_d[3] = {0.f, 0.f, 0.f}, g_near = 0.f, g_far = 0.f;
         for (int p = 0; p < P; ++p) {
             const int64_t gs = ray * P + p;
-            const float u = G.perturb ? G.rand[gs] : 0.f;
-            const float t = pe_sample_t(pr, p, P, G.perturb != 0, u);
+            const float u = (G.perturb && !G.t_in) ? G.rand[gs] : 0.f;
+            const float t = pe_sample_t_or(G.t_in, gs, pr, p, P, G.perturb != 0, u);
             const float gx[3] = {G.g_pos[gs * 3], G.g_pos[gs * 3 + 1], G.g_pos[gs * 3 + 2]};
             float gt = G.g_t[gs];
             for (int a = 0; a < 3; ++a) {
@@ -360,6 +360,10 @@ __global__ void __launch_bounds__(128) pe_geometry_bwd_kernel(const PeGeometryBw
             }
             if (G.g_od) {
                 for (int a = 0; a < 3; ++a) { g_o[a] += G.g_od[gs * 6 + a]; g_d[a] += G.g_od[gs * 6 + 3 + a]; }
+            }
+            if (G.t_in) {                 // explicit ray parameters: dL/dt goes back to the caller (the coarse members depend on the ray)
+                if (G.g_t_in) G.g_t_in[gs] = gt;
+                continue;
             }
             g_near = fmaf(gt, pe_sample_t(unit_near, p, P, G.perturb != 0, u), g_near);
             g_far = fmaf(gt, pe_sample_t(unit_far, p, P, G.perturb != 0, u), g_far);

@@ -81,8 +81,8 @@ __device__ __forceinline__ void load_row(const PeBwdTcArgs& B, int64_t tile, int
         const int ray = r.slot / P, p = r.slot - ray * P;
         const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)r.img * A.objects + A.k) * 12, A.origins + (int64_t)r.img * 3,
                                      A.dirs + ((int64_t)r.img * A.rays + ray) * 3, r.in_scene);
-        const float u = A.perturb ? A.rand[r.gs] : 0.f;
-        const float t = pe_sample_t(pr, p, P, A.perturb != 0, u);
+        const float u = (A.perturb && !A.t_in) ? A.rand[r.gs] : 0.f;
+        const float t = pe_sample_t_or(A.t_in, r.gs, pr, p, P, A.perturb != 0, u);
         float x[3];
         pe_position(pr, t, x);
         r.active = pe_in_box(ob, x);
@@ -917,8 +917,8 @@ __device__ __forceinline__ void load_row_prebend(const PeBwdTcArgs& B, int64_t t
     const int ray = r.slot / P, p = r.slot - ray * P;
     const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)r.img * A.objects + A.k) * 12, A.origins + (int64_t)r.img * 3,
                                  A.dirs + ((int64_t)r.img * A.rays + ray) * 3, r.in_scene);
-    const float u = A.perturb ? A.rand[r.gs] : 0.f;
-    const float t = pe_sample_t(pr, p, P, A.perturb != 0, u);
+    const float u = (A.perturb && !A.t_in) ? A.rand[r.gs] : 0.f;
+    const float t = pe_sample_t_or(A.t_in, r.gs, pr, p, P, A.perturb != 0, u);
     pe_position(pr, t, r.x);
     r.active = pe_in_box(ob, r.x);
 }

@@ -230,6 +230,12 @@ __device__ __forceinline__ float pe_sample_t(const PeRay& ray, int p, int P, boo
     return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
 }
 
+// Hierarchical ("fine") pass: the caller supplies the ray parameters (RayHelper.create_ray_positions_weighted, ray_helper.py:1320-1347:
+// coarse samples merged with inverse-CDF samples of the coarse weights, sorted) -- `t_in` [images][rays][P] replaces the stratified samples.
+__device__ __forceinline__ float pe_sample_t_or(const float* __restrict__ t_in, int64_t gs, const PeRay& ray, int p, int P, bool perturb, float u) {
+    return t_in ? t_in[gs] : pe_sample_t(ray, p, P, perturb, u);
+}
+
 __device__ __forceinline__ void pe_position(const PeRay& ray, float t, float x[3]) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(ray.o[a], __fmul_rn(ray.d[a], t));

@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
                 const int64_t gs = gsi + s;
                 const PeRay ray = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3,
                                               A.dirs + ((int64_t)img * A.rays + r) * 3, in_scene);
-                const float u = A.perturb ? A.rand[gs] : 0.f;
-                const float t = pe_sample_t(ray, p, P, A.perturb != 0, u);
+                const float u = (A.perturb && !A.t_in) ? A.rand[gs] : 0.f;
+                const float t = pe_sample_t_or(A.t_in, gs, ray, p, P, A.perturb != 0, u);
                 pe_position(ray, t, x);
                 for (int a = 0; a < 3; ++a) { S.aux[a * TB + tid] = ray.o[a]; S.aux[(3 + a) * TB + tid] = ray.d[a]; }
                 if (pe_in_box(ob, x)) flag |= 1;

@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_fp32_kernel(const PeFieldArgs 
                 } else {
                     const PeRay ray = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3,
                                                   A.dirs + ((int64_t)img * A.rays + r) * 3, in_scene);
-                    const float u = A.perturb ? A.rand[gs] : 0.f;
-                    const float t = pe_sample_t(ray, p, P, A.perturb != 0, u);
+                    const float u = (A.perturb && !A.t_in) ? A.rand[gs] : 0.f;
+                    const float t = pe_sample_t_or(A.t_in, gs, ray, p, P, A.perturb != 0, u);
                     pe_position(ray, t, x);
                     if (A.t_out) A.t_out[gs] = t;
                     for (int a = 0; a < 3; ++a) { S.aux[a * TM + tid] = ray.o[a]; S.aux[(3 + a) * TM + tid] = ray.d[a]; }

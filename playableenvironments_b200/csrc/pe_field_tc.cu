@@ -487,8 +487,8 @@ __global__ void __launch_bounds__(256) pe_sample_kernel(const PeFieldArgs A) {
         const bool in_scene = A.ois ? A.ois[(int64_t)img * A.objects + A.k] != 0 : true;
         const PeRay ray = pe_make_ray(ob, A.w2o + ((int64_t)img * A.objects + A.k) * 12, A.origins + (int64_t)img * 3,
                                       A.dirs + ((int64_t)img * A.rays + r) * 3, in_scene);
-        const float u = A.perturb ? A.rand[gs] : 0.f;
-        const float t = pe_sample_t(ray, p, P, A.perturb != 0, u);
+        const float u = (A.perturb && !A.t_in) ? A.rand[gs] : 0.f;
+        const float t = pe_sample_t_or(A.t_in, gs, ray, p, P, A.perturb != 0, u);
         float x[3];
         pe_position(ray, t, x);
         A.t_out[gs] = t;

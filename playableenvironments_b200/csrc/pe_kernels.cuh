@@ -14,6 +14,7 @@ struct PeFieldArgs {
     const float* w2o;            // [images][objects][12]
     const float* deformation;    // [images][D]
     const float* rand;           // [images][rays][P]
+    const float* t_in;           // [images][rays][P] explicit ray parameters (fine pass) or NULL: stratified sampling
     const float* positions;      // explicit positions [images][rays][3]
     const uint8_t* ois;          // [images][objects]
     const float* aff1;           // [images][2][W]    effective AdaIn scale/shift (BatchNorm folded)
@@ -136,6 +137,8 @@ struct PeGeometryBwdArgs {
     PeObjectDesc ob;
     int32_t images, rays, objects, k, perturb;
     const float* origins; const float* dirs; const float* w2o; const uint8_t* ois; const float* rand;
+    const float* t_in;             // explicit ray parameters of the forward (fine pass) or NULL
+    float* g_t_in;                 // [images][rays][P] dL/dt of the explicit ray parameters or NULL
     const float* g_pos;            // [images][rays][P][3]
     const float* g_t;              // [images][rays][P]
     const float* g_od;             // skybox: [images][rays][P][6] or NULL

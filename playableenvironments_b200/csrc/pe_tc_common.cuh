@@ -225,7 +225,7 @@ __device__ __forceinline__ void prefetch_row(const TileCtx& X, int64_t tile, Ray
     const int64_t ray = (int64_t)img * A.rays + r;
     const float* dw = A.dirs + ray * 3;
     pf.d[0] = dw[0]; pf.d[1] = dw[1]; pf.d[2] = dw[2];
-    if (A.perturb) pf.u = A.rand[ray * X.P + (X.m % X.P)];
+    if (A.perturb && !A.t_in) pf.u = A.rand[ray * X.P + (X.m % X.P)];
 }
 
 template <bool kNoPrepass = false>
@@ -259,8 +259,8 @@ __device__ __forceinline__ void sample_row(const TileCtx& X, int64_t tile, RowSa
                 if (s.inbox) { s.x[0] = A.bent[gs * 3]; s.x[1] = A.bent[gs * 3 + 1]; s.x[2] = A.bent[gs * 3 + 2]; }
             } else {
                 const PeRay pr = pe_make_ray(ob, A.w2o + ((int64_t)s.img * A.objects + A.k) * 12, A.origins + (int64_t)s.img * 3, dw, s.in_scene);
-                const float u = A.perturb ? (pf ? pf->u : A.rand[s.ray * P + s.p]) : 0.f;
-                s.t = pe_sample_t(pr, s.p, P, A.perturb != 0, u);
+                const float u = (A.perturb && !A.t_in) ? (pf ? pf->u : A.rand[s.ray * P + s.p]) : 0.f;
+                s.t = pe_sample_t_or(A.t_in, s.ray * P + s.p, pr, s.p, P, A.perturb != 0, u);
                 pe_position(pr, s.t, s.x);
                 s.inbox = pe_in_box(ob, s.x);
             }

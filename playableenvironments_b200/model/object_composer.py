@@ -38,9 +38,6 @@ class ObjectComposer(nn.Module):
         for current_object_config in self.config["model"]["object_models"]:
             if fine and "use_fine" in current_object_config and current_object_config["use_fine"] == False:  # noqa: E712
                 current_model = None
-            elif fine:
-                raise NotImplementedError("hierarchical fine sampling (use_fine: True) is not on the B200 path yet; "
-                                          "every shipped config sets use_fine: False")
             else:
                 current_model = registry.build(current_object_config["architecture"], self.config, current_object_config)
             object_models.append(current_model)
@@ -55,16 +52,70 @@ class ObjectComposer(nn.Module):
 
     def _any_parameter_requires_grad(self) -> bool:
         """Attribute walk instead of ``self.parameters()``: on nn.DataParallel replicas the weights are plain tensor attributes."""
-        return any(t.requires_grad for m in self.object_models_coarse for t in m.state_tensors())
+        models = list(self.object_models_coarse) + [m for m in self.object_models_fine if m is not None]
+        return any(t.requires_grad for m in models for t in m.state_tensors())
 
-    def _descs(self, canonical_pose: bool):
+    def _descs(self, canonical_pose: bool, fine: bool = False):
+        """One PeObjectDesc per object instance.  ``fine``: the fine model of each instance on positions_count_coarse +
+        positions_count_fine samples per ray (the coarse samples merged with the resampled ones, reference :563-566)."""
         helper = self.object_id_helper
         descs = []
         for object_idx in range(helper.objects_count):
             model_idx = helper.model_idx_by_object_idx(object_idx)
-            m = self.object_models_coarse[model_idx]
-            descs.append(m.object_desc(m.model_config["positions_count_coarse"], helper.is_static(model_idx), canonical_pose))
+            coarse = self.object_models_coarse[model_idx]
+            positions = coarse.model_config["positions_count_coarse"]
+            m = coarse
+            if fine:
+                m = self.object_models_fine[model_idx]
+                positions += m.model_config["positions_count_fine"]
+            descs.append(m.object_desc(positions, helper.is_static(model_idx), canonical_pose))
         return descs
+
+    def _uses_fine(self) -> bool:
+        """The reference iterates over the result keys of object 0 (:847): a fine model on object 0 makes every object need one."""
+        helper = self.object_id_helper
+        fine = [self.object_models_fine[helper.model_idx_by_object_idx(k)] is not None for k in range(helper.objects_count)]
+        if fine[0] and not all(fine):
+            raise Exception("use_fine must be set for every object model or for none (the reference composes the 'fine' results of all objects)")
+        return fine[0]
+
+    @staticmethod
+    def compute_raywise_object_z_bounds(ray_origins: torch.Tensor, ray_directions: torch.Tensor, bounding_box, object_validity: torch.Tensor):
+        """Reference :104-151 (slab test per ray; rays that miss the box or belong to an absent object get z_near = z_far = 0).  The
+        kernels evaluate this in registers; the torch form serves the fine pass, whose merged ray parameters are built on the host side."""
+        eps = 1e-6
+        corners = bounding_box.get_corner_points()[[0, 6]].to(ray_directions.device)
+        z = (corners - ray_origins.unsqueeze(-2)).unsqueeze(-3) / (ray_directions.unsqueeze(-2) + eps)
+        z_near = z.min(dim=-2)[0].max(dim=-1)[0]
+        z_far = z.max(dim=-2)[0].min(dim=-1)[0]
+        mask = torch.logical_or(z_far <= z_near, torch.logical_not(object_validity.unsqueeze(-1).expand_as(z_far)))
+        return torch.where(mask, torch.zeros_like(z_near), z_near), torch.where(mask, torch.zeros_like(z_far), z_far)
+
+    def _fine_ray_parameters(self, ray_origins, ray_directions, focal_normals, transformation_matrix_w2o, object_in_scene, perturb: bool,
+                             rand, coarse_results) -> List[torch.Tensor]:
+        """RayHelper.create_ray_positions_weighted per object (reference :563-566): the object's coarse ray parameters (a differentiable
+        function of the rays, evaluated here with the torch helpers) merged with ``positions_count_fine`` inverse-CDF samples of its own
+        coarse compositing weights (detached, like the reference), sorted.  (With ``perturb`` the reference draws a separate raw-alpha
+        noise for these weights, :553; here they are the weights the coarse pass returns.)"""
+        from ..utils.lib_3d.ray_helper import RayHelper
+        helper = self.object_id_helper
+        merged = []
+        for k in range(helper.objects_count):
+            model_idx = helper.model_idx_by_object_idx(k)
+            coarse, fine = self.object_models_coarse[model_idx], self.object_models_fine[model_idx]
+            cfg = coarse.model_config
+            if cfg["positions_count_coarse"] < 3:
+                raise Exception("fine sampling needs at least 3 coarse samples per ray (sample_pdf over the interior bins, ray_helper.py:1336)")
+            o, d, _ = RayHelper.transform_rays(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o[..., k])
+            z_near, z_far = self.compute_raywise_object_z_bounds(o, d, coarse.bounding_box, object_in_scene[..., k])
+            z_near = torch.clamp(z_near, min=cfg["z_near_min"], max=cfg["z_far_max"])
+            z_far = torch.clamp(z_far, min=cfg["z_near_min"], max=cfg["z_far_max"])
+            t_coarse = RayHelper.ray_parameters(z_near, z_far, cfg["positions_count_coarse"], rand[k] if perturb else None)
+            weights = coarse_results[f"object_{k}"]["weights"].detach()
+            mid = (t_coarse[..., 1:] + t_coarse[..., :-1]) / 2
+            t_new = RayHelper.sample_pdf(mid.detach(), weights[..., 1:-1], fine.model_config["positions_count_fine"], perturb).detach()
+            merged.append(torch.sort(torch.cat([t_coarse, t_new], dim=-1), dim=-1)[0])
+        return merged
 
     def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
                 transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
@@ -83,24 +134,43 @@ class ObjectComposer(nn.Module):
             self._any_parameter_requires_grad()
             or any(torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
         helper = self.object_id_helper
-        models = None
-        if needs_grad and not getattr(self, "allow_forward_without_grad", False):
-            models = [self.object_models_coarse[helper.model_idx_by_object_idx(k)] for k in range(objects_count)]
-        bn_running: List = []
-        res = render.render_scene(self._descs(canonical_pose), helper.static_objects_count, ray_origins,
-                                  ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
-                                  self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
-                                  _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, bn_running=bn_running,
-                                  return_raw_alphas=self.return_raw_alphas, models=models, peer_features=peer_features)
-        if self.training:
-            with torch.no_grad():
-                self._update_running_statistics(bn_running)
-        results = {"coarse": {}}
-        for k in range(objects_count):
-            r = res[f"object_{k}"]
-            r["extra_outputs"] = {}
-            results["coarse"][f"object_{k}"] = r
-        results["coarse"]["global"] = res["global"]
+        use_fine = self._uses_fine()
+        record = needs_grad and not getattr(self, "allow_forward_without_grad", False)
+        if use_fine and perturb and rand is None:
+            # the fine pass re-derives the coarse ray parameters from the same stratified jitter the coarse kernels used
+            lead_r = list(ray_directions.shape[:-1])
+            counts = [d.positions for d in self._descs(canonical_pose)]
+            rand = [torch.rand(lead_r + [p], device=ray_directions.device) for p in counts]
+            noise = {f"object_{k}": torch.randn(lead_r + [p], device=ray_directions.device) for k, p in enumerate(counts)}
+            noise["global"] = torch.randn(lead_r + [sum(counts)], device=ray_directions.device)
+        results = {}
+
+        def run(model_type, model_list, descs, **extra):
+            models = [model_list[helper.model_idx_by_object_idx(k)] for k in range(objects_count)] if record else None
+            bn_running: List = []
+            res = render.render_scene(descs, helper.static_objects_count, ray_origins,
+                                      ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
+                                      self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
+                                      _cabi.PRECISIONS[self.precision], bn_running=bn_running,
+                                      return_raw_alphas=self.return_raw_alphas, models=models, **extra)
+            if self.training:
+                with torch.no_grad():
+                    self._update_running_statistics(bn_running, model_list)
+            results[model_type] = {}
+            for k in range(objects_count):
+                r = res[f"object_{k}"]
+                r["extra_outputs"] = {}
+                results[model_type][f"object_{k}"] = r
+            results[model_type]["global"] = res["global"]
+            return res
+
+        coarse = run("coarse", self.object_models_coarse, self._descs(canonical_pose), rand=rand, noise=noise,
+                     peer_features=None if use_fine else peer_features)
+        if use_fine:
+            # hierarchical pass (reference :561-578): the fine models on the merged ray parameters, composed like the coarse results
+            sample_t = self._fine_ray_parameters(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o, object_in_scene,
+                                                 perturb, rand, coarse)
+            run("fine", self.object_models_fine, self._descs(canonical_pose, fine=True), sample_t=sample_t, peer_features=peer_features)
         # dummy tensor the reference adds for nn.DataParallel's hook handling (:889-890)
         results["pytorch_hook"] = torch.zeros((1, 1, 1, 1, 1, 1, 1, 1, 1), device=ray_directions.device)
         return results
@@ -138,12 +208,13 @@ class ObjectComposer(nn.Module):
         expected = self.compute_expected_positions(positions, res["displacements"], res["weights"])
         return {"coarse": (expected, res["opacity"])}
 
-    def _update_running_statistics(self, bn_running):
+    def _update_running_statistics(self, bn_running, model_list=None):
         """BatchNorm running-stat update of the two AdaIn layers, in object order like the reference's sequential
         per-instance model calls (a model shared by two instances is updated twice)."""
         helper = self.object_id_helper
+        model_list = self.object_models_coarse if model_list is None else model_list
         for object_idx, (b1, b2) in enumerate(bn_running):
-            head = self.object_models_coarse[helper.model_idx_by_object_idx(object_idx)].nerf_model.features_head
+            head = model_list[helper.model_idx_by_object_idx(object_idx)].nerf_model.features_head
             for layer, b in ((head[1], b1), (head[4], b2)):
                 bn = layer.ada_in.normalization
                 momentum = bn.momentum if bn.momentum is not None else 0.1

@@ -79,6 +79,7 @@ def _scene_struct(meta, images: int, rays: int) -> _cabi.PeScene:
     scene.perturb, scene.training = int(bool(meta["perturb"])), int(bool(meta["training"]))
     scene.fix_object_overlaps, scene.apply_activation = int(bool(meta["fix_object_overlaps"])), int(bool(meta["apply_activation"]))
     scene.precision, scene.explicit_positions = meta["precision"], 0
+    scene.explicit_t = 1 if meta.get("sample_t") is not None else 0
     for k, d in enumerate(descs):
         scene.object[k] = d
     return scene
@@ -92,6 +93,14 @@ def _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep) 
         ins.style[k] = _cabi.ptr(styles[k])
         ins.deformation[k] = _cabi.ptr(deforms[k])
     ins.object_in_scene = _cabi.ptr(meta["ois"])
+    sample_t = meta.get("sample_t")
+    if sample_t is not None:          # fine pass: explicit ray parameters per object (object_composer.py:563-578)
+        for k, d in enumerate(descs):
+            t = _cabi.f32(sample_t[k]).reshape(-1)
+            if t.numel() != dirs.size(0) * rays * d.positions:
+                raise _cabi.PeError(f"sample_t[{k}]: expected (..., {rays}, {d.positions}) ray parameters")
+            keep.append(t)
+            ins.sample_t[k] = _cabi.ptr(t)
     if meta["perturb"]:
         rand, noise = meta["rand"], meta["noise"]
 
@@ -101,7 +110,8 @@ def _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep) 
             return c
 
         for k, d in enumerate(descs):
-            ins.rand[k] = _cabi.ptr(dev(rand[k], lead + [rays, d.positions]))
+            if sample_t is None:
+                ins.rand[k] = _cabi.ptr(dev(rand[k], lead + [rays, d.positions]))
             ins.noise[k] = _cabi.ptr(dev(noise[f"object_{k}"], lead + [rays, d.positions]))
         ins.noise_global = _cabi.ptr(dev(noise["global"], lead + [rays, sum(d.positions for d in descs)]))
     return ins
@@ -192,6 +202,10 @@ class RenderFunction(torch.autograd.Function):
     def forward(ctx, meta, origins, dirs, w2o, *flat):
         K = len(meta["descs"])
         styles, deforms = list(flat[:K]), list(flat[K:2 * K])
+        n_t = K if meta.get("sample_t") is not None else 0       # fine pass: the explicit ray parameters are differentiable inputs
+        meta = dict(meta)
+        if n_t:
+            meta["sample_t"] = [t.detach() for t in flat[2 * K:3 * K]]
         saved = [] if _save_forward(meta) else None
         res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms, saved)
         ctx.saved_forward = saved[0] if saved else None
@@ -199,7 +213,8 @@ class RenderFunction(torch.autograd.Function):
         # the descs in ``meta`` hold RAW pointers into each model's packed blob: keep those tensors alive with the graph (a second
         # forward before this node's backward may repack -- train-mode BatchNorm bumps the running statistics every call)
         ctx.packed_keepalive = [m.packed_parameters() for m in meta["models"]] if meta.get("models") else []
-        ctx.save_for_backward(origins, dirs, w2o, *styles, *deforms)
+        ctx.n_t = n_t
+        ctx.save_for_backward(origins, dirs, w2o, *styles, *deforms, *(meta["sample_t"] if n_t else []))
         names = [f"object_{k}" for k in range(K)] + ["global"]
         outs = [res[n][key] for n in names for key in DIFF_KEYS]
         extra = [res[n]["integrated_divergence"] for n in names]
@@ -216,6 +231,10 @@ class RenderFunction(torch.autograd.Function):
         saved = ctx.saved_tensors
         origins, dirs, w2o = saved[0], saved[1], saved[2]
         styles, deforms = list(saved[3:3 + K]), list(saved[3 + K:3 + 2 * K])
+        n_t = ctx.n_t
+        if n_t:
+            meta = dict(meta)
+            meta["sample_t"] = list(saved[3 + 2 * K:3 + 3 * K])
         device = dirs.device
         L = _cabi.lib()
         images, rays = dirs.size(0), dirs.size(1)
@@ -242,9 +261,13 @@ class RenderFunction(torch.autograd.Function):
         g_deforms = [zeros(deforms[k]) if need[4 + K + k] else None for k in range(K)]
         for k in range(K):
             gin.style[k], gin.deformation[k] = _cabi.ptr(g_styles[k]), _cabi.ptr(g_deforms[k])
+        g_ts = [torch.zeros_like(meta["sample_t"][k], dtype=torch.float32, memory_format=torch.contiguous_format)
+                if need[4 + 2 * K + k] else None for k in range(n_t)]
+        for k in range(n_t):
+            gin.sample_t[k] = _cabi.ptr(g_ts[k])
         params = (_cabi.PeObjectParams * _cabi.PE_MAX_OBJECTS)()
         g_params: List = []
-        idx = 4 + 2 * K
+        idx = 4 + 2 * K + n_t
         for k, m in enumerate(models):
             ps, kp = m.parameter_struct()
             keep.append(kp)
@@ -272,7 +295,7 @@ class RenderFunction(torch.autograd.Function):
                 _cabi.check(L.pe_render_backward(C.byref(scene), C.byref(ins), params, C.byref(gout), C.byref(gin), _cabi.ptr(ws), ws.numel(),
                                                  _cabi.current_stream(device)))
         del keep
-        return (None, g_origins, g_dirs, g_w2o, *g_styles, *g_deforms, *g_params)
+        return (None, g_origins, g_dirs, g_w2o, *g_styles, *g_deforms, *g_ts, *g_params)
 
 
 def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origins: torch.Tensor, ray_directions: torch.Tensor,
@@ -280,9 +303,11 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  perturb: bool, training: bool, fix_object_overlaps: bool, apply_activation: bool, precision: int,
                  rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
                  bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
-                 return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None) -> Dict:
+                 return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None,
+                 sample_t: Optional[List[torch.Tensor]] = None) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
-    With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node."""
+    With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node.
+    ``sample_t`` (fine pass, :563-578): per object the explicit ray parameters (..., R, P_k) that replace the stratified samples."""
     device = ray_directions.device
     if device.type != "cuda":
         raise _cabi.PeError("ObjectComposer.forward needs CUDA tensors: the B200 render path has no CPU implementation")
@@ -293,18 +318,20 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                                                                                  object_in_scene)
     if perturb and (rand is None or noise is None):
         # torch's generator replaces the reference's torch.rand (ray_helper.py:1275) / torch.randn (object_composer.py:194)
-        rand = [torch.rand(lead + [rays, d.positions], device=device) for d in descs]
+        rand = [torch.rand(lead + [rays, d.positions], device=device) for d in descs] if sample_t is None else None
         noise = {f"object_{k}": torch.randn(lead + [rays, d.positions], device=device) for k, d in enumerate(descs)}
         noise["global"] = torch.randn(lead + [rays, sum(d.positions for d in descs)], device=device)
     meta = {"descs": descs, "static_objects": static_objects, "perturb": perturb, "training": training,
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
-            "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features}
+            "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features,
+            "sample_t": sample_t}
     if peer_features and models is not None and torch.is_grad_enabled():
         raise _cabi.PeError("peer_features (fused all-gather of the feature grid) is an inference feature: call under torch.no_grad()")
     if models is not None and torch.is_grad_enabled():
         flat_params = [t for mdl in models for _, _, t in mdl.parameter_slots()]
-        flat = RenderFunction.apply(meta, origins, dirs, m, *styles, *deforms, *flat_params)
+        ts = [t.to(torch.float32).reshape(images, rays, -1) for t in sample_t] if sample_t is not None else []
+        flat = RenderFunction.apply(meta, origins, dirs, m, *styles, *deforms, *ts, *flat_params)
         names = [f"object_{k}" for k in range(K)] + ["global"]
         results: Dict = {}
         it = iter(flat)

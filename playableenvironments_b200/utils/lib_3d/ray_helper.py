@@ -339,6 +339,19 @@ class RayHelper:
         return o, d, n
 
     @staticmethod
+    def ray_parameters(z_near: torch.Tensor, z_far: torch.Tensor, positions_count: int, rand: torch.Tensor = None) -> torch.Tensor:
+        """The ray parameters ``t`` of create_ray_positions (reference :1253-1277) for per-ray bounds (..., R): uniform in [z_near, z_far],
+        jittered inside their strata by ``rand`` (..., R, P) when given."""
+        s = torch.linspace(0.0, 1.0, positions_count, device=z_near.device)
+        t = z_near.unsqueeze(-1) * (1.0 - s) + z_far.unsqueeze(-1) * s
+        if rand is not None:
+            mid = (t[..., 1:] + t[..., :-1]) / 2
+            upper = torch.cat([mid, t[..., -1:]], dim=-1)
+            lower = torch.cat([t[..., :1], mid], dim=-1)
+            t = lower + (upper - lower) * rand
+        return t
+
+    @staticmethod
     def create_ray_positions(ray_origins, ray_directions, z_near, z_far, positions_count: int, perturb: bool):
         """Reference :1229-1282."""
         device = ray_directions.device
@@ -359,8 +372,8 @@ class RayHelper:
         return positions, t
 
     # ------------------------------------------------------------------------------------------------------------------
-    # hierarchical ("fine") sampling helpers (reference :1284-1403).  No shipped config enables a fine model (``use_fine: False``
-    # everywhere) and the fused composer raises for one; the helpers keep the reference API for callers that use them.
+    # hierarchical ("fine") sampling helpers (reference :1284-1403), used by ObjectComposer's fine pass (``use_fine: True``; no shipped
+    # config enables it).
     # ------------------------------------------------------------------------------------------------------------------
     @staticmethod
     def transform_ray_positions(ray_origins, ray_directions, focal_normals, ray_positions, transformation_matrix):

@@ -128,6 +128,10 @@ def scene_state(seed: int, config: dict, current_step: int = 60000) -> Dict[str,
     for mi, cfg in enumerate(config["model"]["object_models"]):
         for k, v in object_state(rng, cfg, current_step).items():
             state[f"object_models_coarse.{mi}.{k}"] = v
+    for mi, cfg in enumerate(config["model"]["object_models"]):        # fine models (object_composer.py:27, 44-53) have their own weights
+        if cfg.get("use_fine", True):
+            for k, v in object_state(rng, cfg, current_step).items():
+                state[f"object_models_fine.{mi}.{k}"] = v
     return state
 
 
@@ -296,6 +300,56 @@ def scene_toy_world(seed=18, height=64, width=64, stride=4, lead=(1, 2, 1)):
             state[k] = state[k] * 8.0
     return config, state, inputs
 
+
+def with_fine(scene, fine_counts: List[int]):
+    """The same scene with a fine model per object model (use_fine, positions_count_fine = fine_counts[model]); weights re-seeded."""
+    config, _, inputs = scene
+    for cfg, pf in zip(config["model"]["object_models"], fine_counts):
+        cfg["use_fine"] = True
+        cfg["positions_count_fine"] = pf
+    return config, None, inputs
+
+
+def scene_static_fine(seed=21):
+    """Shipped field shape, 64 coarse + 64 fine samples per ray: the fine pass is a 128-sample tensor-core frame on explicit ray parameters."""
+    config, _, inputs = with_fine(scene_static(seed=seed, P=64), [64])
+    return config, scene_state(seed, config), inputs
+
+
+def scene_tennis_fine(seed=22):
+    """Tennis shape with fine models everywhere: court 4 + 4, players 32 + 32 samples per ray (ray benders on explicit ray parameters)."""
+    config, _, inputs = with_fine(scene_tennis(seed=seed, height=64, width=64, stride=4, lead=(1, 1, 1), dense=True), [4, 32, 32])
+    return config, scene_state(seed, config), inputs
+
+
+def scene_toy_fine(seed=23, height=64, width=64, stride=4, lead=(1, 2, 1)):
+    """Small well-conditioned networks (like toy_world, without the one-sample skybox -- the reference's sample_pdf needs >= 3 coarse
+    samples): ground 8 + 8, a player model shared by 2 instances 12 + 12, fix_object_overlaps on; pins the fine pass's gradients."""
+    toy = lambda: nerf_cfg(64, 4, 2, 4, 8)
+    ground = object_cfg([[-10, 10], [-0.6, 2.0], [-10, 10]], 8, 0.05, 30.0, 16, 8, toy(), bender_cfg("zeroed"))
+    player = object_cfg([[-0.6, 0.6], [0.0, 2.1], [-1.2, 1.2]], 12, 0.05, 30.0, 16, 8, toy(),
+                        bender_cfg("positional", width=32, layers=3, skip=1, octaves=3))
+    config = scene_config([ground, player], 1, [1, 2], True)
+    for cfg, pf in zip(config["model"]["object_models"], [8, 12]):
+        cfg["use_fine"] = True
+        cfg["positions_count_fine"] = pf
+    c2w = homogeneous(rot_x(-0.25), [0.0, 1.6, 6.0])
+    orig, dirs, norm = camera_rays(lead, height, width, 0.8 * width, c2w, stride)
+    pa = np.linalg.inv(homogeneous(rot_z(0.1), [-0.8, 0.0, 1.0]))
+    pb = np.linalg.inv(homogeneous(np.eye(3), [1.0, 0.0, -0.5]))
+    inputs = build_inputs(seed, config, lead, orig, dirs, norm, [np.eye(4), pa, pb])
+    state = scene_state(seed, config)
+    for k in list(state):
+        if k.endswith("ray_bender.output_head.weight"):
+            state[k] = state[k] * 8.0
+    return config, state, inputs
+
+
+FINE_SCENES = {
+    "static_fine": lambda: scene_static_fine(),
+    "tennis_fine": lambda: scene_tennis_fine(),
+    "toy_fine": lambda: scene_toy_fine(),
+}
 
 SCENES = {
     "cfg1": lambda: scene_cfg1(),

@@ -159,3 +159,28 @@ def test_gradient_allreduce_world_size_2(tmp_path):
     port = 31500 + os.getpid() % 2000
     mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_fine_ray_parameters_match_the_oracle():
+    """Host side of the fine pass (ObjectComposer._fine_ray_parameters: torch z-bounds + coarse ray parameters + inverse-CDF resampling
+    + merge) against the oracle's restatement of create_ray_positions_weighted, itself pinned to the upstream goldens."""
+    import copy
+    import scenes
+    from helpers import INPUT_KEYS
+    from oracle import render_oracle as O
+    from playableenvironments_b200.model.object_composer import ObjectComposer
+    config, state, inputs = scenes.FINE_SCENES["toy_fine"]()
+    comp = ObjectComposer(copy.deepcopy(config))
+    assert comp._uses_fine()
+    args = [inputs[k] for k in INPUT_KEYS]
+    ref = O.composer_forward(config, state, *args, perturb=False)
+    ts = comp._fine_ray_parameters(inputs["ray_origins"], inputs["ray_directions"], inputs["focal_normals"],
+                                   inputs["transformation_matrix_w2o"], inputs["object_in_scene"], False, None, ref["coarse"])
+    model_of, _ = O.object_ids(config)
+    for k, t in enumerate(ts):
+        cfg = config["model"]["object_models"][model_of[k]]
+        assert t.shape[-1] == cfg["positions_count_coarse"] + cfg["positions_count_fine"]
+        assert bool((t[..., 1:] >= t[..., :-1]).all())
+        # the fine object's weights live on exactly these ray parameters: depth = sum w t
+        w = ref["fine"][f"object_{k}"]["weights"]
+        torch.testing.assert_close((w * t).sum(-1), ref["fine"][f"object_{k}"]["depth"], rtol=1e-4, atol=1e-5)

@@ -110,3 +110,31 @@ def test_oracle_expected_positions_match_the_reference():
         for got, key in ((exp, "expected_positions"), (opacity, "opacity")):
             ref = golden[f"{name}/{k}/{key}"]
             assert float(np.abs(got.numpy() - ref).max()) <= 2e-5 * max(float(np.abs(ref).max()), 1e-6), (name, k, key)
+
+
+# ---- hierarchical ("fine") pass: use_fine object models (object_composer.py:561-578, ray_helper.py:1320-1403) ----
+@pytest.mark.parametrize("name", list(scenes.FINE_SCENES))
+def test_fine_pass_matches_reference(name):
+    config, state, inputs = scenes.FINE_SCENES[name]()
+    res = O.composer_forward(config, state, *[inputs[k] for k in INPUT_KEYS], perturb=False)
+    golden = load_golden(name)
+    assert any(k.startswith("fine/") for k in golden)
+    for family in ("coarse/", "fine/"):
+        bad = compare(flatten(res), golden, 5e-5, only_prefix=family)
+        assert not bad, bad
+
+
+def test_fine_pass_train_mode_matches_reference():
+    config, state, inputs = scenes.FINE_SCENES["toy_fine"]()
+    new_stats = {}
+    res = O.composer_forward(config, state, *[inputs[k] for k in INPUT_KEYS], perturb=False, training=True, new_stats=new_stats)
+    golden = load_golden("toy_fine_train")
+    for family in ("coarse/", "fine/"):
+        bad = compare(flatten(res), golden, 1e-4, skip=("integrated_divergence",), only_prefix=family)
+        assert not bad, bad
+    fine_stats = [k for k in golden if k.startswith("state/object_models_fine.")]
+    assert fine_stats
+    for k, ref in golden.items():
+        if k.startswith("state/"):
+            key = k[len("state/"):]
+            np.testing.assert_allclose(new_stats.get(key, state[key]).numpy(), ref, rtol=1e-4, atol=1e-6, err_msg=key)
