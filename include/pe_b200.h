@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 5
+#define PE_ABI_VERSION 6
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -94,6 +94,10 @@ typedef struct PeScene {
                                   backward of such a call runs the exact fp32 kernels: on the resampled (clustered) ray parameters the
                                   tensor-core backward deviates by 5-10 % on the fine model's trunk gradients (measured on the
                                   static_fine golden, tests/gpu_fine_diag.py; cause not isolated), the fp32 one by 1e-2              */
+    int32_t divergence;        /* 1: the forward also evaluates the Hutchinson divergence of every positional ray bender's displacement
+                                  field (object_composer.py:582-601) from PeInputs.divergence_noise / divergence_params               */
+    int32_t bent_gradients;    /* 1: the backward also takes dL/d (sample position + displacement) from PeOutGrads.bent_positions -- the
+                                  backward of forward_expected_positions (object_composer.py:603-722)                                 */
     PeObjectDesc object[PE_MAX_OBJECTS];
 } PeScene;
 
@@ -112,6 +116,12 @@ typedef struct PeInputs {
      * along P: RayHelper.create_ray_positions_weighted, utils/lib_3d/ray_helper.py:1320-1347) instead of the stratified samples of
      * create_ray_positions; NULL = stratified.  rand[k] is not read for such an object.                                          */
     const float* sample_t[PE_MAX_OBJECTS];
+    /* Hutchinson divergence (scene.divergence): [images][rays][P_k][3] normal e, replaces torch.randn_like (object_composer.py:597); the
+     * per-sample value e . (d displacement / d position) e enters integrated_divergence = mean(alpha |div|) (:776-778).  NULL for an
+     * object: zeros.  divergence_params[k]: the fp32 parameter tensors of instance k (the vector-Jacobian product reads the nn.Linear
+     * layout, like the backward).                                                                                                   */
+    const float* divergence_noise[PE_MAX_OBJECTS];
+    const PeObjectParams* divergence_params;
 } PeInputs;
 
 /* Result of ObjectComposer.integrate (model/object_composer.py:724-784). Any pointer may be NULL. */
@@ -183,6 +193,8 @@ typedef struct PeIntegratedGrads {             /* dL/d(outputs of ObjectComposer
 typedef struct PeOutGrads {
     PeIntegratedGrads object[PE_MAX_OBJECTS];
     PeIntegratedGrads global;
+    /* scene.bent_gradients: [images][rays][P_k][3] dL/d (sample position + displacement) of object k, object space, or NULL */
+    const float* bent_positions[PE_MAX_OBJECTS];
 } PeOutGrads;
 
 typedef struct PeObjectParamGrads {            /* same tensors and layouts as PeObjectParams (nn.Linear [out][in]) */

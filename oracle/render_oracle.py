@@ -22,6 +22,7 @@ Parameters are passed as a flat ``dict[str, Tensor]`` using the reference's
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -460,15 +461,16 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
                      focal_normals: Tensor, transformation_matrix_w2o: Tensor, style: Tensor, deformation: Tensor,
                      object_in_scene: Tensor, perturb: bool, canonical_pose: bool = False, training: bool = False,
                      rand: Optional[List[Tensor]] = None, noise: Optional[Dict[str, Tensor]] = None,
-                     new_stats: Optional[Dict[str, Tensor]] = None) -> Dict:
+                     new_stats: Optional[Dict[str, Tensor]] = None, divergence_noise: Optional[List[Tensor]] = None) -> Dict:
     """model/object_composer.py:786-892 (+ forward_object :486-580); with ``use_fine`` object models also the fine pass (:561-578:
     ``object_models_fine.{m}.<param>`` on the coarse samples merged with inverse-CDF samples of the coarse weights).
 
     ``state`` holds ``object_models_coarse.{m}.<param>`` tensors.  ``rand[k]``
     (uniform, shape (..., R, P_k)) and ``noise["object_k"|"global"]`` (normal)
     stand in for the reference's RNG calls when ``perturb`` is set.  The
-    Hutchinson divergence (:582-601) is returned as zeros: its weight is 0 in
-    every shipped config and it is random by construction."""
+    Hutchinson divergence (:582-601) is random by construction: it is evaluated
+    when its probe vectors ``divergence_noise[k]`` (..., R, P_k, 3) are given
+    (training only, like the reference), else returned as zeros."""
     m = config["model"]
     model_of, static_count = object_ids(config)
     objects_count = len(model_of)
@@ -493,13 +495,24 @@ def composer_forward(config: dict, state: Dict[str, Tensor], ray_origins: Tensor
         P = cfg["positions_count_coarse"]
         pos, t = create_ray_positions(o, d, zn, zf, P, perturb, None if rand is None else rand[k])
         o_exp = o.unsqueeze(-2).expand(list(d.shape))
-        f, a, disp = ray_bending_style_nerf(sd, cfg, pos, o_exp, d, style[..., k].unsqueeze(-2), deformation[..., k].unsqueeze(-2),
-                                            canonical_pose, training, None if new_stats is None else _Prefixed(new_stats, prefix))
+        want_div = training and divergence_noise is not None and divergence_noise[k] is not None
+        if want_div:
+            pos = pos.detach().requires_grad_(True)
+        with torch.enable_grad() if want_div else contextlib.nullcontext():
+            f, a, disp = ray_bending_style_nerf(sd, cfg, pos, o_exp, d, style[..., k].unsqueeze(-2), deformation[..., k].unsqueeze(-2),
+                                                canonical_pose, training, None if new_stats is None else _Prefixed(new_stats, prefix))
+        div = torch.zeros_like(a)
+        if want_div:
+            # compute_approximate_divergence :582-601: e^T (d displacement / d position) e by one vector-Jacobian product
+            e = divergence_noise[k]
+            e_dydx = torch.autograd.grad(disp, pos, e, allow_unused=True)[0] if disp.requires_grad else None
+            div = (e_dydx * e).sum(dim=-1) if e_dydx is not None else div
+            f, a, disp, pos, div = f.detach(), a.detach(), disp.detach(), pos.detach(), div.detach()
         absent = torch.logical_not(ois)
         a = torch.where(absent.reshape(list(absent.shape) + [1] * (a.dim() - absent.dim())), torch.full_like(a, cfg["empty_space_alpha"]), a)
         if m["apply_activation"]:
             f = torch.sigmoid(f)
-        per_obj.append((f, a, t, pos, disp, torch.zeros_like(a)))
+        per_obj.append((f, a, t, pos, disp, div))
         if use_fine:
             # :552-578 -- coarse weights of THIS object (no raw-alpha noise here: the fine goldens are unperturbed), resampling, fine model
             w_c = compute_weights(compute_alphas(a, position_distances(t, d), None))
@@ -555,7 +568,10 @@ def forward_expected_positions(config: dict, state: Dict[str, Tensor], ray_origi
     _, a, disp = ray_bending_style_nerf(sd, cfg, pos, o_exp, d, style.unsqueeze(-2), deformation.unsqueeze(-2), canonical_pose, training)
     absent = torch.logical_not(object_in_scene)
     a = torch.where(absent.reshape(list(absent.shape) + [1] * (a.dim() - absent.dim())), torch.full_like(a, cfg["empty_space_alpha"]), a)
-    weights = compute_weights(compute_alphas(a, position_distances(t, ray_directions), noise if perturb else None))
+    # :687 -- the reference has re-bound ``ray_directions`` to the OBJECT-space directions by now (:656), so the sample spacing is
+    # scaled by |R d| here (forward() scales by the world-space |d|, :880): the same value for a rigid pose, but its gradient w.r.t.
+    # the rotation block has the extra component R d d^T / |d|
+    weights = compute_weights(compute_alphas(a, position_distances(t, d), noise if perturb else None))
     w = weights.detach().unsqueeze(-1)
     expected = ((pos + disp) * w).sum(dim=-2) / (w.sum(dim=-2) + 1e-8)          # :603-622
     return {"coarse": (expected, weights.sum(dim=-1))}

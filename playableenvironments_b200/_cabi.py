@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 5
+PE_ABI_VERSION = 6
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -60,7 +60,7 @@ class PeScene(C.Structure):
         ("images", C.c_int32), ("rays", C.c_int32), ("objects", C.c_int32), ("static_objects", C.c_int32),
         ("perturb", C.c_int32), ("training", C.c_int32), ("fix_object_overlaps", C.c_int32), ("apply_activation", C.c_int32),
         ("precision", C.c_int32), ("explicit_positions", C.c_int32), ("keep_samples", C.c_int32),
-        ("explicit_t", C.c_int32),
+        ("explicit_t", C.c_int32), ("divergence", C.c_int32), ("bent_gradients", C.c_int32),
         ("object", PeObjectDesc * PE_MAX_OBJECTS),
     ]
 
@@ -72,6 +72,7 @@ class PeInputs(C.Structure):
         ("object_in_scene", C.c_void_p),
         ("rand", C.c_void_p * PE_MAX_OBJECTS), ("noise", C.c_void_p * PE_MAX_OBJECTS), ("noise_global", C.c_void_p),
         ("positions", C.c_void_p), ("sample_t", C.c_void_p * PE_MAX_OBJECTS),
+        ("divergence_noise", C.c_void_p * PE_MAX_OBJECTS), ("divergence_params", C.c_void_p),
     ]
 
 
@@ -100,7 +101,8 @@ class PeIntegratedGrads(C.Structure):
 
 
 class PeOutGrads(C.Structure):
-    _fields_ = [("object", PeIntegratedGrads * PE_MAX_OBJECTS), ("global_", PeIntegratedGrads)]
+    _fields_ = [("object", PeIntegratedGrads * PE_MAX_OBJECTS), ("global_", PeIntegratedGrads),
+                ("bent_positions", C.c_void_p * PE_MAX_OBJECTS)]
 
 
 class PeObjectParamGrads(C.Structure):

@@ -57,7 +57,7 @@ extern "C" int pe_pack_object(const PeObjectDesc* desc, const PeObjectParams* pa
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct ObjWorkspace {
-    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s, *bent, *h7;
+    float *t, *raw, *dispmag, *feat, *aff1, *aff2, *run1, *run2, *fold_v, *fold_s, *bent, *h7, *div, *div_gpos;
     uint8_t* flags;
     int32_t *tile_list, *tile_count;
     uint8_t* inbox;
@@ -66,8 +66,15 @@ struct ObjWorkspace {
 
 struct Workspace {
     ObjWorkspace obj[PE_MAX_OBJECTS];
+    float* div_stash;          // activation stash of the divergence pass (pe_field_bwd_kernel, ray-bender-only mode), per block
+    int64_t div_stash_floats;
     size_t bytes;
 };
+
+static bool object_has_divergence(const PeScene& s, int k) {
+    return s.divergence && !s.explicit_positions && s.object[k].bender_kind == PE_BENDER_POSITIONAL && !s.object[k].canonical_pose;
+}
+static int backward_grid();
 
 // Train mode (batch-statistics BatchNorm: three launches with the statistics phases of the tcgen05 kernel) runs on the tensor cores
 // too; PE_TC_TRAIN=0 keeps it on the fp32 field kernel.
@@ -163,7 +170,15 @@ static Workspace carve(const PeScene& s, void* base) {
         o.stats = (double*)take((size_t)(3 * d.width + 4) * 8);
         o.run1 = (float*)take((size_t)2 * d.width * 4);
         o.run2 = (float*)take((size_t)d.width * 4);
+        const bool dv = object_has_divergence(s, k);
+        o.div = dv ? (float*)take(n * 4) : nullptr;
+        o.div_gpos = dv ? (float*)take(n * 12) : nullptr;
+        if (dv) {
+            const int64_t f = pe_field_bwd_stash_floats(d, pe_layout(d));
+            w.div_stash_floats = f > w.div_stash_floats ? f : w.div_stash_floats;
+        }
     }
+    w.div_stash = w.div_stash_floats ? (float*)take((size_t)w.div_stash_floats * backward_grid() * 4) : nullptr;
     w.bytes = off;
     return w;
 }
@@ -323,6 +338,21 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
             rc = pe_launch_style(s2, stream); if (rc) return rc;
             rc = launch_field(0); if (rc) return rc;
         }
+        if (object_has_divergence(s, k) && in->divergence_noise[k]) {
+            // Hutchinson divergence of the displacement field (object_composer.py:582-601): e . (J e) per sample by ONE vector-Jacobian
+            // product through the ray bender -- the ray-bender-only mode of the fp32 field backward with dL/d displacement = e and no
+            // parameter gradients (what torch.autograd.grad(displacements, positions, e) is to the reference)
+            if (!in->divergence_params) { pe_set_error("divergence_noise needs divergence_params"); return PE_ERR_INVALID; }
+            PeFieldBwdArgs dvb = {};
+            dvb.f = fa;
+            dvb.f.integ = PeIntegrated{};
+            dvb.w = in->divergence_params[k];
+            dvb.g_bent_in = in->divergence_noise[k]; dvb.g_bent_flag = 1;
+            dvb.g_pos = o.div_gpos; dvb.div_out = o.div;
+            dvb.stash = ws.div_stash; dvb.stash_floats = ws.div_stash_floats;
+            dvb.bwd_phase = 0;
+            rc = pe_launch_field_bwd(dvb, sm_count, stream); if (rc) return rc;
+        }
     }
     if (s.explicit_positions) return PE_OK;
 
@@ -340,6 +370,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         ca.raw[k] = out->raw_alphas[k] ? out->raw_alphas[k] : o.raw;
         ca.feat[k] = out->raw_features[k] ? out->raw_features[k] : o.feat;
         ca.dispmag[k] = o.dispmag;
+        ca.div[k] = (object_has_divergence(s, k) && in->divergence_noise[k]) ? o.div : nullptr;
         ca.inbox[k] = o.inbox;
         ca.noise[k] = s.perturb ? in->noise[k] : nullptr;
         ca.object[k] = out->object[k];
@@ -381,6 +412,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
 // ------------------------------------------------------------------------------------------------
 struct ObjBwdWorkspace {
     float *cw_obj, *cw_glob, *g_raw, *g_t, *g_dm, *g_pos, *g_od, *adain_sums, *bn_fix;
+    float* g_pos2;                                     // scene.bent_gradients: dL/d position of the extra pass
     float *g_bent, *scale;                             // tensor-core field backward: dL/d bent position, gradient scale [S, 1/S] + scratch
     double* bn_sums;
     int32_t *slot_list, *slot_count, *tile_begin;      // compacted tiles of the field backward (NULL: dense tiles)
@@ -452,6 +484,7 @@ static BwdWorkspace carve_backward(const PeScene& s, void* base, int grid) {
         o.g_raw = (float*)take(n * 4); o.g_t = (float*)take(n * 4); o.g_dm = (float*)take(n * 4);
         o.g_pos = (float*)take(n * 12);
         o.g_od = d.nerf_kind == PE_NERF_SKYBOX_V3 ? (float*)take(n * 24) : nullptr;
+        o.g_pos2 = (s.bent_gradients && d.bender_kind == PE_BENDER_POSITIONAL) ? (float*)take(n * 12) : nullptr;
         const bool compact = backward_compacts(s, k);
         o.slot_list = compact ? (int32_t*)take(n * 4) : nullptr;
         o.slot_count = compact ? (int32_t*)take((size_t)s.images * 4) : nullptr;
@@ -684,6 +717,34 @@ extern "C" int pe_render_backward_saved(const PeScene* scene, const PeInputs* in
             gb.g_pos = b.g_pos; gb.g_t = b.g_t; gb.g_od = b.g_od;
             gb.g_origins = grad_in->ray_origins; gb.g_dirs = grad_in->ray_directions; gb.g_w2o = grad_in->w2o;
             rc = pe_launch_geometry_bwd(gb, stream); if (rc) return rc;
+        }
+
+        if (s.bent_gradients && grad_out->bent_positions[k]) {
+            // backward of forward_expected_positions (object_composer.py:603-722): an upstream gradient on the bent sample positions
+            // x + displacement(x).  The backward is linear in its upstream gradients, so this is one more pass: the ray bender
+            // (ray-bender-only mode of the fp32 field backward: parameter / deformation gradients accumulate, dL/dx to g_pos2), then the
+            // ray geometry once more.
+            const float* g_x = grad_out->bent_positions[k];
+            if (d.bender_kind == PE_BENDER_POSITIONAL) {
+                PeFieldBwdArgs xb = {};
+                xb.f = fb.f; xb.w = fb.w; xb.gw = fb.gw;
+                xb.g_deformation = grad_in->deformation[k];
+                xb.g_bent_in = g_x; xb.g_bent_flag = 1;
+                xb.g_pos = b.g_pos2;
+                xb.stash = bw.stash; xb.stash_floats = bw.stash_floats;
+                xb.bwd_phase = 0;
+                rc = pe_launch_field_bwd(xb, sm_count, stream); if (rc) return rc;
+                g_x = b.g_pos2;
+            }
+            if (grad_in->ray_origins || grad_in->ray_directions || grad_in->w2o || (in->sample_t[k] && grad_in->sample_t[k])) {
+                PeGeometryBwdArgs gb = {};
+                gb.ob = d; gb.images = s.images; gb.rays = s.rays; gb.objects = s.objects; gb.k = k; gb.perturb = s.perturb;
+                gb.origins = in->ray_origins; gb.dirs = in->ray_directions; gb.w2o = in->w2o; gb.ois = in->object_in_scene; gb.rand = in->rand[k];
+                gb.t_in = in->sample_t[k]; gb.g_t_in = nullptr;
+                gb.g_pos = g_x; gb.g_t = nullptr; gb.g_od = nullptr;
+                gb.g_origins = grad_in->ray_origins; gb.g_dirs = grad_in->ray_directions; gb.g_w2o = grad_in->w2o;
+                rc = pe_launch_geometry_bwd(gb, stream); if (rc) return rc;
+            }
         }
     }
     return PE_OK;

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(128) pe_geometry_bwd_kernel(const PeGeometryBw
             const float u = (G.perturb && !G.t_in) ? G.rand[gs] : 0.f;
             const float t = pe_sample_t_or(G.t_in, gs, pr, p, P, G.perturb != 0, u);
             const float gx[3] = {G.g_pos[gs * 3], G.g_pos[gs * 3 + 1], G.g_pos[gs * 3 + 2]};
-            float gt = G.g_t[gs];
+            float gt = G.g_t ? G.g_t[gs] : 0.f;
             for (int a = 0; a < 3; ++a) {
                 g_o[a] += gx[a];
                 g_d[a] = fmaf(gx[a], t, g_d[a]);

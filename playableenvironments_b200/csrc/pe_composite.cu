@@ -11,6 +11,7 @@ struct RayLists {       // per-warp shared-memory sample list
     float* t;
     float* raw;
     float* dm;          // |displacement|
+    float* dv;          // divergence of the displacement field
     int* src;           // (object << 16) | sample, -1 for "features are zero"
 };
 
@@ -21,13 +22,14 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    float carry = 1.f, opacity = 0.f, depth = 0.f, dsum = 0.f;
+    float carry = 1.f, opacity = 0.f, depth = 0.f, dsum = 0.f, vsum = 0.f;
     for (int c0 = 0; c0 < n; c0 += 32) {
         const int j = c0 + lane;
-        float alpha = 0.f, t = 0.f, dm = 0.f;
+        float alpha = 0.f, t = 0.f, dm = 0.f, dv = 0.f;
         if (j < n) {
             t = S.t[j];
             dm = S.dm[j];
+            dv = S.dv[j];
             // compute_position_distances :153-178 — last interval 1e10, scaled by |d|
             const float delta = __fmul_rn(j == n - 1 ? 1e10f : __fsub_rn(S.t[j + 1], t), dnorm);
             float raw = S.raw[j];
@@ -50,6 +52,7 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         opacity += w;
         depth += w * t;
         dsum += w * dm;
+        vsum += alpha * fabsf(dv);                 // mean(alphas * |divergence|) :777-778
         const int src = j < n ? S.src[j] : -1;
         const int cnt = min(32, n - c0);
         for (int jj = 0; jj < cnt; ++jj) {
@@ -71,6 +74,7 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         opacity += __shfl_xor_sync(0xffffffffu, opacity, o);
         depth += __shfl_xor_sync(0xffffffffu, depth, o);
         dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
     }
     if (out.integrated_features) {
 #pragma unroll
@@ -87,7 +91,7 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
             out.disparity[ray] = 1.f / (q != q ? q : fmaxf(q, 1e-10f));
         }
         if (out.integrated_displacements_magnitude) out.integrated_displacements_magnitude[ray] = dsum / (float)n;  // mean :772
-        if (out.integrated_divergence) out.integrated_divergence[ray] = 0.f;            // Hutchinson term: see DESIGN.md
+        if (out.integrated_divergence) out.integrated_divergence[ray] = vsum / (float)n;   // zero unless the caller asked for the Hutchinson term
     }
 }
 
@@ -95,9 +99,9 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TP = (A.total_positions + 31) & ~31;
-    float* base = reinterpret_cast<float*>(smem_raw) + (size_t)warp * TP * 8;
-    RayLists S{base, base + TP, base + 2 * TP, reinterpret_cast<int*>(base + 3 * TP)};
-    RayLists U{base + 4 * TP, base + 5 * TP, base + 6 * TP, reinterpret_cast<int*>(base + 7 * TP)};
+    float* base = reinterpret_cast<float*>(smem_raw) + (size_t)warp * TP * 10;
+    RayLists S{base, base + TP, base + 2 * TP, base + 3 * TP, reinterpret_cast<int*>(base + 4 * TP)};
+    RayLists U{base + 5 * TP, base + 6 * TP, base + 7 * TP, base + 8 * TP, reinterpret_cast<int*>(base + 9 * TP)};
     const int64_t n_rays = (int64_t)A.images * A.rays;
     for (int64_t ray = (int64_t)blockIdx.x * WARPS + warp; ray < n_rays; ray += (int64_t)gridDim.x * WARPS) {
         const float* d = A.dirs + ray * 3;
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
                     S.t[p] = A.t[k][b + p];
                     S.raw[p] = A.raw[k][b + p];
                     S.dm[p] = A.dispmag[k] ? A.dispmag[k][b + p] : 0.f;
+                    S.dv[p] = A.div[k] ? A.div[k][b + p] : 0.f;
                     S.src[p] = A.inbox[k][b + p] ? ((k << 16) | p) : -1;
                 }
                 __syncwarp();
@@ -127,12 +132,13 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
                 const int64_t b = ray * P;
                 for (int p0 = 0; p0 < P; p0 += 32) {
                     const int p = p0 + lane;
-                    float t = 0.f, raw = 0.f, dm = 0.f;
+                    float t = 0.f, raw = 0.f, dm = 0.f, dv = 0.f;
                     int src = -1;
                     if (p < P) {
                         t = A.t[k][b + p];
                         raw = A.raw[k][b + p];
                         dm = A.dispmag[k] ? A.dispmag[k][b + p] : 0.f;
+                        dv = A.div[k] ? A.div[k][b + p] : 0.f;
                         src = A.inbox[k][b + p] ? ((k << 16) | p) : -1;
                     }
                     // fix_object_overlap :295-397: static samples between the first and the last sample of a
@@ -151,9 +157,9 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
                             }
                             masked = masked || (p >= lo && p < hi);
                         }
-                        if (masked) { raw = raw * 0.f - 10.f; t = 0.f; dm = 0.f; }
+                        if (masked) { raw = raw * 0.f - 10.f; t = 0.f; dm = 0.f; dv = 0.f; }
                     }
-                    if (p < P) { U.t[off + p] = t; U.raw[off + p] = raw; U.dm[off + p] = dm; U.src[off + p] = src; }
+                    if (p < P) { U.t[off + p] = t; U.raw[off + p] = raw; U.dm[off + p] = dm; U.dv[off + p] = dv; U.src[off + p] = src; }
                 }
                 off += P;
             }
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
                     const float tm = U.t[m];
                     rank += (tm < tj || (tm == tj && m < j)) ? 1 : 0;
                 }
-                S.t[rank] = tj; S.raw[rank] = U.raw[j]; S.dm[rank] = U.dm[j]; S.src[rank] = U.src[j];
+                S.t[rank] = tj; S.raw[rank] = U.raw[j]; S.dm[rank] = U.dm[j]; S.dv[rank] = U.dv[j]; S.src[rank] = U.src[j];
             }
             __syncwarp();
             integrate_list(A, S, n, dnorm, (A.perturb && A.noise_global) ? A.noise_global + ray * n : nullptr, A.global, ray, lane);
@@ -196,7 +202,7 @@ int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream) {
     const int64_t n_rays = (int64_t)args.images * args.rays;
     if (n_rays == 0) return PE_OK;
     const int TP = (args.total_positions + 31) & ~31;
-    const size_t smem = (size_t)WARPS * TP * 8 * sizeof(float);
+    const size_t smem = (size_t)WARPS * TP * 10 * sizeof(float);
     PE_CUDA_CHECK(cudaFuncSetAttribute(pe_composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)pe_min64((n_rays + WARPS - 1) / WARPS, 148 * 16);
     pe_composite_kernel<<<grid, WARPS * 32, smem, stream>>>(args);

@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
                 pe_position(ray, t, x);
                 for (int a = 0; a < 3; ++a) { S.aux[a * TB + tid] = ray.o[a]; S.aux[(3 + a) * TB + tid] = ray.d[a]; }
                 if (pe_in_box(ob, x)) flag |= 1;
-                graw = B.g_raw[gs];
-                gdm = B.g_dm[gs];
+                graw = B.g_raw ? B.g_raw[gs] : 0.f;
+                gdm = B.g_dm ? B.g_dm[gs] : 0.f;
             }
             S.flags[tid] = flag;
             S.clampf[tid] = 0;
@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         const int any_inbox = __syncthreads_or(tid < TB ? (S.flags[tid] & 1) : 0);
         if (!any_inbox) {
             if (full && tid < TB && (S.flags[tid] & 4)) {
+                if (B.div_out) B.div_out[gsi + S.slot[tid]] = 0.f;
                 for (int a = 0; a < 3; ++a) B.g_pos[(gsi + S.slot[tid]) * 3 + a] = 0.f;
                 if (B.g_od) for (int a = 0; a < 6; ++a) B.g_od[(gsi + S.slot[tid]) * 6 + a] = 0.f;
             }
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         // ---- positional encoding backward -> gradient of the (bent) position, or of origin / direction for the skybox ----
         float gbent[3] = {0.f, 0.f, 0.f};
         if (bender_only) {
-            if (tid < TB && (S.flags[tid] & 2)) {
+            if (tid < TB && (S.flags[tid] & (B.g_bent_flag ? B.g_bent_flag : 2))) {
                 const float* g = B.g_bent_in + (gsi + S.slot[tid]) * 3;
                 gbent[0] = g[0]; gbent[1] = g[1]; gbent[2] = g[2];
             }
@@ -674,6 +675,12 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
         if (tid < TB && (S.flags[tid] & 4)) {
             const bool use = (S.flags[tid] & 1) != 0;
             for (int a = 0; a < 3; ++a) B.g_pos[(gsi + S.slot[tid]) * 3 + a] = use ? gpos[a] : 0.f;
+            // e . (J e): gpos = e + J^T e (identity path of bent = x + displacement, plus the path through the bender and its clamp)
+            if (B.div_out) {
+                float dv = 0.f;
+                for (int a = 0; a < 3; ++a) dv = fmaf(gbent[a], gpos[a] - gbent[a], dv);
+                B.div_out[gsi + S.slot[tid]] = use ? dv : 0.f;
+            }
         }
     }
 }

@@ -54,6 +54,7 @@ struct PeCompositeArgs {
     const float* raw[PE_MAX_OBJECTS];
     const float* feat[PE_MAX_OBJECTS];
     const float* dispmag[PE_MAX_OBJECTS];
+    const float* div[PE_MAX_OBJECTS];             // per-sample divergence of the ray bender's displacement field or NULL (zeros)
     const uint8_t* inbox[PE_MAX_OBJECTS];
     const float* noise[PE_MAX_OBJECTS];
     const float* noise_global;
@@ -118,6 +119,9 @@ struct PeFieldBwdArgs {
     // ray-bender-only mode (objects whose field backward ran on the tensor cores, pe_bwd_tc.cu): dL/d bent position of every listed
     // slot; the kernel recomputes the bender of a tile, back-propagates through it and writes g_pos
     const float* g_bent_in;        // [images][rays][P][3] or NULL
+    int32_t g_bent_flag;           // which samples read g_bent_in: flag bit 2 (field evaluated; 0 means this) or 1 (inside the box)
+    // Hutchinson divergence (object_composer.py:582-601): with g_bent_in = e, div_out = e . (J e) where J = d displacement / d position
+    float* div_out;                // [images][rays][P] or NULL
 };
 
 // Style / BatchNorm backward (pe_backward.cu)

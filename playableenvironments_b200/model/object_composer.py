@@ -32,6 +32,15 @@ class ObjectComposer(nn.Module):
         self.precision = self.config["model"].get("b200_precision", "mixed")
         # diagnostic switch: also return the per-sample raw alphas of every object under results["coarse"]["object_k"]["raw_alphas"]
         self.return_raw_alphas = False
+        # Hutchinson divergence of the ray benders' displacement fields (reference :582-601) in training calls.  Off by default: its loss
+        # weight is 0 in every shipped config (the trainers only log the value), it is random by construction, and it costs one more
+        # pass through every ray bender; ``model.b200_divergence: True`` evaluates it (forward value only -- a non-zero
+        # divergence_loss_lambda would need the second derivative of the bender, which this path does not provide, so it raises).
+        self.compute_divergence = bool(self.config["model"].get("b200_divergence", False))
+        lam = self.config.get("training", {}).get("loss_weights", {}).get("divergence_loss_lambda", 0.0) if isinstance(self.config, dict) else 0.0
+        if lam:
+            raise NotImplementedError("divergence_loss_lambda != 0 needs the second derivative of the ray bender (reference: create_graph=True, "
+                                      ":598); the B200 render path evaluates the divergence forward only")
 
     def create_object_models(self, fine: bool) -> List[nn.Module]:
         object_models = []
@@ -120,10 +129,11 @@ class ObjectComposer(nn.Module):
     def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
                 transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
                 perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None,
-                peer_features=None) -> Dict:
+                peer_features=None, divergence_noise=None) -> Dict:
         """Same contract as the reference (:786-812).  ``rand`` / ``noise`` optionally supply the perturbation tensors
         (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample.  ``peer_features`` (inference):
-        extra destinations of the composed scene's feature grid -- the fused all-gather of ``sharding.PeerGather``."""
+        extra destinations of the composed scene's feature grid -- the fused all-gather of ``sharding.PeerGather``.
+        ``divergence_noise`` ({"coarse": [e_k (..., R, P_k, 3) or None per object]}): the Hutchinson probe vectors (``compute_divergence``)."""
         objects_count = self.object_id_helper.objects_count
         if transformation_matrix_w2o.size(-1) != objects_count:
             raise Exception(f"Transformation matrix must specifies transformations for"
@@ -148,6 +158,13 @@ class ObjectComposer(nn.Module):
         def run(model_type, model_list, descs, **extra):
             models = [model_list[helper.model_idx_by_object_idx(k)] for k in range(objects_count)] if record else None
             bn_running: List = []
+            if self.compute_divergence and self.training and record:
+                # reference :592-593: only in training and only where the displacements carry a graph (positional ray benders)
+                shape = list(ray_directions.shape[:-1])
+                given = divergence_noise.get(model_type) if divergence_noise else None
+                extra["divergence_noise"] = [
+                    (given[k] if given is not None else torch.randn(shape + [d.positions, 3], device=ray_directions.device))
+                    if d.bender_kind == _cabi.BENDER_POSITIONAL else None for k, d in enumerate(descs)]
             res = render.render_scene(descs, helper.static_objects_count, ray_origins,
                                       ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
                                       self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
@@ -189,16 +206,26 @@ class ObjectComposer(nn.Module):
         and (...) presence flag.  Returns {"coarse": (expected_positions (..., R, 3) in object space, opacity (..., R))}.
 
         The samples (ray parameter t, displacement, compositing weights) come from the same kernels as ``forward`` in a single-object
-        scene; the weighted average itself is three small tensor ops.  Forward only: the pose-consistency / keypoint losses that
-        differentiate through it have weight 0 in every shipped config, so a call that would need a graph raises."""
-        if torch.is_grad_enabled() and (self._any_parameter_requires_grad() or any(
-                torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation))):
-            raise Exception("forward_expected_positions is forward-only in the B200 render path: call it under torch.no_grad()")
+        scene; the weighted average itself is three small tensor ops.  With autograd on, the bent sample positions are a differentiable
+        output of the render node: their upstream gradient goes back through the ray bender (parameters, deformation code) and the ray
+        geometry (PeOutGrads.bent_positions); the weights are detached like the reference's (:614) and the opacity is differentiable."""
+        needs_grad = torch.is_grad_enabled() and (self._any_parameter_requires_grad() or any(
+            torch.is_tensor(t) and t.requires_grad for t in (ray_origins, ray_directions, transformation_matrix_w2o, style, deformation)))
         from ..utils.lib_3d.ray_helper import RayHelper
         helper = self.object_id_helper
         model_idx = helper.model_idx_by_object_idx(object_id)
         m = self.object_models_coarse[model_idx]
+        if self.object_models_fine[model_idx] is not None:
+            raise NotImplementedError("forward_expected_positions with a fine model (reference :698-720) is not provided")
         desc = m.object_desc(m.model_config["positions_count_coarse"], helper.is_static(model_idx), canonical_pose)
+        if needs_grad:
+            res = render.render_scene([desc], 1 if helper.is_static(model_idx) else 0, ray_origins, ray_directions,
+                                      transformation_matrix_w2o.unsqueeze(-1), style.unsqueeze(-1), deformation.unsqueeze(-1),
+                                      object_in_scene.unsqueeze(-1), perturb, self.training, False, self.apply_activation,
+                                      _cabi.PRECISIONS[self.precision], rand=rand, noise=noise, models=[m], bent_gradients=True)["object_0"]
+            w = res["weights"].detach().unsqueeze(-1)
+            expected = (res["bent_positions"] * w).sum(dim=-2) / (w.sum(dim=-2) + 1e-8)
+            return {"coarse": (expected, res["opacity"])}
         res = render.render_scene([desc], 1 if helper.is_static(model_idx) else 0, ray_origins, ray_directions,
                                   transformation_matrix_w2o.unsqueeze(-1), style.unsqueeze(-1), deformation.unsqueeze(-1),
                                   object_in_scene.unsqueeze(-1), perturb, self.training, False, self.apply_activation,

@@ -80,6 +80,8 @@ def _scene_struct(meta, images: int, rays: int) -> _cabi.PeScene:
     scene.fix_object_overlaps, scene.apply_activation = int(bool(meta["fix_object_overlaps"])), int(bool(meta["apply_activation"]))
     scene.precision, scene.explicit_positions = meta["precision"], 0
     scene.explicit_t = 1 if meta.get("sample_t") is not None else 0
+    scene.divergence = 1 if meta.get("divergence_noise") is not None else 0
+    scene.bent_gradients = 1 if meta.get("bent_gradients") else 0
     for k, d in enumerate(descs):
         scene.object[k] = d
     return scene
@@ -101,6 +103,21 @@ def _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep) 
                 raise _cabi.PeError(f"sample_t[{k}]: expected (..., {rays}, {d.positions}) ray parameters")
             keep.append(t)
             ins.sample_t[k] = _cabi.ptr(t)
+    div_noise = meta.get("divergence_noise")
+    if div_noise is not None:         # Hutchinson divergence (object_composer.py:582-601): e per sample of every positional ray bender
+        params = (_cabi.PeObjectParams * _cabi.PE_MAX_OBJECTS)()
+        for k, m in enumerate(meta["models"]):
+            ps, kp = m.parameter_struct()
+            keep.append(kp)
+            params[k] = ps
+            if div_noise[k] is not None:
+                e = _cabi.f32(div_noise[k]).reshape(-1)
+                if e.numel() != dirs.size(0) * rays * descs[k].positions * 3:
+                    raise _cabi.PeError(f"divergence_noise[{k}]: expected (..., {rays}, {descs[k].positions}, 3)")
+                keep.append(e)
+                ins.divergence_noise[k] = _cabi.ptr(e)
+        keep.append(params)
+        ins.divergence_params = C.cast(params, C.c_void_p)
     if meta["perturb"]:
         rand, noise = meta["rand"], meta["noise"]
 
@@ -122,6 +139,8 @@ def _save_forward(meta) -> bool:
     backward instead of recomputing the forward there (PE_SAVE_FORWARD=0: recompute; the exact fp32 mode always recomputes,
     in the fp32-class tensor-core mode)."""
     import os
+    if meta.get("return_samples"):      # per-sample outputs are redirected to the caller's tensors: the workspace copy would be stale
+        return False
     return meta["precision"] != _cabi.PRECISION_FP32 and os.environ.get("PE_SAVE_FORWARD", "1") != "0"
 
 
@@ -217,6 +236,18 @@ class RenderFunction(torch.autograd.Function):
         ctx.save_for_backward(origins, dirs, w2o, *styles, *deforms, *(meta["sample_t"] if n_t else []))
         names = [f"object_{k}" for k in range(K)] + ["global"]
         outs = [res[n][key] for n in names for key in DIFF_KEYS]
+        ctx.n_bent = 0
+        if meta.get("bent_gradients"):
+            # per-sample bent positions x + displacement(x), object space: differentiable outputs whose upstream gradient the backward
+            # hands to the library (PeOutGrads.bent_positions) -- forward_expected_positions builds its weighted average on them
+            for k in range(K):
+                rot, tr = w2o[:, k, :, :3], w2o[:, k, :, 3]
+                o_k = torch.einsum("iab,ib->ia", rot, origins) + tr
+                d_k = torch.einsum("iab,irb->ira", rot, dirs)
+                r = res[f"object_{k}"]
+                outs.append(o_k[:, None, None, :] + d_k[:, :, None, :] * r["positions_t"].reshape(dirs.size(0), dirs.size(1), -1, 1)
+                            + r["displacements"].reshape(dirs.size(0), dirs.size(1), -1, 3))
+            ctx.n_bent = K
         extra = [res[n]["integrated_divergence"] for n in names]
         if meta.get("return_raw_alphas"):
             extra += [res[f"object_{k}"]["raw_alphas"] for k in range(K)]
@@ -250,6 +281,12 @@ class RenderFunction(torch.autograd.Function):
                     g = g.to(torch.float32).contiguous()
                     keep.append(g)
                     setattr(target, key, _cabi.ptr(g))
+        for k in range(ctx.n_bent):
+            g = grads[(K + 1) * len(DIFF_KEYS) + k]
+            if g is not None:
+                g = g.to(torch.float32).contiguous()
+                keep.append(g)
+                gout.bent_positions[k] = _cabi.ptr(g)
         need = ctx.needs_input_grad
         gin = _cabi.PeInGrads()
         zeros = lambda t: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format)
@@ -304,7 +341,8 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  rand: Optional[List[torch.Tensor]] = None, noise: Optional[Dict[str, torch.Tensor]] = None,
                  bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
                  return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None,
-                 sample_t: Optional[List[torch.Tensor]] = None) -> Dict:
+                 sample_t: Optional[List[torch.Tensor]] = None, divergence_noise: Optional[List] = None,
+                 bent_gradients: bool = False) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
     With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node.
     ``sample_t`` (fine pass, :563-578): per object the explicit ray parameters (..., R, P_k) that replace the stratified samples."""
@@ -325,7 +363,11 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
             "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features,
-            "sample_t": sample_t}
+            "sample_t": sample_t, "divergence_noise": divergence_noise, "bent_gradients": bent_gradients}
+    if divergence_noise is not None and models is None:
+        raise _cabi.PeError("the Hutchinson divergence needs the object models (it is a training-time quantity)")
+    if bent_gradients:
+        meta["return_samples"] = True
     if peer_features and models is not None and torch.is_grad_enabled():
         raise _cabi.PeError("peer_features (fused all-gather of the feature grid) is an inference feature: call under torch.no_grad()")
     if models is not None and torch.is_grad_enabled():
@@ -337,6 +379,9 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
         it = iter(flat)
         for n in names:
             results[n] = {key: next(it) for key in DIFF_KEYS}
+        if bent_gradients:
+            for k in range(K):
+                results[f"object_{k}"]["bent_positions"] = next(it).reshape(lead + [rays, descs[k].positions, 3])
         for n in names:
             results[n]["integrated_divergence"] = next(it)
         if return_raw_alphas:

@@ -212,6 +212,17 @@ def perturbation_tensors(seed: int, config: dict, inputs: dict):
     return rand, noise
 
 
+def divergence_noise(seed: int, config: dict, inputs: dict):
+    """Normal probe vectors ``e`` of the Hutchinson divergence (object_composer.py:597), one (..., R, P_k, 3) tensor per object instance."""
+    rng = np.random.default_rng(seed + 3000)
+    lead_r = tuple(inputs["ray_directions"].shape[:-1])
+    model_of = []
+    for mi, c in enumerate(config["model"]["object_parameters_encoder"]):
+        model_of += [mi] * c["objects_count"]
+    Ps = [config["model"]["object_models"][mi]["positions_count_coarse"] for mi in model_of]
+    return [torch.from_numpy(rng.normal(0, 1, lead_r + (p, 3)).astype(np.float32)) for p in Ps]
+
+
 # ----------------------------------------------------------------------------
 # the scenes (BASELINE.json configs, SURVEY.md section 8d)
 # ----------------------------------------------------------------------------

@@ -379,9 +379,6 @@ def test_forward_expected_positions_matches_reference(precision, tol):
         torch.cuda.synchronize()
         assert scale_rel_err(exp.cpu().numpy(), golden[f"{name}/{k}/expected_positions"]) < tol, (name, k)
         assert scale_rel_err(opacity.cpu().numpy(), golden[f"{name}/{k}/opacity"]) < tol, (name, k)
-    comp.allow_forward_without_grad = False
-    with pytest.raises(Exception, match="forward-only"):
-        comp.forward_expected_positions(*args, k, False)
 
 
 def test_launch_accounting_and_no_fallback():

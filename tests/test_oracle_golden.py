@@ -1,5 +1,7 @@
 """The CPU oracle (oracle/render_oracle.py) against outputs of the upstream reference
 (tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -138,3 +140,36 @@ def test_fine_pass_train_mode_matches_reference():
         if k.startswith("state/"):
             key = k[len("state/"):]
             np.testing.assert_allclose(new_stats.get(key, state[key]).numpy(), ref, rtol=1e-4, atol=1e-6, err_msg=key)
+
+
+@pytest.mark.parametrize("name", ["toy_world", "tennis_dense"])
+def test_hutchinson_divergence_matches_reference(name):
+    """compute_approximate_divergence (object_composer.py:582-601) with the probe vectors of the golden run
+    (tests/golden/make_golden_div.py): integrated_divergence = mean(alpha |e . J e|) per object and for the composed scene."""
+    config, state, inputs = scenes.SCENES[name]()
+    e = scenes.divergence_noise(9, config, inputs)
+    res = O.composer_forward(config, state, *[inputs[k] for k in INPUT_KEYS], perturb=False, training=True, new_stats={},
+                             divergence_noise=e)
+    golden = load_golden(name + "_div")
+    assert float(np.abs(golden["coarse/global/integrated_divergence"]).max()) > 1e-3
+    bad = compare(flatten(res), golden, 1e-4)
+    assert not bad, bad
+
+
+def test_oracle_expected_positions_gradients_match_the_reference():
+    """Autograd through the oracle's forward_expected_positions against the upstream autograd (tests/golden/make_golden_div.py) --
+    including the w2o gradient, whose rotation block carries the |R d| term of the object-space sample spacing (:656, :687)."""
+    from make_golden_expected import object_inputs
+    from make_golden_div_cases import expected_loss
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "expected_positions_grad.npz"))
+    name, k = "toy_world", 2
+    config, state, inputs = scenes.SCENES[name]()
+    args = object_inputs(inputs, k)
+    for i in (0, 1, 3, 4, 5):
+        args[i] = args[i].clone().requires_grad_(True)
+    exp, opacity = O.forward_expected_positions(config, state, *args, k, False)["coarse"]
+    expected_loss(name, k, exp, opacity).backward()
+    for i, n in ((0, "ray_origins"), (1, "ray_directions"), (3, "transformation_matrix_w2o"), (4, "style"), (5, "deformation")):
+        ref = golden[f"{name}/{k}/input/{n}"]
+        got = args[i].grad.numpy() if args[i].grad is not None else np.zeros_like(ref)
+        assert np.abs(got - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-6), n
