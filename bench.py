@@ -489,7 +489,7 @@ def run_b200(args):
         line = {
             "metric": "ray-samples/sec (style-MLP ray-march, fwd)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"mixed": "f16 operands (weights hi+lo on trunk layers L3-L7), f32 accumulate",
+            "vs_baseline": None, "dtype": {"mixed": "f16 operands (activation-aware weight rounding, weights hi+lo on trunk layers L6-L7), f32 accumulate",
                                            "fp16": "f16 operands, f32 accumulate", "fp16x2": "f16 operands (weights hi+lo), f32 accumulate",
                                            "fp16x3": "f16 operands (weights and activations hi+lo), f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
@@ -502,7 +502,7 @@ def run_b200(args):
                          # (profiles/r1c_final_summary.md; fp16: 3.4 MB + 146.8 MB, fp16x2: 4.1 MB + 147.7 MB)
                          "traffic": {"fp16": 150208768, "fp16x2": 151788032, "mixed": TRAFFIC_MIXED}.get(args.precision), "peak_source": peaks["source"] + " bf16 burst",
                          "frac_of_sustained": achieved_tflops / peaks["sustained"],
-                         "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0, "mixed": "2 on L3-L7, 1 on L0-L2 and the head"}[args.precision]},
+                         "tensor_passes": {"fp16": 1, "fp16x2": 2, "fp16x3": 3, "fp32": 0, "mixed": "2 on L6-L7, 1 on L0-L5 and the head (activation-aware fp16 weight stream)"}[args.precision]},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),

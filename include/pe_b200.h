@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 6
+#define PE_ABI_VERSION 7
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -60,6 +60,9 @@ typedef struct PeObjectDesc {
     float z_near_min, z_far_max, empty_space_alpha;
     float b_anneal[PE_MAX_OCTAVES];                      /* annealable_positional_encoder.py:54-58, evaluated on the host from current_step */
     const void* packed;                                  /* blob written by pe_pack_object (device)*/
+    int32_t aware_rounding;                              /* the blob's fp16 weight stream was rounded against activation statistics
+                                                            (PeObjectParams.backbone_in_moments): the `mixed` mode then runs objects
+                                                            with >= 96 samples per ray in ONE weight pass                         */
 } PeObjectDesc;
 
 /* fp32 parameter tensors of one object model, nn.Linear layout [out][in]
@@ -74,6 +77,13 @@ typedef struct PeObjectParams {
     const float* head6_w;  const float* head6_b;                                        /* features_head.6                */
     const float* bender_w[PE_MAX_LAYERS];    const float* bender_b[PE_MAX_LAYERS];     /* ray_bender.backbone_layers.{i} */
     const float* bender_out_w;                                                          /* ray_bender.output_head (no bias) */
+    /* pe_pack_object only, optional (shipped field shape): second-moment matrices E[a a^T] ([in][in], fp32) of the fp16-rounded INPUTS of
+     * backbone layer l / of features_head.0, measured by the caller on sample positions inside the bounding box.  Where given, the
+     * fp16 weight stream is rounded "activation-aware": per output row the fp16 neighbour (down / up) of every weight is chosen so
+     * that the expected squared error e^T E[a a^T] e of the single-pass product is minimal (coordinate descent), instead of the
+     * data-free zero-sum rounding.  Removes most of the systematic part of the single-pass error.          */
+    const float* backbone_in_moments[PE_MAX_LAYERS];
+    const float* head0_in_moments;
 } PeObjectParams;
 
 /* One composer call: model/object_composer.py:786-812 (ObjectComposer.forward). */
@@ -263,6 +273,11 @@ int pe_debug_umma_gemm(const float* a, const float* b, const float* bias, float*
  * K = its 128 rows: d[m][n] = sum_r a[r][m] * b[r][n] (a: [k][128], b: [k][n], rows >= k zero; lbo / sbo = descriptor byte strides).
  * mode 2: A operand from TMEM (TS form, written with tcgen05.st): d[m][n] = sum_k a[m][k] * b[n][k] (a: [128][k], b: [n][k]).     */
 int pe_debug_umma_gemm2(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, int32_t lbo, int32_t sbo,
+                        pe_stream_t stream);
+/* One layer ([N][K_src] fp32, nn.Linear layout) through the fp16 weight packing of pe_pack_object: zero-sum rounding, or -- with
+ * `moments` ([K_src][K_src]) -- the activation-aware rounding of PeObjectParams.backbone_in_moments.  hi / lo: N * K_pad fp16 each in
+ * the slab layout of the tensor-core stream (element (n, k) of K = 32 slab s at s*N*64 + (k%32/8)*16N + (n/8)*128 + (n%8)*16 + (k%8)*2). */
+int pe_debug_pack_layer(const float* w, const float* moments, int32_t N, int32_t K_src, int32_t K_pad, int32_t sweeps, void* hi, void* lo,
                         pe_stream_t stream);
 
 #ifdef __cplusplus

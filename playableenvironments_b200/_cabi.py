@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 6
+PE_ABI_VERSION = 7
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -37,7 +37,7 @@ class PeObjectDesc(C.Structure):
         ("bbox", C.c_float * 6),
         ("z_near_min", C.c_float), ("z_far_max", C.c_float), ("empty_space_alpha", C.c_float),
         ("b_anneal", C.c_float * PE_MAX_OCTAVES),
-        ("packed", C.c_void_p),
+        ("packed", C.c_void_p), ("aware_rounding", C.c_int32),
     ]
 
 
@@ -52,6 +52,7 @@ class PeObjectParams(C.Structure):
         ("head6_w", C.c_void_p), ("head6_b", C.c_void_p),
         ("bender_w", C.c_void_p * PE_MAX_LAYERS), ("bender_b", C.c_void_p * PE_MAX_LAYERS),
         ("bender_out_w", C.c_void_p),
+        ("backbone_in_moments", C.c_void_p * PE_MAX_LAYERS), ("head0_in_moments", C.c_void_p),
     ]
 
 
@@ -130,7 +131,7 @@ class PeInGrads(C.Structure):
 EXPORTS = [
     "pe_abi_version", "pe_last_error", "pe_take_launch_count", "pe_packed_bytes", "pe_pack_object",
     "pe_workspace_bytes", "pe_render_forward", "pe_backward_workspace_bytes", "pe_render_backward", "pe_render_backward_saved", "pe_positional_encoding", "pe_generate_rays",
-    "pe_fold_feature_grids", "pe_debug_umma_gemm", "pe_debug_umma_gemm2",
+    "pe_fold_feature_grids", "pe_debug_umma_gemm", "pe_debug_umma_gemm2", "pe_debug_pack_layer",
 ]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpe_b200.so")
@@ -179,6 +180,8 @@ def lib() -> C.CDLL:
                                         C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
     L.pe_debug_umma_gemm.restype = C.c_int
     L.pe_debug_umma_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    L.pe_debug_pack_layer.restype = C.c_int
+    L.pe_debug_pack_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pe_debug_umma_gemm2.restype = C.c_int
     L.pe_debug_umma_gemm2.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     if L.pe_abi_version() != PE_ABI_VERSION:

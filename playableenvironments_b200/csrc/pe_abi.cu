@@ -104,6 +104,15 @@ static int object_precision(const PeScene& s, int k) {
     return s.precision;
 }
 
+// Two-pass layers of a `mixed` object (bit l = layer l, pe_field_tc.cu), -1: the kernel's default (PE_TC_MIXED_MASK).  With an
+// activation-aware weight stream (PeObjectDesc.aware_rounding) and >= 96 samples per ray far fewer layers need the second pass
+// (PE_TC_AWARE_MASK, measured in profiles/r2_aware_rounding.md; emulation: 7e-4 worst output at 128 samples per ray, 1.0e-3 at 64).
+static int object_pass2_mask(const PeScene& s, int k) {
+    if (s.precision != PE_PRECISION_MIXED || !s.object[k].aware_rounding || s.object[k].positions < 96 || s.training) return -1;
+    const char* env = getenv("PE_TC_AWARE_MASK");
+    return env ? (int)strtol(env, nullptr, 0) : PE_TC_AWARE_MASK;
+}
+
 static bool object_uses_tc(const PeScene& s, int k) { return tc_allowed(s) && pe_tc_shape_ok(s.object[k]); }
 static bool object_uses_prepass(const PeScene& s, int k);
 static bool prepass_object(const PeScene& s, int k) { return object_uses_prepass(s, k); }
@@ -239,7 +248,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         fa.ob = d; fa.L = L;
         fa.images = s.images; fa.rays = s.rays; fa.objects = s.objects; fa.k = k;
         fa.perturb = s.perturb; fa.explicit_positions = s.explicit_positions; fa.training = s.training;
-        fa.apply_activation = s.apply_activation; fa.precision = object_precision(s, k);
+        fa.apply_activation = s.apply_activation; fa.precision = object_precision(s, k); fa.pass2_mask = object_pass2_mask(s, k) < 0 ? 0 : (object_pass2_mask(s, k) | 0x10000);
         fa.origins = in->ray_origins; fa.dirs = in->ray_directions; fa.w2o = in->w2o;
         fa.deformation = in->deformation[k]; fa.rand = in->rand[k]; fa.t_in = in->sample_t[k]; fa.positions = in->positions; fa.ois = in->object_in_scene;
         fa.aff1 = o.aff1; fa.aff2 = o.aff2;

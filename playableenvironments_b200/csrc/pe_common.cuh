@@ -99,6 +99,7 @@ __host__ __device__ inline int64_t pe_tcT_pass_bytes() { return 6LL * 128 * 64 +
 // bender: OUTT (N'128,K'32) L5T L4T (128,128) L3encT (96,128) L3T L2T L1T (128,128) L0T (96,128)
 __host__ __device__ inline int64_t pe_tcbT_pass_bytes() { return 1LL * 128 * 64 + 5LL * 4 * 128 * 64 + 2LL * 4 * 96 * 64; }
 
+#define PE_TC_AWARE_MASK 0x0C0                // ... with an activation-aware weight stream and >= 96 samples per ray
 #define PE_TC_MIXED_MASK 0x0F8                // two-pass layers of the mixed mode: trunk layers L3-L7 (the head gains nothing, profiles/r2_mixed_mode.md)
 #define PE_TC_SLAB_K 32                       // K elements per streamed weight slab
 // number of K=32 slabs of one weight pass of the shipped field:

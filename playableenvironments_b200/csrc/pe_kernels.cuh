@@ -9,6 +9,7 @@ struct PeFieldArgs {
     PeLayout L;
     int32_t images, rays, objects, k;
     int32_t perturb, explicit_positions, training, phase, apply_activation, precision;
+    int32_t pass2_mask;          // mixed mode: 0 = the default two-pass layers, else 0x10000 | mask (bit l = layer l runs hi + lo)
     const float* origins;        // [images][3]
     const float* dirs;           // [images][rays][3]
     const float* w2o;            // [images][objects][12]

@@ -3,7 +3,8 @@
 One object model = ray bender + style-modulated NeRF field + bounding box.  Sub-models are chosen through the
 config-string registry exactly as in the reference (:36-37).  Besides owning the parameters, the class keeps the PACKED
 copy the kernels read (fp32 transposed + fp16 tensor-core slabs), refreshed whenever a parameter changes."""
-from typing import Dict, Optional, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import ctypes as C
 
@@ -32,6 +33,7 @@ class RayBendingStyleNerfModel(nn.Module):
         self.ray_bender = registry.build(self.ray_bender_model_config["architecture"], config, self.ray_bender_model_config)
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._packed_aware = False
 
     def transfer_attributes_to_submodels_configs(self):
         for current_config in [self.nerf_model_config, self.ray_bender_model_config]:      # reference :39-50
@@ -48,8 +50,10 @@ class RayBendingStyleNerfModel(nn.Module):
 
     # ---- C-ABI description -----------------------------------------------------------------------
     def object_desc(self, positions: int, is_static: bool, canonical_pose: bool = False) -> _cabi.PeObjectDesc:
-        return build_object_desc(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config, positions, is_static,
+        desc = build_object_desc(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config, positions, is_static,
                                  canonical_pose, self.packed_parameters())
+        desc.aware_rounding = 1 if self._packed_aware else 0
+        return desc
 
     def state_tensors(self):
         """Every tensor the packed blob is built from (learnable tensors + the BatchNorm running statistics), collected by
@@ -64,10 +68,14 @@ class RayBendingStyleNerfModel(nn.Module):
 
     def packed_parameters(self) -> torch.Tensor:
         tensors = self.state_tensors()
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        # inference packs the weight stream against activation statistics (one calibration pass per parameter version); in training
+        # the parameters change every step and the blob is repacked with the data-free zero-sum rounding
+        aware = (not self.training) and _aware_shape(self.nerf_model) and os.environ.get("PE_TC_AWARE", "1") != "0"
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors) + (aware,)
         if self._packed is None or key != self._packed_key:
-            self._packed = pack_object(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config)
+            self._packed = pack_object(self.nerf_model, self.ray_bender, self.bounding_box, self.model_config, aware=aware)
             self._packed_key = key
+            self._packed_aware = aware
         return self._packed
 
     def parameter_struct(self):
@@ -175,8 +183,42 @@ def build_object_desc(nerf, bender, bounding_box: BoundingBox, model_config: Dic
     return d
 
 
-def pack_object(nerf, bender, bounding_box: BoundingBox, model_config: Dict) -> torch.Tensor:
-    """Packs the parameters into the kernel-side blob (pe_pack_object)."""
+def _aware_shape(nerf) -> bool:
+    """The field shape with a tensor-core weight stream (pe_tc_field_ok, csrc/pe_common.cuh)."""
+    return (nerf.KIND == _cabi.NERF_ADAIN and nerf.layers_width == 256 and nerf.backbone_layers_count == 8 and nerf.skip_layer_idx == 4
+            and nerf.position_encoder.octaves_count == 10 and nerf.output_features == 192)
+
+
+AWARE_CALIBRATION_POSITIONS = 8192
+
+
+def activation_moments(nerf, bounding_box: BoundingBox, device) -> List[torch.Tensor]:
+    """Second-moment matrices E[a a^T] of the fp16-rounded inputs of every trunk layer and of features_head.0, measured on
+    AWARE_CALIBRATION_POSITIONS positions drawn uniformly in the bounding box (fixed seed; the trunk sees positions only, so the
+    statistics depend on nothing but the weights and the box).  Packing-time calibration for the activation-aware rounding of the
+    tensor-core weight stream (PeObjectParams.backbone_in_moments): a few small fp32 matmuls, not part of the render path."""
+    with torch.no_grad():
+        g = torch.Generator(device=device).manual_seed(0x5EED)
+        dims = bounding_box.dimensions.to(device=device, dtype=torch.float32)
+        size = dims[:, 1] - dims[:, 0]
+        pos = dims[:, 0] + size * torch.rand((AWARE_CALIBRATION_POSITIONS, 3), generator=g, device=device)
+        enc = nerf.position_encoder(pos / size)
+        moments = []
+        h = enc
+        for i, layer in enumerate(nerf.backbone_layers):
+            if i == nerf.skip_layer_idx:
+                h = torch.cat([h, enc], dim=-1)
+            q = h.half().float()
+            moments.append((q.t() @ q / q.size(0)).contiguous())
+            h = torch.relu(torch.nn.functional.linear(h, layer.weight.float(), layer.bias.float()))
+        q = h.half().float()
+        moments.append((q.t() @ q / q.size(0)).contiguous())
+    return moments
+
+
+def pack_object(nerf, bender, bounding_box: BoundingBox, model_config: Dict, aware: bool = False) -> torch.Tensor:
+    """Packs the parameters into the kernel-side blob (pe_pack_object).  ``aware``: round the tensor-core weight stream against
+    activation statistics (``activation_moments``)."""
     device = nerf.backbone_layers[0].weight.device        # attribute access: valid on nn.DataParallel replicas too
     if device.type != "cuda":
         raise _cabi.PeError("parameters must live on a CUDA device: the render path has no CPU implementation")
@@ -188,6 +230,17 @@ def pack_object(nerf, bender, bounding_box: BoundingBox, model_config: Dict) -> 
     packed = torch.zeros(nbytes, dtype=torch.uint8, device=device)
     with torch.cuda.device(device):
         ps, keep = _param_struct(nerf, bender)
+        if aware:
+            allow = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                moments = activation_moments(nerf, bounding_box, device)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = allow
+            keep.append(moments)
+            for i in range(len(nerf.backbone_layers)):
+                ps.backbone_in_moments[i] = _cabi.ptr(moments[i])
+            ps.head0_in_moments = _cabi.ptr(moments[-1])
         _cabi.check(L.pe_pack_object(C.byref(desc), C.byref(ps), _cabi.ptr(packed), _cabi.current_stream(device)))
     del keep
     return packed

@@ -404,3 +404,68 @@ def test_composer_runs_as_a_dataparallel_replica():
     assert set(got) == set(want)
     for k in want:
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)
+
+
+def _unpack_slabs(buf: torch.Tensor, N: int, K_pad: int) -> np.ndarray:
+    """fp16 weight-stream slabs (include/pe_b200.h, pe_debug_pack_layer) -> [N][K_pad] float32."""
+    raw = buf.cpu().numpy().view(np.float16)
+    n, k = np.meshgrid(np.arange(N), np.arange(K_pad), indexing="ij")
+    off = (k // 32) * (N * 64) + ((k % 32) // 8) * (16 * N) + (n // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+    return raw[off // 2].astype(np.float32)
+
+
+def test_activation_aware_rounding():
+    """pe_tc_pack_layer_aware_kernel: every weight goes to one of its two fp16 neighbours, hi + lo reproduces the weight, and the
+    expected squared error e^T E[a a^T] e of the single-pass product is far below the zero-sum and nearest roundings' (the quantity the
+    coordinate descent minimises); against a float64 numpy restatement of the same descent the choices agree almost everywhere."""
+    from playableenvironments_b200 import _cabi
+    g = torch.Generator().manual_seed(11)
+    N, K_src, K_pad = 64, 95, 96
+    w = (torch.randn(N, K_src, generator=g) * 0.2).cuda()
+    # post-ReLU-like inputs: positive mean, strongly correlated (12 latent directions) like the activations of a trained trunk
+    a = torch.relu(torch.randn(4096, 12, generator=g) @ torch.randn(12, K_src, generator=g) * 0.5 + 0.5).half().float()
+    Cm = (a.t() @ a / a.size(0)).contiguous().cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    for kind, moments in (("zero_sum", None), ("aware", Cm)):
+        hi = torch.zeros(N * K_pad * 2, dtype=torch.uint8, device="cuda")
+        lo = torch.zeros_like(hi)
+        _cabi.check(_cabi.lib().pe_debug_pack_layer(w.data_ptr(), 0 if moments is None else moments.data_ptr(), N, K_src, K_pad, 1,
+                                                    hi.data_ptr(), lo.data_ptr(), stream))
+        torch.cuda.synchronize()
+        out[kind] = (_unpack_slabs(hi, N, K_pad), _unpack_slabs(lo, N, K_pad))
+    wn, C64 = w.cpu().numpy(), Cm.cpu().double().numpy()
+    near = wn.astype(np.float16).astype(np.float32)
+    up = np.nextafter(near.astype(np.float16), np.float16(np.inf)).astype(np.float32)
+    down = np.nextafter(near.astype(np.float16), np.float16(-np.inf)).astype(np.float32)
+    other = np.where(near < wn, up, np.where(near > wn, down, near))
+    cost = lambda h: float(np.einsum("nk,kj,nj->", (h - wn).astype(np.float64), C64, (h - wn).astype(np.float64)))
+    for kind, (hi, lo) in out.items():
+        assert np.all(hi[:, K_src:] == 0) and np.all(lo[:, K_src:] == 0)
+        h = hi[:, :K_src]
+        assert np.all((h == near) | (h == other)), kind
+        assert np.abs(h + lo[:, :K_src] - wn).max() <= 2.0 ** -21 * np.abs(wn).max(), kind
+    c_aware, c_zero, c_near = cost(out["aware"][0][:, :K_src]), cost(out["zero_sum"][0][:, :K_src]), cost(near)
+    assert c_aware < 0.5 * c_zero and c_aware < 0.5 * c_near, (c_aware, c_zero, c_near)
+    # float64 restatement of the descent (greedy pass + one sweep)
+    e0, e1 = (near - wn).astype(np.float64), (other - wn).astype(np.float64)
+    e, r, pick = np.zeros((N, K_src)), np.zeros((N, K_src)), np.zeros((N, K_src), bool)
+    for sweep in range(2):
+        for k in range(K_src):
+            rr = r[:, k] - e[:, k] * C64[k, k]
+            p = (2 * e1[:, k] * rr + e1[:, k] ** 2 * C64[k, k]) < (2 * e0[:, k] * rr + e0[:, k] ** 2 * C64[k, k])
+            en = np.where(p, e1[:, k], e0[:, k])
+            r += np.outer(en - e[:, k], C64[k])
+            e[:, k], pick[:, k] = en, p
+    ref = np.where(pick, other, near)
+    agree = float((ref == out["aware"][0][:, :K_src]).mean())
+    assert agree > 0.98, agree
+    assert cost(out["aware"][0][:, :K_src]) < 1.05 * cost(ref)
+
+
+def test_mixed_mode_without_activation_statistics_still_within_1e_3(monkeypatch):
+    """PE_TC_AWARE=0: the data-free zero-sum stream with its five two-pass layers (what training-mode forwards use)."""
+    monkeypatch.setenv("PE_TC_AWARE", "0")
+    _, _, _, comp, dev = _build("static_small", "mixed")
+    bad = compare(flatten(_run(comp, dev)), load_golden("static_small"), 1e-3)
+    assert not bad, bad
