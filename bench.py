@@ -28,7 +28,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "
 
 FLOP_PER_SAMPLE = 2 * 614144          # matmul MACs of the shipped field x 2
 HEIGHT, WIDTH, POSITIONS = 256, 256, 128
-TRAFFIC_MIXED = 65526784          # dram bytes of one pe_field_tc_kernel launch in mixed mode (profiles/r2_mixed_mode.md: 3.81 MB read + 61.72 MB written)
+TRAFFIC_MIXED = 65513984          # dram bytes of one pe_field_tc_kernel launch in mixed mode (profiles/r2_aware_rounding.md: 2.82 MB read + 62.69 MB written)
 WORKLOAD = "cfg2: 1 static field (W=256,L=8,skip=4,10 oct,F=192), 256x256 rays x 128 samples/ray, 100% in-box, forward"
 
 
