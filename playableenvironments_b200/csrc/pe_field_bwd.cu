@@ -689,22 +689,47 @@ __global__ void __launch_bounds__(NT, 1) pe_field_bwd_kernel(const PeFieldBwdArg
 // warp-shuffle scan + per-warp totals).
 __global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* __restrict__ flags, int mask, int64_t slots_per_image,
                                                                  int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    // gridDim.x blocks share an image: each takes a contiguous range of slots (a multiple of the 4096 slots of one scan step), counts
+    // its listed slots, reserves that many entries of the image's list with ONE atomic (count[] is zeroed by the launcher) and fills them
+    // in slot order.  The ranges of different blocks land in reservation order: the list is ordered inside every range, which is all the
+    // consumers need (tiles are independent; neighbouring slots stay neighbours).
     __shared__ int warp_tot[32];
     __shared__ int base;
-    const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int img = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t* f = flags + (int64_t)img * slots_per_image;
     int32_t* out = list + (int64_t)img * slots_per_image;
-    if (threadIdx.x == 0) base = 0;
+    const int64_t step = 4 * (int64_t)blockDim.x;
+    const int64_t steps = (slots_per_image + step - 1) / step;
+    const int64_t per_block = (steps + gridDim.x - 1) / gridDim.x;
+    const int64_t begin = (int64_t)blockIdx.x * per_block * step;
+    const int64_t end = begin + per_block * step < slots_per_image ? begin + per_block * step : slots_per_image;
+    if (begin >= end) return;
+    int mine = 0;
+    for (int64_t s0 = begin; s0 < end; s0 += step) {
+        const int64_t s = s0 + 4 * (int64_t)threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mine += (s + i < end && (f[s + i] & mask) != 0) ? 1 : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if (lane == 0) warp_tot[warp] = mine;
     __syncthreads();
-    for (int64_t s0 = 0; s0 < slots_per_image; s0 += 4 * (int64_t)blockDim.x) {
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+        base = t ? atomicAdd(count + img, t) : 0;
+    }
+    __syncthreads();
+    for (int64_t s0 = begin; s0 < end; s0 += step) {
         const int64_t s = s0 + 4 * (int64_t)threadIdx.x;
         bool keep[4];
         int c = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { keep[i] = s + i < slots_per_image && (f[s + i] & mask) != 0; c += keep[i] ? 1 : 0; }
+        for (int i = 0; i < 4; ++i) { keep[i] = s + i < end && (f[s + i] & mask) != 0; c += keep[i] ? 1 : 0; }
         int incl = c;                                   // inclusive scan of the per-thread counts inside the warp
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+        __syncthreads();                                // (warp_tot of the previous step / of the counting pass has been read)
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         int off = base + incl - c;
@@ -713,9 +738,7 @@ __global__ void __launch_bounds__(1024) pe_compact_slots_kernel(const uint8_t* _
         for (int i = 0; i < 4; ++i) if (keep[i]) out[off++] = (int32_t)(s + i);
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w]; base += t; }
-        __syncthreads();
     }
-    if (threadIdx.x == 0) count[img] = base;
 }
 
 __global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int images, int32_t* __restrict__ tile_begin, int tile_rows) {
@@ -731,7 +754,10 @@ __global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int ima
 int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
                             int32_t* tile_begin, cudaStream_t stream, int tile_rows) {
     if (images == 0 || slots_per_image == 0) return PE_OK;
-    pe_compact_slots_kernel<<<images, 1024, 0, stream>>>(flags, flag_mask, slots_per_image, slot_list, slot_count);
+    PE_CUDA_CHECK(cudaMemsetAsync(slot_count, 0, (size_t)images * sizeof(int32_t), stream));
+    const int64_t steps = (slots_per_image + 4095) / 4096;
+    const int per_image = (int)pe_min64(steps, images >= 64 ? 4 : 256 / images);
+    pe_compact_slots_kernel<<<dim3(per_image, images), 1024, 0, stream>>>(flags, flag_mask, slots_per_image, slot_list, slot_count);
     PE_LAUNCH_CHECK("pe_compact_slots_kernel");
     pe_tile_prefix_kernel<<<1, 32, 0, stream>>>(slot_count, images, tile_begin, tile_rows);
     PE_LAUNCH_CHECK("pe_tile_prefix_kernel");
