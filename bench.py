@@ -82,8 +82,47 @@ def build_scene():
     return scenes.scene_static(seed=12, height=HEIGHT, width=WIDTH, P=POSITIONS)
 
 
+UPSTREAM_ZIP = os.path.join(ROOT, "oracle", "_ref", "reference_path.zip")
+
+
+def upstream_composer_class(cpu: bool):
+    """The UPSTREAM ObjectComposer out of oracle/_ref/reference_path.zip (import closure of the reference's render path, built by
+    oracle/make_ref.py in the build container; git-ignored, travels with the snapshot) or None when the zip is absent."""
+    if not os.path.exists(UPSTREAM_ZIP):
+        return None
+    from oracle import make_ref
+    make_ref.install_shims(cpu)
+    if UPSTREAM_ZIP not in sys.path:
+        sys.path.insert(0, UPSTREAM_ZIP)
+    from model.object_composer import ObjectComposer
+    return ObjectComposer
+
+
+def upstream_composer(config, state, device=None):
+    import copy
+    cls = upstream_composer_class(cpu=device is None)
+    if cls is None:
+        return None
+    comp = cls(copy.deepcopy(config))
+    missing, unexpected = comp.load_state_dict(state, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return comp if device is None else comp.to(device)
+
+
+def chunked_call(comp, args, chunk: int):
+    """The caller's chunking (EnvironmentModel.batchified_composer_call, environment_model.py:474-521): rays in chunks of `chunk`."""
+    rays = args[1].size(-2)
+    out = []
+    for b in range(0, rays, chunk):
+        a = list(args)
+        a[1] = args[1][..., b:b + chunk, :]
+        out.append(comp(*a, False)["coarse"]["global"]["integrated_features"])
+    return out
+
+
 def cpu_reference(sample_rays: int, reps: int, warmup: int):
-    """Times the CPU port of the reference path on `sample_rays` rays of the workload, all host threads."""
+    """Times the reference path on the CPU on `sample_rays` rays of the workload, all host threads: the upstream ObjectComposer itself
+    when oracle/_ref holds it (kind "reference"), else the oracle port (kind "port")."""
     import scenes  # noqa: F401
     from helpers import INPUT_KEYS
     from oracle import render_oracle as O
@@ -92,17 +131,23 @@ def cpu_reference(sample_rays: int, reps: int, warmup: int):
     inputs = dict(inputs)
     inputs["ray_directions"] = inputs["ray_directions"][..., :sample_rays, :].contiguous()
     args = [inputs[k] for k in INPUT_KEYS]
+    comp = upstream_composer(config, state)
+    if comp is not None:
+        comp.eval()
     times = []
     with torch.no_grad():
         for i in range(warmup + reps):
             t0 = time.perf_counter()
             # the reference bounds activation memory with samples_per_image_batching=1000 (environment_model.py:584)
-            O.batchified_composer_call(config, state, *args, perturb=False, samples_per_image_batching=1000)
+            if comp is not None:
+                chunked_call(comp, args, 1000)
+            else:
+                O.batchified_composer_call(config, state, *args, perturb=False, samples_per_image_batching=1000)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
     samples = sample_rays * POSITIONS
-    return samples, times
+    return samples, times, ("reference" if comp is not None else "port")
 
 
 def run_reference(args):
@@ -110,7 +155,7 @@ def run_reference(args):
     if rank != 0:
         return
     sample_rays = 2048
-    samples, times = cpu_reference(sample_rays, max(args.steps, 1), min(args.warmup, 1))
+    samples, times, kind = cpu_reference(sample_rays, max(args.steps, 1), min(args.warmup, 1))
     mean = sum(times) / len(times)
     value = samples / mean
     cores = torch.get_num_threads()
@@ -119,7 +164,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{sample_rays} rays x {POSITIONS} samples of the frame per step"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
                          "sample": f"{sample_rays} of 65536 rays ({samples} samples) per step, chunks of 1000 rays like the reference"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -134,7 +179,10 @@ def gpu_eager_reference(device, tennis_hw=(144, 256)):
     import scenes
     from helpers import INPUT_KEYS
     from oracle import render_oracle as O
-    out = {"kind": "port (oracle/render_oracle.py under torch.device(cuda): ATen / cuBLAS kernels, like the upstream eager path)"}
+    real = upstream_composer_class(cpu=False) is not None
+    out = {"kind": ("reference (the upstream ObjectComposer itself, oracle/_ref/reference_path.zip, eager on this GPU; its train step includes "
+                    "its Hutchinson divergence pass, object_composer.py:582-601)") if real else
+           "port (oracle/render_oracle.py under torch.device(cuda): ATen / cuBLAS kernels, like the upstream eager path)"}
 
     def timed(fn, reps):
         fn()
@@ -154,9 +202,16 @@ def gpu_eager_reference(device, tennis_hw=(144, 256)):
             state_d = {k: v.to(device) for k, v in state.items()}
             args = [inputs[k].to(device) for k in INPUT_KEYS]
 
+            comp2 = upstream_composer(config, state, device) if real else None
+            if comp2 is not None:
+                comp2.eval()
+
             def fwd():
                 with torch.no_grad():
-                    O.batchified_composer_call(config, state_d, *args, perturb=False, samples_per_image_batching=8192)
+                    if comp2 is not None:
+                        chunked_call(comp2, args, 8192)
+                    else:
+                        O.batchified_composer_call(config, state_d, *args, perturb=False, samples_per_image_batching=8192)
 
             tscene = scenes.scene_tennis(seed=13, height=tennis_hw[0], width=tennis_hw[1], stride=1, lead=(1, 1, 1), dense=True)
             tconfig, tstate, tinputs = tscene
@@ -166,10 +221,18 @@ def gpu_eager_reference(device, tennis_hw=(144, 256)):
             rays = tinputs["ray_directions"].size(-2)
             cot = torch.randn(rays, 192)
 
+            comp3 = upstream_composer(tconfig, tstate, device) if real else None
+            if comp3 is not None:
+                comp3.train()
+
             def train():
                 for t in list(tstate_d.values()) + targs:
                     t.grad = None
-                res = O.composer_forward(tconfig, tstate_d, *targs, perturb=False, training=True)["coarse"]["global"]
+                if comp3 is not None:
+                    comp3.zero_grad(set_to_none=True)
+                    res = comp3(*targs, False)["coarse"]["global"]
+                else:
+                    res = O.composer_forward(tconfig, tstate_d, *targs, perturb=False, training=True)["coarse"]["global"]
                 loss = (res["integrated_features"].reshape(rays, 192) * cot).sum() + res["opacity"].sum()
                 loss.backward()
 
@@ -521,10 +584,14 @@ def run_b200(args):
         if parity:
             line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            samples, times = cpu_reference(1024, 2, 1)
-            mean = sum(times) / len(times)
-            line["cpu_baseline"] = {"value": samples / mean, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"1024 of 65536 rays ({samples} samples), 2 timed reps after 1 warm-up, chunks of 1000 rays"}
+            # in its own process: the CPU shims of the upstream code (no-op .cuda()) must not leak into this one
+            import subprocess
+            proc = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                                  capture_output=True, text=True, timeout=900)
+            ref_line = next((json.loads(l) for l in proc.stdout.splitlines() if l.startswith("{")), None)
+            if ref_line is None:
+                raise RuntimeError("cpu baseline failed: " + proc.stderr[-400:])
+            line["cpu_baseline"] = ref_line["cpu_baseline"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

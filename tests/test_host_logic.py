@@ -184,3 +184,29 @@ def test_fine_ray_parameters_match_the_oracle():
         # the fine object's weights live on exactly these ray parameters: depth = sum w t
         w = ref["fine"][f"object_{k}"]["weights"]
         torch.testing.assert_close((w * t).sum(-1), ref["fine"][f"object_{k}"]["depth"], rtol=1e-4, atol=1e-5)
+
+
+def test_reference_arm_zip_is_the_upstream_composer():
+    """bench.py's reference arms (cpu_baseline / --impl reference / gpu_eager_baseline) run the UPSTREAM composer out of
+    oracle/_ref/reference_path.zip (built by oracle/make_ref.py in the build container).  In a subprocess (its CPU shims are global):
+    the zip imports and reproduces a committed golden bit for bit on this CPU... to 1e-6."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "reference_path.zip")):
+        pytest.skip("oracle/_ref/reference_path.zip not built (python oracle/make_ref.py in the build container)")
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path[:0] = [{root!r}, {os.path.join(root, 'tests')!r}, {os.path.join(root, 'tests', 'golden')!r}]\n"
+        "import bench, scenes\n"
+        "from helpers import INPUT_KEYS, load_golden\n"
+        "config, state, inputs = scenes.SCENES['cfg1']()\n"
+        "comp = bench.upstream_composer(config, state).eval()\n"
+        "assert type(comp).__module__ == 'model.object_composer' and 'reference_path.zip' in sys.modules['model.object_composer'].__file__\n"
+        "with torch.no_grad():\n"
+        "    out = comp(*[inputs[k] for k in INPUT_KEYS], False)['coarse']['global']['integrated_features'].numpy()\n"
+        "ref = load_golden('cfg1')['coarse/global/integrated_features']\n"
+        "assert np.abs(out - ref).max() <= 1e-6 * np.abs(ref).max(), np.abs(out - ref).max()\n"
+        "print('ok')\n")
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and "ok" in proc.stdout, proc.stderr[-800:]
