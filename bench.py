@@ -397,6 +397,31 @@ def t_frame_report(device):
         e0.record()
         torch.cuda.synchronize()
         out[f"{precision}_ms"] = s0.elapsed_time(e0) / 10
+        if precision == "mixed":
+            # the same frame replayed from ONE CUDA graph (the composer call allocates nothing, syncs nothing and sizes its tile lists on
+            # the device, so the whole ~30-launch sequence is capturable): what an interactive caller (play.py) should do per frame
+            try:
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        frame()
+                torch.cuda.current_stream(device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    captured = frame()
+                graph.replay()
+                torch.cuda.synchronize()
+                same = all(torch.equal(a, b) for a, b in zip(captured, grids))
+                s0.record()
+                for _ in range(20):
+                    graph.replay()
+                e0.record()
+                torch.cuda.synchronize()
+                out["mixed_cuda_graph_ms"] = s0.elapsed_time(e0) / 20
+                out["cuda_graph_equals_eager"] = bool(same)
+            except Exception as exc:      # noqa: BLE001  (a diagnostic figure: never fail the bench line for it)
+                out["cuda_graph_error"] = str(exc)[:200]
     out["grids"] = [list(g.shape) for g in grids]
     return out
 
