@@ -100,7 +100,10 @@ struct KeepSamples {
 // players P = 32: the fp16 rounding of the ACTIVATIONS alone leaves 2-3e-3 on the compositing weights, measured, profiles/r2_mixed_mode.md),
 // and their share of a frame's FLOPs is small.
 static int object_precision(const PeScene& s, int k) {
-    if (s.precision == PE_PRECISION_MIXED && s.object[k].positions < 64) return PE_PRECISION_FP16X3;
+    if (s.precision == PE_PRECISION_MIXED) {
+        const char* env = getenv("PE_TC_X3_BELOW");           // diagnostic: the samples-per-ray threshold below which objects run fp16x3
+        if (s.object[k].positions < (env ? atoi(env) : 64)) return PE_PRECISION_FP16X3;
+    }
     return s.precision;
 }
 
@@ -108,7 +111,8 @@ static int object_precision(const PeScene& s, int k) {
 // activation-aware weight stream (PeObjectDesc.aware_rounding) and >= 96 samples per ray far fewer layers need the second pass
 // (PE_TC_AWARE_MASK, measured in profiles/r2_aware_rounding.md; emulation: 7e-4 worst output at 128 samples per ray, 1.0e-3 at 64).
 static int object_pass2_mask(const PeScene& s, int k) {
-    if (s.precision != PE_PRECISION_MIXED || !s.object[k].aware_rounding || s.object[k].positions < 96 || s.training) return -1;
+    const char* amin = getenv("PE_TC_AWARE_MIN_POSITIONS");  // diagnostic
+    if (s.precision != PE_PRECISION_MIXED || !s.object[k].aware_rounding || s.object[k].positions < (amin ? atoi(amin) : 96) || s.training) return -1;
     const char* env = getenv("PE_TC_AWARE_MASK");
     return env ? (int)strtol(env, nullptr, 0) : PE_TC_AWARE_MASK;
 }
