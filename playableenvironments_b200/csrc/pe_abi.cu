@@ -172,11 +172,11 @@ static Workspace carve(const PeScene& s, void* base) {
         o.flags = prepass ? (uint8_t*)take(n) : nullptr;
         o.tile_list = prepass ? (int32_t*)take(tiles * 4) : nullptr;
         o.tile_count = prepass ? (int32_t*)take(4) : nullptr;
-        // train-mode recompute for the backward on the tensor cores: the trunk output of every evaluated sample, so that the two
-        // BatchNorm-reduction passes of the field backward start from it (PE_BWD_TRUNK_CACHE=0 disables)
-        const char* cenv = getenv("PE_BWD_TRUNK_CACHE");
-        const bool cache = g_keep_samples && s.training && (object_uses_tc(s, k) || prepass) && !(cenv && atoi(cenv) == 0) &&
-                           !backward_on_tc(s, k);      // (only the fp32 field backward reads it)
+        // train mode on the tensor cores: the trunk output of every sample (fp32, 1 KB), written by the first BatchNorm phase and read by
+        // the other two (and by the BatchNorm passes of the fp32 field backward) instead of re-evaluating encoding + trunk
+        // (PE_TC_TRUNK_CACHE=0 disables)
+        const char* cenv = getenv("PE_TC_TRUNK_CACHE");
+        const bool cache = s.training && (object_uses_tc(s, k) || prepass) && !(cenv && atoi(cenv) == 0);
         o.h7 = cache ? (float*)take(n * d.width * 4) : nullptr;
         o.aff1 = (float*)take((size_t)s.images * 2 * d.width * 4);
         o.aff2 = (float*)take((size_t)s.images * d.width * 4);

@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
     // head layer 0 and accumulates its column sums, phase 2 after head layer 3 (three launches, two global reductions)
     const int stat_phase = (kStats && A.training) ? A.phase : 0;
     const int num_layers = stat_phase == 1 ? 9 : (stat_phase == 2 ? 10 : (fold ? NUM_LAYERS - 1 : NUM_LAYERS));
+    // train mode with a trunk cache (A.h7_out): phase 1 (the first launch) writes every row's trunk output, phases 2 and 0 start at
+    // head layer 0 from it instead of evaluating encoding + trunk two more times
+    const int first_layer = (kStats && A.training && A.h7_out != nullptr && A.phase != 1) ? 8 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NUM_STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     const uint32_t bytes = (uint32_t)n * PE_TC_SLAB_K * 2;
+                    if (l < first_layer) { src += (int64_t)slabs * bytes + (has_bias ? n * 32 : 0); continue; }
                     const int num_passes = layer_passes(l);
                     for (int s = 0; s < slabs; ++s) {
                         for (int pass = 0; pass < num_passes; ++pass) {
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
             R.stage = 0; R.phase = 0; R.num_passes = layer_passes(0); R.x3 = x3;
             const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
             for (int64_t pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
-                for (int l = 0; l < num_layers; ++l) {
+                for (int l = first_layer; l < num_layers; ++l) {
                     int n, slabs, chunk0; bool has_bias;
                     layer_spec(l, n, slabs, chunk0, has_bias);
                     if (!kPasses) R.num_passes = layer_passes(l);
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
         X.dbg = dbg;
         X.fold = fold != 0;
         X.stat_phase = stat_phase;
+        X.resume = first_layer != 0;
         X.single = G2.integrated_features != nullptr || G2.opacity != nullptr || G2.weights != nullptr;   // this object IS the scene
         Sync1 sync{acc_full + g, a_ready + g, 0u, lane, h6_full + g, h6_done + g, 0u};
         if constexpr (kX3) {

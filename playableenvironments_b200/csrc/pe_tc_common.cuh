@@ -140,6 +140,37 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* a
     return alpha;
 }
 
+// Train mode, BatchNorm phases 2 and 0: the trunk output of this row comes from the cache phase 1 wrote (fp32, post-ReLU: the very
+// values hidden_epilogue<1> saw in the accumulators), so the alpha head and the next A operand are bit-identical to a recompute.
+template <int N, bool kHiLo>
+__device__ __forceinline__ float trunk_from_cache(const float* __restrict__ h_in, unsigned char* abuf, int chunk0, int m,
+                                                  const float* __restrict__ aw, unsigned char* abuf_lo) {
+    float alpha = 0.f;
+#pragma unroll
+    for (int c = 0; c < N / 32; ++c) {
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = h_in ? __ldg(reinterpret_cast<const float4*>(h_in + c * 32 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(aw + c * 32 + 4 * q);
+            alpha = fmaf(fmaxf(y[4 * q + 0], 0.f), w4.x, alpha);
+            alpha = fmaf(fmaxf(y[4 * q + 1], 0.f), w4.y, alpha);
+            alpha = fmaf(fmaxf(y[4 * q + 2], 0.f), w4.z, alpha);
+            alpha = fmaf(fmaxf(y[4 * q + 3], 0.f), w4.w, alpha);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            if (kHiLo) store_a8_hilo(abuf, abuf_lo, chunk0 + c * 4 + cc, m, y + 8 * cc, true);
+            else store_a8_relu(abuf, chunk0 + c * 4 + cc, m, y + 8 * cc);
+        }
+    }
+    return alpha;
+}
+
 // 16-column variants of the TMEM load / wait
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -175,6 +206,7 @@ struct TileCtx {
     const float* alpha_w;
     bool single;
     int stat_phase;              // train-mode BatchNorm: 1 / 2 = this launch accumulates the statistics of head layer 0 / 3 and stops there
+    bool resume;                 // train mode, phases 2 and 0 with a trunk cache (PeFieldArgs.h7_out): the layers start at head layer 0
     bool fold;                   // folded-head mode: composite the 128-wide input of head layer 6, skip that layer's MMAs
     int dbg;                     // PE_TC_TIMELINE=1: thread 0 of epilogue group 0 of CTA 0 prints clock64 stamps of its third tile
 };
@@ -369,12 +401,17 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
 #endif
     PE_STAMP(0);
     // ---- sampling + Fourier features (unless the previous tile's epilogue already did them) ----
-    if (!ahead.have) {
-        sample_row<kFoldOnly>(X, tile, ahead.rs);
-        encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
+    const bool resume = kStats && X.resume;
+    if (resume) {
+        sample_row<kFoldOnly>(X, tile, ahead.rs);       // masks and ray parameters; the encoding and the trunk are not evaluated again
+    } else {
+        if (!ahead.have) {
+            sample_row<kFoldOnly>(X, tile, ahead.rs);
+            encode_row<kSplit, kHiLo>(X, ahead.rs.x, ahead.enc);
+        }
+        store_enc<kSplit, kHiLo>(X, ahead.enc);
+        sync.arrive_ready();
     }
-    store_enc<kSplit, kHiLo>(X, ahead.enc);
-    sync.arrive_ready();
     PE_STAMP(1);
     ahead.have = false;
     const bool tile_valid = ahead.rs.tile_valid, valid = ahead.rs.valid, inbox = ahead.rs.inbox, in_scene = ahead.rs.in_scene;
@@ -471,7 +508,7 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
     float4 pre[2 / kSplit];
     const uint32_t tcol = taddr + hf * (256 / kSplit);        // first accumulator column of this thread for 256-wide layers
 #pragma unroll 1
-    for (int l = 0; l < 10; ++l) {
+    for (int l = resume ? 7 : 0; l < 10; ++l) {
         if (fold && l == 8) {
             // folded-head mode: the raw alphas are known after L7, so the compositing weights are computed here, while the
             // tensor core runs head layer 0
@@ -500,9 +537,10 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             ahead.have = true;
         }
         PE_STAMP(2 + 3 * l);
-        sync.wait_acc();
+        const bool cached = resume && l == 7;           // this "layer" is the trunk cache: no accumulators to wait for
+        if (!cached) sync.wait_acc();
         PE_STAMP(3 + 3 * l);
-        if (l == 4) {
+        if (l == 4 || cached) {
             // the encoding columns are dead once L4 has run: reuse them for the constants of the later epilogues
             // (AdaIn scale/shift of this image and the alpha-head weights); the loads overlap this layer's epilogue
             const float* a1 = A.aff1 + (int64_t)img * 512;
@@ -513,6 +551,10 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
                 const float* src = i0 < 512 ? a1 + i0 : (i0 < 768 ? a2 + (i0 - 512) : X.alpha_w + (i0 - 768));
                 pre[j] = __ldg(reinterpret_cast<const float4*>(src));
             }
+        }
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < 2 / kSplit; ++j) *reinterpret_cast<float4*>(cst + (j * GROUP + tid) * 4) = pre[j];
         }
         if (l == 7) named_bar_sync(bar_id, GROUP);                         // constants written by the whole group at l == 4
         constexpr int W = 256 / kSplit, W2 = 128 / kSplit;
@@ -628,8 +670,12 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
         else if (l == 7) {
             // train-mode recompute for the backward: the trunk output goes to memory so that the BatchNorm-reduction passes of
             // pe_field_bwd_kernel start from it instead of recomputing bender, encoding and trunk
-            float* h_out = (kStats && A.h7_out && X.stat_phase == 0 && valid) ? A.h7_out + gs * 256 + hf * W : nullptr;
-            raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo, h_out);
+            // train mode with a trunk cache: phase 1 writes this row's trunk output, phases 2 and 0 (and the fp32 field backward's
+            // BatchNorm passes) start from it
+            float* h_out = (kStats && A.h7_out && X.stat_phase == 1 && valid) ? A.h7_out + gs * 256 + hf * W : nullptr;
+            if (cached) raw_alpha = trunk_from_cache<W, kHiLo>(valid ? A.h7_out + gs * 256 + hf * W : nullptr, abuf, hf * (W / 8), m,
+                                                               cst + CST_AW + hf * W, X.abuf_lo);
+            else raw_alpha = hidden_epilogue<1, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_AW + hf * W, nullptr, X.abuf_lo, h_out);
         }
         else if (l == 8) hidden_epilogue<2, W, kHiLo>(tcol, abuf, hf * (W / 8), m, cst + CST_SC1 + hf * W, cst + CST_SH1 + hf * W, X.abuf_lo);
         else hidden_epilogue<2, W2, kHiLo>(taddr + hf * W2, abuf, hf * (W2 / 8), m, cst + CST_SC2 + hf * W2, cst + CST_SH2 + hf * W2, X.abuf_lo);
