@@ -542,25 +542,74 @@ __host__ __device__ __forceinline__ int64_t slab_offset(int N, int n, int k) {
 // neighbour (down or up) that keeps the running sum of rounding errors of the row closest to zero.  Post-ReLU activations
 // have a large common positive mean, so the systematic part sum_k dW[n][k] * mean(a) of the single-pass error cancels
 // (measured: -10..-30 % error on the rendered frame); lo = fp16(w - hi) is the second pass of the fp16x2 mode.
-__global__ void pe_tc_pack_layer_kernel(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
-                                        unsigned char* __restrict__ lo, int N_real) {
-    // N: rows of the slab layout; rows >= N_real (padding up to the smallest MMA N) are zero
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float run = 0.f;
-    for (int k = 0; k < K_pad; ++k) {
-        const float v = (k < K_src && n < N_real) ? w[(int64_t)n * K_src + k] : 0.f;
-        const __half near = __float2half_rn(v);
+constexpr int PACK_ROWS = 8;           // rows of a layer per block of the zero-sum packing
+__host__ __device__ inline size_t pack_layer_smem(int K_pad) { return (size_t)3 * PACK_ROWS * (K_pad + 1) * 4 + (size_t)PACK_ROWS * 16 * 4; }
+
+__global__ void __launch_bounds__(128) pe_tc_pack_layer_kernel(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
+                                                               unsigned char* __restrict__ lo, int N_real) {
+    // N: rows of the slab layout; rows >= N_real (padding up to the smallest MMA N) are zero.  This kernel runs for every layer of
+    // every model whenever a parameter changes, i.e. every training step, so only the decision itself is sequential: (a) all threads
+    // load the block's PACK_ROWS rows (coalesced) and compute both candidates' rounding errors; (b) one thread per row walks along K
+    // with nothing but `run` in its dependency chain and records the picks as bits; (c) all threads build the hi / lo halves and store
+    // the slab layout in 16-byte pieces.
+    extern __shared__ __align__(16) unsigned char pack_smem[];
+    const int ld = K_pad + 1;
+    float* ws = reinterpret_cast<float*>(pack_smem);                   // [PACK_ROWS][ld] weights
+    float* en = ws + PACK_ROWS * ld;                                   // error of the nearest fp16
+    float* eo = en + PACK_ROWS * ld;                                   // error of the other neighbour
+    uint32_t* bits = reinterpret_cast<uint32_t*>(eo + PACK_ROWS * ld); // [PACK_ROWS][16] picks (K_pad <= 512)
+    const int n0 = blockIdx.x * PACK_ROWS, tid = threadIdx.x;
+    auto candidates = [](float v, __half& near, __half& other) {
+        near = __float2half_rn(v);
         const float fn = __half2float(near);
-        __half other = near;
+        other = near;
         if (fn != v) other = fn < v ? __float2half_ru(v) : __float2half_rd(v);
-        const float e_near = fn - v, e_other = __half2float(other) - v;
-        const bool pick_other = fabsf(run + e_other) < fabsf(run + e_near);
-        const __half h = pick_other ? other : near;
-        run += pick_other ? e_other : e_near;
-        const int64_t off = slab_offset(N, n, k);
-        *reinterpret_cast<__half*>(hi + off) = h;
-        *reinterpret_cast<__half*>(lo + off) = __float2half_rn(v - __half2float(h));
+    };
+    for (int idx = tid; idx < PACK_ROWS * K_pad; idx += blockDim.x) {
+        const int r = idx / K_pad, k = idx - r * K_pad, n = n0 + r;
+        const float v = (k < K_src && n < N_real && n < N) ? w[(int64_t)n * K_src + k] : 0.f;
+        __half near, other;
+        candidates(v, near, other);
+        ws[r * ld + k] = v;
+        en[r * ld + k] = __half2float(near) - v;
+        eo[r * ld + k] = __half2float(other) - v;
+    }
+    __syncthreads();
+    if (tid < PACK_ROWS) {
+        const float* a = en + tid * ld;
+        const float* b = eo + tid * ld;
+        float run = 0.f;
+        for (int k0 = 0; k0 < K_pad; k0 += 32) {
+            uint32_t word = 0;
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) {
+                const float e_near = a[k0 + kk], e_other = b[k0 + kk];
+                const bool pick_other = fabsf(run + e_other) < fabsf(run + e_near);
+                run += pick_other ? e_other : e_near;
+                word |= (pick_other ? 1u : 0u) << kk;
+            }
+            bits[tid * 16 + (k0 >> 5)] = word;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < PACK_ROWS * (K_pad / 8); idx += blockDim.x) {
+        const int r = idx % PACK_ROWS, k8 = idx / PACK_ROWS, n = n0 + r;
+        if (n >= N) continue;
+        const uint32_t word = bits[r * 16 + (k8 >> 2)] >> ((k8 & 3) * 8);
+        __align__(16) __half h8[8];
+        __align__(16) __half l8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float v = ws[r * ld + k8 * 8 + q];
+            __half near, other;
+            candidates(v, near, other);
+            const __half h = ((word >> q) & 1u) ? other : near;
+            h8[q] = h;
+            l8[q] = __float2half_rn(v - __half2float(h));
+        }
+        const int64_t off = slab_offset(N, n, k8 * 8);
+        *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h8);
+        *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l8);
     }
 }
 
@@ -801,7 +850,7 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
             pe_tc_pack_layer_aware_kernel<<<it.N, (it.K_pad + 31) / 32 * 32, 0, stream>>>(it.w, it.moments, it.N, it.K_src, it.K_pad, hi + off, lo + off, 1);
             PE_LAUNCH_CHECK("pe_tc_pack_layer_aware_kernel");
         } else {
-            pe_tc_pack_layer_kernel<<<(it.N + 63) / 64, 64, 0, stream>>>(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off, it.N);
+            pe_tc_pack_layer_kernel<<<(it.N + PACK_ROWS - 1) / PACK_ROWS, 128, pack_layer_smem(it.K_pad), stream>>>(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off, it.N);
             PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
         }
         off += total * 2;
@@ -820,7 +869,7 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
         for (int l = 0; l < 6; ++l) {
             if (!p.bender_w[l] || !p.bender_b[l]) { pe_set_error("missing ray-bender parameter tensor of layer %d", l); return PE_ERR_INVALID; }
             const int K_src = l == 0 ? 71 : (l == 3 ? 199 : 128), K_pad = l == 0 ? 96 : (l == 3 ? 224 : 128);
-            pe_tc_pack_layer_kernel<<<2, 64, 0, stream>>>(p.bender_w[l], 128, K_src, K_pad, bhi + boff, blo + boff, 128);
+            pe_tc_pack_layer_kernel<<<128 / PACK_ROWS, 128, pack_layer_smem(K_pad), stream>>>(p.bender_w[l], 128, K_src, K_pad, bhi + boff, blo + boff, 128);
             PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
             boff += (int64_t)128 * K_pad * 2;
             pe_tc_pack_bias_kernel<<<(128 * 16 + 255) / 256, 256, 0, stream>>>(p.bender_b[l], 128, bhi + boff);
@@ -828,7 +877,7 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
             boff += 128 * 32;
         }
         if (!p.bender_out_w) { pe_set_error("missing ray-bender output layer"); return PE_ERR_INVALID; }
-        pe_tc_pack_layer_kernel<<<1, 64, 0, stream>>>(p.bender_out_w, 16, 128, 128, bhi + boff, blo + boff, 3);
+        pe_tc_pack_layer_kernel<<<(16 + PACK_ROWS - 1) / PACK_ROWS, 128, pack_layer_smem(128), stream>>>(p.bender_out_w, 16, 128, 128, bhi + boff, blo + boff, 3);
         PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
         boff += (int64_t)16 * 128 * 2;
         if (boff != L.tcb_bytes_per_pass) { pe_set_error("internal: ray-bender weight stream size mismatch"); return PE_ERR_INVALID; }
@@ -925,9 +974,9 @@ int pe_launch_bender_tc(const PeFieldArgs& args, int sm_count, cudaStream_t stre
 // N * K_pad fp16 each -- tests/test_gpu_parity.py::test_activation_aware_rounding unpacks them and checks the rounding choices.
 extern "C" int pe_debug_pack_layer(const float* w, const float* moments, int32_t N, int32_t K_src, int32_t K_pad, int32_t sweeps, void* hi,
                                    void* lo, pe_stream_t stream) {
-    if (N < 8 || N % 8 || K_pad % 32 || K_src > K_pad || K_pad > 1024 || !w || !hi || !lo) { pe_set_error("debug pack: bad shape"); return PE_ERR_INVALID; }
+    if (N < 8 || N % 8 || K_pad % 32 || K_src > K_pad || K_pad > (moments ? 1024 : 448) || !w || !hi || !lo) { pe_set_error("debug pack: bad shape"); return PE_ERR_INVALID; }
     if (moments) pe_tc_pack_layer_aware_kernel<<<N, K_pad, 0, (cudaStream_t)stream>>>(w, moments, N, K_src, K_pad, (unsigned char*)hi, (unsigned char*)lo, sweeps);
-    else pe_tc_pack_layer_kernel<<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>(w, N, K_src, K_pad, (unsigned char*)hi, (unsigned char*)lo, N);
+    else pe_tc_pack_layer_kernel<<<(N + PACK_ROWS - 1) / PACK_ROWS, 128, pack_layer_smem(K_pad), (cudaStream_t)stream>>>(w, N, K_src, K_pad, (unsigned char*)hi, (unsigned char*)lo, N);
     PE_LAUNCH_CHECK("pe_debug_pack_layer");
     return PE_OK;
 }
