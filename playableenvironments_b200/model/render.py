@@ -305,12 +305,23 @@ class RenderFunction(torch.autograd.Function):
         params = (_cabi.PeObjectParams * _cabi.PE_MAX_OBJECTS)()
         g_params: List = []
         idx = 4 + 2 * K + n_t
+        # one zero-filled buffer for every parameter gradient of the call (the kernels accumulate into it): one fill instead of one per
+        # tensor (~60 per object model); 16-byte aligned pieces
+        slots = [(k, field, i, tensor) for k, m in enumerate(models) for field, i, tensor in m.parameter_slots()]
+        sizes = [((t.numel() + 3) // 4 * 4) if need[idx + j] else 0 for j, (_, _, _, t) in enumerate(slots)]
+        flat_grads = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        offsets, off = [], 0
+        for sz in sizes:
+            offsets.append(off)
+            off += sz
+        slot_iter = iter(range(len(slots)))
         for k, m in enumerate(models):
             ps, kp = m.parameter_struct()
             keep.append(kp)
             params[k] = ps
             for field, i, tensor in m.parameter_slots():
-                g = zeros(tensor) if need[idx] else None
+                j = next(slot_iter)
+                g = flat_grads[offsets[j]:offsets[j] + tensor.numel()].view(tensor.shape) if need[idx] else None
                 idx += 1
                 g_params.append(g)
                 if g is not None:
