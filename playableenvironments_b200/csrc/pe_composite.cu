@@ -54,18 +54,20 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         dsum += w * dm;
         vsum += alpha * fabsf(dv);                 // mean(alphas * |divergence|) :777-778
         const int src = j < n ? S.src[j] : -1;
-        const int cnt = min(32, n - c0);
-        for (int jj = 0; jj < cnt; ++jj) {
+        // only the samples that carry features and weight (in sample order: the sum is evaluated like the reference's); in a sparse view
+        // most of a ray's samples lie outside every box
+        unsigned todo = __ballot_sync(0xffffffffu, j < n && w != 0.f && src >= 0);
+        while (todo) {
+            const int jj = __ffs(todo) - 1;
+            todo &= todo - 1;
             const float wj = __shfl_sync(0xffffffffu, w, jj);
             const int sj = __shfl_sync(0xffffffffu, src, jj);
-            if (wj != 0.f && sj >= 0) {
-                const int k = sj >> 16, p = sj & 0xffff;
-                const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+            const int k = sj >> 16, p = sj & 0xffff;
+            const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = lane + 32 * i;
-                    if (c < F) acc[i] = fmaf(wj, __ldg(f + c), acc[i]);
-                }
+            for (int i = 0; i < 8; ++i) {
+                const int c = lane + 32 * i;
+                if (c < F) acc[i] = fmaf(wj, __ldg(f + c), acc[i]);
             }
         }
     }
