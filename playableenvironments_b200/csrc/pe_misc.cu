@@ -8,17 +8,28 @@ namespace {
 constexpr float BN_EPS = 1e-5f;       // torch.nn.BatchNorm1d default (model/layers/adain.py:47)
 
 // [scale|bias] = affine_transform(style) (adain.py:30-32); BatchNorm1d(affine=False) folded: y = x*sc + sh.
-__global__ void pe_style_kernel(const PeStyleArgs A) {
+__global__ void __launch_bounds__(256) pe_style_kernel(const PeStyleArgs A) {
+    // one warp per channel (the two rows of the affine transform read coalesced, lanes stride the style features): this kernel sits
+    // on the critical path in front of every field launch, twice per object
     const int img = blockIdx.x;
     const int C = A.channels, S = A.style_features;
     const float* style = A.style + (int64_t)img * S;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float scale = A.aff_b[c], bias = A.aff_b[C + c];
-        for (int s = 0; s < S; ++s) {
+    const int lane = threadIdx.x & 31;
+    for (int c = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5); c < C; c += gridDim.y * (blockDim.x >> 5)) {
+        float scale = 0.f, bias = 0.f;
+        for (int s = lane; s < S; s += 32) {
             const float v = style[s];
             scale = fmaf(A.aff_w[(int64_t)c * S + s], v, scale);
             bias = fmaf(A.aff_w[(int64_t)(C + c) * S + s], v, bias);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            scale += __shfl_xor_sync(0xffffffffu, scale, o);
+            bias += __shfl_xor_sync(0xffffffffu, bias, o);
+        }
+        if (lane != 0) continue;
+        scale += A.aff_b[c];
+        bias += A.aff_b[C + c];
         float mean = A.run_mean[c], var = A.run_var[c];
         if (A.training) {
             const double n = A.stats[2 * C];          // in-box sample count, written after the sums
@@ -130,7 +141,7 @@ inline int grid_for(int64_t n, int block = 256) { return (int)pe_min64((n + bloc
 
 int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream) {
     if (args.images == 0) return PE_OK;
-    pe_style_kernel<<<args.images, 128, 0, stream>>>(args);
+    pe_style_kernel<<<dim3(args.images, (args.channels + 7) / 8), 256, 0, stream>>>(args);
     PE_LAUNCH_CHECK("pe_style_kernel");
     return PE_OK;
 }
