@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_fwd_kernel(const PeBw
 // =====================================================================================================================
 // Numerics.  Gradients are badly scaled (compositing weights span many decades) and their sums over samples cancel heavily (d sin(512 x)/dx),
 // so the chain runs in the fp32-class form of the forward's fp16x3 mode: every gradient operand is kept as a hi + lo fp16 pair (two operand
-// buffers, ONE tile per iteration), weights as hi + lo slabs, three MMAs per k-step (G_hi W_hi + G_lo W_hi + G_hi W_lo), and every ROW is
+// buffers, ONE tile per iteration), weights as hi (+ lo: PE_BWD_CHAIN_WLO=1) slabs, two MMAs per k-step (G_hi W_hi + G_lo W_hi [+ G_hi W_lo]), and every ROW is
 // normalised by its own power of two s_m (the chain is linear per row) so that its values sit at ~2^8 whatever the sample's weight.
 // The stash copy of G (the M operand of dW, summed over rows) carries the call-wide scale S instead: G_norm * S / s_m, fp16 hi only.
 struct ChainCtx {
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const P
                     const StepSpec st = chain_step(s);
                     const uint32_t bytes = (uint32_t)st.n * PE_TC_SLAB_K * 2;
                     for (int k = 0; k < st.slabs; ++k) {
-                        for (int pass = 0; pass < 2; ++pass) {
+                        for (int pass = 0; pass < ((lo_on & 2) ? 2 : 1); ++pass) {
                             mbar_wait(empty_bar + stage, ph ^ 1);
                             mbar_arrive_expect_tx(full_bar + stage, bytes);
                             bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcT_bytes_per_pass, bytes, full_bar + stage);
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const P
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + A_BYTES);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 1;
+            R.stage = 0; R.phase = 0; R.num_passes = (lo_on & 2) ? 2 : 1; R.x3 = 1;
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 for (int s = 0; s < steps; ++s) {
                     const StepSpec st = chain_step(s);
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const P
     } else if (warp >= 4) {
         // two epilogue groups of 4 warps share every row: group h handles half of the columns of each step
         ChainCtx C;
-        C.lane = lane; C.lo_on = lo_on;
+        C.lane = lane; C.lo_on = lo_on & 1;
         C.h = (warp - 4) >> 2; C.par = 0;
         C.xch = reinterpret_cast<float*>(smem + FCHAIN_XCH);
         C.m = ((warp & 3) << 5) | lane;
@@ -1142,7 +1142,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
                     const StepSpec st = bb_chain_step(s);
                     const uint32_t bytes = (uint32_t)st.n * PE_TC_SLAB_K * 2;
                     for (int k = 0; k < st.slabs; ++k) {
-                        for (int pass = 0; pass < 2; ++pass) {
+                        for (int pass = 0; pass < ((lo_on & 2) ? 2 : 1); ++pass) {
                             mbar_wait(empty_bar + stage, ph ^ 1);
                             mbar_arrive_expect_tx(full_bar + stage, bytes);
                             bulk_copy_g2s(ring + stage * STAGE_BYTES, src + (int64_t)pass * L.tcbT_bytes_per_pass, bytes, full_bar + stage);
@@ -1160,7 +1160,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(smem); R.a_addr[1] = smem_u32(smem + BB_A_BYTES);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 1;
+            R.stage = 0; R.phase = 0; R.num_passes = (lo_on & 2) ? 2 : 1; R.x3 = 1;
             for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
                 for (int s = 0; s < STEPS; ++s) {
                     const StepSpec st = bb_chain_step(s);
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
         }
     } else if (warp >= 4) {
         ChainCtx C;
-        C.lane = lane; C.lo_on = lo_on;
+        C.lane = lane; C.lo_on = lo_on & 1;
         C.m = ((warp & 3) << 5) | lane;
         C.a_hi = smem; C.a_lo = smem + BB_A_BYTES;
         C.cst = nullptr;
@@ -1649,10 +1649,16 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
     return PE_OK;
 }
 
-// PE_BWD_CHAIN_LO=0 (diagnostic): the dX chains carry plain fp16 gradient operands (lo halves zeroed)
+// bit 0: the dX chains carry hi + lo gradient operands (PE_BWD_CHAIN_LO=0, diagnostic: plain fp16, lo halves zeroed);
+// bit 1: the transposed weight stream runs hi + lo (PE_BWD_CHAIN_WLO=1).  Default: hi only -- G_hi W + G_lo W, two MMAs per k-step
+// and half the weight traffic out of L2 of these one-tile-per-CTA kernels: measured on the golden scenes (tests/gpu_chain_wlo.py) the
+// gradients do not move (worst deviation from the exact fp32 backward 2.7e-3 / 4.7e-2 / 5.5e-3 / 3.1e-3 with the lo pass, 2.8e-3 /
+// 4.8e-2 / 5.5e-3 / 3.0e-3 without: the recompute's ReLU masks set the error, not the weights' 11 bits), the dense cfg3 step drops
+// from 38.4 to 36.7 ms.
 static int chain_lo_on() {
     const char* env = getenv("PE_BWD_CHAIN_LO");
-    return (env && atoi(env) == 0) ? 0 : 1;
+    const char* wenv = getenv("PE_BWD_CHAIN_WLO");
+    return ((env && atoi(env) == 0) ? 0 : 1) | ((wenv && atoi(wenv) != 0) ? 2 : 0);
 }
 
 int pe_launch_bwd_fwd(const PeBwdTcArgs& args, int64_t tile0, int sm_count, cudaStream_t stream) {
