@@ -453,7 +453,19 @@ def run_b200(args):
     side = torch.cuda.Stream(device=device)
 
     fused = world > 1 and args.gather == "fused"
-    pg = sharding.PeerGather(rays, F, device) if fused else None
+    pg, fused_note = None, None
+    if fused:
+        # symmetric memory needs P2P-capable GPUs under one driver; if the rendezvous fails on ANY rank, all ranks fall back to NCCL
+        try:
+            pg = sharding.PeerGather(rays, F, device)
+            ok = torch.ones(1, device=device)
+        except Exception as exc:      # noqa: BLE001
+            fused_note = f"PeerGather unavailable ({type(exc).__name__}: {str(exc)[:120]}): NCCL all-gather instead"
+            ok = torch.zeros(1, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            fused, pg = False, None
+            fused_note = fused_note or "PeerGather unavailable on another rank: NCCL all-gather instead"
 
     def step():
         with torch.no_grad():
@@ -582,7 +594,7 @@ def run_b200(args):
                                            "fp16x3": "f16 operands (weights and activations hi+lo), f32 accumulate", "fp32": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "precision": args.precision, "frames_per_gpu_per_step": 1, "l2": "flushed between steps (256 MB memset)",
-                       "frames_per_s": world * args.steps / total_s, "collective": ("none" if world == 1 else "all-gather of the feature grid fused into the render kernel (P2P stores over NVLink into symmetric memory, sharding.PeerGather) + one signal-pad barrier"
+                       "frames_per_s": world * args.steps / total_s, "collective_note": fused_note, "collective": ("none" if world == 1 else "all-gather of the feature grid fused into the render kernel (P2P stores over NVLink into symmetric memory, sharding.PeerGather) + one signal-pad barrier"
                                       if fused else f"NCCL all_gather(feature grid) per ray chunk, {args.chunks} chunks, on a side stream")},
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["burst"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / peaks["burst"],
