@@ -80,3 +80,16 @@ def install(environment_model, precision: str = None, ray_selection: bool = Fals
 
     environment_model.batchified_composer_call = types.MethodType(_call, environment_model)
     return environment_model
+
+
+def build_environment_model(reference_architecture: str, config):
+    """Builds the reference's environment model ``reference_architecture`` (a dotted module path of the upstream tree exporting
+    ``model(config)``) and installs the B200 composer in it (``install``): the factory behind the
+    ``playableenvironments_b200.model.environment_model_*`` architecture strings."""
+    import importlib
+    try:
+        module = importlib.import_module(reference_architecture)
+    except ImportError as exc:
+        raise ImportError(f"{reference_architecture} is the reference's own module: put the PlayableEnvironments tree on PYTHONPATH "
+                          f"(this package replaces its render path, not its encoders / decoder / trainers)") from exc
+    return install(module.model(config))

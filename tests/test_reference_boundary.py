@@ -141,3 +141,34 @@ def test_decoder_hand_off_matches_the_reference_methods():
     folded = RayHelper.fold_strided_grid_samples(feats, strides, (H, W), dim=-2)
     for got, ref in zip(folded, results["coarse"]["global"]["integrated_features"]):
         assert torch.equal(got, ref)
+
+
+def test_architecture_string_factory_installs_the_composer(monkeypatch):
+    """SURVEY 8b face 1: ``model.architecture: playableenvironments_b200.model.environment_model_multiresolution_backpropagated_decoder``
+    builds the reference's environment model through its own ``model(config)`` factory and swaps the composer.  The upstream class needs
+    encoders / an autoencoder checkpoint to construct, which are out of scope here: the upstream module's factory is stubbed with a
+    minimal EnvironmentModel carrying a reference composer -- what is pinned is the resolution by dotted path, the hand-over to
+    ``install`` and the state_dict round trip."""
+    import importlib
+    import scenes
+    from playableenvironments_b200.model.object_composer import ObjectComposer as B200Composer
+    EnvironmentModel, RefComposer = _import_reference()
+    config, state, _ = scenes.SCENES["tennis_small"]()
+    upstream = importlib.import_module("model.environment_model_multiresolution_backpropagated_decoder")
+
+    def factory(cfg):
+        env = EnvironmentModel.__new__(EnvironmentModel)
+        torch.nn.Module.__init__(env)
+        env.config = copy.deepcopy(cfg)
+        env.object_composer = RefComposer(copy.deepcopy(cfg))
+        env.object_composer.load_state_dict(state, strict=False)
+        return env
+
+    monkeypatch.setattr(upstream, "model", factory)
+    ours = importlib.import_module("playableenvironments_b200.model.environment_model_multiresolution_backpropagated_decoder")
+    env = ours.model(config)
+    assert isinstance(env, EnvironmentModel) and isinstance(env.object_composer, B200Composer)
+    for k, v in env.object_composer.state_dict().items():
+        assert torch.equal(v, state[k]), k
+    for name in ("environment_model_multiresolution_backpropagated_autoencoder", "environment_model_backpropagated_autoencoder"):
+        assert callable(importlib.import_module("playableenvironments_b200.model." + name).model)
