@@ -469,3 +469,31 @@ def test_mixed_mode_without_activation_statistics_still_within_1e_3(monkeypatch)
     _, _, _, comp, dev = _build("static_small", "mixed")
     bad = compare(flatten(_run(comp, dev)), load_golden("static_small"), 1e-3)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("mixed", 1e-3)])
+def test_edge_shapes_empty_single_and_ragged_ray_sets(precision, tol):
+    """Edge cases of the caller's chunking (TensorBatchifier leaves ragged last chunks, utils/tensor_batchifier.py:9-45): no rays at
+    all, a single ray, and ray counts that fill neither a warp nor a 128-sample tile, on a multi-object scene with two images; every
+    output of the composer against the CPU oracle on exactly those rays."""
+    from gpu_common import build_composer, run_composer
+    from oracle import render_oracle as O
+    scene = scenes.scene_tennis(seed=21, height=16, width=24, stride=1, lead=(1, 2, 1), dense=True)
+    config, state, inputs = scene
+    _, _, _, comp, dev = build_composer(scene, precision)
+    for rays in (0, 1, 37, 131):
+        sub = dict(inputs)
+        sub["ray_directions"] = inputs["ray_directions"][..., :rays, :].contiguous()
+        dsub = dict(dev)
+        dsub["ray_directions"] = dev["ray_directions"][..., :rays, :].contiguous()
+        got = flatten(run_composer(comp, dsub))
+        torch.cuda.synchronize()
+        if rays == 0:
+            assert got["coarse/global/integrated_features"].shape[-2:] == (0, 192)
+            assert got["coarse/object_1/weights"].shape[-2:] == (0, 32)
+            continue
+        ref = flatten(O.composer_forward(config, state, *[sub[k] for k in INPUT_KEYS], perturb=False))
+        for k, want in ref.items():
+            if k.startswith("coarse/") and "divergence" not in k:
+                assert got[k].shape == want.shape, (rays, k)
+                assert scale_rel_err(got[k], want) <= tol, (rays, k, scale_rel_err(got[k], want))
