@@ -125,3 +125,24 @@ if __name__ == "__main__":          # diagnostic: per-key errors of every case a
         print(json.dumps({k: out[k] for k in list(out)[-1:]}), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/diag_backward.json", "w"), indent=1)
+
+
+@pytest.mark.parametrize("training", [False, True])
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+def test_backward_on_empty_single_and_ragged_ray_sets(precision, training):
+    """The backward over the ray counts a ragged chunk of the caller can have (0, 1, 37): runs, returns gradients of the inputs' shapes,
+    everything finite."""
+    from gpu_common import build_composer
+    scene = scenes.scene_tennis(seed=21, height=16, width=24, stride=1, lead=(1, 2, 1), dense=True)
+    _, _, _, comp, dev = build_composer(scene, precision, training=training)
+    comp.allow_forward_without_grad = False
+    for rays in (0, 1, 37):
+        d = dict(dev)
+        d["ray_directions"] = dev["ray_directions"][..., :rays, :].contiguous().requires_grad_(True)
+        comp.zero_grad(set_to_none=True)
+        res = comp(*[d[k] for k in INPUT_KEYS], False)["coarse"]["global"]
+        (res["integrated_features"].sum() + res["opacity"].sum()).backward()
+        torch.cuda.synchronize()
+        assert tuple(d["ray_directions"].grad.shape) == tuple(d["ray_directions"].shape)
+        assert bool(torch.isfinite(d["ray_directions"].grad).all())
+        assert all(bool(torch.isfinite(p.grad).all()) for p in comp.parameters() if p.grad is not None)
