@@ -827,9 +827,10 @@ __global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const P
                     const float xn[3] = {__fdiv_rn(r.x[0], size[0]), __fdiv_rn(r.x[1], size[1]), __fdiv_rn(r.x[2], size[2])};
                     auto columns = [&](auto half) {
                         constexpr int H = decltype(half)::value;
-#pragma unroll
+                        // rolled: 32 inlined sincosf bodies per half made this epilogue the largest piece of the kernel's code, and the
+                        // kernel's instruction fetch stalls (profiles/r2_bwd_tc.md) are what this step can give back
+#pragma unroll 1
                         for (int i = 0; i < 32; ++i) {
-                            constexpr int dummy = 0; (void)dummy;
                             const int e = 32 * H + i;
                             if (e < 3) gx[e] += ge[i];
                             else if (e < 63) {
