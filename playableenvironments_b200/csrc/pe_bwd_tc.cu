@@ -426,15 +426,16 @@ __device__ __forceinline__ void store_g8_hilo(unsigned char* a_hi, unsigned char
     *reinterpret_cast<uint4*>(a_lo + chunk * CHUNK_BYTES + m * 16) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// KIND 0: G = mask ? acc : 0;  KIND 2: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
-template <int KIND, int NB = 8, int NH = 1>
-__device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, float graw, bool store) {
+// G = mask ? acc : 0;  with_alpha: G = mask ? acc + graw * aw[c] : 0 (the alpha head joins at the trunk output)
+template <int NB = 8, int NH = 1>
+__device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t* __restrict__ mask_words, unsigned char* st_g, bool with_alpha,
+                                                     float graw, bool store) {
     // NH == 2: this thread handles the NB / 2 column blocks of half C.h; C.mop leaves as this half's maximum (the caller exchanges it)
     constexpr int MB = NB / NH;
     const int c0 = NH == 1 ? 0 : C.h * MB;
     const int fexp = renorm_exp(C.mop, C.km);
     const int km = C.km + fexp;
-    const float f = ldexpf(1.f, fexp - TCT_WEXP), r_stash = ldexpf(1.f, C.kS - km), graw_n = ldexpf(graw, km);
+    const float f = ldexpf(1.f, fexp - TCT_WEXP), r_stash = ldexpf(1.f, C.kS - km), graw_n = with_alpha ? ldexpf(graw, km) : 0.f;
     uint32_t bits[MB];
 #pragma unroll
     for (int w = 0; w < MB; ++w) bits[w] = mask_words[(c0 + w) * PE_BWD_TILE + C.m];
@@ -450,7 +451,7 @@ __device__ __forceinline__ void chain_epilogue_plain(ChainCtx& C, const uint32_t
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             float a = __uint_as_float(v[cb & 1][q]) * f;
-            if (KIND == 2) a = fmaf(graw_n, C.cst[CC_AW + c * 32 + q], a);
+            if (with_alpha) a = fmaf(graw_n, C.cst[CC_AW + c * 32 + q], a);
             y[q] = ((bits[cb] >> q) & 1u) ? a : 0.f;
             mx = fmaxf(mx, fabsf(y[q]));
         }
@@ -763,44 +764,35 @@ __global__ void __launch_bounds__(FCHAIN_THREADS, 1) pe_bwd_chain_kernel(const P
             if (phase == 2) { tc_fence_before(); named_bar_sync(CHAIN_BAR, 256); continue; }
             sync.arrive_ready();
             C.mop = row_max_exchange<2>(C, C.mop);
-            // ---- step 2: gh7 = gx1 H0 + graw alpha_w -> relu'(h7) ----
-            sync.wait_acc();
-            chain_epilogue_plain<2, 8, 2>(C, mask + 8 * 7 * PE_BWD_TILE, st + FS_GP(7) * CHUNK_BYTES, graw, st_ok);
-            sync.arrive_ready();
-            C.mop = row_max_exchange<2>(C, C.mop);
-            // ---- steps 3-5: trunk layers 7, 6, 5 -> gradients of the pre-activations of layers 6, 5, 4 ----
-#pragma unroll 1
-            for (int l = 6; l >= 4; --l) {
-                sync.wait_acc();
-                chain_epilogue_plain<0, 8, 2>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
-                sync.arrive_ready();
-                C.mop = row_max_exchange<2>(C, C.mop);
-            }
-            // ---- step 6: the encoding half of the skip layer's input gradient, parked (hi + lo) in the encoding columns ----
+            // ---- steps 2-10 share ONE copy of the plain epilogue (instruction fetch: profiles/r2_bwd_tc.md) ----
+            //   step 2: gh7 = gx1 H0 + graw alpha_w -> relu'(h7) (the alpha head joins at the trunk output)
+            //   steps 3-5: trunk layers 7, 6, 5 -> gradients of the pre-activations of layers 6, 5, 4
+            //   step 6: the encoding half of the skip layer's input gradient, parked (hi + lo) in the encoding columns
+            //   steps 7-10: trunk layers 4 (hidden half), 3, 2, 1 -> gradients of the pre-activations of layers 3, 2, 1, 0
             int km_parked = 0;
-            sync.wait_acc();
-            {
-                uint32_t v[32];
-                tmem_ld32(C.taddr + 32 * h, v);
-                tmem_wait_ld_regs(v);
-                named_bar_sync(CHAIN_BAR, 256);            // every reader of the constants is done
-                const int fexp = renorm_exp(C.mop, C.km);  // (the operand stays: the next step reads it again with the same factor)
-                km_parked = C.km + fexp;
-                const float f = ldexpf(1.f, fexp - TCT_WEXP);
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    float y[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[8 * cc + i]) * f;
-                    store_g8_hilo(C.a_hi, C.a_lo, PE_CHUNK0 + h * 4 + cc, m, y);
-                }
-            }
-            sync.arrive_ready();
-            // ---- steps 7-10: trunk layers 4 (hidden half), 3, 2, 1 -> gradients of the pre-activations of layers 3, 2, 1, 0 ----
 #pragma unroll 1
-            for (int l = 3; l >= 0; --l) {
+            for (int step = 2; step <= 10; ++step) {
                 sync.wait_acc();
-                chain_epilogue_plain<0, 8, 2>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, 0.f, st_ok);
+                if (step == 6) {
+                    uint32_t v[32];
+                    tmem_ld32(C.taddr + 32 * h, v);
+                    tmem_wait_ld_regs(v);
+                    named_bar_sync(CHAIN_BAR, 256);            // every reader of the constants is done
+                    const int fexp = renorm_exp(C.mop, C.km);  // (the operand stays: the next step reads it again with the same factor)
+                    km_parked = C.km + fexp;
+                    const float f = ldexpf(1.f, fexp - TCT_WEXP);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float y[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[8 * cc + i]) * f;
+                        store_g8_hilo(C.a_hi, C.a_lo, PE_CHUNK0 + h * 4 + cc, m, y);
+                    }
+                    sync.arrive_ready();
+                    continue;
+                }
+                const int l = step < 6 ? 9 - step : 10 - step;         // layer whose pre-activation gradient this step produces
+                chain_epilogue_plain<8, 2>(C, mask + 8 * l * PE_BWD_TILE, st + FS_GP(l) * CHUNK_BYTES, step == 2, graw, st_ok);
                 sync.arrive_ready();
                 C.mop = row_max_exchange<2>(C, C.mop);
             }
@@ -1244,7 +1236,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
 #pragma unroll 1
             for (int l = 5; l >= 3; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0, 4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                chain_epilogue_plain<4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, false, 0.f, r.store);
                 sync.arrive_ready();
             }
             // ---- step 3: the input half of the skip layer's input gradient, parked (hi + lo) behind the activations ----
@@ -1276,7 +1268,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
 #pragma unroll 1
             for (int l = 2; l >= 0; --l) {
                 sync.wait_acc();
-                chain_epilogue_plain<0, 4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, 0.f, r.store);
+                chain_epilogue_plain<4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, false, 0.f, r.store);
                 sync.arrive_ready();
             }
             // ---- step 7: gradient of the bender's input = layer 0's input gradient + the parked half ----
