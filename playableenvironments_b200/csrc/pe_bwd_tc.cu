@@ -1232,42 +1232,38 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) pe_bwd_bchain_kernel(const P
                 }
             }
             sync.arrive_ready();
-            // ---- step 0: output head; steps 1, 2: layers 5, 4 -> gradients of the pre-activations of layers 5, 4, 3 ----
-#pragma unroll 1
-            for (int l = 5; l >= 3; --l) {
-                sync.wait_acc();
-                chain_epilogue_plain<4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, false, 0.f, r.store);
-                sync.arrive_ready();
-            }
-            // ---- step 3: the input half of the skip layer's input gradient, parked (hi + lo) behind the activations ----
+            // ---- steps 0-6 share one copy of the plain epilogue ----
+            //   step 0: output head; steps 1, 2: layers 5, 4 -> gradients of the pre-activations of layers 5, 4, 3
+            //   step 3: the input half of the skip layer's input gradient, parked (hi + lo) behind the activations
+            //   steps 4-6: layers 3 (hidden half), 2, 1 -> gradients of the pre-activations of layers 2, 1, 0
             int km_parked = 0;
-            sync.wait_acc();
-            {
-                uint32_t v[3][32];
-                tmem_ld32(C.taddr, v[0]);
-                tmem_ld32(C.taddr + 32, v[1]);
-                tmem_ld32(C.taddr + 64, v[2]);
-                tmem_wait_ld_regs(v[0]);
-                tmem_wait_ld_regs(v[1]);
-                tmem_wait_ld_regs(v[2]);
-                const int fexp = renorm_exp(C.mop, C.km);
-                km_parked = C.km + fexp;
-                const float f = ldexpf(1.f, fexp - TCT_WEXP);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float y[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]) * f;
-                        store_g8_hilo(C.a_hi, C.a_lo, BB_ENC_CHUNK0 + c * 4 + cc, m, y);
-                    }
-            }
-            sync.arrive_ready();
-            // ---- steps 4-6: layers 3 (hidden half), 2, 1 -> gradients of the pre-activations of layers 2, 1, 0 ----
 #pragma unroll 1
-            for (int l = 2; l >= 0; --l) {
+            for (int step = 0; step <= 6; ++step) {
                 sync.wait_acc();
+                if (step == 3) {
+                    uint32_t v[3][32];
+                    tmem_ld32(C.taddr, v[0]);
+                    tmem_ld32(C.taddr + 32, v[1]);
+                    tmem_ld32(C.taddr + 64, v[2]);
+                    tmem_wait_ld_regs(v[0]);
+                    tmem_wait_ld_regs(v[1]);
+                    tmem_wait_ld_regs(v[2]);
+                    const int fexp = renorm_exp(C.mop, C.km);
+                    km_parked = C.km + fexp;
+                    const float f = ldexpf(1.f, fexp - TCT_WEXP);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            float y[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[c][8 * cc + i]) * f;
+                            store_g8_hilo(C.a_hi, C.a_lo, BB_ENC_CHUNK0 + c * 4 + cc, m, y);
+                        }
+                    sync.arrive_ready();
+                    continue;
+                }
+                const int l = step < 3 ? 5 - step : 6 - step;
                 chain_epilogue_plain<4>(C, mask + l * 4 * PE_BWD_TILE, st + BS_GP(l) * CHUNK_BYTES, false, 0.f, r.store);
                 sync.arrive_ready();
             }
