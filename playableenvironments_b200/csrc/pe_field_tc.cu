@@ -224,16 +224,17 @@ __global__ void __launch_bounds__(THREADS, 1) pe_field_tc_kernel(const PeFieldAr
                     }
                 }
             }
+            // destinations: the object's grid, the scene's grid, and -- fused all-gather -- every peer's copy of the grid (the same
+            // 128-byte warp stores, P2P over NVLink).  The destination loop is the OUTER, rolled one: 24 stores of code, not 24 per target.
+#pragma unroll 1
+            for (int dsti = -2; dsti < A.peers; ++dsti) {
+                float* dst = dsti == -2 ? out0 : (dsti == -1 ? out1 : A.peer_features[dsti]);
+                if (!dst) continue;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (r < nr) {
+                for (int r = 0; r < 4; ++r) {
+                    if (r < nr) {
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const int64_t o = (gr0 + r) * 192 + lane + 32 * j;
-                        if (out0) out0[o] = acc[r][j];
-                        if (out1) out1[o] = acc[r][j];
-                        // fused all-gather: the same 128-byte warp store to every peer's copy of the grid (P2P over NVLink)
-                        for (int q = 0; q < A.peers; ++q) A.peer_features[q][o] = acc[r][j];
+                        for (int j = 0; j < 6; ++j) dst[(gr0 + r) * 192 + lane + 32 * j] = acc[r][j];
                     }
                 }
             }

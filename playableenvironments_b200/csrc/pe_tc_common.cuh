@@ -140,6 +140,10 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, unsigned char* a
     return alpha;
 }
 
+// torch.sigmoid of the rarely used colour-output path, kept out of line so that its expf / division bodies do not sit 96 times in the
+// epilogue's instruction stream
+static __device__ __noinline__ float sigmoid_out_of_line(float f) { return 1.f / (1.f + expf(-f)); }
+
 // Train mode, BatchNorm phases 2 and 0: the trunk output of this row comes from the cache phase 1 wrote (fp32, post-ReLU: the very
 // values hidden_epilogue<1> saw in the accumulators), so the alpha head and the next A operand are bit-identical to a recompute.
 template <int N, bool kHiLo>
@@ -702,19 +706,16 @@ __device__ __forceinline__ void epilogue_tile(const TileCtx& X, int64_t tile, Sy
             uint32_t v[16];
             tmem_ld16(taddr + c_first + c * 16, v);
             tmem_wait_ld_regs16(v);
-            if (!A.apply_activation && !A.feat_out) {                  // nothing per-sample leaves the SM
+            if (A.apply_activation) {      // sigmoid on colour outputs (object_composer.py:548-549; no shipped config): out of line
 #pragma unroll
-                for (int q = 0; q < 16; ++q) scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = wf * __uint_as_float(v[q]);
-            } else {
-                // per-sample features are an output (multi-object scenes: input of the compositor): the scratch holds the
-                // masked, UNWEIGHTED feature so that it can be written out coalesced; the reduction below applies the weights
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    float f = __uint_as_float(v[q]);                   // head-6 bias already added by the rank-1 MMA
-                    if (A.apply_activation) f = 1.f / (1.f + expf(-f));
-                    scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = A.feat_out ? (inbox ? f : 0.f) : wf * f;
-                }
+                for (int q = 0; q < 16; ++q) v[q] = __float_as_uint(sigmoid_out_of_line(__uint_as_float(v[q])));
             }
+            // per-sample features an output (multi-object scenes: input of the compositor): the scratch holds the masked, UNWEIGHTED
+            // feature so that it can be written out coalesced and the reduction below applies the weights; else the weighted feature
+            const float scale = A.feat_out ? (inbox ? 1.f : 0.f) : wf;       // (head-6 bias already added by the rank-1 MMA)
+            const bool zero = A.feat_out && !inbox;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) scr[m * SCRATCH_STRIDE + hf * FC + c * 16 + q] = zero ? 0.f : scale * __uint_as_float(v[q]);
         }
         named_bar_sync(bar_id, GROUP);
         if (A.feat_out && tile_valid) {
