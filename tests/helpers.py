@@ -74,3 +74,11 @@ def compare_grads(got_inputs, got_params, golden, tol):
         if not (e <= tol):
             bad[k] = e
     return bad
+
+
+def free_port() -> int:
+    """A TCP port that is free right now on 127.0.0.1 (rendezvous of the multi-process tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]

@@ -14,6 +14,8 @@ for _p in (os.path.dirname(_HERE), _HERE, os.path.join(_HERE, "golden")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+from helpers import free_port  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 
@@ -80,7 +82,7 @@ def _worker(rank, world, port, tmp):
 def test_sharded_and_pipelined_render_on_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 33500 + os.getpid() % 2000
+    port = free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         flags = open(tmp_path / f"ok{r}").read().split(",")

@@ -10,6 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import scenes
+from helpers import free_port
 from oracle import render_oracle as O
 from playableenvironments_b200 import registry, sharding
 from playableenvironments_b200.model.annealable_positional_encoder import annealing_weights
@@ -129,7 +130,7 @@ def _gather_worker(rank, world, port, rays, tmp):
 @pytest.mark.parametrize("rays", [11, 64])
 def test_all_gather_of_ray_shards_world_size_2(tmp_path, rays):
     """The single collective of the path (feature-grid all-gather) on the gloo backend, 2 ranks, uneven shards."""
-    port = 29500 + (os.getpid() + rays) % 2000
+    port = free_port()
     mp.spawn(_gather_worker, args=(2, port, rays, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
 
@@ -156,7 +157,7 @@ def _allreduce_worker(rank, world, port, tmp):
 
 def test_gradient_allreduce_world_size_2(tmp_path):
     """Data-parallel training step: one flat bucket, one all-reduce, averaged like nn.DataParallel's replica reduction (train.py:61)."""
-    port = 31500 + os.getpid() % 2000
+    port = free_port()
     mp.spawn(_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
 
