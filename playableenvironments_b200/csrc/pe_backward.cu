@@ -275,22 +275,28 @@ __global__ void pe_style_bwd_kernel(const PeStyleBwdArgs A) {
         denc[C + c] = sums[c];
     }
     __syncthreads();
+    // gridDim.y blocks share an image: each recomputes the 2C coefficients above (cheap) and takes a slice of the outer product and of
+    // the style gradient (one warp per style feature, lanes stride the 2C rows)
     const float* style = A.style + (int64_t)img * S;
-    if (A.g_aff_b)
+    const int part = blockIdx.y, parts = gridDim.y;
+    if (A.g_aff_b && part == 0)
         for (int j = threadIdx.x; j < 2 * C; j += blockDim.x)
             if (denc[j] != 0.f) atomicAdd(A.g_aff_b + j, denc[j]);
     if (A.g_aff_w)
-        for (int i = threadIdx.x; i < 2 * C * S; i += blockDim.x) {
+        for (int i = part * blockDim.x + threadIdx.x; i < 2 * C * S; i += parts * blockDim.x) {
             const int j = i / S, s = i - j * S;
             const float v = denc[j] * style[s];
             if (v != 0.f) atomicAdd(A.g_aff_w + i, v);
         }
-    if (A.g_style)
-        for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    if (A.g_style) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+        for (int s = part * warps + warp; s < S; s += parts * warps) {
             float v = 0.f;
-            for (int j = 0; j < 2 * C; ++j) v = fmaf(A.aff_w[(int64_t)j * S + s], denc[j], v);
-            A.g_style[(int64_t)img * S + s] += v;
+            for (int j = lane; j < 2 * C; j += 32) v = fmaf(A.aff_w[(int64_t)j * S + s], denc[j], v);
+            v = warp_sum(v);
+            if (lane == 0) A.g_style[(int64_t)img * S + s] += v;
         }
+    }
 }
 
 // fwd: sum x [C], sum x^2 [C], count; sums: S1 = sum g*sc [C], S2 = sum g*sc*x [C]  ->  fix: k1 [C], k2 [C] with
@@ -425,7 +431,7 @@ int pe_launch_composite_bwd(const PeCompositeBwdArgs& args, cudaStream_t stream)
 
 int pe_launch_style_bwd(const PeStyleBwdArgs& args, cudaStream_t stream) {
     if (args.images == 0) return PE_OK;
-    pe_style_bwd_kernel<<<args.images, 256, (size_t)2 * args.channels * sizeof(float), stream>>>(args);
+    pe_style_bwd_kernel<<<dim3(args.images, 8), 256, (size_t)2 * args.channels * sizeof(float), stream>>>(args);
     PE_LAUNCH_CHECK("pe_style_bwd_kernel");
     return PE_OK;
 }
