@@ -1572,8 +1572,20 @@ __global__ void pe_bwd_scale_bender_kernel(const unsigned int* __restrict__ mx, 
 }
 
 // transposed operand of one chain step: element (n, k) = w[k * ld + col0 + n] (nn.Linear weight [out][in], n = input, k = output)
-__global__ void pe_tcT_pack_kernel(const float* __restrict__ w, int ld, int col0, int n_real, int N, int K, int k_real,
-                                   unsigned char* __restrict__ hi, unsigned char* __restrict__ lo) {
+// every step of the transposed streams of a model in ONE launch (blockIdx.y = step): packing runs every training step
+constexpr int TCT_TABLE = 24;
+struct TcTTable {
+    const float* w[TCT_TABLE];
+    unsigned char* hi[TCT_TABLE];
+    unsigned char* lo[TCT_TABLE];
+    int32_t ld[TCT_TABLE], col0[TCT_TABLE], n_real[TCT_TABLE], N[TCT_TABLE], K[TCT_TABLE], k_real[TCT_TABLE];
+};
+__global__ void pe_tcT_pack_kernel(const __grid_constant__ TcTTable T) {
+    const int it = blockIdx.y;
+    const float* __restrict__ w = T.w[it];
+    unsigned char* __restrict__ hi = T.hi[it];
+    unsigned char* __restrict__ lo = T.lo[it];
+    const int ld = T.ld[it], col0 = T.col0[it], n_real = T.n_real[it], N = T.N[it], K = T.K[it], k_real = T.k_real[it];
     const int total = N * K;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i / N, n = i - k * N;
@@ -1599,6 +1611,13 @@ bool pe_bwd_tc_object_ok(const PeObjectDesc& ob) {
 int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
     (void)d;
     if (!L.tcT_base) return PE_OK;
+    TcTTable T = {};
+    int n = 0, max_total = 0;
+    auto add = [&](const float* w, int ld, int col0, int n_real, int N, int K, int k_real, unsigned char* hi, unsigned char* lo) {
+        T.w[n] = w; T.hi[n] = hi; T.lo[n] = lo; T.ld[n] = ld; T.col0[n] = col0; T.n_real[n] = n_real; T.N[n] = N; T.K[n] = K; T.k_real[n] = k_real;
+        ++n;
+        max_total = N * K > max_total ? N * K : max_total;
+    };
     unsigned char* hi = (unsigned char*)packed + L.tcT_base;
     unsigned char* lo = hi + L.tcT_bytes_per_pass;
     struct Item { const float* w; int ld, col0, n_real, N, K; };
@@ -1611,8 +1630,7 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
     for (int s = 0; s < 12; ++s) {
         const Item& it = items[s];
         if (!it.w) { pe_set_error("missing parameter tensor for the transposed weight stream (step %d)", s); return PE_ERR_INVALID; }
-        pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.K, hi + off, lo + off);
-        PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
+        add(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.K, hi + off, lo + off);
         off += (int64_t)it.N * it.K * 2;
     }
     if (off != L.tcT_bytes_per_pass) { pe_set_error("internal: transposed weight stream size mismatch"); return PE_ERR_INVALID; }
@@ -1629,12 +1647,14 @@ int pe_tcT_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& 
         for (int s = 0; s < 8; ++s) {
             const BItem& it = bitems[s];
             if (!it.w) { pe_set_error("missing ray-bender parameter tensor for the transposed weight stream (step %d)", s); return PE_ERR_INVALID; }
-            pe_tcT_pack_kernel<<<(it.N * it.K + 255) / 256, 256, 0, stream>>>(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.k_real, bhi + boff, blo + boff);
-            PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
+            add(it.w, it.ld, it.col0, it.n_real, it.N, it.K, it.k_real, bhi + boff, blo + boff);
             boff += (int64_t)it.N * it.K * 2;
         }
         if (boff != L.tcbT_bytes_per_pass) { pe_set_error("internal: transposed ray-bender weight stream size mismatch"); return PE_ERR_INVALID; }
     }
+    static_assert(12 + 8 <= TCT_TABLE, "transposed-stream table too small");
+    pe_tcT_pack_kernel<<<dim3((max_total + 255) / 256 > 64 ? 64 : (max_total + 255) / 256, n), 256, 0, stream>>>(T);
+    PE_LAUNCH_CHECK("pe_tcT_pack_kernel");
     return PE_OK;
 }
 

@@ -546,8 +546,17 @@ __host__ __device__ __forceinline__ int64_t slab_offset(int N, int n, int k) {
 constexpr int PACK_ROWS = 8;           // rows of a layer per block of the zero-sum packing
 __host__ __device__ inline size_t pack_layer_smem(int K_pad) { return (size_t)3 * PACK_ROWS * (K_pad + 1) * 4 + (size_t)PACK_ROWS * 16 * 4; }
 
-__global__ void __launch_bounds__(128) pe_tc_pack_layer_kernel(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
-                                                               unsigned char* __restrict__ lo, int N_real) {
+// table of layers for one launch (blockIdx.y = item)
+constexpr int TC_PACK_TABLE = 24;
+struct TcPackTable {
+    const float* w[TC_PACK_TABLE];           // layer weights [N_real][K_src] (zero-sum items) / bias [N] (bias items)
+    unsigned char* hi[TC_PACK_TABLE];
+    unsigned char* lo[TC_PACK_TABLE];
+    int32_t N[TC_PACK_TABLE], K_src[TC_PACK_TABLE], K_pad[TC_PACK_TABLE], N_real[TC_PACK_TABLE];
+};
+
+__device__ __forceinline__ void pack_layer_rows(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
+                                                unsigned char* __restrict__ lo, int N_real, int block) {
     // N: rows of the slab layout; rows >= N_real (padding up to the smallest MMA N) are zero.  This kernel runs for every layer of
     // every model whenever a parameter changes, i.e. every training step, so only the decision itself is sequential: (a) all threads
     // load the block's PACK_ROWS rows (coalesced) and compute both candidates' rounding errors; (b) one thread per row walks along K
@@ -559,7 +568,8 @@ __global__ void __launch_bounds__(128) pe_tc_pack_layer_kernel(const float* __re
     float* en = ws + PACK_ROWS * ld;                                   // error of the nearest fp16
     float* eo = en + PACK_ROWS * ld;                                   // error of the other neighbour
     uint32_t* bits = reinterpret_cast<uint32_t*>(eo + PACK_ROWS * ld); // [PACK_ROWS][16] picks (K_pad <= 512)
-    const int n0 = blockIdx.x * PACK_ROWS, tid = threadIdx.x;
+    const int n0 = block * PACK_ROWS, tid = threadIdx.x;
+    if (n0 >= N) return;
     auto candidates = [](float v, __half& near, __half& other) {
         near = __float2half_rn(v);
         const float fn = __half2float(near);
@@ -614,6 +624,17 @@ __global__ void __launch_bounds__(128) pe_tc_pack_layer_kernel(const float* __re
     }
 }
 
+__global__ void __launch_bounds__(128) pe_tc_pack_layer_kernel(const float* __restrict__ w, int N, int K_src, int K_pad, unsigned char* __restrict__ hi,
+                                                               unsigned char* __restrict__ lo, int N_real) {
+    pack_layer_rows(w, N, K_src, K_pad, hi, lo, N_real, blockIdx.x);
+}
+
+// every zero-sum layer of a model in ONE launch (grid.x = row blocks of the tallest layer, grid.y = layers)
+__global__ void __launch_bounds__(128) pe_tc_pack_layers_kernel(const __grid_constant__ TcPackTable T) {
+    const int it = blockIdx.y;
+    pack_layer_rows(T.w[it], T.N[it], T.K_src[it], T.K_pad[it], T.hi[it], T.lo[it], T.N_real[it], blockIdx.x);
+}
+
 // Activation-aware rounding of one layer's hi stream (one block per output row, thread j = input j).  Every weight may go to either
 // fp16 neighbour; with e the row's vector of rounding errors and C = E[a a^T] the second moments of the layer's (fp16-rounded) inputs,
 // the expected squared error of the single-pass product is e^T C e.  Coordinate descent: visit the inputs in order, pick for input k
@@ -662,6 +683,23 @@ __global__ void pe_tc_pack_layer_aware_kernel(const float* __restrict__ w, const
 }
 
 // bias slab of a layer: N rows x 16 K columns, column 0 = fp16(bias), column 1 = fp16(bias - column 0), rest 0
+__global__ void pe_tc_pack_biases_kernel(const __grid_constant__ TcPackTable T) {      // every bias slab of a model in one launch
+    const int it = blockIdx.y;
+    const float* __restrict__ bias = T.w[it];
+    unsigned char* __restrict__ dst = T.hi[it];
+    const int N = T.N[it], total = N * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / 16, kk = i - n * 16;
+        const float v = bias[n];
+        const __half h = __float2half_rn(v);
+        __half out = __float2half_rn(0.f);
+        if (kk == 0) out = h;
+        if (kk == 1) out = __float2half_rn(v - __half2float(h));
+        const int64_t off = (int64_t)(kk >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(dst + off) = out;
+    }
+}
+
 __global__ void pe_tc_pack_bias_kernel(const float* __restrict__ bias, int N, unsigned char* __restrict__ dst) {
     const int total = N * 16;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -842,6 +880,21 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
         {p.backbone_w[6], p.backbone_b[6], 256, 256, 256, p.backbone_in_moments[6]}, {p.backbone_w[7], p.backbone_b[7], 256, 256, 256, p.backbone_in_moments[7]},
         {p.head0_w, nullptr, 256, 256, 256, p.head0_in_moments},                     {p.head3_w, nullptr, 128, 256, 256, nullptr},
         {p.head6_w, p.head6_b, 192, 128, 128, nullptr}};
+    // zero-sum layers and bias slabs are collected into tables and packed by ONE launch each (this runs every training step);
+    // activation-aware layers (inference packs) keep their own launches
+    TcPackTable layers = {}, biases = {};
+    int n_layers = 0, n_biases = 0, max_rows = 0, max_kpad = 0, max_bias_n = 0;
+    auto add_layer = [&](const float* w, int N, int K_src, int K_pad, unsigned char* h, unsigned char* l_, int N_real) {
+        layers.w[n_layers] = w; layers.hi[n_layers] = h; layers.lo[n_layers] = l_;
+        layers.N[n_layers] = N; layers.K_src[n_layers] = K_src; layers.K_pad[n_layers] = K_pad; layers.N_real[n_layers] = N_real;
+        ++n_layers;
+        max_rows = N > max_rows ? N : max_rows; max_kpad = K_pad > max_kpad ? K_pad : max_kpad;
+    };
+    auto add_bias = [&](const float* b, int N, unsigned char* dst) {
+        biases.w[n_biases] = b; biases.hi[n_biases] = dst; biases.N[n_biases] = N;
+        ++n_biases;
+        max_bias_n = N > max_bias_n ? N : max_bias_n;
+    };
     int64_t off = 0;
     for (int l = 0; l < NUM_LAYERS; ++l) {
         const Item& it = items[l];
@@ -851,13 +904,11 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
             pe_tc_pack_layer_aware_kernel<<<it.N, (it.K_pad + 31) / 32 * 32, 0, stream>>>(it.w, it.moments, it.N, it.K_src, it.K_pad, hi + off, lo + off, 1);
             PE_LAUNCH_CHECK("pe_tc_pack_layer_aware_kernel");
         } else {
-            pe_tc_pack_layer_kernel<<<(it.N + PACK_ROWS - 1) / PACK_ROWS, 128, pack_layer_smem(it.K_pad), stream>>>(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off, it.N);
-            PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
+            add_layer(it.w, it.N, it.K_src, it.K_pad, hi + off, lo + off, it.N);
         }
         off += total * 2;
         if (it.b) {
-            pe_tc_pack_bias_kernel<<<(it.N * 16 + 255) / 256, 256, 0, stream>>>(it.b, it.N, hi + off);
-            PE_LAUNCH_CHECK("pe_tc_pack_bias_kernel");
+            add_bias(it.b, it.N, hi + off);
             off += (int64_t)it.N * 32;
         }
     }
@@ -870,18 +921,24 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
         for (int l = 0; l < 6; ++l) {
             if (!p.bender_w[l] || !p.bender_b[l]) { pe_set_error("missing ray-bender parameter tensor of layer %d", l); return PE_ERR_INVALID; }
             const int K_src = l == 0 ? 71 : (l == 3 ? 199 : 128), K_pad = l == 0 ? 96 : (l == 3 ? 224 : 128);
-            pe_tc_pack_layer_kernel<<<128 / PACK_ROWS, 128, pack_layer_smem(K_pad), stream>>>(p.bender_w[l], 128, K_src, K_pad, bhi + boff, blo + boff, 128);
-            PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
+            add_layer(p.bender_w[l], 128, K_src, K_pad, bhi + boff, blo + boff, 128);
             boff += (int64_t)128 * K_pad * 2;
-            pe_tc_pack_bias_kernel<<<(128 * 16 + 255) / 256, 256, 0, stream>>>(p.bender_b[l], 128, bhi + boff);
-            PE_LAUNCH_CHECK("pe_tc_pack_bias_kernel");
+            add_bias(p.bender_b[l], 128, bhi + boff);
             boff += 128 * 32;
         }
         if (!p.bender_out_w) { pe_set_error("missing ray-bender output layer"); return PE_ERR_INVALID; }
-        pe_tc_pack_layer_kernel<<<(16 + PACK_ROWS - 1) / PACK_ROWS, 128, pack_layer_smem(128), stream>>>(p.bender_out_w, 16, 128, 128, bhi + boff, blo + boff, 3);
-        PE_LAUNCH_CHECK("pe_tc_pack_layer_kernel");
+        add_layer(p.bender_out_w, 16, 128, 128, bhi + boff, blo + boff, 3);
         boff += (int64_t)16 * 128 * 2;
         if (boff != L.tcb_bytes_per_pass) { pe_set_error("internal: ray-bender weight stream size mismatch"); return PE_ERR_INVALID; }
+    }
+    static_assert(NUM_LAYERS + 7 <= TC_PACK_TABLE, "pack table too small");
+    if (n_layers) {
+        pe_tc_pack_layers_kernel<<<dim3((max_rows + PACK_ROWS - 1) / PACK_ROWS, n_layers), 128, pack_layer_smem(max_kpad), stream>>>(layers);
+        PE_LAUNCH_CHECK("pe_tc_pack_layers_kernel");
+    }
+    if (n_biases) {
+        pe_tc_pack_biases_kernel<<<dim3((max_bias_n * 16 + 255) / 256, n_biases), 256, 0, stream>>>(biases);
+        PE_LAUNCH_CHECK("pe_tc_pack_biases_kernel");
     }
     return PE_OK;
 }

@@ -65,6 +65,26 @@ __global__ void pe_copy_kernel(const float* __restrict__ src, float* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// The fp32 section of the packed blob in ONE launch: a table of copies (K == 0: N floats) and transposes ([N][K] -> [K][N]), one
+// item per blockIdx.y.  (Packing runs for every model whenever a parameter changes -- every training step -- and was ~50 launches.)
+constexpr int PACK_TABLE = 64;
+struct PackTable {
+    const float* src[PACK_TABLE];
+    float* dst[PACK_TABLE];
+    int32_t N[PACK_TABLE], K[PACK_TABLE];
+};
+__global__ void pe_pack_table_kernel(const __grid_constant__ PackTable T) {
+    const int it = blockIdx.y;
+    const float* __restrict__ src = T.src[it];
+    float* __restrict__ dst = T.dst[it];
+    const int N = T.N[it], K = T.K[it];
+    const int64_t total = K ? (int64_t)N * K : N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (K) { const int k = (int)(i / N), n = (int)(i - (int64_t)k * N); dst[i] = src[(int64_t)n * K + k]; }
+        else dst[i] = src[i];
+    }
+}
+
 // PositionalEncoder.forward / AnnealablePositionalEncoder.forward (model/positional_encoder.py:41-65,
 // model/annealable_positional_encoder.py:46-76)
 __global__ void pe_posenc_kernel(const float* __restrict__ x, int64_t n, int dims, int octaves, int append,
@@ -146,25 +166,28 @@ int pe_launch_style(const PeStyleArgs& args, cudaStream_t stream) {
     return PE_OK;
 }
 
-static int transpose_to(const float* src, void* blob, int64_t off, int N, int K, cudaStream_t stream) {
-    if (!src) { pe_set_error("missing parameter tensor"); return PE_ERR_INVALID; }
-    pe_transpose_kernel<<<grid_for((int64_t)N * K), 256, 0, stream>>>(src, reinterpret_cast<float*>((char*)blob + off), N, K);
-    PE_LAUNCH_CHECK("pe_transpose_kernel");
-    return PE_OK;
-}
-
-static int copy_to(const float* src, void* blob, int64_t off, int64_t n, cudaStream_t stream) {
-    if (!src) { pe_set_error("missing parameter tensor"); return PE_ERR_INVALID; }
-    pe_copy_kernel<<<grid_for(n), 256, 0, stream>>>(src, reinterpret_cast<float*>((char*)blob + off), n);
-    PE_LAUNCH_CHECK("pe_copy_kernel");
-    return PE_OK;
-}
-
 int pe_tc_pack(const PeObjectDesc& desc, const PeLayout& L, const PeObjectParams& params, void* packed, cudaStream_t stream);
 
 int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p, void* packed, cudaStream_t stream) {
     int rc;
     const int W = d.width, F = d.features, S = d.style_features;
+    PackTable table;
+    int items = 0;
+    // transposes and copies are collected and launched together below
+    auto transpose_to = [&](const float* src, void* blob, int64_t off, int N, int K, cudaStream_t) -> int {
+        if (!src) { pe_set_error("missing parameter tensor"); return PE_ERR_INVALID; }
+        if (items == PACK_TABLE) { pe_set_error("internal: pack table overflow"); return PE_ERR_INVALID; }
+        table.src[items] = src; table.dst[items] = reinterpret_cast<float*>((char*)blob + off); table.N[items] = N; table.K[items] = K;
+        ++items;
+        return PE_OK;
+    };
+    auto copy_to = [&](const float* src, void* blob, int64_t off, int64_t n, cudaStream_t) -> int {
+        if (!src) { pe_set_error("missing parameter tensor"); return PE_ERR_INVALID; }
+        if (items == PACK_TABLE) { pe_set_error("internal: pack table overflow"); return PE_ERR_INVALID; }
+        table.src[items] = src; table.dst[items] = reinterpret_cast<float*>((char*)blob + off); table.N[items] = (int)n; table.K[items] = 0;
+        ++items;
+        return PE_OK;
+    };
 #define PE_TRY(x) do { rc = (x); if (rc != PE_OK) return rc; } while (0)
     for (int l = 0; l < d.layers; ++l) {
         PE_TRY(transpose_to(p.backbone_w[l], packed, L.bb_w[l], W, L.k_in[l], stream));
@@ -192,6 +215,10 @@ int pe_launch_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParam
             PE_TRY(copy_to(p.bender_b[l], packed, L.bd_b[l], d.b_width, stream));
         }
         PE_TRY(transpose_to(p.bender_out_w, packed, L.bd_out_w, 3, d.b_width, stream));
+    }
+    if (items) {
+        pe_pack_table_kernel<<<dim3(32, items), 256, 0, stream>>>(table);
+        PE_LAUNCH_CHECK("pe_pack_table_kernel");
     }
     if (L.tc_supported) {
         PE_TRY(pe_tc_pack(d, L, p, packed, stream));
