@@ -240,14 +240,26 @@ class ObjectComposer(nn.Module):
         per-instance model calls (a model shared by two instances is updated twice)."""
         helper = self.object_id_helper
         model_list = self.object_models_coarse if model_list is None else model_list
+        # grouped by momentum and applied with multi-tensor ops (a handful of launches instead of five per BatchNorm layer); a model
+        # shared by several instances appears once per instance, so its updates stay sequential: one group per repetition
+        seen = {}
+        groups = {}
         for object_idx, (b1, b2) in enumerate(bn_running):
-            head = model_list[helper.model_idx_by_object_idx(object_idx)].nerf_model.features_head
+            model_idx = helper.model_idx_by_object_idx(object_idx)
+            rep = seen.get(model_idx, 0)
+            seen[model_idx] = rep + 1
+            head = model_list[model_idx].nerf_model.features_head
             for layer, b in ((head[1], b1), (head[4], b2)):
                 bn = layer.ada_in.normalization
                 momentum = bn.momentum if bn.momentum is not None else 0.1
-                bn.running_mean.mul_(1.0 - momentum).add_(b[0], alpha=momentum)
-                bn.running_var.mul_(1.0 - momentum).add_(b[1], alpha=momentum)
-                bn.num_batches_tracked += 1
+                g = groups.setdefault((rep, momentum), ([], [], []))
+                g[0].extend([bn.running_mean, bn.running_var])
+                g[1].extend([b[0], b[1]])
+                g[2].append(bn.num_batches_tracked)
+        for (rep, momentum), (running, batch, counters) in sorted(groups.items(), key=lambda kv: kv[0][0]):
+            torch._foreach_mul_(running, 1.0 - momentum)
+            torch._foreach_add_(running, batch, alpha=momentum)
+            torch._foreach_add_(counters, 1)
 
 
 def model(config):
