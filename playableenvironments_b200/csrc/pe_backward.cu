@@ -81,22 +81,33 @@ __device__ void backward_list(const PeCompositeBwdArgs& B, const Lists& S, int n
         const int c = lane + 32 * i;
         dF[i] = (G.integrated_features && c < F) ? G.integrated_features[ray * F + c] : 0.f;
     }
-    // dL/dw_j = <dF, f_j> + d_opacity + d_depth * t_j + d_weights_j
-    for (int j = 0; j < n; ++j) {
-        float v = 0.f;
-        if (G.integrated_features && (S.fl[j] & 1)) {
-            const int id = S.id[j];
-            const int k = id >> 16, p = id & 0xffff;
-            const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+    // dL/dw_j = <dF, f_j> + d_opacity + d_depth * t_j + d_weights_j.  The feature term exists only for the samples inside a box: the
+    // (sequential, warp-wide) dot products visit just those; the other terms are added for all samples in parallel, in the same order
+    for (int j = lane; j < n; j += 32) S.gw[j] = 0.f;
+    __syncwarp();
+    if (G.integrated_features) {
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int j = c0 + lane;
+            unsigned todo = __ballot_sync(0xffffffffu, j < n && (S.fl[j] & 1));
+            while (todo) {
+                const int jj = c0 + __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int id = S.id[jj];
+                const int k = id >> 16, p = id & 0xffff;
+                const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+                float v = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = lane + 32 * i;
-                if (c < F) v = fmaf(dF[i], __ldg(f + c), v);
+                for (int i = 0; i < 8; ++i) {
+                    const int c = lane + 32 * i;
+                    if (c < F) v = fmaf(dF[i], __ldg(f + c), v);
+                }
+                v = warp_sum(v);
+                if (lane == 0) S.gw[jj] = v;
             }
-            v = warp_sum(v);
         }
-        if (lane == 0) S.gw[j] = v + d_op + d_depth * S.t[j] + (G.weights ? G.weights[ray * n + j] : 0.f);
+        __syncwarp();
     }
+    for (int j = lane; j < n; j += 32) S.gw[j] = S.gw[j] + d_op + d_depth * S.t[j] + (G.weights ? G.weights[ray * n + j] : 0.f);
     __syncwarp();
     // dL/d alpha_j = gw_j * T_j - (sum_{i>j} gw_i w_i) / (1 - alpha_j + 1e-10)        (compute_weights :199-214)
     float suffix = 0.f;
