@@ -1534,7 +1534,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) pe_bwd_dw_kernel(const DwArgs D
 // gradient scale: S = 2^k with S * (largest upstream gradient magnitude) ~ 256 (fp16 operands: 256 x headroom below overflow,
 // 2^-32 of it above the smallest subnormal)
 // =====================================================================================================================
-__global__ void pe_bwd_absmax_kernel(const float* __restrict__ x, int64_t n, unsigned int* __restrict__ out) {
+struct AbsmaxSegments {
+    const float* x[4];
+    int64_t n[4];
+};
+
+// one launch for every tensor whose largest magnitude sets a scale: blockIdx.y selects the segment
+__global__ void pe_bwd_absmax_kernel(const __grid_constant__ AbsmaxSegments S, unsigned int* __restrict__ out) {
+    const float* __restrict__ x = S.x[blockIdx.y];
+    const int64_t n = S.n[blockIdx.y];
+    if (!x || n == 0) return;
     float mx = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = fabsf(x[i]);
@@ -1542,7 +1551,17 @@ __global__ void pe_bwd_absmax_kernel(const float* __restrict__ x, int64_t n, uns
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out, __float_as_uint(mx));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out + blockIdx.y, __float_as_uint(mx));
+}
+
+static int launch_absmax(const AbsmaxSegments& S, int segments, unsigned int* out, cudaStream_t stream) {
+    int64_t most = 0;
+    for (int i = 0; i < segments; ++i)
+        if (S.x[i]) most = S.n[i] > most ? S.n[i] : most;
+    if (most == 0) return PE_OK;
+    pe_bwd_absmax_kernel<<<dim3((unsigned)pe_min64((most + 255) / 256, 592), segments), 256, 0, stream>>>(S, out);
+    PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
+    return PE_OK;
 }
 
 __global__ void pe_bwd_scale_kernel(const unsigned int* __restrict__ mx, float* __restrict__ scale) {
@@ -1692,17 +1711,12 @@ int pe_launch_bwd_scale(const PeBwdTcArgs& args, float* scale, unsigned int* scr
     const PeFieldArgs& A = args.f;
     PE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(unsigned int), stream));
     const int64_t nf = (int64_t)A.images * A.rays * A.ob.features, ns = (int64_t)A.images * A.rays * A.ob.positions;
-    auto absmax = [&](const float* x, int64_t n, unsigned int* out) {
-        if (!x || n == 0) return PE_OK;
-        pe_bwd_absmax_kernel<<<(int)pe_min64((n + 255) / 256, 1024), 256, 0, stream>>>(x, n, out);
-        PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
-        return PE_OK;
-    };
-    int rc;
-    if ((rc = absmax(args.g_feat_obj, nf, scratch + 0))) return rc;
-    if ((rc = absmax(args.g_feat_glob, nf, scratch + 1))) return rc;
-    if ((rc = absmax(args.g_raw, ns, scratch + 2))) return rc;
-    if ((rc = absmax(reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(A.ob.packed) + A.L.alpha_w), A.ob.width, scratch + 3))) return rc;
+    AbsmaxSegments S{};
+    S.x[0] = args.g_feat_obj, S.n[0] = nf;
+    S.x[1] = args.g_feat_glob, S.n[1] = nf;
+    S.x[2] = args.g_raw, S.n[2] = ns;
+    S.x[3] = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(A.ob.packed) + A.L.alpha_w), S.n[3] = A.ob.width;
+    if (int rc = launch_absmax(S, 4, scratch, stream)) return rc;
     pe_bwd_scale_kernel<<<1, 1, 0, stream>>>(scratch, scale);
     PE_LAUNCH_CHECK("pe_bwd_scale_kernel");
     return PE_OK;
@@ -1733,10 +1747,10 @@ int pe_launch_bwd_scale_bender(const PeBwdTcArgs& args, float* scale, unsigned i
     PE_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4 * sizeof(unsigned int), stream));
     const int64_t ns = (int64_t)A.images * A.rays * A.ob.positions;
     if (ns == 0) return PE_OK;
-    pe_bwd_absmax_kernel<<<(int)pe_min64((3 * ns + 255) / 256, 1024), 256, 0, stream>>>(args.g_bent, 3 * ns, scratch + 0);
-    PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
-    pe_bwd_absmax_kernel<<<(int)pe_min64((ns + 255) / 256, 1024), 256, 0, stream>>>(args.g_dm, ns, scratch + 1);
-    PE_LAUNCH_CHECK("pe_bwd_absmax_kernel");
+    AbsmaxSegments S{};
+    S.x[0] = args.g_bent, S.n[0] = 3 * ns;
+    S.x[1] = args.g_dm, S.n[1] = ns;
+    if (int rc = launch_absmax(S, 2, scratch, stream)) return rc;
     const PeObjectDesc& ob = A.ob;
     const float msize = fmaxf(ob.bbox[1] - ob.bbox[0], fmaxf(ob.bbox[3] - ob.bbox[2], ob.bbox[5] - ob.bbox[4]));
     pe_bwd_scale_bender_kernel<<<1, 1, 0, stream>>>(scratch, msize, scale);

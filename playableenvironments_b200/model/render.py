@@ -252,6 +252,9 @@ class RenderFunction(torch.autograd.Function):
         if meta.get("return_raw_alphas"):
             extra += [res[f"object_{k}"]["raw_alphas"] for k in range(K)]
         ctx.mark_non_differentiable(*extra)
+        # outputs the loss never touches reach backward as None instead of zero tensors: no fills, and the compositing backward skips the
+        # per-object lists of objects whose integrated outputs are unused (the usual training case: only "global" carries a gradient)
+        ctx.set_materialize_grads(False)
         return tuple(outs + extra)
 
     @staticmethod
@@ -289,17 +292,21 @@ class RenderFunction(torch.autograd.Function):
                 gout.bent_positions[k] = _cabi.ptr(g)
         need = ctx.needs_input_grad
         gin = _cabi.PeInGrads()
-        zeros = lambda t: torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format)
-        g_origins = zeros(origins) if need[1] else None
-        g_dirs = zeros(dirs) if need[2] else None
-        g_w2o = zeros(w2o) if need[3] else None
+        # every input gradient is a 16-byte aligned piece of ONE zero-filled buffer (the kernels accumulate into them)
+        wanted = [(origins, need[1]), (dirs, need[2]), (w2o, need[3])]
+        wanted += [(styles[k], need[4 + k]) for k in range(K)] + [(deforms[k], need[4 + K + k]) for k in range(K)]
+        wanted += [(meta["sample_t"][k], need[4 + 2 * K + k]) for k in range(n_t)]
+        in_sizes = [((t.numel() + 3) // 4 * 4) if want else 0 for t, want in wanted]
+        flat_in = torch.zeros(sum(in_sizes), dtype=torch.float32, device=device)
+        pieces, off = [], 0
+        for (t, want), sz in zip(wanted, in_sizes):
+            pieces.append(flat_in[off:off + t.numel()].view(t.shape) if want else None)
+            off += sz
+        g_origins, g_dirs, g_w2o = pieces[0], pieces[1], pieces[2]
+        g_styles, g_deforms, g_ts = pieces[3:3 + K], pieces[3 + K:3 + 2 * K], pieces[3 + 2 * K:]
         gin.ray_origins, gin.ray_directions, gin.w2o = _cabi.ptr(g_origins), _cabi.ptr(g_dirs), _cabi.ptr(g_w2o)
-        g_styles = [zeros(styles[k]) if need[4 + k] else None for k in range(K)]
-        g_deforms = [zeros(deforms[k]) if need[4 + K + k] else None for k in range(K)]
         for k in range(K):
             gin.style[k], gin.deformation[k] = _cabi.ptr(g_styles[k]), _cabi.ptr(g_deforms[k])
-        g_ts = [torch.zeros_like(meta["sample_t"][k], dtype=torch.float32, memory_format=torch.contiguous_format)
-                if need[4 + 2 * K + k] else None for k in range(n_t)]
         for k in range(n_t):
             gin.sample_t[k] = _cabi.ptr(g_ts[k])
         params = (_cabi.PeObjectParams * _cabi.PE_MAX_OBJECTS)()
