@@ -18,6 +18,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+constexpr int DOT_BATCH = 4;        // feature rows in flight per warp in the dL/dw dot products
+
 struct Lists {                 // per-warp shared memory, TP entries each
     float *t, *raw, *dm;       // the ordered sample list
     int *id, *fl;              // (object << 16) | sample;  bit0: features present (in-box), bit1: masked by fix_object_overlaps
@@ -89,20 +91,44 @@ __device__ void backward_list(const PeCompositeBwdArgs& B, const Lists& S, int n
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int j = c0 + lane;
             unsigned todo = __ballot_sync(0xffffffffu, j < n && (S.fl[j] & 1));
+            // DOT_BATCH feature rows in flight per warp (latency bound otherwise); every dot product is evaluated as before
             while (todo) {
-                const int jj = c0 + __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int id = S.id[jj];
-                const int k = id >> 16, p = id & 0xffff;
-                const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
-                float v = 0.f;
+                int js[DOT_BATCH];
+                const float* fp[DOT_BATCH];
+                int cnt = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = lane + 32 * i;
-                    if (c < F) v = fmaf(dF[i], __ldg(f + c), v);
+                for (int u = 0; u < DOT_BATCH; ++u) {
+                    js[u] = 0;
+                    fp[u] = nullptr;
+                    if (todo) {                               // warp-uniform
+                        js[u] = c0 + __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int id = S.id[js[u]];
+                        const int k = id >> 16, p = id & 0xffff;
+                        fp[u] = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+                        cnt = u + 1;
+                    }
                 }
-                v = warp_sum(v);
-                if (lane == 0) S.gw[jj] = v;
+                float v[DOT_BATCH];
+#pragma unroll
+                for (int u = 0; u < DOT_BATCH; ++u) {
+                    float fv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = lane + 32 * i;
+                        fv[i] = (u < cnt && c < F) ? __ldg(fp[u] + c) : 0.f;
+                    }
+                    v[u] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[u] = fmaf(dF[i], fv[i], v[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < DOT_BATCH; ++u) {
+                    if (u < cnt) {
+                        const float r = warp_sum(v[u]);
+                        if (lane == 0) S.gw[js[u]] = r;
+                    }
+                }
             }
         }
         __syncwarp();
@@ -248,13 +274,10 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_bwd_kernel(const PeCo
             }
             __syncwarp();
             const int n = A.total_positions;
+            const bool ordered = pe_lists_ordered(S.ut, n, A.positions, A.objects, lane);
             for (int j = lane; j < n; j += 32) {               // stable sort by t, same tie order as the forward
                 const float tj = S.ut[j];
-                int rank = 0;
-                for (int m = 0; m < n; ++m) {
-                    const float tm = S.ut[m];
-                    rank += (tm < tj || (tm == tj && m < j)) ? 1 : 0;
-                }
+                const int rank = pe_compose_rank(S.ut, n, j, A.positions, A.objects, ordered);
                 S.t[rank] = tj; S.raw[rank] = S.uraw[j]; S.dm[rank] = S.udm[j]; S.id[rank] = S.uid[j]; S.fl[rank] = S.ufl[j];
             }
             __syncwarp();

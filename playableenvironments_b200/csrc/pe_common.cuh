@@ -275,3 +275,56 @@ __device__ __forceinline__ PeRay pe_make_ray(const PeObjectDesc& ob, const float
     pe_z_bounds(ob, in_scene, ray);
     return ray;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// compose (model/object_composer.py:399-447) sorts the concatenation of the objects' sample lists by t; ties keep the concatenation
+// order.  Position of every entry in that order, for the warp that owns the ray: `ut` = the concatenated t values (shared memory, n
+// entries, object k at [start_k, start_k + positions[k])).  Each object's list is non-decreasing by construction (stratified or merged
+// samples), so an entry's position is its own index in its list plus a binary search in every other list -- upper bound in the lists
+// before it (ties go first there), lower bound in the lists after it.  A ray whose lists are not ordered (samples masked by
+// fix_object_overlaps get t = 0; a NaN) takes the all-pairs count, which is the definition.  Both give the same permutation.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pe_lists_ordered(const float* __restrict__ ut, int n, const int32_t* __restrict__ positions, int objects, int lane) {
+    bool ok = true;
+    int start = 0;
+    for (int k = 0; k < objects; ++k) {
+        const int P = positions[k];
+        for (int p = 1 + lane; p < P; p += 32) ok = ok && (ut[start + p] >= ut[start + p - 1]);
+        if (lane == 0 && P > 0) ok = ok && (ut[start] == ut[start]);           // a single NaN entry
+        start += P;
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+__device__ __forceinline__ int pe_compose_rank(const float* __restrict__ ut, int n, int j, const int32_t* __restrict__ positions, int objects,
+                                               bool ordered) {
+    const float tj = ut[j];
+    int rank = 0;
+    if (!ordered) {
+        for (int m = 0; m < n; ++m) {
+            const float tm = ut[m];
+            rank += (tm < tj || (tm == tj && m < j)) ? 1 : 0;
+        }
+        return rank;
+    }
+    int start = 0;
+    for (int k = 0; k < objects; ++k) {
+        const int P = positions[k];
+        if (j >= start && j < start + P) {
+            rank += j - start;
+        } else {
+            const bool before = start < j;                 // the whole list precedes j in the concatenation: ties count
+            const float* __restrict__ base = ut + start;
+            int lo = 0, len = P;
+            while (len > 0) {
+                const int half = len >> 1;
+                const float v = base[lo + half];
+                const bool right = before ? (v <= tj) : (v < tj);
+                if (right) { lo += half + 1; len -= half + 1; } else len = half;
+            }
+            rank += lo;
+        }
+        start += P;
+    }
+    return rank;
+}

@@ -6,6 +6,7 @@
 namespace {
 
 constexpr int WARPS = 4;
+constexpr int FEAT_BATCH = 1;      // feature rows in flight per warp in the weighted sum
 
 struct RayLists {       // per-warp shared-memory sample list
     float* t;
@@ -57,18 +58,40 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         // only the samples that carry features and weight (in sample order: the sum is evaluated like the reference's); in a sparse view
         // most of a ray's samples lie outside every box
         unsigned todo = __ballot_sync(0xffffffffu, j < n && w != 0.f && src >= 0);
+        // FEAT_BATCH samples' feature rows are requested before the first of them is used: the sums stay in sample order, but a ray's
+        // in-box samples cost one memory round trip per batch instead of one each (this kernel is latency bound: profiles/r2_compositor.md)
         while (todo) {
-            const int jj = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const float wj = __shfl_sync(0xffffffffu, w, jj);
-            const int sj = __shfl_sync(0xffffffffu, src, jj);
-            const int k = sj >> 16, p = sj & 0xffff;
-            const float* f = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+            float wv[FEAT_BATCH];
+            const float* fp[FEAT_BATCH];
+            int cnt = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int c = lane + 32 * i;
-                if (c < F) acc[i] = fmaf(wj, __ldg(f + c), acc[i]);
+            for (int u = 0; u < FEAT_BATCH; ++u) {
+                wv[u] = 0.f;
+                fp[u] = nullptr;
+                if (todo) {                                   // warp-uniform
+                    const int jj = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    wv[u] = __shfl_sync(0xffffffffu, w, jj);
+                    const int sj = __shfl_sync(0xffffffffu, src, jj);
+                    const int k = sj >> 16, p = sj & 0xffff;
+                    fp[u] = A.feat[k] + (ray * A.positions[k] + p) * (int64_t)F;
+                    cnt = u + 1;
+                }
             }
+            float fv[FEAT_BATCH][8];
+#pragma unroll
+            for (int u = 0; u < FEAT_BATCH; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = lane + 32 * i;
+                    fv[u][i] = (u < cnt && c < F) ? __ldg(fp[u] + c) : 0.f;
+                }
+#pragma unroll
+            for (int u = 0; u < FEAT_BATCH; ++u)
+                if (u < cnt) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv[u], fv[u][i], acc[i]);
+                }
         }
     }
 #pragma unroll
@@ -168,13 +191,10 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
             __syncwarp();
             const int n = A.total_positions;
             // stable sort by t (torch.sort :435 with a deterministic tie order: concatenation index)
+            const bool ordered = pe_lists_ordered(U.t, n, A.positions, A.objects, lane);
             for (int j = lane; j < n; j += 32) {
                 const float tj = U.t[j];
-                int rank = 0;
-                for (int m = 0; m < n; ++m) {
-                    const float tm = U.t[m];
-                    rank += (tm < tj || (tm == tj && m < j)) ? 1 : 0;
-                }
+                const int rank = pe_compose_rank(U.t, n, j, A.positions, A.objects, ordered);
                 S.t[rank] = tj; S.raw[rank] = U.raw[j]; S.dm[rank] = U.dm[j]; S.dv[rank] = U.dv[j]; S.src[rank] = U.src[j];
             }
             __syncwarp();

@@ -66,8 +66,9 @@ def _flatten_inputs(K: int, ray_origins, ray_directions, w2o, style, deformation
     S, D = style.size(-2), deformation.size(-2)
     sty = f32(style).expand(lead + [S, style.size(-1)]).reshape(images, S, -1)
     dfm = f32(deformation).expand(lead + [D, deformation.size(-1)]).reshape(images, D, -1)
-    styles = [sty[:, :, k].contiguous() for k in range(K)]
-    deforms = [dfm[:, :, k].contiguous() for k in range(K)]
+    # objects-major copies, one kernel each; unbind (not K selects) so that autograd returns the K gradients with one stack
+    styles = list(sty.permute(2, 0, 1).contiguous().unbind(0))[:K]
+    deforms = list(dfm.permute(2, 0, 1).contiguous().unbind(0))[:K]
     ois = object_in_scene.expand(lead + [object_in_scene.size(-1)]).reshape(images, -1)[:, :K].to(torch.uint8).contiguous()
     return lead, images, rays, origins, dirs, m, styles, deforms, ois
 
