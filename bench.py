@@ -353,6 +353,123 @@ def eval_frame_report(device, dense: bool):
     return out
 
 
+def tennis_four_objects(lead, dirs_of):
+    """The shipped Tennis scene (SURVEY section 8, T-frame / T-train): 2 static boxes with 4 samples per ray + 2 players with 32 samples
+    per ray and positional ray benders = 72 samples per ray.  ``dirs_of(stride)`` -> (origins, directions, normals) of one strided grid."""
+    import numpy as np
+    import scenes
+    court = scenes.object_cfg([[-30, 30], [-40, 20.585], [-0.5, 0.0]], 4, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
+    stands = scenes.object_cfg([[-40, 40], [20.585, 45.0], [0.0, 12.0]], 4, 5.0, 120.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
+    player = lambda: scenes.object_cfg([[-0.75, 0.75], [-0.5, 0.5], [0.0, 2.15]], 32, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("positional"))
+    config = scenes.scene_config([court, stands, player(), player()], 2, [1, 1, 1, 1], True)
+    parts = [dirs_of(st) for st in (4, 8)]
+    orig, norm = parts[0][0], parts[0][2]
+    dirs = torch.cat([p[1] for p in parts], dim=-2)
+    p1 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(0.3), [2.0, -11.0, 0.01]))
+    p2 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(-0.2), [-2.0, 11.0, 0.01]))
+    inputs = scenes.build_inputs(17, config, lead, orig, dirs, norm, [np.eye(4), np.eye(4), p1, p2])
+    return config, scenes.scene_state(17, config), inputs
+
+
+def t_train_scene(B: int):
+    """The T-train batch (see t_train_report): lead dimensions (B, 4, 1), 5 120 patch rays per image on the near player."""
+    import numpy as np
+    import scenes
+    H, W = 288, 512
+    focal = 1700.0 * 0.51417 * 0.5 * (W / 256.0)
+    c2w = scenes.tennis_camera()
+    # pixel of the near player's centre: the patches the reference's sampler draws are weighted towards the objects' boxes
+    pc = c2w[:3, :3].T @ (np.array([2.0, -11.0, 1.0]) - c2w[:3, 3])
+    col_c, row_c = W / 2 + focal * pc[0] / -pc[2], H / 2 - focal * pc[1] / -pc[2]
+    lead = (B, 4, 1)
+
+    def dirs_of(stride):
+        o, d, n = scenes.camera_rays(lead, H, W, focal, c2w, stride)
+        gh, gw, side = H // stride, W // stride, 256 // stride
+        r0 = int(min(max(row_c / stride - side / 2, 0), gh - side))
+        c0 = int(min(max(col_c / stride - side / 2, 0), gw - side))
+        d = d.reshape(lead + (gh, gw, 3))[..., r0:r0 + side, c0:c0 + side, :].reshape(lead + (side * side, 3)).contiguous()
+        return o, d, n
+
+    return tennis_four_objects(lead, dirs_of), lead
+
+
+def t_train_report(device, batches=(1, 8), eager=True):
+    """What train.py differentiates per step on the shipped Tennis config ("T-train"): B x 4 observations = 4 B images
+    of 288x512, per image a 64x64 patch of the stride-4 grid + a 32x32 patch of the stride-8 grid (5 120 rays, both patches on the near
+    player), 4 object instances (72 samples per ray), train-mode BatchNorm, perturb=True (stratified jitter + raw-alpha noise), every
+    parameter and differentiable input requiring a gradient.  B = 1 is one nn.DataParallel replica of the reference's 8-GPU run
+    (train.py:61), B = 8 the whole batch on ONE B200.  Beside it the UPSTREAM composer in eager PyTorch on this GPU (B = 1)."""
+    import scenes
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            fn()
+        e0.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(e0) / reps
+
+    out = []
+    for B in batches:
+        scene, lead = t_train_scene(B)
+        config, state, inputs, comp, dev = build_composer(scene, "mixed", device=device, training=True)
+        comp.allow_forward_without_grad = False
+        dev = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in dev.items()}
+        call = [dev[k] for k in INPUT_KEYS]
+        rays = dev["ray_directions"].size(-2)
+        cot = torch.randn(lead + (rays, 192), device=device)
+
+        def loss_of(res):
+            return (res["global"]["integrated_features"] * cot).sum() + res["global"]["opacity"].sum()
+
+        def fwd_bwd():
+            comp.zero_grad(set_to_none=True)
+            loss_of(comp(*call, True)["coarse"]).backward()
+
+        comp.return_raw_alphas = True
+        with torch.no_grad():
+            res = comp(*call, False)["coarse"]
+        comp.return_raw_alphas = False
+        inbox = sum(int((res[f"object_{k}"]["raw_alphas"] != float(m["empty_space_alpha"])).sum().item())
+                    for k, m in enumerate(config["model"]["object_models"]))
+        del res
+        row = {"workload": f"T-train: Tennis, {4 * B} images x 5120 patch rays (64x64 @ stride 4 + 32x32 @ stride 8), 4 objects, 72 samples per ray, "
+                           "train-mode BatchNorm, perturb=True, forward + backward", "batch": B, "rays": 4 * B * rays,
+               "sample_slots": 4 * B * rays * 72, "in_box_samples": inbox, "fwd_bwd_ms": timed(fwd_bwd, 3)}
+        row["in_box_samples_per_s_fwd_bwd"] = inbox / (row["fwd_bwd_ms"] / 1e3)
+        del comp
+        if eager and B == 1 and upstream_composer_class(cpu=False) is not None:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            try:
+                with torch.device(device):
+                    up = upstream_composer(config, state, device)
+                    up.train()
+
+                    def up_step():
+                        up.zero_grad(set_to_none=True)
+                        for t in call:
+                            t.grad = None
+                        loss_of(up(*call, True)["coarse"]).backward()
+
+                    for tf32 in (False, True):
+                        torch.backends.cuda.matmul.allow_tf32 = tf32
+                        row[f"upstream_eager_{'tf32' if tf32 else 'fp32'}_ms"] = timed(up_step, 2)
+                    del up
+            except Exception as exc:      # noqa: BLE001  (a secondary figure: never fail the bench line for it)
+                row["upstream_eager_error"] = f"{type(exc).__name__}: {str(exc)[:200]}"
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        torch.cuda.empty_cache()
+        out.append(row)
+    return out
+
+
 def t_frame_report(device):
     """What play.py renders per frame ("T-frame"): the Tennis full frame 288x512 sampled on the strided grids of the
     multiresolution decoder (strides 4 and 8: 9216 + 2304 = 11 520 rays), 4 object instances (2 static boxes with 4 samples per ray, 2
@@ -364,19 +481,10 @@ def t_frame_report(device):
     from gpu_common import build_composer
     from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper
     H, W, strides = 288, 512, [4, 8]
-    court = scenes.object_cfg([[-30, 30], [-40, 20.585], [-0.5, 0.0]], 4, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
-    stands = scenes.object_cfg([[-40, 40], [20.585, 45.0], [0.0, 12.0]], 4, 5.0, 120.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("zeroed"))
-    player = lambda: scenes.object_cfg([[-0.75, 0.75], [-0.5, 0.5], [0.0, 2.15]], 32, 5.0, 70.0, 64, 32, scenes.nerf_cfg(), scenes.bender_cfg("positional"))
-    config = scenes.scene_config([court, stands, player(), player()], 2, [1, 1, 1, 1], True)
     lead = (1, 1, 1)
     focal = 1700.0 * 0.51417 * 0.5 * (W / 256.0)
-    parts = [scenes.camera_rays(lead, H, W, focal, scenes.tennis_camera(), st) for st in strides]
-    orig, norm = parts[0][0], parts[0][2]
-    dirs = torch.cat([p[1] for p in parts], dim=-2)
-    p1 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(0.3), [2.0, -11.0, 0.01]))
-    p2 = np.linalg.inv(scenes.homogeneous(scenes.rot_z(-0.2), [-2.0, 11.0, 0.01]))
-    inputs = scenes.build_inputs(17, config, lead, orig, dirs, norm, [np.eye(4), np.eye(4), p1, p2])
-    scene = (config, scenes.scene_state(17, config), inputs)
+    scene = tennis_four_objects(lead, lambda st: scenes.camera_rays(lead, H, W, focal, scenes.tennis_camera(), st))
+    dirs = scene[2]["ray_directions"]
     out = {"workload": "T-frame: Tennis 288x512 on the stride-4 + stride-8 grids = 11520 rays, 2 static objects (P=4) + 2 players (P=32, ray benders), "
                        "eval forward + fold into the decoder's CHW grids, one composer call", "rays": int(dirs.size(-2)), "sample_slots": int(dirs.size(-2)) * 72}
     for precision in ("mixed", "fp16x3", "fp16"):
@@ -613,6 +721,7 @@ def run_b200(args):
                                   train_step_report(device, False, "fp32"), train_step_report(device, True, "fp32")]
             line["eval_frame"] = [eval_frame_report(device, False), eval_frame_report(device, True)]
             line["t_frame"] = t_frame_report(device)
+            line["t_train"] = t_train_report(device)
             line["gpu_eager_baseline"] = gpu_eager_reference(device)
         if train_multi:
             line["train_step"] = [train_multi]

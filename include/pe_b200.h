@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 7
+#define PE_ABI_VERSION 8
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -109,6 +109,11 @@ typedef struct PeScene {
     int32_t bent_gradients;    /* 1: the backward also takes dL/d (sample position + displacement) from PeOutGrads.bent_positions -- the
                                   backward of forward_expected_positions (object_composer.py:603-722)                                 */
     PeObjectDesc object[PE_MAX_OBJECTS];
+    /* backward only, optional: 1 + the exact number of 128-sample tiles the tensor-core backward of object k will walk, as counted by
+     * pe_forward_tile_counts on the kept forward of this very call; 0 = unknown (the backward then sizes its activation stash and its
+     * batch count for the worst case, every slot inside the box).  A training step whose worst case exceeds the stash would otherwise
+     * run in batches and repeat the recompute in each of the three BatchNorm phases.                                                  */
+    int64_t bwd_tiles[PE_MAX_OBJECTS];
 } PeScene;
 
 typedef struct PeInputs {
@@ -241,6 +246,14 @@ int    pe_render_backward_saved(const PeScene* scene, const PeInputs* in, const 
                                 const PeOutGrads* grad_out, const PeInGrads* grad_in,
                                 const void* saved_forward, size_t saved_forward_bytes,
                                 void* workspace, size_t workspace_bytes, pe_stream_t stream);
+
+/* How many 128-sample tiles the tensor-core backward of each object will walk, from the in-box masks of a kept forward
+ * (scene->keep_samples = 1): counts[k] (device memory, PE_MAX_OBJECTS entries) = sum over images of ceil(in-box samples / 128), 0 for
+ * objects whose backward does not run on the tensor cores.  The caller copies the counts to the host while the loss is computed and
+ * hands them back as scene->bwd_tiles[k] = 1 + counts[k] (what autograd knows from its saved tensors' shapes: the number of rows of
+ * the gathered in-box samples, model/nerf_models/ray_bending_style_nerf_model.py:170-176).                                          */
+int    pe_forward_tile_counts(const PeScene* scene, const void* saved_forward, size_t saved_forward_bytes, int64_t* counts,
+                              pe_stream_t stream);
 
 /* -- stand-alone operators (module-level API of the reference) ---------------------------------- */
 /* PositionalEncoder.forward / AnnealablePositionalEncoder.forward

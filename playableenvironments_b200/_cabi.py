@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 7
+PE_ABI_VERSION = 8
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -63,6 +63,7 @@ class PeScene(C.Structure):
         ("precision", C.c_int32), ("explicit_positions", C.c_int32), ("keep_samples", C.c_int32),
         ("explicit_t", C.c_int32), ("divergence", C.c_int32), ("bent_gradients", C.c_int32),
         ("object", PeObjectDesc * PE_MAX_OBJECTS),
+        ("bwd_tiles", C.c_int64 * PE_MAX_OBJECTS),
     ]
 
 
@@ -130,7 +131,7 @@ class PeInGrads(C.Structure):
 
 EXPORTS = [
     "pe_abi_version", "pe_last_error", "pe_take_launch_count", "pe_packed_bytes", "pe_pack_object",
-    "pe_workspace_bytes", "pe_render_forward", "pe_backward_workspace_bytes", "pe_render_backward", "pe_render_backward_saved", "pe_positional_encoding", "pe_generate_rays",
+    "pe_workspace_bytes", "pe_render_forward", "pe_backward_workspace_bytes", "pe_render_backward", "pe_render_backward_saved", "pe_forward_tile_counts", "pe_positional_encoding", "pe_generate_rays",
     "pe_fold_feature_grids", "pe_debug_umma_gemm", "pe_debug_umma_gemm2", "pe_debug_pack_layer",
 ]
 
@@ -170,6 +171,8 @@ def lib() -> C.CDLL:
     L.pe_render_backward_saved.restype = C.c_int
     L.pe_render_backward_saved.argtypes = [C.POINTER(PeScene), C.POINTER(PeInputs), C.POINTER(PeObjectParams), C.POINTER(PeOutGrads),
                                            C.POINTER(PeInGrads), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.pe_forward_tile_counts.restype = C.c_int
+    L.pe_forward_tile_counts.argtypes = [C.POINTER(PeScene), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.pe_positional_encoding.restype = C.c_int
     L.pe_positional_encoding.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pe_generate_rays.restype = C.c_int

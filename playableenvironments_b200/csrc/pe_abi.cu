@@ -448,7 +448,10 @@ static bool backward_on_tc(const PeScene& s, int k) {
     return backward_compacts(s, k) && !s.apply_activation && pe_bwd_tc_object_ok(s.object[k]) && pe_layout(s.object[k]).tcT_base != 0;
 }
 static int64_t bwd_tc_tiles_upper_bound(const PeScene& s, int k) {
-    return (int64_t)s.images * (((int64_t)s.rays * s.object[k].positions + PE_BWD_TILE - 1) / PE_BWD_TILE);
+    const int64_t worst = (int64_t)s.images * (((int64_t)s.rays * s.object[k].positions + PE_BWD_TILE - 1) / PE_BWD_TILE);
+    // the caller knows the exact count from the kept forward (pe_forward_tile_counts): no surplus batches, a stash of the real size
+    if (s.bwd_tiles[k] > 0) return pe_min64(worst, s.bwd_tiles[k] - 1 > 1 ? s.bwd_tiles[k] - 1 : 1);
+    return worst;
 }
 static int64_t bwd_tc_capacity(const PeScene& s) {
     int64_t ub = 0;
@@ -543,6 +546,28 @@ extern "C" size_t pe_backward_workspace_bytes(const PeScene* scene) {
     if (!scene || validate_scene(*scene) != PE_OK) return 0;
     if (scene->explicit_positions) { pe_set_error("backward on explicit positions is not supported"); return 0; }
     return carve_backward(backward_scene_for(*scene), nullptr, backward_grid()).bytes + 256;
+}
+
+extern "C" int pe_forward_tile_counts(const PeScene* scene, const void* saved_forward, size_t saved_forward_bytes, int64_t* counts,
+                                      pe_stream_t stream_) {
+    if (!scene || !saved_forward || !counts) { pe_set_error("null argument"); return PE_ERR_INVALID; }
+    int rc = validate_scene(*scene);
+    if (rc != PE_OK) return rc;
+    if (!scene->keep_samples) { pe_set_error("pe_forward_tile_counts reads the workspace of a forward with scene.keep_samples = 1"); return PE_ERR_INVALID; }
+    const PeScene& s = *scene;
+    if ((size_t)saved_forward % 256 || carve(s, nullptr).bytes > saved_forward_bytes) { pe_set_error("saved forward workspace: misaligned or too small"); return PE_ERR_WORKSPACE; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PE_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(int64_t) * PE_MAX_OBJECTS, stream));
+    if (s.images == 0 || s.rays == 0) return PE_OK;
+    const Workspace ws = carve(s, const_cast<void*>(saved_forward));
+    for (int k = 0; k < s.objects; ++k) {
+        if (!backward_on_tc(s, k)) continue;
+        // the very masks pe_render_backward_saved compacts (outer mask of a ray-bender object, in-box flags otherwise)
+        const uint8_t* mask_src = object_uses_prepass(s, k) ? ws.obj[k].flags : ws.obj[k].inbox;
+        rc = pe_launch_count_tiles(mask_src, 1, s.images, (int64_t)s.rays * s.object[k].positions, PE_BWD_TILE, counts + k, stream);
+        if (rc) return rc;
+    }
+    return PE_OK;
 }
 
 extern "C" int pe_render_backward(const PeScene* scene, const PeInputs* in, const PeObjectParams* params, const PeOutGrads* grad_out,

@@ -749,7 +749,34 @@ __global__ void pe_tile_prefix_kernel(const int32_t* __restrict__ count, int ima
     }
 }
 
+// Per image: ceil(#flagged slots / tile_rows), summed over the images into *out -- the tile count pe_compact_slots_kernel +
+// pe_tile_prefix_kernel will arrive at for the same flags (pe_forward_tile_counts).
+__global__ void __launch_bounds__(1024) pe_count_tiles_kernel(const uint8_t* __restrict__ flags, int mask, int64_t slots_per_image, int tile_rows,
+                                                               unsigned long long* __restrict__ out) {
+    __shared__ int warp_tot[32];
+    const uint8_t* f = flags + (int64_t)blockIdx.x * slots_per_image;
+    int mine = 0;
+    for (int64_t s = threadIdx.x; s < slots_per_image; s += blockDim.x) mine += (f[s] & mask) != 0 ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+        if (t) atomicAdd(out, (unsigned long long)((t + tile_rows - 1) / tile_rows));
+    }
+}
+
 }  // namespace
+
+int pe_launch_count_tiles(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int tile_rows, int64_t* out,
+                          cudaStream_t stream) {
+    if (images == 0 || slots_per_image == 0) return PE_OK;
+    pe_count_tiles_kernel<<<images, 1024, 0, stream>>>(flags, flag_mask, slots_per_image, tile_rows, reinterpret_cast<unsigned long long*>(out));
+    PE_LAUNCH_CHECK("pe_count_tiles_kernel");
+    return PE_OK;
+}
 
 int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
                             int32_t* tile_begin, cudaStream_t stream, int tile_rows) {

@@ -199,6 +199,8 @@ size_t pe_field_bwd_smem_bytes();
 int64_t pe_field_bwd_stash_floats(const PeObjectDesc& ob, const PeLayout& L);
 int pe_field_bwd_grid(int sm_count);
 int pe_launch_field_bwd(const PeFieldBwdArgs& args, int sm_count, cudaStream_t stream);
+int pe_launch_count_tiles(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int tile_rows, int64_t* out,
+                          cudaStream_t stream);
 int pe_launch_compact_slots(const uint8_t* flags, int flag_mask, int images, int64_t slots_per_image, int32_t* slot_list, int32_t* slot_count,
                             int32_t* tile_begin, cudaStream_t stream, int tile_rows = 32);
 int pe_launch_composite_bwd(const PeCompositeBwdArgs& args, cudaStream_t stream);

@@ -6,6 +6,7 @@ No arithmetic of the render path happens in Python."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -209,6 +210,17 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Opti
             ws = _Workspace.get(device, nbytes)
         _cabi.check(L.pe_render_forward(C.byref(scene), C.byref(ins), C.byref(outs), _cabi.ptr(ws), ws.numel(),
                                         _cabi.current_stream(device)))
+        if saved is not None and not torch.cuda.is_current_stream_capturing() and os.environ.get("PE_BWD_TILE_COUNTS", "1") != "0":
+            # how many tiles the tensor-core backward will walk per object, counted on the kept masks and copied to pinned host memory
+            # behind the forward: by the time backward runs (the loss sits in between) the copy has landed, and the backward sizes its
+            # stash and batch count exactly instead of for the worst case (what autograd knows from the shapes of its saved tensors)
+            counts = torch.empty(_cabi.PE_MAX_OBJECTS, dtype=torch.int64, device=device)
+            _cabi.check(L.pe_forward_tile_counts(C.byref(scene), _cabi.ptr(ws), ws.numel(), _cabi.ptr(counts), _cabi.current_stream(device)))
+            host = torch.empty(_cabi.PE_MAX_OBJECTS, dtype=torch.int64, pin_memory=True)
+            host.copy_(counts, non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(torch.cuda.current_stream(device))
+            saved.append((host, landed, counts))
     del keep
     return results
 
@@ -229,6 +241,7 @@ class RenderFunction(torch.autograd.Function):
         saved = [] if _save_forward(meta) else None
         res = _launch_forward(meta, meta["lead"], origins, dirs, w2o, styles, deforms, saved)
         ctx.saved_forward = saved[0] if saved else None
+        ctx.tile_counts = saved[1] if saved and len(saved) > 1 else None
         ctx.meta = meta
         # the descs in ``meta`` hold RAW pointers into each model's packed blob: keep those tensors alive with the graph (a second
         # forward before this node's backward may repack -- train-mode BatchNorm bumps the running statistics every call)
@@ -340,6 +353,11 @@ class RenderFunction(torch.autograd.Function):
         with torch.cuda.device(device):
             fwd_ws = ctx.saved_forward
             scene.keep_samples = 1 if fwd_ws is not None else 0
+            if fwd_ws is not None and ctx.tile_counts is not None:
+                host, landed, _ = ctx.tile_counts
+                landed.synchronize()
+                for k in range(K):
+                    scene.bwd_tiles[k] = int(host[k]) + 1
             nbytes = L.pe_backward_workspace_bytes(C.byref(scene))
             if nbytes == 0:
                 raise _cabi.PeError(f"pe_backward_workspace_bytes: {L.pe_last_error().decode()}")

@@ -178,3 +178,41 @@ def test_outputs_without_a_gradient_are_skipped_not_zero_filled(name, precision,
         scale = max(float(full[k].abs().max()), 1e-12)
         # fp32 path: the skipped lists only ever added zeros; tensor-core path: float atomics in dW reorder sums run to run
         assert float((lazy[k] - full[k]).abs().max()) <= (1e-6 if precision == "fp32" else 1e-4) * scale, k
+
+
+@pytest.mark.parametrize("max_tiles", [None, "3"])
+def test_exact_tile_counts_from_the_kept_forward(max_tiles, monkeypatch):
+    """pe_forward_tile_counts: the backward sized from the kept forward's exact tile counts (stash, batch count) walks the same tiles as
+    the worst-case sizing -- also when the stash is so small (3 tiles) that the step runs in batches and repeats the recompute per
+    BatchNorm phase.  Gradients agree to the order of the fp32 atomics' summation noise."""
+    from gpu_common import build_composer
+    import ctypes as C
+    from playableenvironments_b200 import _cabi
+    if max_tiles:
+        monkeypatch.setenv("PE_BWD_TC_MAX_TILES", max_tiles)
+
+    def grads(counts_on):
+        monkeypatch.setenv("PE_BWD_TILE_COUNTS", "1" if counts_on else "0")
+        config, state, inputs, comp, dev = build_composer("tennis_dense", "mixed", training=True)
+        comp.allow_forward_without_grad = False
+        dev = {k: (v.clone().requires_grad_(True) if k in scenes.GRAD_INPUT_KEYS else v) for k, v in dev.items()}
+        res = comp(*[dev[k] for k in INPUT_KEYS], False)["coarse"]
+        node = res["global"]["integrated_features"].grad_fn
+        while node is not None and not hasattr(node, "saved_forward"):          # the RenderFunction node (behind any view)
+            node = node.next_functions[0][0] if node.next_functions else None
+        scenes.grad_loss(res, ["global/integrated_features", "global/opacity", "global/depth", "object_1/opacity"]).backward()
+        torch.cuda.synchronize()
+        out = {k: dev[k].grad.clone() for k in scenes.GRAD_INPUT_KEYS if dev[k].grad is not None}
+        out.update({k: p.grad.clone() for k, p in comp.named_parameters() if p.grad is not None})
+        return out, node
+
+    ref, node0 = grads(False)
+    got, node1 = grads(True)
+    assert getattr(node0, "tile_counts", None) is None
+    host = node1.tile_counts[0]
+    # the court and the player in view have samples inside their boxes, the second player is out of view (an exact count of 0 tiles)
+    assert int(host[0]) > 0 and int(host[1]) > 0 and int(host[3:].sum()) == 0, host
+    assert ref.keys() == got.keys()
+    for k in ref:
+        scale = float(ref[k].abs().max())
+        assert float((got[k] - ref[k]).abs().max()) <= 2e-4 * max(scale, 1e-12), k
