@@ -129,6 +129,19 @@ static bool object_uses_prepass(const PeScene& s, int k) {
     return tc_allowed(s) && pe_tc_prepass_ok(s.object[k]);
 }
 
+// Static (zeroed-bender) objects of a multi-object scene take the same hand-off without a bender: sampling as its own pass
+// (pe_sample_kernel), the field over the tiles that hold a sample inside the box only, the compositor integrates the object.  An object
+// that covers part of the view (the shipped Tennis scene's upright slab behind the court, a Minecraft block) no longer pays for the
+// rays that miss it -- the reference gathers the in-box samples before its MLP, ray_bending_style_nerf_model.py:170-176.  The backward
+// is unchanged: it walks compacted in-box samples already.  PE_TC_SKIP_EMPTY=0: every tile, sampling inside the kernel, as before.
+static bool object_lists_tiles(const PeScene& s, int k) {
+    const char* env = getenv("PE_TC_SKIP_EMPTY");
+    if (env && atoi(env) == 0) return false;
+    return object_uses_tc(s, k) && s.objects > 1 && s.object[k].positions <= 128;
+}
+// objects whose integrated outputs come out of the fused field kernel itself (the compositor integrates the others)
+static bool object_integrates_itself(const PeScene& s, int k) { return object_uses_tc(s, k) && !object_lists_tiles(s, k); }
+
 // per-sample features are only materialised where something downstream reads them
 static bool needs_feature_buffer(const PeScene& s, int k) {
     if (s.explicit_positions) return false;                 // caller supplies raw_features
@@ -166,7 +179,7 @@ static Workspace carve(const PeScene& s, void* base) {
         const bool fold = object_folds_head(s, k);
         o.fold_v = fold ? (float*)take((size_t)s.images * s.rays * 128 * 4) : nullptr;
         o.fold_s = fold ? (float*)take((size_t)s.images * s.rays * 4) : nullptr;
-        const bool prepass = object_uses_prepass(s, k);
+        const bool prepass = object_uses_prepass(s, k) || object_lists_tiles(s, k);
         const size_t rpt = prepass ? 128 / P : 1, tiles = ((size_t)s.rays + rpt - 1) / rpt * (size_t)s.images;   // pre-pass objects have P <= 128
         o.bent = prepass ? (float*)take(n * 12) : nullptr;
         o.flags = prepass ? (uint8_t*)take(n) : nullptr;
@@ -289,9 +302,20 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         s2.run_mean = P32(L.bn2_mean); s2.run_var = P32(L.bn2_var); s2.stats = o.stats + 2 * d.width + 2; s2.out = o.aff2; s2.running_out = o.run2;
 
         const bool prepass = object_uses_prepass(s, k);
+        const bool lists = object_lists_tiles(s, k);
         auto launch_field = [&](int phase) {
             fa.phase = phase;
             const PeIntegrated none = {};
+            if (lists) {
+                PeFieldArgs pre = fa;
+                pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
+                pre.tile_list = o.tile_list; pre.tile_count = o.tile_count;
+                if (!(s.training && phase != 1)) {       // (train mode: the samples and the tile list of phase 1 stay valid for phases 2 and 0)
+                    int rc2 = pe_launch_sample(pre, sm_count, stream); if (rc2) return rc2;
+                    rc2 = pe_launch_tile_list(pre, 2, o.tile_list, o.tile_count, stream); if (rc2) return rc2;
+                }
+                return pe_launch_field_tc(pre, none, sm_count, stream);
+            }
             if (prepass) {
                 PeFieldArgs pre = fa;
                 pre.bent = o.bent; pre.flags = o.flags; pre.integ = none;
@@ -387,7 +411,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         ca.inbox[k] = o.inbox;
         ca.noise[k] = s.perturb ? in->noise[k] : nullptr;
         ca.object[k] = out->object[k];
-        all_tc = all_tc && object_uses_tc(s, k);
+        all_tc = all_tc && object_integrates_itself(s, k);
     }
     ca.global = out->global;
     // objects evaluated by the tcgen05 kernel integrate themselves in its epilogue; a single such object IS the scene
@@ -397,7 +421,7 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     if (!all_tc) {
         // mixed scenes: the compositor integrates the fp32 objects; tc objects already wrote theirs
         for (int k = 0; k < s.objects; ++k)
-            if (object_uses_tc(s, k)) memset(&ca.object[k], 0, sizeof(PeIntegrated));
+            if (object_integrates_itself(s, k)) memset(&ca.object[k], 0, sizeof(PeIntegrated));
     }
     auto wants = [](const PeIntegrated& o) {
         return o.integrated_features || o.opacity || o.weights || o.depth || o.disparity || o.integrated_displacements_magnitude || o.integrated_divergence;

@@ -134,6 +134,10 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
         // ---- per-object integration (object_composer.py:880) ----
         if (A.do_objects) {
             for (int k = 0; k < A.objects; ++k) {
+                const PeIntegrated& ok = A.object[k];
+                // objects that integrated themselves in the fused field kernel (or whose outputs nobody asked for) are not walked again
+                if (!(ok.integrated_features || ok.opacity || ok.weights || ok.depth || ok.disparity || ok.integrated_displacements_magnitude ||
+                      ok.integrated_divergence)) continue;
                 const int P = A.positions[k];
                 const int64_t b = ray * P;
                 __syncwarp();

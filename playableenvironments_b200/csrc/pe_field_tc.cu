@@ -500,7 +500,9 @@ __global__ void __launch_bounds__(256) pe_sample_kernel(const PeFieldArgs A) {
         A.t_out[gs] = t;
         A.raw_out[gs] = ob.empty_space_alpha;
         A.inbox_out[gs] = 0;
-        A.flags[gs] = pe_in_box(ob, x) ? 1 : 0;
+        // bit 0: inside the box before bending, bit 1: to be evaluated by the field (set by the ray bender for bent samples; a zeroed
+        // bender bends nothing, so the two masks coincide)
+        A.flags[gs] = pe_in_box(ob, x) ? (ob.bender_kind == PE_BENDER_ZEROED ? 3 : 1) : 0;
         A.bent[gs * 3] = x[0]; A.bent[gs * 3 + 1] = x[1]; A.bent[gs * 3 + 2] = x[2];
         if (A.disp_out) { A.disp_out[gs * 3] = 0.f; A.disp_out[gs * 3 + 1] = 0.f; A.disp_out[gs * 3 + 2] = 0.f; }
         if (A.dispmag_out) A.dispmag_out[gs] = 0.f;
@@ -945,7 +947,7 @@ int pe_tc_pack(const PeObjectDesc& d, const PeLayout& L, const PeObjectParams& p
 
 int pe_launch_field_tc(const PeFieldArgs& args, const PeIntegrated& global_out, int sm_count, cudaStream_t stream) {
     const bool prepass = args.bent != nullptr;
-    if (!(prepass ? pe_tc_prepass_ok(args.ob) : pe_tc_shape_ok(args.ob)) || args.explicit_positions || args.phase < 0 || args.phase > 2 ||
+    if (!(prepass ? pe_tc_field_ok(args.ob) : pe_tc_shape_ok(args.ob)) || args.explicit_positions || args.phase < 0 || args.phase > 2 ||
         (args.phase != 0 && (!args.training || !args.stats))) {
         pe_set_error("tensor-core field kernel: unsupported configuration");
         return PE_ERR_UNSUPPORTED;

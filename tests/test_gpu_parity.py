@@ -260,15 +260,40 @@ def test_tensor_core_ray_bender_against_the_fp32_bender(name, monkeypatch):
 
 
 def test_ray_bender_prepass_launches(monkeypatch):
-    """Tennis frame: court = 2 style prologues + fused kernel; each player = sampling pass + tile list + tensor-core ray bender +
-    tile list + 2 style prologues + tensor-core field (fp16x2; fp16x3: fp32 pre-pass + tile list + ...); one compositor launch."""
+    """Tennis frame: court = 2 style prologues + sampling pass + tile list + tensor-core field over the non-empty tiles (a static object of
+    a multi-object scene; PE_TC_SKIP_EMPTY=0: 2 style prologues + the fused kernel over every tile); each player = sampling pass + tile
+    list + tensor-core ray bender + tile list + 2 style prologues + tensor-core field (fp16x2; fp16x3: fp32 pre-pass + tile list + ...);
+    one compositor launch."""
     from playableenvironments_b200.model import render
-    for precision, per_player in (("fp16x2", 7), ("fp16x3", 5)):
-        _, _, _, comp, dev = _build("tennis_small", precision)
-        _run(comp, dev)
-        render.take_launch_count()
-        _run(comp, dev)
-        assert render.take_launch_count() == 3 + 2 * per_player + 1
+    for skip_empty, court in (("1", 5), ("0", 3)):
+        monkeypatch.setenv("PE_TC_SKIP_EMPTY", skip_empty)
+        for precision, per_player in (("fp16x2", 7), ("fp16x3", 5)):
+            _, _, _, comp, dev = _build("tennis_small", precision)
+            _run(comp, dev)
+            render.take_launch_count()
+            _run(comp, dev)
+            assert render.take_launch_count() == court + 2 * per_player + 1
+
+
+@pytest.mark.parametrize("name", ["tennis_small", "minecraft_small", "minecraft_absent", "toy_world"])
+def test_static_objects_skip_empty_tiles_bit_exactly(name, monkeypatch):
+    """Static objects of a multi-object scene evaluated over their non-empty tiles only (sampling pass + tile list) against the same
+    objects evaluated over every tile with the sampling inside the fused kernel: the same device functions, the same arithmetic per
+    sample -- the composed scene is identical bit for bit; an object's own integrated outputs now come out of the compositor instead of
+    the fused kernel's epilogue (another summation order: rounding-level differences)."""
+    monkeypatch.setenv("PE_TC_SKIP_EMPTY", "1")
+    _, _, _, comp, dev = _build(name, "fp16x3")
+    a = flatten(_run(comp, dev))
+    monkeypatch.setenv("PE_TC_SKIP_EMPTY", "0")
+    _, _, _, comp2, dev2 = _build(name, "fp16x3")
+    b = flatten(_run(comp2, dev2))
+    assert a.keys() == b.keys()
+    for k in b:
+        if k.startswith("coarse/"):
+            if k.startswith("coarse/global/"):
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+            elif "disparity" not in k:
+                assert scale_rel_err(a[k], b[k]) < 2e-6, (k, scale_rel_err(a[k], b[k]))
 
 
 def test_tensor_core_path_with_perturbation():
