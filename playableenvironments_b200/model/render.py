@@ -146,6 +146,18 @@ def _save_forward(meta) -> bool:
     return meta["precision"] != _cabi.PRECISION_FP32 and os.environ.get("PE_SAVE_FORWARD", "1") != "0"
 
 
+def _wants_tile_counts(descs, images: int, rays: int) -> bool:
+    """Exact backward tile counts (pe_forward_tile_counts) cost the backward a host-side wait for the forward's last copy -- nothing when a
+    loss sits between the two, the launch latency of the backward when it follows immediately.  They pay when the worst case (every
+    slot inside its box) does not fit the activation stash: the backward would run in batches and repeat its recompute in each BatchNorm
+    phase.  PE_BWD_TILE_COUNTS=1 / 0 forces them on / off."""
+    env = os.environ.get("PE_BWD_TILE_COUNTS")
+    if env is not None:
+        return env != "0"
+    cap = int(os.environ.get("PE_BWD_TC_MAX_TILES", "12288"))
+    return any(images * ((rays * d.positions + 127) // 128) > cap for d in descs)
+
+
 def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Optional[List] = None, alias_single: bool = False) -> Dict:
     """``saved``: a list that receives the kept forward workspace (autograd path, see ``_save_forward``).
     ``alias_single`` (inference): in a scene with ONE object instance the composed scene is that object -- same samples, same order, same
@@ -210,7 +222,7 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Opti
             ws = _Workspace.get(device, nbytes)
         _cabi.check(L.pe_render_forward(C.byref(scene), C.byref(ins), C.byref(outs), _cabi.ptr(ws), ws.numel(),
                                         _cabi.current_stream(device)))
-        if saved is not None and not torch.cuda.is_current_stream_capturing() and os.environ.get("PE_BWD_TILE_COUNTS", "1") != "0":
+        if saved is not None and _wants_tile_counts(descs, images, rays) and not torch.cuda.is_current_stream_capturing():
             # how many tiles the tensor-core backward will walk per object, counted on the kept masks and copied to pinned host memory
             # behind the forward: by the time backward runs (the loss sits in between) the copy has landed, and the backward sizes its
             # stash and batch count exactly instead of for the worst case (what autograd knows from the shapes of its saved tensors)

@@ -191,6 +191,16 @@ def test_exact_tile_counts_from_the_kept_forward(max_tiles, monkeypatch):
     if max_tiles:
         monkeypatch.setenv("PE_BWD_TC_MAX_TILES", max_tiles)
 
+    def render_wants(rays):
+        from playableenvironments_b200.model import render
+        monkeypatch.delenv("PE_BWD_TILE_COUNTS", raising=False)
+        monkeypatch.delenv("PE_BWD_TC_MAX_TILES", raising=False)
+        try:
+            return render._wants_tile_counts([type("D", (), {"positions": 32})()], 4, rays)
+        finally:
+            if max_tiles:
+                monkeypatch.setenv("PE_BWD_TC_MAX_TILES", max_tiles)
+
     def grads(counts_on):
         monkeypatch.setenv("PE_BWD_TILE_COUNTS", "1" if counts_on else "0")
         config, state, inputs, comp, dev = build_composer("tennis_dense", "mixed", training=True)
@@ -206,6 +216,7 @@ def test_exact_tile_counts_from_the_kept_forward(max_tiles, monkeypatch):
         out.update({k: p.grad.clone() for k, p in comp.named_parameters() if p.grad is not None})
         return out, node
 
+    assert not render_wants(8192) and render_wants(1 << 20)          # by default only when the worst case overflows the stash
     ref, node0 = grads(False)
     got, node1 = grads(True)
     assert getattr(node0, "tile_counts", None) is None
