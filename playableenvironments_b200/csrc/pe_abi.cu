@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <stdlib.h>
+#include <mutex>
 
 #include "pe_kernels.cuh"
 
@@ -221,6 +222,30 @@ static int validate_scene(const PeScene& s) {
     return PE_OK;
 }
 
+// Streams the objects of a scene run on (pe_render_forward), one pool per device, created on first use and kept for the process.
+struct ObjectStreams {
+    std::mutex mutex;
+    cudaStream_t stream[PE_MAX_OBJECTS];
+    cudaEvent_t fork, join[PE_MAX_OBJECTS];
+};
+static ObjectStreams* object_streams() {
+    static std::mutex table_mutex;
+    static ObjectStreams* table[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(table_mutex);
+    if (!table[dev]) {
+        ObjectStreams* p = new ObjectStreams();
+        bool ok = cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; k < PE_MAX_OBJECTS && ok; ++k)
+            ok = cudaStreamCreateWithFlags(&p->stream[k], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->join[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); delete p; return nullptr; }      // (no pool: the caller's stream takes everything)
+        table[dev] = p;
+    }
+    return table[dev];
+}
+
 extern "C" size_t pe_workspace_bytes(const PeScene* scene) {
     if (!scene || validate_scene(*scene) != PE_OK) return 0;
     if (scene->keep_samples) { KeepSamples keep; return carve(*scene, nullptr).bytes + 256; }
@@ -253,7 +278,9 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
 
     if (out->peers < 0 || out->peers > PE_MAX_PEERS) { pe_set_error("peers must be in [0,%d]", PE_MAX_PEERS); return PE_ERR_INVALID; }
     bool peers_fused = false;
-    for (int k = 0; k < s.objects; ++k) {
+    // one object instance: style prologues, sampling / ray bender / tile lists, field kernel(s) -- everything before the compositor
+    auto render_object = [&](int k, cudaStream_t stream) -> int {
+        int rc = PE_OK;
         const PeObjectDesc& d = s.object[k];
         const PeLayout L = pe_layout(d);
         const ObjWorkspace& o = ws.obj[k];
@@ -389,6 +416,35 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
             dvb.stash = ws.div_stash; dvb.stash_floats = ws.div_stash_floats;
             dvb.bwd_phase = 0;
             rc = pe_launch_field_bwd(dvb, sm_count, stream); if (rc) return rc;
+        }
+        return PE_OK;
+    };
+    // The objects of a scene are independent until the compositor, and in the frames the callers render (play.py: 11 520 rays, one
+    // train.py replica: 20 480) an object's launches are a few tiles per SM or less: each object runs on its own stream of a per-device
+    // pool (fork from the caller's stream, join before the compositor), so one object's kernels fill the SMs another's leave idle.
+    // Stream capture sees an ordinary fork / join.  PE_CONCURRENT_OBJECTS=0: everything on the caller's stream.
+    ObjectStreams* pool = nullptr;
+    {
+        const char* cenv = getenv("PE_CONCURRENT_OBJECTS");
+        const bool concurrent = s.objects > 1 && !s.explicit_positions && !s.divergence && !(cenv && atoi(cenv) == 0);
+        if (concurrent) pool = object_streams();
+    }
+    if (pool) {
+        std::lock_guard<std::mutex> lock(pool->mutex);      // the pool's events are re-recorded by every call: one call enqueues at a time
+        PE_CUDA_CHECK(cudaEventRecord(pool->fork, stream));
+        int first_rc = PE_OK;
+        int forked = 0;
+        for (int k = 0; k < s.objects && first_rc == PE_OK; ++k, ++forked) {
+            cudaError_t e = cudaStreamWaitEvent(pool->stream[k], pool->fork, 0);
+            if (e == cudaSuccess) { first_rc = render_object(k, pool->stream[k]); e = cudaEventRecord(pool->join[k], pool->stream[k]); }
+            if (e != cudaSuccess && first_rc == PE_OK) { pe_set_error("CUDA error: %s", cudaGetErrorString(e)); first_rc = PE_ERR_CUDA; }
+        }
+        for (int k = 0; k < forked; ++k) cudaStreamWaitEvent(stream, pool->join[k], 0);      // always join what was forked (stream capture)
+        if (first_rc != PE_OK) return first_rc;
+    } else {
+        for (int k = 0; k < s.objects; ++k) {
+            rc = render_object(k, stream);
+            if (rc != PE_OK) return rc;
         }
     }
     if (s.explicit_positions) return PE_OK;
