@@ -87,3 +87,41 @@ def test_sharded_and_pipelined_render_on_two_gpus(tmp_path):
     for r in range(2):
         flags = open(tmp_path / f"ok{r}").read().split(",")
         assert flags and all(f == "1" for f in flags), (r, flags)
+
+
+def test_data_parallel_replicas_on_two_gpus():
+    """The reference's own multi-GPU wrapper (train.py:61: nn.DataParallel): the batch dimension scattered over two replicas running in two
+    Python threads, one device each -- every object of a replica on its own stream of that device's pool.  Eval-mode images are
+    independent, so outputs equal the single-device call image by image and the reduced parameter gradients equal its gradients."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import scenes
+    from helpers import INPUT_KEYS
+    from gpu_common import build_composer
+    scene = scenes.scene_tennis(seed=13, stride=8, lead=(2, 2, 1))
+    _, _, _, comp, dev = build_composer(scene, "mixed", device=torch.device("cuda", 0))
+    comp.allow_forward_without_grad = False
+    args = [dev[k] for k in INPUT_KEYS]
+
+    def loss_of(res):
+        return (res["coarse"]["global"]["integrated_features"].sum() + res["coarse"]["global"]["opacity"].sum()
+                + res["coarse"]["object_1"]["depth"].sum())
+
+    single = comp(*args, False)
+    loss_of(single).backward()
+    ref_grads = {k: p.grad.clone() for k, p in comp.named_parameters() if p.grad is not None}
+    comp.zero_grad(set_to_none=True)
+    parallel = torch.nn.DataParallel(comp, device_ids=[0, 1])
+    for _ in range(2):                                   # (second pass: cached packed weights and stream pools of both devices)
+        comp.zero_grad(set_to_none=True)
+        both = parallel(*args, False)
+        loss_of(both).backward()
+    torch.cuda.synchronize()
+    for name in ("global", "object_0", "object_1", "object_2"):
+        for key in ("integrated_features", "opacity", "depth", "weights"):
+            assert torch.equal(both["coarse"][name][key], single["coarse"][name][key]), (name, key)
+    assert ref_grads
+    for k, p in comp.named_parameters():
+        if k in ref_grads:
+            scale = float(ref_grads[k].abs().max())
+            assert float((p.grad - ref_grads[k]).abs().max()) <= 2e-4 * max(scale, 1e-12), k
