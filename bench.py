@@ -494,9 +494,8 @@ def t_frame_report(device):
         call = [dev[k] for k in INPUT_KEYS]
 
         def frame():
-            with torch.no_grad():
-                feats = comp(*call, False)["coarse"]["global"]["integrated_features"]
-                return RayHelper.fold_feature_grids(feats, strides, (H, W), [64, 128])
+            with torch.no_grad():      # the compositor writes the decoder's per-stride CHW grids itself (PeHandoff)
+                return comp(*call, False, handoff=(strides, (H, W), [64, 128]))["coarse"]["global"]["feature_grids"]
 
         frame()
         torch.cuda.synchronize()

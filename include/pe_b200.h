@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PE_ABI_VERSION 8
+#define PE_ABI_VERSION 9
 #define PE_MAX_OBJECTS 8      /* object instances composed in one call                     */
 #define PE_MAX_LAYERS 12      /* backbone layers of a field / ray bender                   */
 #define PE_MAX_OCTAVES 16
@@ -150,6 +150,23 @@ typedef struct PeIntegrated {
     float* integrated_divergence;    /* [images][rays]  (zeros: Hutchinson term, see DESIGN)  */
 } PeIntegrated;
 
+/* Decoder hand-off written by the kernel that composes the scene: the rays of a frame are the concatenation of
+ * the decoder's strided grids (RayHelper.sample_all_rays_strided_grid, utils/lib_3d/ray_helper.py:433-482), every grid keeps its own
+ * channel range of the composed features and wants them channels-first (fold_strided_tensors + split_features_by_layer + permute,
+ * model/environment_model_backpropagated_autoencoder.py:129-168, ..._multiresolution_backpropagated_autoencoder.py:29-99).  Segment q =
+ * rays [ray_begin, ray_begin + ray_count) of every image, channels [channel_begin, channel_begin + channel_count) (multiples of 32),
+ * grid[q] = [images][channel_count][ray_count].  With global.integrated_features == NULL only those channels are accumulated (the rest
+ * of the per-sample features is never read) and only the grids are written.                                                         */
+#define PE_MAX_HANDOFF 4
+typedef struct PeHandoff {
+    int32_t segments;                          /* 0: no hand-off                                */
+    int32_t ray_begin[PE_MAX_HANDOFF];
+    int32_t ray_count[PE_MAX_HANDOFF];
+    int32_t channel_begin[PE_MAX_HANDOFF];
+    int32_t channel_count[PE_MAX_HANDOFF];
+    float*  grid[PE_MAX_HANDOFF];
+} PeHandoff;
+
 typedef struct PeOutputs {
     PeIntegrated object[PE_MAX_OBJECTS];        /* results["coarse"]["object_k"]             */
     PeIntegrated global;                        /* results["coarse"]["global"]               */
@@ -170,6 +187,8 @@ typedef struct PeOutputs {
      * The caller orders the peers' reads after this call with its own cross-rank synchronisation.                                   */
     int32_t peers;
     float* peer_features[PE_MAX_PEERS];
+    /* multi-object scenes (the compositor produces the scene's grid), inference: see PeHandoff */
+    PeHandoff handoff;
 } PeOutputs;
 
 /* -- library ------------------------------------------------------------------------------- */

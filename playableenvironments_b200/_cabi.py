@@ -11,7 +11,7 @@ from typing import Optional
 
 import torch
 
-PE_ABI_VERSION = 8
+PE_ABI_VERSION = 9
 PE_MAX_OBJECTS = 8
 PE_MAX_LAYERS = 12
 PE_MAX_OCTAVES = 16
@@ -85,6 +85,17 @@ class PeIntegrated(C.Structure):
     ]
 
 
+PE_MAX_HANDOFF = 4
+
+
+class PeHandoff(C.Structure):
+    _fields_ = [
+        ("segments", C.c_int32), ("ray_begin", C.c_int32 * PE_MAX_HANDOFF), ("ray_count", C.c_int32 * PE_MAX_HANDOFF),
+        ("channel_begin", C.c_int32 * PE_MAX_HANDOFF), ("channel_count", C.c_int32 * PE_MAX_HANDOFF),
+        ("grid", C.c_void_p * PE_MAX_HANDOFF),
+    ]
+
+
 class PeOutputs(C.Structure):
     _fields_ = [
         ("object", PeIntegrated * PE_MAX_OBJECTS), ("global_", PeIntegrated),
@@ -92,6 +103,7 @@ class PeOutputs(C.Structure):
         ("displacements", C.c_void_p * PE_MAX_OBJECTS), ("positions_t", C.c_void_p * PE_MAX_OBJECTS),
         ("bn1_running", C.c_void_p * PE_MAX_OBJECTS), ("bn2_running", C.c_void_p * PE_MAX_OBJECTS),
         ("peers", C.c_int32), ("peer_features", C.c_void_p * PE_MAX_PEERS),
+        ("handoff", PeHandoff),
     ]
 
 

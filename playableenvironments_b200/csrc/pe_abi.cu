@@ -470,6 +470,10 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
         all_tc = all_tc && object_integrates_itself(s, k);
     }
     ca.global = out->global;
+    if (out->handoff.segments) {
+        if (s.objects < 2 || s.perturb) { pe_set_error("the decoder hand-off is written by the compositor: multi-object scenes without perturbation"); return PE_ERR_UNSUPPORTED; }
+        ca.handoff = out->handoff;
+    }
     // objects evaluated by the tcgen05 kernel integrate themselves in its epilogue; a single such object IS the scene
     ca.do_objects = all_tc ? 0 : 1;
     ca.do_global = (all_tc && s.objects == 1 && !s.perturb) ? 0 : 1;
@@ -482,8 +486,8 @@ extern "C" int pe_render_forward(const PeScene* scene, const PeInputs* in, const
     auto wants = [](const PeIntegrated& o) {
         return o.integrated_features || o.opacity || o.weights || o.depth || o.disparity || o.integrated_displacements_magnitude || o.integrated_divergence;
     };
-    if (!wants(ca.global)) ca.do_global = 0;      // (inference, single object: the caller aliases the scene's outputs to the object's)
-    bool any_out = wants(ca.global);
+    if (!wants(ca.global) && !ca.handoff.segments) ca.do_global = 0;      // (inference, single object: the caller aliases the scene's outputs to the object's)
+    bool any_out = wants(ca.global) || ca.handoff.segments != 0;
     for (int k = 0; k < s.objects; ++k) any_out = any_out || wants(ca.object[k]);
     if ((ca.do_objects || ca.do_global) && any_out) {
         rc = pe_launch_composite(ca, stream);

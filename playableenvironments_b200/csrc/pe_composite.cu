@@ -17,9 +17,16 @@ struct RayLists {       // per-warp shared-memory sample list
 };
 
 // ObjectComposer.integrate (model/object_composer.py:724-784) over a list already ordered by t.
+// `hand`: the decoder hand-off of the composed scene (PeHandoff) or NULL; `seg` = the segment this ray belongs to (-1: none)
 __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int n, float dnorm, const float* __restrict__ noise,
-                               const PeIntegrated& out, int64_t ray, int lane) {
+                               const PeIntegrated& out, int64_t ray, int lane, const PeHandoff* hand = nullptr, int seg = -1) {
     const int F = A.features;
+    // channel groups of 32 whose weighted sum anybody reads: all of them, or -- hand-off only -- the segment's channel range
+    unsigned groups = 0xffu;
+    if (hand && !out.integrated_features) {
+        groups = 0u;
+        if (seg >= 0) for (int i = 0; i < 8; ++i) if (32 * i >= hand->channel_begin[seg] && 32 * i < hand->channel_begin[seg] + hand->channel_count[seg]) groups |= 1u << i;
+    }
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -57,7 +64,7 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         const int src = j < n ? S.src[j] : -1;
         // only the samples that carry features and weight (in sample order: the sum is evaluated like the reference's); in a sparse view
         // most of a ray's samples lie outside every box
-        unsigned todo = __ballot_sync(0xffffffffu, j < n && w != 0.f && src >= 0);
+        unsigned todo = groups ? __ballot_sync(0xffffffffu, j < n && w != 0.f && src >= 0) : 0u;
         // FEAT_BATCH samples' feature rows are requested before the first of them is used: the sums stay in sample order, but a ray's
         // in-box samples cost one memory round trip per batch instead of one each (this kernel is latency bound: profiles/r2_compositor.md)
         while (todo) {
@@ -84,7 +91,7 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int c = lane + 32 * i;
-                    fv[u][i] = (u < cnt && c < F) ? __ldg(fp[u] + c) : 0.f;
+                    fv[u][i] = (u < cnt && c < F && ((groups >> i) & 1u)) ? __ldg(fp[u] + c) : 0.f;
                 }
 #pragma unroll
             for (int u = 0; u < FEAT_BATCH; ++u)
@@ -106,6 +113,17 @@ __device__ void integrate_list(const PeCompositeArgs& A, const RayLists& S, int 
         for (int i = 0; i < 8; ++i) {
             const int c = lane + 32 * i;
             if (c < F) out.integrated_features[ray * F + c] = acc[i];
+        }
+    }
+    if (hand && seg >= 0) {
+        // channels-first store into the segment's grid: [image][channel - channel_begin][ray - ray_begin]
+        const int img = (int)(ray / A.rays), r = (int)(ray - (int64_t)img * A.rays);
+        const int cb = hand->channel_begin[seg], cc = hand->channel_count[seg], rc = hand->ray_count[seg];
+        float* g = hand->grid[seg] + (int64_t)img * cc * rc + (r - hand->ray_begin[seg]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + 32 * i - cb;
+            if (c >= 0 && c < cc) g[(int64_t)c * rc] = acc[i];
         }
     }
     if (lane == 0) {
@@ -202,7 +220,14 @@ __global__ void __launch_bounds__(WARPS * 32) pe_composite_kernel(const PeCompos
                 S.t[rank] = tj; S.raw[rank] = U.raw[j]; S.dm[rank] = U.dm[j]; S.dv[rank] = U.dv[j]; S.src[rank] = U.src[j];
             }
             __syncwarp();
-            integrate_list(A, S, n, dnorm, (A.perturb && A.noise_global) ? A.noise_global + ray * n : nullptr, A.global, ray, lane);
+            int seg = -1;
+            if (A.handoff.segments) {
+                const int r = (int)(ray % A.rays);
+                for (int q = 0; q < A.handoff.segments; ++q)
+                    if (r >= A.handoff.ray_begin[q] && r < A.handoff.ray_begin[q] + A.handoff.ray_count[q]) seg = q;
+            }
+            integrate_list(A, S, n, dnorm, (A.perturb && A.noise_global) ? A.noise_global + ray * n : nullptr, A.global, ray, lane,
+                           A.handoff.segments ? &A.handoff : nullptr, seg);
         }
     }
 }
@@ -215,6 +240,15 @@ int pe_launch_composite(const PeCompositeArgs& args, cudaStream_t stream) {
         return PE_ERR_UNSUPPORTED;
     }
     if (args.features > 256) { pe_set_error("compositor supports up to 256 features"); return PE_ERR_UNSUPPORTED; }
+    if (args.handoff.segments < 0 || args.handoff.segments > PE_MAX_HANDOFF) { pe_set_error("hand-off: segments must be in [0,%d]", PE_MAX_HANDOFF); return PE_ERR_INVALID; }
+    for (int q = 0; q < args.handoff.segments; ++q) {
+        const PeHandoff& h = args.handoff;
+        if (!h.grid[q] || h.ray_begin[q] < 0 || h.ray_count[q] < 0 || h.ray_begin[q] + h.ray_count[q] > args.rays || h.channel_begin[q] % 32 ||
+            h.channel_count[q] % 32 || h.channel_begin[q] < 0 || h.channel_begin[q] + h.channel_count[q] > args.features) {
+            pe_set_error("hand-off segment %d: ray range inside the frame, channel range a multiple of 32 inside the features, a grid", q);
+            return PE_ERR_INVALID;
+        }
+    }
     if (args.fix_overlaps) {
         for (int s = 0; s < args.static_objects; ++s)
             for (int d = args.static_objects; d < args.objects; ++d)

@@ -61,6 +61,7 @@ struct PeCompositeArgs {
     const float* noise_global;
     PeIntegrated object[PE_MAX_OBJECTS];
     PeIntegrated global;
+    PeHandoff handoff;                            // decoder hand-off of the composed scene's features (segments == 0: none)
 };
 
 // Arguments of the style prologue: [scale|bias] = Linear(style) (adain.py:30-32) with the BatchNorm

@@ -129,11 +129,16 @@ class ObjectComposer(nn.Module):
     def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
                 transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
                 perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None,
-                peer_features=None, divergence_noise=None) -> Dict:
+                peer_features=None, divergence_noise=None, handoff=None) -> Dict:
         """Same contract as the reference (:786-812).  ``rand`` / ``noise`` optionally supply the perturbation tensors
         (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample.  ``peer_features`` (inference):
         extra destinations of the composed scene's feature grid -- the fused all-gather of ``sharding.PeerGather``.
-        ``divergence_noise`` ({"coarse": [e_k (..., R, P_k, 3) or None per object]}): the Hutchinson probe vectors (``compute_divergence``)."""
+        ``divergence_noise`` ({"coarse": [e_k (..., R, P_k, 3) or None per object]}): the Hutchinson probe vectors (``compute_divergence``).
+        ``handoff`` (inference): ``(strides, (H, W), channels)`` of the multiresolution decoder (reference: fold_strided_tensors +
+        split_features_by_layer + CHW permute, environment_model_multiresolution_backpropagated_autoencoder.py:29-99) for a frame whose rays
+        are the concatenated strided grids: ``results[...]["global"]["feature_grids"]`` holds one (..., channels_i, H/s_i, W/s_i) grid per
+        stride.  In multi-object scenes the compositor writes them directly and reads only each ray's own channel range of the
+        per-sample features (``integrated_features`` of the composed scene is then None); otherwise they are folded from it."""
         objects_count = self.object_id_helper.objects_count
         if transformation_matrix_w2o.size(-1) != objects_count:
             raise Exception(f"Transformation matrix must specifies transformations for"
@@ -146,6 +151,8 @@ class ObjectComposer(nn.Module):
         helper = self.object_id_helper
         use_fine = self._uses_fine()
         record = needs_grad and not getattr(self, "allow_forward_without_grad", False)
+        if handoff is not None and record:
+            raise Exception("handoff (decoder grids written by the render path) is an inference feature: call under torch.no_grad()")
         if use_fine and perturb and rand is None:
             # the fine pass re-derives the coarse ray parameters from the same stratified jitter the coarse kernels used
             lead_r = list(ray_directions.shape[:-1])
@@ -182,12 +189,19 @@ class ObjectComposer(nn.Module):
             return res
 
         coarse = run("coarse", self.object_models_coarse, self._descs(canonical_pose), rand=rand, noise=noise,
-                     peer_features=None if use_fine else peer_features)
+                     peer_features=None if use_fine else peer_features, handoff=None if use_fine else handoff)
         if use_fine:
             # hierarchical pass (reference :561-578): the fine models on the merged ray parameters, composed like the coarse results
             sample_t = self._fine_ray_parameters(ray_origins, ray_directions, focal_normals, transformation_matrix_w2o, object_in_scene,
                                                  perturb, rand, coarse)
-            run("fine", self.object_models_fine, self._descs(canonical_pose, fine=True), sample_t=sample_t, peer_features=peer_features)
+            run("fine", self.object_models_fine, self._descs(canonical_pose, fine=True), sample_t=sample_t, peer_features=peer_features,
+                handoff=handoff)
+        if handoff is not None:
+            # scenes whose grid does not come out of the compositor (one object: the fused kernel; training): fold from the (R, F) tensor
+            from ..utils.lib_3d.ray_helper import RayHelper
+            g = results["fine" if use_fine else "coarse"]["global"]
+            if "feature_grids" not in g:
+                g["feature_grids"] = RayHelper.fold_feature_grids(g["integrated_features"], handoff[0], handoff[1], handoff[2])
         # dummy tensor the reference adds for nn.DataParallel's hook handling (:889-890)
         results["pytorch_hook"] = torch.zeros((1, 1, 1, 1, 1, 1, 1, 1, 1), device=ray_directions.device)
         return results

@@ -146,6 +146,13 @@ def _save_forward(meta) -> bool:
     return meta["precision"] != _cabi.PRECISION_FP32 and os.environ.get("PE_SAVE_FORWARD", "1") != "0"
 
 
+def handoff_supported(hand, rays: int, features: int) -> bool:
+    """(strides, (H, W), channels): the frame's rays are the concatenation of the strided grids, channel ranges are multiples of 32."""
+    strides, (H, W), channels = hand
+    return (0 < len(strides) <= _cabi.PE_MAX_HANDOFF and len(strides) == len(channels) and all(c % 32 == 0 and c > 0 for c in channels)
+            and sum(channels) <= features and sum((H // st) * (W // st) for st in strides) == rays)
+
+
 def _wants_tile_counts(descs, images: int, rays: int) -> bool:
     """Exact backward tile counts (pe_forward_tile_counts) cost the backward a host-side wait for the forward's last copy -- nothing when a
     loss sits between the two, the launch latency of the backward when it follows immediately.  They pay when the worst case (every
@@ -199,6 +206,24 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Opti
         g = _alloc_integrated(lead, rays, sum(d.positions for d in descs), F, device)
         _fill(outs.global_, g)
         results["global"] = g
+        hand = meta.get("handoff")
+        if hand is not None and len(descs) > 1 and not meta["perturb"] and handoff_supported(hand, rays, F):
+            # decoder hand-off written by the compositor (PeHandoff): per strided grid its own channel range, channels first; the
+            # (R, F) feature tensor of the composed scene is neither accumulated in full nor written
+            strides, (H, W), channels = hand
+            grids, r0, c0 = [], 0, 0
+            outs.handoff.segments = len(strides)
+            for q, (st, ch) in enumerate(zip(strides, channels)):
+                gh, gw = H // st, W // st
+                grid = torch.empty(lead + [ch, gh, gw], dtype=torch.float32, device=device)
+                outs.handoff.ray_begin[q], outs.handoff.ray_count[q] = r0, gh * gw
+                outs.handoff.channel_begin[q], outs.handoff.channel_count[q] = c0, ch
+                outs.handoff.grid[q] = _cabi.ptr(grid)
+                grids.append(grid)
+                r0, c0 = r0 + gh * gw, c0 + ch
+            outs.global_.integrated_features = None
+            g["integrated_features"] = None
+            g["feature_grids"] = grids
     peers = meta.get("peer_features") or []
     if peers:
         # fused all-gather: extra destinations of the scene's feature grid (peer-mapped buffers of the other GPUs, sharding.PeerGather)
@@ -391,7 +416,7 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
                  return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None,
                  sample_t: Optional[List[torch.Tensor]] = None, divergence_noise: Optional[List] = None,
-                 bent_gradients: bool = False) -> Dict:
+                 bent_gradients: bool = False, handoff=None) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
     With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node.
     ``sample_t`` (fine pass, :563-578): per object the explicit ray parameters (..., R, P_k) that replace the stratified samples."""
@@ -412,13 +437,15 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
             "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features,
-            "sample_t": sample_t, "divergence_noise": divergence_noise, "bent_gradients": bent_gradients}
+            "sample_t": sample_t, "divergence_noise": divergence_noise, "bent_gradients": bent_gradients, "handoff": handoff}
     if divergence_noise is not None and models is None:
         raise _cabi.PeError("the Hutchinson divergence needs the object models (it is a training-time quantity)")
     if bent_gradients:
         meta["return_samples"] = True
     if peer_features and models is not None and torch.is_grad_enabled():
         raise _cabi.PeError("peer_features (fused all-gather of the feature grid) is an inference feature: call under torch.no_grad()")
+    if handoff is not None and models is not None and torch.is_grad_enabled():
+        raise _cabi.PeError("handoff (decoder grids written by the compositor) is an inference feature: call under torch.no_grad()")
     if models is not None and torch.is_grad_enabled():
         flat_params = [t for mdl in models for _, _, t in mdl.parameter_slots()]
         ts = [t.to(torch.float32).reshape(images, rays, -1) for t in sample_t] if sample_t is not None else []

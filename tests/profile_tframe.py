@@ -24,8 +24,11 @@ for i in range(3):
     if i == 2:
         torch.cuda.profiler.start()
     with torch.no_grad():
-        feats = comp(*call, False)["coarse"]["global"]["integrated_features"]
-        grids = RayHelper.fold_feature_grids(feats, strides, (H, W), [64, 128])
+        if os.environ.get("PE_PROFILE_FOLD") == "1":
+            feats = comp(*call, False)["coarse"]["global"]["integrated_features"]
+            grids = RayHelper.fold_feature_grids(feats, strides, (H, W), [64, 128])
+        else:
+            grids = comp(*call, False, handoff=(strides, (H, W), [64, 128]))["coarse"]["global"]["feature_grids"]
     torch.cuda.synchronize()
     if i == 2:
         torch.cuda.profiler.stop()

@@ -522,3 +522,41 @@ def test_edge_shapes_empty_single_and_ragged_ray_sets(precision, tol):
             if k.startswith("coarse/") and "divergence" not in k:
                 assert got[k].shape == want.shape, (rays, k)
                 assert scale_rel_err(got[k], want) <= tol, (rays, k, scale_rel_err(got[k], want))
+
+
+def test_decoder_hand_off_written_by_the_compositor():
+    """PeHandoff: the compositor stores the composed features straight into the decoder's per-stride CHW grids and accumulates only each
+    ray's own channel range -- bit-equal to folding the full (R, 192) tensor (pe_fold_kernel, itself pinned against the reference's
+    fold_strided_tensors / split_features_by_layer in tests/test_reference_boundary.py); the other outputs are untouched; a
+    single-object scene (no compositor) falls back to the fold."""
+    from gpu_common import build_composer
+    from playableenvironments_b200.utils.lib_3d.ray_helper import RayHelper
+    H, W, strides, channels = 32, 64, [4, 8], [64, 128]
+    lead = (1, 2, 1)
+    parts = [scenes.camera_rays(lead, H, W, 60.0, scenes.tennis_camera(), st) for st in strides]
+    base = scenes.scene_tennis(seed=13, height=H, width=W, stride=4, lead=lead)
+    inputs = dict(base[2])
+    inputs["ray_directions"] = torch.cat([p[1] for p in parts], dim=-2)
+    _, _, _, comp, dev = build_composer((base[0], base[1], inputs), "mixed")
+    call = [dev[k] for k in INPUT_KEYS]
+    with torch.no_grad():
+        plain = comp(*call, False)["coarse"]
+        direct = comp(*call, False, handoff=(strides, (H, W), channels))["coarse"]
+    want = RayHelper.fold_feature_grids(plain["global"]["integrated_features"], strides, (H, W), channels)
+    assert direct["global"]["integrated_features"] is None
+    got = direct["global"]["feature_grids"]
+    assert [tuple(g.shape) for g in got] == [lead + (64, H // 4, W // 4), lead + (128, H // 8, W // 8)]
+    for a, b in zip(got, want):
+        assert float(b.abs().max()) > 0 and torch.equal(a, b)
+    for key in ("opacity", "depth", "weights"):
+        assert torch.equal(direct["global"][key], plain["global"][key]), key
+    assert torch.equal(direct["object_1"]["integrated_features"], plain["object_1"]["integrated_features"])
+    # one object: the fused kernel produces the (R, F) tensor, the grids are folded from it
+    static = scenes.scene_static(seed=12, height=8, width=8, P=128)
+    s_inputs = dict(static[2])
+    s_inputs["ray_directions"] = torch.cat([scenes.camera_rays((1, 1, 1), 16, 16, 40.0, np.eye(4), st)[1] for st in (4, 8)], dim=-2)
+    _, _, _, comp1, dev1 = build_composer((static[0], static[1], s_inputs), "mixed")
+    with torch.no_grad():
+        res = comp1(*[dev1[k] for k in INPUT_KEYS], False, handoff=([4, 8], (16, 16), [64, 128]))["coarse"]["global"]
+    want1 = RayHelper.fold_feature_grids(res["integrated_features"], [4, 8], (16, 16), [64, 128])
+    assert all(torch.equal(a, b) for a, b in zip(res["feature_grids"], want1))
