@@ -475,8 +475,9 @@ def t_train_report(device, batches=(1, 8), eager=True):
 def t_frame_report(device):
     """What play.py renders per frame ("T-frame"): the Tennis full frame 288x512 sampled on the strided grids of the
     multiresolution decoder (strides 4 and 8: 9216 + 2304 = 11 520 rays), 4 object instances (2 static boxes with 4 samples per ray, 2
-    players with 32 samples per ray and positional ray benders: 72 samples per ray, 829 440 sample slots), eval mode, followed by the
-    hand-off fold into the decoder's per-stride CHW grids.  ONE composer call per frame (the reference: 12 chunks of 1000 rays)."""
+    players with 32 samples per ray and positional ray benders: 72 samples per ray, 829 440 sample slots), eval mode, the composed features
+    handed off as the decoder's per-stride CHW grids (written by the compositor).  ONE composer call per frame (the reference: 12 chunks
+    of 1000 rays)."""
     import numpy as np
     import scenes
     from helpers import INPUT_KEYS
@@ -488,7 +489,7 @@ def t_frame_report(device):
     scene = tennis_four_objects(lead, lambda st: scenes.camera_rays(lead, H, W, focal, scenes.tennis_camera(), st))
     dirs = scene[2]["ray_directions"]
     out = {"workload": "T-frame: Tennis 288x512 on the stride-4 + stride-8 grids = 11520 rays, 2 static objects (P=4) + 2 players (P=32, ray benders), "
-                       "eval forward + fold into the decoder's CHW grids, one composer call", "rays": int(dirs.size(-2)), "sample_slots": int(dirs.size(-2)) * 72}
+                       "eval forward, the decoder's per-stride CHW grids written by the compositor (PeHandoff), one composer call", "rays": int(dirs.size(-2)), "sample_slots": int(dirs.size(-2)) * 72}
     for precision in ("mixed", "fp16x3", "fp16"):
         _, _, _, comp, dev = build_composer(scene, precision, device=device)
         call = [dev[k] for k in INPUT_KEYS]
