@@ -494,9 +494,11 @@ def t_frame_report(device):
         _, _, _, comp, dev = build_composer(scene, precision, device=device)
         call = [dev[k] for k in INPUT_KEYS]
 
+        only_global = [False]
+
         def frame():
             with torch.no_grad():      # the compositor writes the decoder's per-stride CHW grids itself (PeHandoff)
-                return comp(*call, False, handoff=(strides, (H, W), [64, 128]))["coarse"]["global"]["feature_grids"]
+                return comp(*call, False, handoff=(strides, (H, W), [64, 128]), global_only=only_global[0])["coarse"]["global"]["feature_grids"]
 
         frame()
         torch.cuda.synchronize()
@@ -508,30 +510,45 @@ def t_frame_report(device):
         torch.cuda.synchronize()
         out[f"{precision}_ms"] = s0.elapsed_time(e0) / 10
         if precision == "mixed":
+            # what the decoder path consumes (environment_model_multiresolution_backpropagated_decoder.py:84): the composed scene only
+            only_global[0] = True
+            frame()
+            torch.cuda.synchronize()
+            s0.record()
+            for _ in range(10):
+                grids_g = frame()
+            e0.record()
+            torch.cuda.synchronize()
+            out["mixed_global_only_ms"] = s0.elapsed_time(e0) / 10
+            out["global_only_equals_full"] = bool(all(torch.equal(a, b) for a, b in zip(grids_g, grids)))
             # the same frame replayed from ONE CUDA graph (the composer call allocates nothing, syncs nothing and sizes its tile lists on
             # the device, so the whole ~30-launch sequence is capturable): what an interactive caller (play.py) should do per frame
-            try:
-                side = torch.cuda.Stream(device=device)
-                side.wait_stream(torch.cuda.current_stream(device))
-                with torch.cuda.stream(side):
-                    for _ in range(2):
-                        frame()
-                torch.cuda.current_stream(device).wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    captured = frame()
-                graph.replay()
-                torch.cuda.synchronize()
-                same = all(torch.equal(a, b) for a, b in zip(captured, grids))
-                s0.record()
-                for _ in range(20):
+            for tag, flag in (("mixed_cuda_graph", False), ("mixed_global_only_cuda_graph", True)):
+                only_global[0] = flag
+                try:
+                    side = torch.cuda.Stream(device=device)
+                    side.wait_stream(torch.cuda.current_stream(device))
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            frame()
+                    torch.cuda.current_stream(device).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        captured = frame()
                     graph.replay()
-                e0.record()
-                torch.cuda.synchronize()
-                out["mixed_cuda_graph_ms"] = s0.elapsed_time(e0) / 20
-                out["cuda_graph_equals_eager"] = bool(same)
-            except Exception as exc:      # noqa: BLE001  (a diagnostic figure: never fail the bench line for it)
-                out["cuda_graph_error"] = str(exc)[:200]
+                    torch.cuda.synchronize()
+                    same = all(torch.equal(a, b) for a, b in zip(captured, grids))
+                    s0.record()
+                    for _ in range(20):
+                        graph.replay()
+                    e0.record()
+                    torch.cuda.synchronize()
+                    out[f"{tag}_ms"] = s0.elapsed_time(e0) / 20
+                    out["cuda_graph_equals_eager"] = bool(same) and out.get("cuda_graph_equals_eager", True)
+                    del graph
+                except Exception as exc:      # noqa: BLE001  (a diagnostic figure: never fail the bench line for it)
+                    out["cuda_graph_error"] = str(exc)[:200]
+            only_global[0] = False
     out["grids"] = [list(g.shape) for g in grids]
     return out
 

@@ -129,7 +129,7 @@ class ObjectComposer(nn.Module):
     def forward(self, ray_origins: torch.Tensor, ray_directions: torch.Tensor, focal_normals: torch.Tensor,
                 transformation_matrix_w2o: torch.Tensor, style: torch.Tensor, deformation: torch.Tensor, object_in_scene: torch.Tensor,
                 perturb: bool, video_indexes: torch.Tensor = None, canonical_pose: bool = False, rand=None, noise=None,
-                peer_features=None, divergence_noise=None, handoff=None) -> Dict:
+                peer_features=None, divergence_noise=None, handoff=None, global_only: bool = False) -> Dict:
         """Same contract as the reference (:786-812).  ``rand`` / ``noise`` optionally supply the perturbation tensors
         (otherwise drawn from torch's generator), so that a run can be reproduced sample for sample.  ``peer_features`` (inference):
         extra destinations of the composed scene's feature grid -- the fused all-gather of ``sharding.PeerGather``.
@@ -138,7 +138,9 @@ class ObjectComposer(nn.Module):
         split_features_by_layer + CHW permute, environment_model_multiresolution_backpropagated_autoencoder.py:29-99) for a frame whose rays
         are the concatenated strided grids: ``results[...]["global"]["feature_grids"]`` holds one (..., channels_i, H/s_i, W/s_i) grid per
         stride.  In multi-object scenes the compositor writes them directly and reads only each ray's own channel range of the
-        per-sample features (``integrated_features`` of the composed scene is then None); otherwise they are folded from it."""
+        per-sample features (``integrated_features`` of the composed scene is then None); otherwise they are folded from it.
+        ``global_only`` (inference, several objects): only ``results[...]["global"]`` is produced -- what the decoder path reads
+        (environment_model_multiresolution_backpropagated_decoder.py:84); the ``object_k`` entries hold ``extra_outputs`` only."""
         objects_count = self.object_id_helper.objects_count
         if transformation_matrix_w2o.size(-1) != objects_count:
             raise Exception(f"Transformation matrix must specifies transformations for"
@@ -151,8 +153,10 @@ class ObjectComposer(nn.Module):
         helper = self.object_id_helper
         use_fine = self._uses_fine()
         record = needs_grad and not getattr(self, "allow_forward_without_grad", False)
-        if handoff is not None and record:
-            raise Exception("handoff (decoder grids written by the render path) is an inference feature: call under torch.no_grad()")
+        if (handoff is not None or global_only) and record:
+            raise Exception("handoff / global_only are inference features: call under torch.no_grad()")
+        if global_only and use_fine:
+            raise Exception("global_only is not available with fine models (the fine pass resamples from every object's coarse weights)")
         if use_fine and perturb and rand is None:
             # the fine pass re-derives the coarse ray parameters from the same stratified jitter the coarse kernels used
             lead_r = list(ray_directions.shape[:-1])
@@ -176,7 +180,7 @@ class ObjectComposer(nn.Module):
                                       ray_directions, transformation_matrix_w2o, style, deformation, object_in_scene, perturb,
                                       self.training, self.config["model"].get("fix_object_overlaps", True), self.apply_activation,
                                       _cabi.PRECISIONS[self.precision], bn_running=bn_running,
-                                      return_raw_alphas=self.return_raw_alphas, models=models, **extra)
+                                      return_raw_alphas=self.return_raw_alphas, models=models, global_only=global_only, **extra)
             if self.training:
                 with torch.no_grad():
                     self._update_running_statistics(bn_running, model_list)

@@ -180,9 +180,13 @@ def _launch_forward(meta, lead, origins, dirs, w2o, styles, deforms, saved: Opti
     ins = _inputs_struct(meta, lead, rays, origins, dirs, w2o, styles, deforms, keep)
     outs = _cabi.PeOutputs()
     results: Dict = {}
+    # inference callers that read the composed scene only (the decoder path: environment_model_multiresolution_backpropagated_decoder.py:84):
+    # no per-object outputs are allocated and the compositor does not integrate the objects' own lists
+    global_only = bool(meta.get("global_only")) and len(descs) > 1 and saved is None and not meta["training"]
     for k, d in enumerate(descs):
-        r = _alloc_integrated(lead, rays, d.positions, F, device)
-        _fill(outs.object[k], r)
+        r = {} if global_only else _alloc_integrated(lead, rays, d.positions, F, device)
+        if not global_only:
+            _fill(outs.object[k], r)
         results[f"object_{k}"] = r
         if meta.get("return_raw_alphas"):   # diagnostic: per-sample raw alphas (first return value family of the object models)
             r["raw_alphas"] = torch.empty(lead + [rays, d.positions], dtype=torch.float32, device=device)
@@ -416,7 +420,7 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
                  bn_running: Optional[List] = None, return_raw_alphas: bool = False, models: Optional[List] = None,
                  return_samples: bool = False, peer_features: Optional[List[torch.Tensor]] = None,
                  sample_t: Optional[List[torch.Tensor]] = None, divergence_noise: Optional[List] = None,
-                 bent_gradients: bool = False, handoff=None) -> Dict:
+                 bent_gradients: bool = False, handoff=None, global_only: bool = False) -> Dict:
     """One ObjectComposer.forward (reference: model/object_composer.py:786-892).  Returns {"object_k": {...}, "global": {...}}.
     With ``models`` (the object model of every instance) and autograd enabled the call is recorded as one RenderFunction node.
     ``sample_t`` (fine pass, :563-578): per object the explicit ray parameters (..., R, P_k) that replace the stratified samples."""
@@ -437,7 +441,8 @@ def render_scene(descs: List[_cabi.PeObjectDesc], static_objects: int, ray_origi
             "fix_object_overlaps": fix_object_overlaps, "apply_activation": apply_activation, "precision": precision,
             "rand": rand, "noise": noise, "ois": ois, "lead": lead, "bn_running": bn_running,
             "return_raw_alphas": return_raw_alphas, "models": models, "return_samples": return_samples, "peer_features": peer_features,
-            "sample_t": sample_t, "divergence_noise": divergence_noise, "bent_gradients": bent_gradients, "handoff": handoff}
+            "sample_t": sample_t, "divergence_noise": divergence_noise, "bent_gradients": bent_gradients, "handoff": handoff,
+            "global_only": global_only}
     if divergence_noise is not None and models is None:
         raise _cabi.PeError("the Hutchinson divergence needs the object models (it is a training-time quantity)")
     if bent_gradients:

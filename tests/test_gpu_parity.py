@@ -560,3 +560,20 @@ def test_decoder_hand_off_written_by_the_compositor():
         res = comp1(*[dev1[k] for k in INPUT_KEYS], False, handoff=([4, 8], (16, 16), [64, 128]))["coarse"]["global"]
     want1 = RayHelper.fold_feature_grids(res["integrated_features"], [4, 8], (16, 16), [64, 128])
     assert all(torch.equal(a, b) for a, b in zip(res["feature_grids"], want1))
+
+
+def test_global_only_inference_call():
+    """global_only: the composed scene alone (what the decoder path reads) -- identical to the full call's "global" entry, no per-object
+    outputs; refused with autograd recording."""
+    from gpu_common import build_composer
+    _, _, _, comp, dev = build_composer("tennis_small", "mixed")
+    call = [dev[k] for k in INPUT_KEYS]
+    with torch.no_grad():
+        full = comp(*call, False)["coarse"]
+        only = comp(*call, False, global_only=True)["coarse"]
+    for key, v in full["global"].items():
+        assert torch.equal(only["global"][key], v) or (key == "disparity" and torch.equal(torch.nan_to_num(only["global"][key]), torch.nan_to_num(v))), key
+    assert set(only["object_0"].keys()) == {"extra_outputs"}
+    comp.allow_forward_without_grad = False
+    with pytest.raises(Exception, match="inference"):
+        comp(*call, False, global_only=True)
