@@ -74,9 +74,13 @@ def l2(a, b):
 
 tc, config, state, dev = ours({})
 fp, _, _, _ = ours({"PE_BWD_TC": "0"})
+wlo, _, _, _ = ours({"PE_BWD_CHAIN_WLO": "1"})
+tc2, _, _, _ = ours({"PE_TC_BENDER": "0"})
+tc3, _, _, _ = ours({"PE_TC_BENDER": "0", "PE_BWD_TC_BENDER": "0"})
 u32 = upstream(config, state, dev, torch.float32)
 u64 = port(config, state, dev, torch.float64)
 p32 = port(config, state, dev, torch.float32)
+print(json.dumps({"L2 tc_wlo_vs_up32": l2(wlo, u32), "L2 tc_fp32bender_vs_up32": l2(tc2, u32), "L2 tc_fp32bender_fwd_and_bwd_vs_up32": l2(tc3, u32)}))
 print(json.dumps({"L2 tc_vs_up32": l2(tc, u32), "L2 fp32bwd_vs_up32": l2(fp, u32), "L2 up32_vs_64": l2(u32, u64), "L2 tc_vs_64": l2(tc, u64)}))
 print(json.dumps({"tc_vs_up32": worst(tc, u32), "fp32bwd_vs_up32": worst(fp, u32), "up32_vs_up64": worst(u32, u64), "port32_vs_up32": worst(p32, u32), "port32_vs_64": worst(p32, u64), "tc_vs_up64": worst(tc, u64),
                   "fp32bwd_vs_up64": worst(fp, u64)}, indent=1))

@@ -99,12 +99,17 @@ def test_training_replica_step_against_the_upstream_composer_on_the_gpu():
         assert e <= 6e-2, (k, e)
 
 
-def test_training_replica_step_exact_backward_against_the_upstream_composer(monkeypatch):
-    """The same step with the exact fp32 field backward (PE_BWD_TC=0): parameter gradients within 1e-2 (relative L2) of the upstream
-    composer's (measured 2.1e-3)."""
+@pytest.mark.parametrize("env,bound", [({"PE_BWD_TC": "0"}, 1e-2), ({"PE_TC_BENDER": "0"}, 5e-3)])
+def test_training_replica_step_exact_variants_against_the_upstream_composer(env, bound, monkeypatch):
+    """The same step (a) with the exact fp32 field backward (PE_BWD_TC=0): parameter gradients within 1e-2 (relative L2) of the upstream
+    composer's (measured 2.1e-3); (b) with the tensor-core backward behind the EXACT fp32 ray bender in the forward (PE_TC_BENDER=0, what
+    precision = fp16x3 does): 1.0e-3 measured -- the distance of the default path (8e-3 ... 3.6e-2) is the tensor-core ray bender's: its
+    ~1e-6 on the bent positions is 3e-3 rad of phase in the 2^9-octave Fourier features, which moves ReLU masks; the field backward on
+    the tensor cores adds nothing measurable."""
     import bench
     from gpu_common import build_composer
-    monkeypatch.setenv("PE_BWD_TC", "0")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     device = torch.device("cuda", 0)
     scene, lead = bench.t_train_scene(1)
     config, state, inputs, comp, dev = build_composer(scene, "mixed", device=device, training=True)
@@ -126,4 +131,4 @@ def test_training_replica_step_exact_backward_against_the_upstream_composer(monk
     ref = {k: p.grad.double() for k, p in up.named_parameters() if p.grad is not None}
     num = sum(float(((got[k] - ref[k]) ** 2).sum()) for k in ref) ** 0.5
     den = sum(float((ref[k] ** 2).sum()) for k in ref) ** 0.5
-    assert num / den <= 1e-2, num / den
+    assert num / den <= bound, num / den
