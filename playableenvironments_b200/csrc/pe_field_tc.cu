@@ -308,6 +308,25 @@ __host__ __device__ __forceinline__ void bender_layer_spec(int l, int& n, int& s
     else if (l == 6) { n = 16; has_bias = false; } // 3 outputs, padded to the smallest MMA N
 }
 
+constexpr uint32_t B_SMALL_OFF = 128;            // TMEM columns 128..255: accumulator of the small partial products (MmaRing::small_off)
+
+// Epilogue of a hidden bender layer with the split accumulator: y = relu(large + small) -> hi + lo fp16 A operand of the next layer
+__device__ __forceinline__ void bender_hidden_epilogue(uint32_t tcol, unsigned char* a_hi, unsigned char* a_lo, int m) {
+    uint32_t v[32], w[32];
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tcol + c * 32, v);
+        tmem_ld32(tcol + B_SMALL_OFF + c * 32, w);
+        tmem_wait_ld_regs(v);
+        tmem_wait_ld_regs(w);
+        float y[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) y[q] = __fadd_rn(__uint_as_float(v[q]), __uint_as_float(w[q]));
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) store_a8_hilo(a_hi, a_lo, c * 4 + cc, m, y + 8 * cc, true);
+    }
+}
+
 __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFieldArgs A) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_hi = smem;
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
         reinterpret_cast<__half*>(ones)[threadIdx.x] = __float2half_rn((r < 8 && c < 2) ? 1.f : 0.f);
     }
     fence_proxy_async();
-    if (warp == 2) tmem_alloc(tmem_slot, 128);
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -381,7 +400,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
             R.full_bar = full_bar; R.empty_bar = empty_bar; R.acc_full = acc_full;
             R.a_addr[0] = smem_u32(a_hi); R.a_addr[1] = smem_u32(a_lo);
             R.ring_addr = smem_u32(ring); R.tmem_base = tmem_base;
-            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 2;
+            R.stage = 0; R.phase = 0; R.num_passes = 2; R.x3 = 2; R.small_off = B_SMALL_OFF;
             const uint64_t ones_desc = umma_smem_desc(smem_u32(ones), 128, 0);
             for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int l = 0; l < B_LAYERS; ++l) {
@@ -442,13 +461,17 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
             sync.arrive_ready();
             for (int l = 0; l < 6; ++l) {
                 sync.wait_acc();
-                hidden_epilogue<0, 128, true>(taddr, a_hi, 0, m, nullptr, nullptr, a_lo);
+                bender_hidden_epilogue(taddr, a_hi, a_lo, m);
                 sync.arrive_ready();
             }
             sync.wait_acc();
-            uint32_t v[16];
+            uint32_t v[16], vs[16];
             tmem_ld16(taddr, v);
+            tmem_ld16(taddr + B_SMALL_OFF, vs);
             tmem_wait_ld_regs16(v);
+            tmem_wait_ld_regs16(vs);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v[a] = __float_as_uint(__fadd_rn(__uint_as_float(v[a]), __uint_as_float(vs[a])));
             tc_fence_before();
             if (valid) {
                 float bent[3], d2 = 0.f;
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) pe_bender_tc_kernel(const PeFiel
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 128);
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -797,6 +797,13 @@ struct MmaRing {
     uint32_t a_addr[2], ring_addr, tmem_base;
     int stage; uint32_t phase;
     int num_passes, x3;
+    // hi/lo-split modes: TMEM column offset of a second accumulator for the SMALL partial products (A_lo W_hi, A_hi W_lo, A_lo W_lo), 0 =
+    // everything into one accumulator.  tcgen05.mma truncates its fp32 accumulation toward zero (measured: tests/gpu_tc_accumulate.py,
+    // -0.5 ulp per instruction on same-sign data, against +-0.3 ulp of a rounded add): every small product added to an accumulator that
+    // already holds the large sum costs a truncation at the LARGE sum's ulp.  Kept apart, the small terms truncate at their own
+    // magnitude (2^-11 of the large one) and the large accumulator sees one add per k-step instead of three or four; the epilogue adds
+    // the two once, rounded.
+    uint32_t small_off = 0;
 };
 
 // Issues the MMAs of one layer for both tiles (slab by slab as the weights land).  kSwap: operand roles exchanged
@@ -827,6 +834,13 @@ __device__ __forceinline__ void mma_layer(MmaRing& R, int l, int n, int slabs, i
                     for (int b = 0; b < mblocks; ++b) {
                         const uint64_t db = umma_smem_desc(b_addr + 2 * j * lbo_b + b * 2048, lbo_b, 128);
                         const uint32_t td = R.tmem_base + b * 128;
+                        if (R.small_off) {
+                            // pass 0: A_hi W_hi -> large accumulator, A_lo W_hi -> small one; pass 1: A_hi W_lo (and A_lo W_lo) -> small one
+                            const uint32_t ts = td + R.small_off;
+                            umma_f16_ss(pass == 0 ? td : ts, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, pass == 0 ? ((s | j) != 0 ? 1u : 0u) : 1u);
+                            if (pass == 0 || kX3Mode == 2) umma_f16_ss(ts, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, accum);
+                            continue;
+                        }
                         umma_f16_ss(td, kSwap ? db : da_hi, kSwap ? da_hi : db, idesc, accum);
                         // x3 == 2 (ray bender): the lo x lo term too -- its output feeds 2^9-octave Fourier features downstream
                         if (pass == 0 || kX3Mode == 2) umma_f16_ss(td, kSwap ? db : da_lo, kSwap ? da_lo : db, idesc, 1u);

@@ -226,4 +226,6 @@ def test_exact_tile_counts_from_the_kept_forward(max_tiles, monkeypatch):
     assert ref.keys() == got.keys()
     for k in ref:
         scale = float(ref[k].abs().max())
-        assert float((got[k] - ref[k]).abs().max()) <= 2e-4 * max(scale, 1e-12), k
+        # (two separate steps: the fp32 atomics of the parameter sums land in another order -- up to 3e-4 of a tensor's largest entry on the
+        # cancellation-heavy ones, tests/gpu_determinism_diag.py; a tile dropped or walked twice would show at the 1e-2 level)
+        assert float((got[k] - ref[k]).abs().max()) <= 2e-3 * max(scale, 1e-12), k

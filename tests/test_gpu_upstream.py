@@ -19,6 +19,24 @@ from helpers import INPUT_KEYS
 
 pytestmark = pytest.mark.gpu
 
+@pytest.fixture(autouse=True)
+def _isolate_the_upstream_import():
+    """The upstream tree's top-level packages are called ``model`` and ``utils`` and need interpreter-wide shims (np.bool,
+    collections.Sequence): everything they touch is put back, so that later test modules see the process as it was."""
+    import collections
+    import numpy as np
+    path, modules = list(sys.path), set(sys.modules)
+    had_seq, np_bool = hasattr(collections, "Sequence"), np.bool
+    yield
+    sys.path[:] = path
+    for name in set(sys.modules) - modules:
+        if name.split(".")[0] in ("model", "utils"):
+            del sys.modules[name]
+    np.bool = np_bool
+    if not had_seq and hasattr(collections, "Sequence"):
+        del collections.Sequence
+
+
 OUTPUT_KEYS = ("integrated_features", "opacity", "depth", "weights", "integrated_displacements_magnitude")
 
 
