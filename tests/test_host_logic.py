@@ -211,3 +211,31 @@ def test_reference_arm_zip_is_the_upstream_composer():
         "print('ok')\n")
     proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "ok" in proc.stdout, proc.stderr[-800:]
+
+
+def test_hand_off_plan_and_tile_count_policy(monkeypatch):
+    """Host-side decisions of the render call: which decoder hand-off plans the compositor can write directly (rays = the concatenated
+    strided grids, channel ranges in multiples of 32), and when the forward counts the backward's tiles (only when the worst case
+    overflows the activation stash)."""
+    from playableenvironments_b200.model import render
+    plan = ([4, 8], (288, 512), [64, 128])
+    assert render.handoff_supported(plan, 72 * 128 + 36 * 64, 192)
+    assert not render.handoff_supported(plan, 72 * 128, 192)                         # rays are not the two grids
+    assert not render.handoff_supported(([4, 8], (288, 512), [64, 100]), 11520, 192)   # channel range not a multiple of 32
+    assert not render.handoff_supported(([4, 8], (288, 512), [128, 128]), 11520, 192)  # more channels than features
+    assert not render.handoff_supported(([4, 8, 16, 32, 64], (288, 512), [32] * 5), 0, 192)
+
+    class D:
+        def __init__(self, positions):
+            self.positions = positions
+    monkeypatch.delenv("PE_BWD_TILE_COUNTS", raising=False)
+    monkeypatch.delenv("PE_BWD_TC_MAX_TILES", raising=False)
+    tennis = [D(4), D(4), D(32), D(32)]
+    assert not render._wants_tile_counts(tennis, 4, 5120)          # one replica: 5 120 tiles per player at most
+    assert render._wants_tile_counts(tennis, 32, 5120)             # the 32-image batch: 40 960 > 12 288
+    monkeypatch.setenv("PE_BWD_TC_MAX_TILES", "100000")
+    assert not render._wants_tile_counts(tennis, 32, 5120)
+    monkeypatch.setenv("PE_BWD_TILE_COUNTS", "1")
+    assert render._wants_tile_counts(tennis, 1, 8)
+    monkeypatch.setenv("PE_BWD_TILE_COUNTS", "0")
+    assert not render._wants_tile_counts(tennis, 32, 5120)
